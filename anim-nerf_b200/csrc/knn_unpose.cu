@@ -1,0 +1,454 @@
+// A5-A8: K-nearest-SMPL-vertex search fused with the inverse-skinning blend ("unpose").
+// Reference: knn_cuda.KNN(k=4) call at models/anim_nerf.py:158-159, get_neighbs :153-178,
+// unpose :180-192, batch_index_select/batch_transform :24-39, point generation
+// models/volume_rendering.py:117-120.
+//
+// Arithmetic contract for the neighbour search (bit-exact indices vs the oracle):
+//   d2 = ((qx-vx)^2 + (qy-vy)^2) + (qz-vz)^2, every operation rounded to fp32 (no FMA
+//   contraction: __fmul_rn/__fadd_rn), neighbours ordered by (d2, vertex index) ascending,
+//   dist = sqrt_rn(d2).
+//
+// Two search kernels share one epilogue:
+//   mode 0  exhaustive: the frame's vertex table (6890 x float4 = 110 KB) is staged once per
+//           CTA in shared memory and every thread scans it with warp-broadcast LDS.128 reads.
+//   mode 1  grid-pruned: a per-frame uniform grid (cell slightly larger than dis_threshold)
+//           built by an_vertex_grid_build.  A query whose 3x3x3 cell block holds no vertex
+//           closer than dis_threshold is invalid *exactly* (valid needs d_min < threshold,
+//           SURVEY App. A) and skips everything; otherwise the block scan is exact whenever
+//           the 4th neighbour lies within one cell width, else the thread falls back to an
+//           exhaustive scan of the global table.  The (d2,index) order key makes the result
+//           independent of the scan order, so both modes return identical bits.
+// The epilogue (confidence from skinning-weight L1 distance, exp(-dist) weights, blend of the
+// 4 neighbours' 3x4 observation->canonical transforms, affine apply, validity) reads the
+// L2-resident tables (lbs 661 KB, ober2cano 441 KB per frame) with 128-bit loads.
+// The search is fp32-ALU bound, not HBM bound: algorithmic HBM bytes per point are 12 B in
+// (or 0 when generated from the ray) + 16 B out (+32 B idx/qw when training).
+#include "common.cuh"
+#include <math_constants.h>
+
+#define KNN_THREADS 256
+#define GRID_MAXC (AN_GRID_MAX_DIM * AN_GRID_MAX_DIM * AN_GRID_MAX_DIM)
+
+struct GridHeader { float ox, oy, oz, cell; int nx, ny, nz, pad; };
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+static inline int64_t grid_frame_bytes(int V) {
+    return align_up(sizeof(GridHeader), 16) + align_up((int64_t)(GRID_MAXC + 1) * 4, 16) +
+           align_up((int64_t)GRID_MAXC * 4, 16) + align_up((int64_t)V * 16, 16);
+}
+#define GRID_OFF_START 32
+#define GRID_OFF_COUNT (GRID_OFF_START + ((GRID_MAXC + 1) * 4 + 15) / 16 * 16)
+#define GRID_OFF_SORTED (GRID_OFF_COUNT + GRID_MAXC * 4)
+
+struct Best4 { float d[4]; int i[4]; };
+
+__device__ __forceinline__ void best_init(Best4& b) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { b.d[j] = CUDART_INF_F; b.i[j] = 0x7fffffff; }
+}
+// ascending-index scan: strict '<' keeps the lowest index on ties
+__device__ __forceinline__ void best_push_ordered(Best4& b, float d2, int idx) {
+    if (d2 < b.d[3]) {
+        if (d2 < b.d[2]) {
+            b.d[3] = b.d[2]; b.i[3] = b.i[2];
+            if (d2 < b.d[1]) {
+                b.d[2] = b.d[1]; b.i[2] = b.i[1];
+                if (d2 < b.d[0]) { b.d[1] = b.d[0]; b.i[1] = b.i[0]; b.d[0] = d2; b.i[0] = idx; }
+                else { b.d[1] = d2; b.i[1] = idx; }
+            } else { b.d[2] = d2; b.i[2] = idx; }
+        } else { b.d[3] = d2; b.i[3] = idx; }
+    }
+}
+__device__ __forceinline__ bool key_less(float d2, int idx, float bd, int bi) {
+    return d2 < bd || (d2 == bd && idx < bi);
+}
+// arbitrary-order scan: explicit (d2, index) key
+__device__ __forceinline__ void best_push_any(Best4& b, float d2, int idx) {
+    if (key_less(d2, idx, b.d[3], b.i[3])) {
+        if (key_less(d2, idx, b.d[2], b.i[2])) {
+            b.d[3] = b.d[2]; b.i[3] = b.i[2];
+            if (key_less(d2, idx, b.d[1], b.i[1])) {
+                b.d[2] = b.d[1]; b.i[2] = b.i[1];
+                if (key_less(d2, idx, b.d[0], b.i[0])) { b.d[1] = b.d[0]; b.i[1] = b.i[0]; b.d[0] = d2; b.i[0] = idx; }
+                else { b.d[1] = d2; b.i[1] = idx; }
+            } else { b.d[2] = d2; b.i[2] = idx; }
+        } else { b.d[3] = d2; b.i[3] = idx; }
+    }
+}
+__device__ __forceinline__ float dist2_rn(float qx, float qy, float qz, float vx, float vy, float vz) {
+    const float dx = __fsub_rn(qx, vx), dy = __fsub_rn(qy, vy), dz = __fsub_rn(qz, vz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ void load_query(const float* __restrict__ xyz, const float* __restrict__ rays,
+                                           const float* __restrict__ z, int64_t gid, int K,
+                                           float& qx, float& qy, float& qz)
+{
+    if (xyz) { qx = xyz[gid * 3]; qy = xyz[gid * 3 + 1]; qz = xyz[gid * 3 + 2]; }
+    else {
+        const int64_t ray = gid / K;                 // rays are (B*R, 8), z is (B*R, K)
+        const float4 r0 = __ldg((const float4*)rays + ray * 2), r1 = __ldg((const float4*)rays + ray * 2 + 1);
+        const float zz = z[gid];
+        qx = r0.x + zz * r0.w; qy = r0.y + zz * r1.x; qz = r0.z + zz * r1.y;
+    }
+}
+
+struct UnposeOut {
+    float* xyz_cano; uint8_t* valid; int32_t* idx; float* dist; float* qw;
+    float* sigma; float* rgb; int32_t* cidx; int32_t* count;
+};
+
+// Epilogue shared by both search kernels.  `found`: best holds the exact 4-NN.
+__device__ __forceinline__ void unpose_epilogue(const Best4& best, bool found, float qx, float qy, float qz,
+                                                int64_t gid, int b, int V, int J,
+                                                const float* __restrict__ ober2cano,
+                                                const float* __restrict__ lbsw, float thr,
+                                                const UnposeOut& o, bool active)
+{
+    bool valid = false;
+    float xc0 = 0.f, xc1 = 0.f, xc2 = 0.f;
+    float dd[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active && found) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dd[j] = __fsqrt_rn(best.d[j]);
+        // confidence: skinning rows of neighbour j vs neighbour 0
+        const float* w0 = lbsw + (int64_t)best.i[0] * J;
+        float l1[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < J; ++c) {
+            const float a = __ldg(w0 + c);
+#pragma unroll
+            for (int j = 1; j < 4; ++j) l1[j] += fabsf(__ldg(lbsw + (int64_t)best.i[j] * J + c) - a);
+        }
+        float qs = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float conf = (expf(-l1[j] / 0.02f) > 0.9f) ? 1.0f : 0.0f;   // weight_std=0.1 -> 2*std^2
+            q[j] = expf(-dd[j]) * conf;
+            qs += q[j];
+        }
+        float dbar = 0.f;
+        float m[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) m[e] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            q[j] = q[j] / qs;
+            dbar += q[j] * dd[j];
+            const float4* M = (const float4*)(ober2cano + ((int64_t)b * V + best.i[j]) * 16);
+            const float4 r0 = __ldg(M), r1 = __ldg(M + 1), r2 = __ldg(M + 2);
+            m[0] += q[j] * r0.x; m[1] += q[j] * r0.y; m[2] += q[j] * r0.z; m[3] += q[j] * r0.w;
+            m[4] += q[j] * r1.x; m[5] += q[j] * r1.y; m[6] += q[j] * r1.z; m[7] += q[j] * r1.w;
+            m[8] += q[j] * r2.x; m[9] += q[j] * r2.y; m[10] += q[j] * r2.z; m[11] += q[j] * r2.w;
+        }
+        valid = dbar < thr;
+        xc0 = m[0] * qx + m[1] * qy + m[2] * qz + m[3];
+        xc1 = m[4] * qx + m[5] * qy + m[6] * qz + m[7];
+        xc2 = m[8] * qx + m[9] * qy + m[10] * qz + m[11];
+    }
+    if (active) {
+        o.xyz_cano[gid * 3] = xc0; o.xyz_cano[gid * 3 + 1] = xc1; o.xyz_cano[gid * 3 + 2] = xc2;
+        o.valid[gid] = valid ? 1 : 0;
+        if (o.idx) {
+            int4 v = found ? make_int4(best.i[0], best.i[1], best.i[2], best.i[3]) : make_int4(-1, -1, -1, -1);
+            ((int4*)o.idx)[gid] = v;
+        }
+        if (o.dist) ((float4*)o.dist)[gid] = make_float4(dd[0], dd[1], dd[2], dd[3]);
+        if (o.qw) ((float4*)o.qw)[gid] = make_float4(q[0], q[1], q[2], q[3]);
+        if (!valid) {
+            if (o.sigma) o.sigma[gid] = -1e5f;
+            if (o.rgb) { o.rgb[gid * 3] = 0.f; o.rgb[gid * 3 + 1] = 0.f; o.rgb[gid * 3 + 2] = 0.f; }
+        }
+    }
+    if (o.cidx) {   // warp-aggregated compaction of valid point ids
+        const unsigned mask = __ballot_sync(0xffffffffu, valid);
+        if (mask) {
+            const int lane = threadIdx.x & 31;
+            const int leader = __ffs(mask) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(o.count, __popc(mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (valid) o.cidx[base + __popc(mask & ((1u << lane) - 1))] = (int32_t)gid;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ mode 0: exhaustive
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_unpose_brute_kernel(const float* __restrict__ xyz, const float* __restrict__ rays,
+                        const float* __restrict__ z, int K, int64_t N,
+                        const float* __restrict__ verts, int V, const float* __restrict__ ober2cano,
+                        const float* __restrict__ lbsw, int J, float thr, UnposeOut o)
+{
+    extern __shared__ float4 s_v[];
+    const int b = blockIdx.y;
+    const float* vb = verts + (int64_t)b * V * 3;
+    for (int v = threadIdx.x; v < V; v += blockDim.x)
+        s_v[v] = make_float4(vb[v * 3], vb[v * 3 + 1], vb[v * 3 + 2], 0.f);
+    __syncthreads();
+    const int64_t per = (int64_t)gridDim.x * blockDim.x;
+    const int64_t rounds = (N + per - 1) / per;
+    for (int64_t it = 0; it < rounds; ++it) {
+        const int64_t n = it * per + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+        const bool active = n < N;
+        const int64_t gid = (int64_t)b * N + (active ? n : 0);
+        float qx = 0.f, qy = 0.f, qz = 0.f;
+        if (active) load_query(xyz, rays, z, gid, K, qx, qy, qz);
+        Best4 best; best_init(best);
+        if (active) {
+#pragma unroll 4
+            for (int v = 0; v < V; ++v) {
+                const float4 p = s_v[v];
+                best_push_ordered(best, dist2_rn(qx, qy, qz, p.x, p.y, p.z), v);
+            }
+        }
+        unpose_epilogue(best, true, qx, qy, qz, gid, b, V, J, ober2cano, lbsw, thr, o, active);
+    }
+}
+
+// ------------------------------------------------------------------ grid build
+__global__ void __launch_bounds__(1024)
+vertex_grid_build_kernel(const float* __restrict__ verts, int V, float cell_in, char* __restrict__ ws,
+                         int64_t frame_bytes)
+{
+    __shared__ float s_red[6][32];
+    __shared__ GridHeader s_h;
+    __shared__ int s_scan[1024];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const float* vb = verts + (int64_t)b * V * 3;
+    char* base = ws + (int64_t)b * frame_bytes;
+    GridHeader* hdr = (GridHeader*)base;
+    int* cell_start = (int*)(base + GRID_OFF_START);
+    int* counts = (int*)(base + GRID_OFF_COUNT);
+    float4* sorted = (float4*)(base + GRID_OFF_SORTED);
+
+    float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    for (int v = tid; v < V; v += blockDim.x)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { const float x = vb[v * 3 + a]; lo[a] = fminf(lo[a], x); hi[a] = fmaxf(hi[a], x); }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+        if (lane == 0) { s_red[a][wid] = lo[a]; s_red[3 + a][wid] = hi[a]; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float l[3], h[3];
+        for (int a = 0; a < 3; ++a) {
+            l[a] = s_red[a][0]; h[a] = s_red[3 + a][0];
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { l[a] = fminf(l[a], s_red[a][w]); h[a] = fmaxf(h[a], s_red[3 + a][w]); }
+        }
+        float cell = cell_in;
+        const float ext = fmaxf(h[0] - l[0], fmaxf(h[1] - l[1], h[2] - l[2]));
+        if (ext / cell > (float)(AN_GRID_MAX_DIM - 1)) cell = ext / (float)(AN_GRID_MAX_DIM - 1);
+        s_h.ox = l[0]; s_h.oy = l[1]; s_h.oz = l[2]; s_h.cell = cell;
+        s_h.nx = min(AN_GRID_MAX_DIM, (int)floorf((h[0] - l[0]) / cell) + 1);
+        s_h.ny = min(AN_GRID_MAX_DIM, (int)floorf((h[1] - l[1]) / cell) + 1);
+        s_h.nz = min(AN_GRID_MAX_DIM, (int)floorf((h[2] - l[2]) / cell) + 1);
+        s_h.pad = 0;
+        *hdr = s_h;
+    }
+    __syncthreads();
+    const GridHeader h = s_h;
+    const int ncell = h.nx * h.ny * h.nz;
+    for (int c = tid; c < ncell; c += blockDim.x) counts[c] = 0;
+    __syncthreads();
+    for (int v = tid; v < V; v += blockDim.x) {
+        const int cx = min(h.nx - 1, max(0, (int)floorf((vb[v * 3] - h.ox) / h.cell)));
+        const int cy = min(h.ny - 1, max(0, (int)floorf((vb[v * 3 + 1] - h.oy) / h.cell)));
+        const int cz = min(h.nz - 1, max(0, (int)floorf((vb[v * 3 + 2] - h.oz) / h.cell)));
+        atomicAdd(&counts[(cz * h.ny + cy) * h.nx + cx], 1);
+    }
+    __syncthreads();
+    // exclusive scan over ncell counts: thread t owns cells [t*per, (t+1)*per)
+    const int per = (ncell + blockDim.x - 1) / blockDim.x;
+    int local = 0;
+    for (int c = tid * per; c < min(ncell, (tid + 1) * per); ++c) local += counts[c];
+    s_scan[tid] = local;
+    __syncthreads();
+    for (int o = 1; o < (int)blockDim.x; o <<= 1) {
+        const int add = tid >= o ? s_scan[tid - o] : 0;
+        __syncthreads();
+        s_scan[tid] += add;
+        __syncthreads();
+    }
+    int run = s_scan[tid] - local;
+    for (int c = tid * per; c < min(ncell, (tid + 1) * per); ++c) { cell_start[c] = run; run += counts[c]; }
+    if (tid == 0) cell_start[ncell] = V;
+    __syncthreads();
+    for (int v = tid; v < V; v += blockDim.x) {
+        const float x = vb[v * 3], y = vb[v * 3 + 1], zc = vb[v * 3 + 2];
+        const int cx = min(h.nx - 1, max(0, (int)floorf((x - h.ox) / h.cell)));
+        const int cy = min(h.ny - 1, max(0, (int)floorf((y - h.oy) / h.cell)));
+        const int cz = min(h.nz - 1, max(0, (int)floorf((zc - h.oz) / h.cell)));
+        const int c = (cz * h.ny + cy) * h.nx + cx;
+        const int pos = cell_start[c] + atomicSub(&counts[c], 1) - 1;
+        sorted[pos] = make_float4(x, y, zc, __int_as_float(v));
+    }
+}
+
+// ------------------------------------------------------------------ mode 1: grid-pruned
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_unpose_grid_kernel(const float* __restrict__ xyz, const float* __restrict__ rays,
+                       const float* __restrict__ z, int K, int64_t N,
+                       const float* __restrict__ verts, int V, const char* __restrict__ ws,
+                       int64_t frame_bytes, const float* __restrict__ ober2cano,
+                       const float* __restrict__ lbsw, int J, float thr, UnposeOut o)
+{
+    const int b = blockIdx.y;
+    const char* base = ws + (int64_t)b * frame_bytes;
+    const GridHeader h = *(const GridHeader*)base;
+    const int* __restrict__ cell_start = (const int*)(base + GRID_OFF_START);
+    const float4* __restrict__ sorted = (const float4*)(base + GRID_OFF_SORTED);
+    const float* vb = verts + (int64_t)b * V * 3;
+    const float thr2 = thr * thr * (1.0f + 1e-5f);   // prune only what is invalid beyond rounding doubt
+    const float rs = h.cell * (1.0f - 1e-4f);
+    const float safe2 = rs * rs;
+    const int64_t per = (int64_t)gridDim.x * blockDim.x;
+    const int64_t rounds = (N + per - 1) / per;
+    for (int64_t it = 0; it < rounds; ++it) {
+        const int64_t n = it * per + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+        const bool active = n < N;
+        const int64_t gid = (int64_t)b * N + (active ? n : 0);
+        float qx = 0.f, qy = 0.f, qz = 0.f;
+        Best4 best; best_init(best);
+        bool found = false;
+        if (active) {
+            load_query(xyz, rays, z, gid, K, qx, qy, qz);
+            const int cx = (int)floorf((qx - h.ox) / h.cell);
+            const int cy = (int)floorf((qy - h.oy) / h.cell);
+            const int cz = (int)floorf((qz - h.oz) / h.cell);
+            if (cx >= -1 && cx <= h.nx && cy >= -1 && cy <= h.ny && cz >= -1 && cz <= h.nz) {
+                const int x0 = max(cx - 1, 0), x1 = min(cx + 1, h.nx - 1);
+                for (int gz = max(cz - 1, 0); gz <= min(cz + 1, h.nz - 1); ++gz)
+                    for (int gy = max(cy - 1, 0); gy <= min(cy + 1, h.ny - 1); ++gy) {
+                        if (x0 > x1) continue;
+                        const int row = (gz * h.ny + gy) * h.nx;
+                        const int s = __ldg(cell_start + row + x0), e = __ldg(cell_start + row + x1 + 1);
+                        for (int p = s; p < e; ++p) {             // x-adjacent cells are contiguous
+                            const float4 v = __ldg(sorted + p);
+                            best_push_any(best, dist2_rn(qx, qy, qz, v.x, v.y, v.z), __float_as_int(v.w));
+                        }
+                    }
+            }
+            if (best.d[0] < thr2) {              // may be valid: need the exact 4-NN
+                if (best.d[3] <= safe2) found = true;
+                else {                           // rare: 4th neighbour not provably inside the block
+                    best_init(best);
+                    for (int v = 0; v < V; ++v)
+                        best_push_ordered(best, dist2_rn(qx, qy, qz, __ldg(vb + v * 3), __ldg(vb + v * 3 + 1), __ldg(vb + v * 3 + 2)), v);
+                    found = true;
+                }
+            }
+        }
+        unpose_epilogue(best, found, qx, qy, qz, gid, b, V, J, ober2cano, lbsw, thr, o, active);
+    }
+}
+
+// ------------------------------------------------------------------ backward
+__global__ void __launch_bounds__(256)
+knn_unpose_bwd_kernel(const float* __restrict__ g_xc, const int32_t* __restrict__ cidx,
+                      const int32_t* __restrict__ count, const float* __restrict__ xyz,
+                      const float* __restrict__ rays, const float* __restrict__ z, int K, int64_t N,
+                      int V, const int32_t* __restrict__ idx, const float* __restrict__ qw,
+                      const float* __restrict__ ober2cano, float* __restrict__ g_o2c,
+                      float* __restrict__ g_xyz)
+{
+    const int n_valid = *count;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_valid; p += gridDim.x * blockDim.x) {
+        const int64_t gid = cidx[p];
+        const int b = (int)(gid / N);
+        float qx, qy, qz;
+        load_query(xyz, rays, z, gid, K, qx, qy, qz);
+        const float g0 = g_xc[gid * 3], g1 = g_xc[gid * 3 + 1], g2 = g_xc[gid * 3 + 2];
+        const int4 nb = ((const int4*)idx)[gid];
+        const float4 q4 = ((const float4*)qw)[gid];
+        const int ni[4] = {nb.x, nb.y, nb.z, nb.w};
+        const float qq[4] = {q4.x, q4.y, q4.z, q4.w};
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (qq[j] == 0.0f) continue;
+            const int64_t rec = ((int64_t)b * V + ni[j]) * 16;
+            const float4* M = (const float4*)(ober2cano + rec);
+            const float4 r0 = __ldg(M), r1 = __ldg(M + 1), r2 = __ldg(M + 2);
+            gx += qq[j] * (r0.x * g0 + r1.x * g1 + r2.x * g2);
+            gy += qq[j] * (r0.y * g0 + r1.y * g1 + r2.y * g2);
+            gz += qq[j] * (r0.z * g0 + r1.z * g1 + r2.z * g2);
+            if (g_o2c) {
+                float* G = g_o2c + rec;
+                const float a0 = qq[j] * g0, a1 = qq[j] * g1, a2 = qq[j] * g2;
+                atomicAdd(G + 0, a0 * qx); atomicAdd(G + 1, a0 * qy); atomicAdd(G + 2, a0 * qz); atomicAdd(G + 3, a0);
+                atomicAdd(G + 4, a1 * qx); atomicAdd(G + 5, a1 * qy); atomicAdd(G + 6, a1 * qz); atomicAdd(G + 7, a1);
+                atomicAdd(G + 8, a2 * qx); atomicAdd(G + 9, a2 * qy); atomicAdd(G + 10, a2 * qz); atomicAdd(G + 11, a2);
+            }
+        }
+        if (g_xyz) { g_xyz[gid * 3] = gx; g_xyz[gid * 3 + 1] = gy; g_xyz[gid * 3 + 2] = gz; }
+    }
+}
+
+// ------------------------------------------------------------------ C ABI
+extern "C" int64_t an_vertex_grid_bytes(int B, int V) { return B > 0 && V > 0 ? (int64_t)B * grid_frame_bytes(V) : 0; }
+
+extern "C" int an_vertex_grid_build(const float* verts, int B, int V, float cell, void* ws, void* stream)
+{
+    if (!verts || !ws || B <= 0 || V <= 0 || !(cell > 0.f)) return AN_ERR_ARG;
+    if (((uintptr_t)ws) & 15) return AN_ERR_ALIGN;
+    vertex_grid_build_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(verts, V, cell, (char*)ws, grid_frame_bytes(V));
+    AN_CHECK_LAUNCH();
+    return AN_OK;
+}
+
+extern "C" int an_knn_unpose_fwd(const float* xyz, const float* rays, const float* z, int B, int R, int K,
+                                 int64_t N, const float* verts, int V, const void* grid_ws,
+                                 const float* ober2cano, const float* lbs_weights, int J,
+                                 float dis_threshold, int mode,
+                                 float* xyz_cano, uint8_t* valid, int32_t* idx, float* dist, float* qw,
+                                 float* sigma, float* rgb, int32_t* cidx, int32_t* count, void* stream)
+{
+    if (!verts || !ober2cano || !lbs_weights || !xyz_cano || !valid || B <= 0 || N <= 0 || V < 4 || J <= 0) return AN_ERR_ARG;
+    if (!xyz && (!rays || !z || K <= 0 || (int64_t)R * K != N)) return AN_ERR_ARG;
+    if (cidx && !count) return AN_ERR_ARG;
+    if ((int64_t)B * N > 0x7fffffffLL) return AN_ERR_UNSUPPORTED;        // compact ids are int32
+    if ((((uintptr_t)ober2cano) | ((uintptr_t)rays) | ((uintptr_t)idx) | ((uintptr_t)dist) | ((uintptr_t)qw)) & 15) return AN_ERR_ALIGN;
+    UnposeOut o{xyz_cano, valid, idx, dist, qw, sigma, rgb, cidx, count};
+    const int sms = an_num_sms();
+    int64_t bx = (N + KNN_THREADS - 1) / KNN_THREADS;
+    if (mode == 0) {
+        const size_t smem = (size_t)V * sizeof(float4);
+        if (smem > 200 * 1024) return AN_ERR_UNSUPPORTED;
+        cudaError_t e = cudaFuncSetAttribute(knn_unpose_brute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        const int64_t cap = (sms * 2 + B - 1) / B;        // staging the table costs 110 KB/CTA: keep CTAs few and fat
+        if (bx > cap) bx = cap;
+        dim3 grid((unsigned)bx, (unsigned)B);
+        knn_unpose_brute_kernel<<<grid, KNN_THREADS, smem, (cudaStream_t)stream>>>(
+            xyz, rays, z, K, N, verts, V, ober2cano, lbs_weights, J, dis_threshold, o);
+    } else if (mode == 1) {
+        if (!grid_ws) return AN_ERR_ARG;
+        const int64_t cap = ((int64_t)sms * 32 + B - 1) / B;
+        if (bx > cap) bx = cap;
+        dim3 grid((unsigned)bx, (unsigned)B);
+        knn_unpose_grid_kernel<<<grid, KNN_THREADS, 0, (cudaStream_t)stream>>>(
+            xyz, rays, z, K, N, verts, V, (const char*)grid_ws, grid_frame_bytes(V), ober2cano, lbs_weights, J,
+            dis_threshold, o);
+    } else return AN_ERR_ARG;
+    AN_CHECK_LAUNCH();
+    return AN_OK;
+}
+
+extern "C" int an_knn_unpose_bwd(const float* g_xyz_cano, const int32_t* cidx, const int32_t* count,
+                                 const float* xyz, const float* rays, const float* z, int B, int R, int K,
+                                 int64_t N, int V, const int32_t* idx, const float* qw, const float* ober2cano,
+                                 float* g_ober2cano, float* g_xyz, void* stream)
+{
+    if (!g_xyz_cano || !cidx || !count || !idx || !qw || !ober2cano || B <= 0 || N <= 0) return AN_ERR_ARG;
+    if (!xyz && (!rays || !z || K <= 0)) return AN_ERR_ARG;
+    knn_unpose_bwd_kernel<<<an_num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(
+        g_xyz_cano, cidx, count, xyz, rays, z, K, N, V, idx, qw, ober2cano, g_ober2cano, g_xyz);
+    AN_CHECK_LAUNCH();
+    return AN_OK;
+}

@@ -1,0 +1,95 @@
+// Packed-parameter layout shared by the MLP kernels (pack / SIMT reference / tcgen05 fwd+bwd).
+//
+// The 8x256 NeRF MLP (reference models/nerf.py:107-127, forward :129-175) has 12 nn.Linear:
+//   id 0..7  xyz_encoding_1..8   (256 x {63,256,256,256,319,256,256,256})  ReLU
+//   id 8     xyz_encoding_final  (256 x 256)                               no activation
+//   id 9     dir_encoding.0      (128 x 256)                               ReLU
+//   id 10    sigma               (1 x 256)                                 raw
+//   id 11    rgb.0               (3 x 128)                                 sigmoid
+// Ten of them (id 0..9, "GEMM layers" g) run on the tensor cores; the two heads are dot
+// products in the epilogues.
+//
+// packed buffer = [ fwd images | dgrad images | small fp32 block | flat fp32 copy ]
+//  * image = one K-chunk (64 bf16 = 128 B per row) of a B operand, rows = output features,
+//    stored exactly as the UMMA K-major SWIZZLE_128B canonical layout wants it in shared
+//    memory (16-byte unit u of row r lives at r*128 + ((u ^ (r&7))*16), 8-row groups 1024 B
+//    apart), so one cp.async.bulk (TMA bulk copy) moves a chunk with no tensor map.
+//  * fwd chunk order = streaming order of the forward kernel: for g, for kc.  Layer 0 has one
+//    chunk (63 inputs + zero pad); layer 4 has five: chunk 0 = encoding columns 0..62 of W5,
+//    chunks 1..4 = hidden columns 63..318.
+//  * dgrad images hold W^T (rows = input features, K = output features) in streaming order of
+//    the backward kernel (see mlp_bwd.cu).
+#pragma once
+#include <stdint.h>
+
+namespace mlp {
+
+constexpr int NLIN = 12;
+constexpr int NG = 10;
+constexpr int W = 256;
+constexpr int ENC = 63;
+
+__host__ __device__ constexpr int lin_out(int id) { return id <= 8 ? 256 : id == 9 ? 128 : id == 10 ? 1 : 3; }
+__host__ __device__ constexpr int lin_in(int id) { return id == 0 ? 63 : id == 4 ? 319 : id == 11 ? 128 : 256; }
+
+// flat fp32 layout (also the layout of the gradient vector): for id: weight (out*in) then bias (out)
+__host__ __device__ constexpr int64_t flat_w_off(int id) {
+    int64_t o = 0;
+    for (int i = 0; i < id; ++i) o += (int64_t)lin_out(i) * lin_in(i) + lin_out(i);
+    return o;
+}
+__host__ __device__ constexpr int64_t flat_b_off(int id) { return flat_w_off(id) + (int64_t)lin_out(id) * lin_in(id); }
+constexpr int64_t FLAT_FLOATS = flat_w_off(NLIN);                 // 592 388
+
+// ---- forward images
+__host__ __device__ constexpr int g_N(int g) { return g == 9 ? 128 : 256; }
+__host__ __device__ constexpr int g_chunks(int g) { return g == 0 ? 1 : g == 4 ? 5 : 4; }
+__host__ __device__ constexpr uint32_t g_chunk_bytes(int g) { return (uint32_t)g_N(g) * 128u; }
+__host__ __device__ constexpr int64_t fwd_chunk_off(int g, int kc) {
+    int64_t o = 0;
+    for (int i = 0; i < g; ++i) o += (int64_t)g_chunks(i) * g_chunk_bytes(i);
+    return o + (int64_t)kc * g_chunk_bytes(g);
+}
+constexpr int64_t FWD_BYTES = fwd_chunk_off(NG, 0);               // 1 179 648 + ...
+constexpr int FWD_CHUNKS = 1 + 4 * 3 + 5 + 4 * 3 + 4 + 4;         // 38
+
+// ---- dgrad images (W^T): step s of the backward kernel, see mlp_bwd.cu
+//  s 0: g9^T  rows 256 (in of dir),  K = 128 (2 chunks)
+//  s 1: g8^T  rows 256, K = 256 (4)
+//  s 2..4: g7,g6,g5 ^T  rows 256, K 256 (4 each)
+//  s 5: g4^T hidden part: rows = in 63..318 (256), K 256 (4)
+//  s 6: g4^T encoding part: rows = in 0..62 (+1 zero row) = 64, K 256 (4 chunks of 8 KB)
+//  s 7..9: g3,g2,g1 ^T rows 256, K 256 (4 each)
+//  s 10: g0^T rows 64 (63 + zero), K 256 (4 chunks of 8 KB)
+constexpr int NBS = 11;
+__host__ __device__ constexpr int bs_layer(int s) { return s == 0 ? 9 : s == 1 ? 8 : s <= 4 ? 9 - s : s == 5 ? 4 : s == 6 ? 4 : s <= 9 ? 10 - s : 0; }
+__host__ __device__ constexpr int bs_rows(int s) { return (s == 6 || s == 10) ? 64 : 256; }
+__host__ __device__ constexpr int bs_chunks(int s) { return s == 0 ? 2 : 4; }
+__host__ __device__ constexpr int bs_in0(int s) { return s == 5 ? 63 : 0; }             // first input feature of the rows
+__host__ __device__ constexpr int bs_in_valid(int s) { return (s == 6 || s == 10) ? 63 : 256; }
+__host__ __device__ constexpr uint32_t bs_chunk_bytes(int s) { return (uint32_t)bs_rows(s) * 128u; }
+__host__ __device__ constexpr int64_t bwd_chunk_off(int s, int kc) {
+    int64_t o = FWD_BYTES;
+    for (int i = 0; i < s; ++i) o += (int64_t)bs_chunks(i) * bs_chunk_bytes(i);
+    return o + (int64_t)kc * bs_chunk_bytes(s);
+}
+constexpr int64_t IMG_BYTES = bwd_chunk_off(NBS, 0);
+constexpr int BWD_CHUNKS = 2 + 4 * 10;                            // 42
+
+// ---- small fp32 block (biases padded to 256 per GEMM layer, heads)
+constexpr int64_t SMALL_OFF = IMG_BYTES;                          // bytes, 1024-aligned by construction
+constexpr int SM_BIAS = 0;                                        // [10][256]
+constexpr int SM_WS = 2560;                                       // sigma weight [256]
+constexpr int SM_BS = 2816;                                       // sigma bias (1, padded to 4)
+constexpr int SM_WR = 2820;                                       // rgb weight [3][128]
+constexpr int SM_BR = 3204;                                       // rgb bias (3, padded to 4)
+constexpr int SMALL_FLOATS = 3208;
+constexpr int64_t FLAT_OFF = SMALL_OFF + ((SMALL_FLOATS * 4 + 1023) / 1024) * 1024;
+constexpr int64_t PACKED_BYTES = FLAT_OFF + ((FLAT_FLOATS * 4 + 1023) / 1024) * 1024;
+
+// byte offset of element (row r, column c in [0,64)) inside a chunk image
+__host__ __device__ constexpr uint32_t img_off(int r, int c) {
+    return (uint32_t)r * 128u + (uint32_t)((((c >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1));
+}
+
+}  // namespace mlp

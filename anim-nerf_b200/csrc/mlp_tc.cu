@@ -1,0 +1,314 @@
+// A9-A11: positional encoding + 8x256 NeRF MLP forward on the 5th-gen tensor cores
+// (tcgen05.mma, accumulators in TMEM, weights streamed by TMA bulk copies, activations never
+// leave the SM).  Reference: models/embedding.py:22-39 + models/nerf.py:129-175.
+//
+// One persistent CTA per SM; each loop iteration owns 256 compacted (valid) points = two
+// 128-row tiles that share every weight chunk (weights cross L2->smem once per 256 rows).
+//   warp 0      weight producer: cp.async.bulk of pre-swizzled 64-wide K-chunk images into a
+//               2-stage ring (full/empty mbarriers); runs ahead across layers and tiles.
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=256|128, K=16),
+//               2 tiles x 4 K-steps per chunk; tcgen05.commit releases the stage / publishes
+//               the accumulators.  Also owns the TMEM allocation (512 columns = 2 x 128x256 fp32).
+//   warps 2-9   epilogue, one thread per row: tcgen05.ld 32 columns at a time, +bias, ReLU,
+//               bf16 pack, st.shared into the K-major SWIZZLE_128B image that is the next
+//               layer's A operand (in place: the layer's MMAs have completed).  The sigma head
+//               is a dot product folded into layer 8's epilogue, the rgb head into the colour
+//               layer's; the encoding (sin/cos by double-angle recurrence from one sincosf per
+//               coordinate; inputs stay fp32 until after the encoding) is the prologue.
+// Training mode (stash != NULL) additionally streams every activation image to HBM with TMA
+// bulk stores plus 1-bit ReLU masks; the backward kernels consume them (mlp_bwd.cu).
+//
+// Roofline: tensor-bound.  1 179 904 FLOP per point; per 256-point iteration the kernel issues
+// 38 chunks x 2 tiles x 4 MMAs.  Algorithmic HBM bytes per point: 16 B in (id + xyz), 16 B out.
+#include "common.cuh"
+#include "mlp_layout.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int THREADS = 320;
+constexpr int NSTAGE = 2;
+constexpr uint32_t SM_ACT = 0;                     // [2 tiles][4 chunks][128 rows x 128 B]
+constexpr uint32_t SM_ENC = 131072;                // [2 tiles][128 rows x 128 B]
+constexpr uint32_t SM_WST = 163840;                // [NSTAGE][32 KB]
+constexpr uint32_t SM_BAR = SM_WST + NSTAGE * 32768;   // 229376
+constexpr uint32_t SM_BYTES = SM_BAR + 128;
+constexpr uint32_t SM_ALLOC = SM_BYTES + 1024;     // slack for manual 1024-B alignment
+
+}  // namespace
+
+namespace mlp {
+// stash layout per 128-row tile (bytes)
+constexpr int64_t ST_ENC = 0;                      // 16 KB image
+constexpr int64_t ST_H = 16384;                    // h1..h8: 8 x 64 KB images
+constexpr int64_t ST_F = ST_H + 8 * 65536;         // 64 KB
+constexpr int64_t ST_C = ST_F + 65536;             // 32 KB (2 chunks)
+constexpr int64_t ST_MASK = ST_C + 32768;          // h1..h8 masks: 8 x (128 rows x 32 B)
+constexpr int64_t ST_CMASK = ST_MASK + 8 * 4096;   // 128 rows x 16 B
+constexpr int64_t ST_TILE = ST_CMASK + 2048;       // 673 792
+}  // namespace mlp
+
+__global__ void __launch_bounds__(THREADS, 1)
+mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ xyz_cano,
+                  const int32_t* __restrict__ cidx, const int32_t* __restrict__ count, int64_t n_max,
+                  float* __restrict__ sigma_out, float* __restrict__ rgb_out, uint8_t* __restrict__ stash)
+{
+    using namespace mlp;
+    using namespace tc;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const uint32_t bar_full = sbase + SM_BAR;            // [NSTAGE]
+    const uint32_t bar_empty = sbase + SM_BAR + 16;      // [NSTAGE]
+    const uint32_t bar_act = sbase + SM_BAR + 32;        // epilogue -> MMA (256 arrivals)
+    const uint32_t bar_acc = sbase + SM_BAR + 40;        // MMA -> epilogue (tcgen05.commit)
+    const uint32_t tmem_slot = sbase + SM_BAR + 48;
+
+    int64_t n = n_max;
+    if (cidx) { const int64_t c = *count; n = c < n_max ? c : n_max; }
+    const int64_t num_iters = (n + 255) / 256;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_act, 256);
+        mbar_init(bar_acc, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *(volatile uint32_t*)(sgen + SM_BAR + 48);
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ weight producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x) {
+                for (int g = 0; g < NG; ++g) {
+                    const uint32_t bytes = g_chunk_bytes(g);
+                    for (int kc = 0; kc < g_chunks(g); ++kc, ++it) {
+                        const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+                        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                        mbar_expect_tx(bar_full + 8 * s, bytes);
+                        bulk_g2s(sbase + SM_WST + s * 32768u, packed + fwd_chunk_off(g, kc), bytes, bar_full + 8 * s);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            uint32_t it = 0, act_phase = 0;
+            for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x) {
+                for (int g = 0; g < NG; ++g) {
+                    mbar_wait(bar_act, act_phase); act_phase ^= 1u;
+                    tc_fence_after();
+                    const uint32_t idesc = make_idesc_bf16(128, g_N(g), 0, 0);
+                    for (int kc = 0; kc < g_chunks(g); ++kc, ++it) {
+                        const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+                        mbar_wait(bar_full + 8 * s, ph);
+                        tc_fence_after();
+                        const uint32_t wb = sbase + SM_WST + s * 32768u;
+                        const bool from_enc = (g == 0) || (g == 4 && kc == 0);
+                        const int ac = (g == 4) ? kc - 1 : kc;
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            const uint32_t ab = from_enc ? (sbase + SM_ENC + t * 16384u)
+                                                         : (sbase + SM_ACT + t * 65536u + ac * 16384u);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma(tmem_base + t * 256u, make_desc(ab + k * 32u, 16, 1024),
+                                     make_desc(wb + k * 32u, 16, 1024), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit(bar_empty + 8 * s);       // stage free once these MMAs retire
+                    }
+                    umma_commit(bar_acc);                      // accumulators of layer g complete
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (1 thread = 1 row)
+        const int e = threadIdx.x - 64;
+        const int t = e >> 7;
+        const int q = warp & 3;                      // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;
+        const uint32_t sw = (uint32_t)(row & 7);
+        uint8_t* act_row = sgen + SM_ACT + t * 65536 + row * 128;
+        uint8_t* enc_row = sgen + SM_ENC + t * 16384 + row * 128;
+        const uint32_t act_s = sbase + SM_ACT + t * 65536u;
+        const uint32_t enc_s = sbase + SM_ENC + t * 16384u;
+        const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
+        const float* small = (const float*)(packed + SMALL_OFF);
+        const bool leader = (e & 127) == 0;          // issues the tile's TMA stores
+        uint32_t acc_phase = 0;
+
+        for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x) {
+            const int64_t p = iter * 256 + t * 128 + row;
+            const bool in = p < n;
+            const int64_t id = in ? (cidx ? (int64_t)cidx[p] : p) : 0;
+            uint8_t* st_tile = stash ? stash + (iter * 2 + t) * ST_TILE : nullptr;
+            float x[3] = {0.f, 0.f, 0.f};
+            if (in) { x[0] = xyz_cano[id * 3]; x[1] = xyz_cano[id * 3 + 1]; x[2] = xyz_cano[id * 3 + 2]; }
+            {   // positional encoding -> bf16 K-major image (64 columns, last one zero)
+                float ev[64];
+                float s[3], c[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { ev[a] = x[a]; sincosf(x[a], &s[a], &c[a]); }
+#pragma unroll
+                for (int k = 0; k < 10; ++k) {
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        ev[3 + 6 * k + a] = s[a]; ev[6 + 6 * k + a] = c[a];
+                        const float s2 = 2.f * s[a] * c[a], c2 = 1.f - 2.f * s[a] * s[a];
+                        s[a] = s2; c[a] = c2;
+                    }
+                }
+                ev[63] = 0.f;
+                if (stash) {      // previous iteration's TMA stores must have drained this tile's smem
+                    if (leader) bulk_wait_read0();
+                    named_bar_sync(1 + t, 128);
+                }
+#pragma unroll
+                for (uint32_t u = 0; u < 8; ++u) {
+                    uint4 v;
+                    v.x = pack_bf16(ev[8 * u], ev[8 * u + 1]); v.y = pack_bf16(ev[8 * u + 2], ev[8 * u + 3]);
+                    v.z = pack_bf16(ev[8 * u + 4], ev[8 * u + 5]); v.w = pack_bf16(ev[8 * u + 6], ev[8 * u + 7]);
+                    *(uint4*)(enc_row + ((u ^ sw) << 4)) = v;
+                }
+            }
+            fence_proxy_async();
+            if (stash) {
+                named_bar_sync(1 + t, 128);
+                if (leader) { bulk_s2g(st_tile + ST_ENC, enc_s, 16384); bulk_commit(); }
+            }
+            mbar_arrive(bar_act);
+
+            float sig = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
+            for (int g = 0; g < NG; ++g) {
+                mbar_wait(bar_acc, acc_phase); acc_phase ^= 1u;
+                tc_fence_after();
+                if (stash && g > 0) {     // act image of layer g-1 is being stored: wait before overwriting it
+                    if (leader) bulk_wait_read0();
+                    named_bar_sync(1 + t, 128);
+                }
+                const float* bias = small + SM_BIAS + g * 256;
+                const int nblk = g_N(g) / 32;
+                uint32_t mask_words[8];
+                for (int cb = 0; cb < nblk; ++cb) {
+                    uint32_t v[32];
+                    tmem_ld32(tm + cb * 32, v);
+                    tmem_ld_wait();
+                    float f[32];
+                    uint32_t mw = 0;
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        const float4 b4 = __ldg((const float4*)(bias + cb * 32) + c4);
+                        f[4 * c4] = __uint_as_float(v[4 * c4]) + b4.x; f[4 * c4 + 1] = __uint_as_float(v[4 * c4 + 1]) + b4.y;
+                        f[4 * c4 + 2] = __uint_as_float(v[4 * c4 + 2]) + b4.z; f[4 * c4 + 3] = __uint_as_float(v[4 * c4 + 3]) + b4.w;
+                    }
+                    if (g != 8) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) { mw |= (f[c] > 0.f ? 1u : 0u) << c; f[c] = fmaxf(f[c], 0.f); }
+                    }
+                    mask_words[cb & 7] = mw;
+                    if (g == 7) {
+                        const float* ws = small + SM_WS + cb * 32;
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            const float4 w4 = __ldg((const float4*)ws + c4);
+                            sig += f[4 * c4] * w4.x + f[4 * c4 + 1] * w4.y + f[4 * c4 + 2] * w4.z + f[4 * c4 + 3] * w4.w;
+                        }
+                    }
+                    if (g == 9) {
+                        const float* wr = small + SM_WR + cb * 32;
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            r0 += f[c] * __ldg(wr + c); r1 += f[c] * __ldg(wr + 128 + c); r2 += f[c] * __ldg(wr + 256 + c);
+                        }
+                    }
+                    if (g < 9 || stash) {
+                        uint8_t* dst = act_row + (cb >> 1) * 16384;
+#pragma unroll
+                        for (uint32_t u = 0; u < 4; ++u) {
+                            uint4 o;
+                            o.x = pack_bf16(f[8 * u], f[8 * u + 1]); o.y = pack_bf16(f[8 * u + 2], f[8 * u + 3]);
+                            o.z = pack_bf16(f[8 * u + 4], f[8 * u + 5]); o.w = pack_bf16(f[8 * u + 6], f[8 * u + 7]);
+                            *(uint4*)(dst + ((((uint32_t)(cb & 1) * 4 + u) ^ sw) << 4)) = o;
+                        }
+                    }
+                }
+                if (stash) {
+                    if (g <= 7) {
+                        uint4* m = (uint4*)(st_tile + ST_MASK + g * 4096 + row * 32);
+                        m[0] = make_uint4(mask_words[0], mask_words[1], mask_words[2], mask_words[3]);
+                        m[1] = make_uint4(mask_words[4], mask_words[5], mask_words[6], mask_words[7]);
+                    } else if (g == 9) {
+                        *(uint4*)(st_tile + ST_CMASK + row * 16) = make_uint4(mask_words[0], mask_words[1], mask_words[2], mask_words[3]);
+                    }
+                }
+                if (g == 9) {
+                    if (in) {
+                        sigma_out[id] = sig + __ldg(small + SM_BS);
+                        rgb_out[id * 3] = 1.f / (1.f + __expf(-(r0 + __ldg(small + SM_BR))));
+                        rgb_out[id * 3 + 1] = 1.f / (1.f + __expf(-(r1 + __ldg(small + SM_BR + 1))));
+                        rgb_out[id * 3 + 2] = 1.f / (1.f + __expf(-(r2 + __ldg(small + SM_BR + 2))));
+                    }
+                    tc_fence_before();            // TMEM reads done before the next iteration's MMAs
+                    if (stash) {
+                        fence_proxy_async();
+                        named_bar_sync(1 + t, 128);
+                        if (leader) { bulk_s2g(st_tile + ST_C, act_s, 32768); bulk_commit(); }
+                    }
+                } else {
+                    tc_fence_before();
+                    fence_proxy_async();
+                    if (stash) {
+                        named_bar_sync(1 + t, 128);
+                        if (leader) {
+                            bulk_s2g(st_tile + (g == 8 ? ST_F : ST_H + (int64_t)g * 65536), act_s, 65536);
+                            bulk_commit();
+                        }
+                    }
+                    mbar_arrive(bar_act);
+                }
+            }
+        }
+        if (stash && leader) bulk_wait0();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+int mlp_fwd_ref_launch(const void* packed, const float* xyz_cano, const int32_t* cidx, const int32_t* count,
+                       int64_t n_max, float* sigma, float* rgb, cudaStream_t stream);
+
+extern "C" int64_t an_mlp_stash_bytes(int64_t n_max)
+{
+    if (n_max <= 0) return 0;
+    return ((n_max + 255) / 256) * 2 * mlp::ST_TILE;
+}
+
+extern "C" int an_mlp_fwd(const void* packed, const float* xyz_cano, const int32_t* cidx, const int32_t* count,
+                          int64_t n_max, float* sigma, float* rgb, void* stash, int impl, void* stream)
+{
+    if (!packed || !xyz_cano || !sigma || !rgb || n_max <= 0) return AN_ERR_ARG;
+    if (cidx && !count) return AN_ERR_ARG;
+    if (((uintptr_t)packed) & 1023) return AN_ERR_ALIGN;
+    if (stash && (((uintptr_t)stash) & 127)) return AN_ERR_ALIGN;
+    if (impl == 1) return mlp_fwd_ref_launch(packed, xyz_cano, cidx, count, n_max, sigma, rgb, (cudaStream_t)stream);
+    if (impl != 0) return AN_ERR_ARG;
+    cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t iters = (n_max + 255) / 256;
+    const int sms = an_num_sms();
+    const int grid = (int)(iters < sms ? iters : sms);
+    mlp_fwd_tc_kernel<<<grid, THREADS, SM_ALLOC, (cudaStream_t)stream>>>(
+        (const uint8_t*)packed, xyz_cano, cidx, count, n_max, sigma, rgb, (uint8_t*)stash);
+    AN_CHECK_LAUNCH();
+    return AN_OK;
+}

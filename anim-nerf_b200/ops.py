@@ -1,0 +1,212 @@
+"""Thin functional wrappers over the C ABI (one Python function per entry point).
+
+Tensors in, tensors out; allocation and stream selection happen here (torch = plumbing), the
+arithmetic happens in the CUDA library.  Every function raises if the library is missing.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ptr, stream, call
+
+K_NEIGH = 4
+
+
+def _f32c(t):
+    return t.contiguous().float() if (t.dtype != torch.float32 or not t.is_contiguous()) else t
+
+
+# ------------------------------------------------------------------------------ rays
+def raygen(c2w, focal, center, H, W, near, far, pix=None, ginv=None):
+    """A1/A2.  c2w (B,3,4), focal (B,2), center (B,2); pix (B,R,2) int32 (row,col) or None for the
+    full frame; ginv (B,4,4) or None.  Returns rays (B,R,8)."""
+    c2w, focal, center = _f32c(c2w), _f32c(focal), _f32c(center)
+    B = c2w.shape[0]
+    R = pix.shape[1] if pix is not None else H * W
+    if pix is not None:
+        pix = pix.contiguous().to(torch.int32)
+    if ginv is not None:
+        ginv = _f32c(ginv)
+    rays = torch.empty(B, R, 8, device=c2w.device, dtype=torch.float32)
+    call("an_raygen_fwd", ptr(c2w), ptr(focal), ptr(center), ptr(pix), ptr(ginv), B, R, H, W,
+         float(near), float(far), ptr(rays), stream())
+    return rays
+
+
+def sample_coarse(rays, n_coarse, perturb=0.0, noise_u=None, seed=0):
+    """A3.  rays (...,8) -> z (...,Kc)."""
+    rays = _f32c(rays)
+    lead = rays.shape[:-1]
+    n = rays.numel() // 8
+    z = torch.empty(*lead, n_coarse, device=rays.device, dtype=torch.float32)
+    if noise_u is not None:
+        noise_u = _f32c(noise_u)
+    call("an_sample_coarse_fwd", ptr(rays), n, n_coarse, float(perturb), ptr(noise_u), int(seed), ptr(z), stream())
+    return z
+
+
+# ------------------------------------------------------------------------ KNN + unpose
+def vertex_grid(verts, dis_threshold):
+    """Per-frame vertex grid for the pruned search.  The cell is 0.1 % larger than the threshold so
+    that 'no vertex in the 3x3x3 block' proves d_min > threshold beyond fp32 rounding."""
+    verts = _f32c(verts)
+    B, V = verts.shape[:2]
+    nbytes = _lib.load().an_vertex_grid_bytes(B, V)
+    ws = torch.empty(nbytes, device=verts.device, dtype=torch.uint8)
+    call("an_vertex_grid_build", ptr(verts), B, V, float(dis_threshold) * 1.001, ptr(ws), stream())
+    return ws
+
+
+def knn_unpose(verts, ober2cano, lbs_weights, dis_threshold, xyz=None, rays=None, z=None, grid=None,
+               mode=1, want_idx=False, want_dist=False, want_qw=False, sigma=None, rgb=None, compact=False):
+    """A5-A8.  Query points: xyz (B,N,3) or rays (B,R,8) + z (B,R,K).  Returns a dict with
+    xyz_cano (B,N,3), valid (B,N) uint8 and the optional idx/dist/qw/cidx/count."""
+    verts, ober2cano, lbs_weights = _f32c(verts), _f32c(ober2cano), _f32c(lbs_weights)
+    B, V = verts.shape[:2]
+    dev = verts.device
+    if xyz is not None:
+        xyz = _f32c(xyz)
+        N, R, K = xyz.shape[1], 0, 0
+    else:
+        rays, z = _f32c(rays), _f32c(z)
+        R, K = z.shape[1], z.shape[2]
+        N = R * K
+    out = dict(xyz_cano=torch.empty(B, N, 3, device=dev), valid=torch.empty(B, N, device=dev, dtype=torch.uint8))
+    out["idx"] = torch.empty(B, N, 4, device=dev, dtype=torch.int32) if want_idx else None
+    out["dist"] = torch.empty(B, N, 4, device=dev) if want_dist else None
+    out["qw"] = torch.empty(B, N, 4, device=dev) if want_qw else None
+    out["cidx"] = torch.empty(B * N, device=dev, dtype=torch.int32) if compact else None
+    out["count"] = torch.zeros(1, device=dev, dtype=torch.int32) if compact else None
+    if mode == 1 and grid is None:
+        grid = vertex_grid(verts, dis_threshold)
+    call("an_knn_unpose_fwd", ptr(xyz), ptr(rays), ptr(z), B, R, K, N, ptr(verts), V, ptr(grid),
+         ptr(ober2cano), ptr(lbs_weights), lbs_weights.shape[1], float(dis_threshold), int(mode),
+         ptr(out["xyz_cano"]), ptr(out["valid"]), ptr(out["idx"]), ptr(out["dist"]), ptr(out["qw"]),
+         ptr(sigma), ptr(rgb), ptr(out["cidx"]), ptr(out["count"]), stream())
+    return out
+
+
+def knn_unpose_bwd(g_xyz_cano, cidx, count, idx, qw, ober2cano, xyz=None, rays=None, z=None, want_g_xyz=True):
+    ober2cano = _f32c(ober2cano)
+    B, V = ober2cano.shape[:2]
+    if xyz is not None:
+        N, R, K = xyz.shape[1], 0, 0
+    else:
+        R, K = z.shape[1], z.shape[2]
+        N = R * K
+    g_o2c = torch.zeros_like(ober2cano)
+    g_xyz = torch.zeros(B, N, 3, device=ober2cano.device) if want_g_xyz else None
+    call("an_knn_unpose_bwd", ptr(g_xyz_cano), ptr(cidx), ptr(count), ptr(xyz), ptr(rays), ptr(z), B, R, K, N, V,
+         ptr(idx), ptr(qw), ptr(ober2cano), ptr(g_o2c), ptr(g_xyz), stream())
+    return g_o2c, g_xyz
+
+
+# ------------------------------------------------------------------------------ MLP
+def mlp_packed_bytes():
+    return _lib.load().an_mlp_packed_bytes()
+
+
+def mlp_grad_floats():
+    return _lib.load().an_mlp_grad_floats()
+
+
+def mlp_pack(weights, biases, packed=None):
+    """weights/biases: 12 fp32 CUDA tensors in the order xyz_encoding_1..8, xyz_encoding_final,
+    dir_encoding.0, sigma, rgb.0 (nn.Linear (out,in) layout).  Returns the packed uint8 buffer."""
+    assert len(weights) == 12 and len(biases) == 12
+    dev = weights[0].device
+    if packed is None:
+        packed = torch.empty(mlp_packed_bytes() + 1024, device=dev, dtype=torch.uint8)
+    off = (-packed.data_ptr()) % 1024
+    view = packed[off:off + mlp_packed_bytes()]
+    keep = [_f32c(w.detach()) for w in weights] + [_f32c(b.detach()) for b in biases]
+    wp = (ctypes.c_void_p * 12)(*[t.data_ptr() for t in keep[:12]])
+    bp = (ctypes.c_void_p * 12)(*[t.data_ptr() for t in keep[12:]])
+    call("an_mlp_pack", wp, bp, ptr(view), stream())
+    return view
+
+
+def mlp_fwd(packed, xyz_cano, sigma, rgb, cidx=None, count=None, n_max=None, stash=None, impl=0):
+    """A9-A11 over compacted ids (or all n_max points when cidx is None); writes sigma/rgb in place."""
+    if n_max is None:
+        n_max = xyz_cano.numel() // 3
+    call("an_mlp_fwd", ptr(packed), ptr(xyz_cano), ptr(cidx), ptr(count), int(n_max), ptr(sigma), ptr(rgb),
+         ptr(stash), int(impl), stream())
+
+
+def mlp_stash(n_max, device):
+    nbytes = _lib.load().an_mlp_stash_bytes(int(n_max))
+    buf = torch.empty(nbytes + 128, device=device, dtype=torch.uint8)
+    off = (-buf.data_ptr()) % 128
+    return buf[off:off + nbytes]
+
+
+def mlp_bwd(packed, stash, xyz_cano, g_sigma, g_rgb, cidx=None, count=None, n_max=None, want_g_xyz=True):
+    if n_max is None:
+        n_max = xyz_cano.numel() // 3
+    dev = xyz_cano.device
+    g_params = torch.zeros(mlp_grad_floats(), device=dev)
+    g_xyz = torch.zeros_like(xyz_cano) if want_g_xyz else None
+    nscr = _lib.load().an_mlp_bwd_scratch_bytes(int(n_max))
+    scratch = torch.empty(nscr + 128, device=dev, dtype=torch.uint8)
+    off = (-scratch.data_ptr()) % 128
+    call("an_mlp_bwd", ptr(packed), ptr(stash), ptr(xyz_cano), ptr(cidx), ptr(count), int(n_max), ptr(g_sigma),
+         ptr(g_rgb), ptr(g_params), ptr(g_xyz), ptr(scratch[off:off + nscr]), stream())
+    return g_params, g_xyz
+
+
+# ------------------------------------------------------------------------ compositing
+def composite(sigma, rgb, z, rays, white_bkgd=True, sigma_noise=None, want_weights=True):
+    """A12.  sigma (...,K), rgb (...,K,3), z (...,K), rays (...,8) -> weights, rgb (...,3), depth (...,1), acc (...,1)."""
+    lead = z.shape[:-1]
+    K = z.shape[-1]
+    n = z.numel() // K
+    dev = z.device
+    w = torch.empty(*lead, K, device=dev) if want_weights else None
+    rgb_o = torch.empty(*lead, 3, device=dev)
+    depth = torch.empty(*lead, 1, device=dev)
+    acc = torch.empty(*lead, 1, device=dev)
+    call("an_composite_fwd", ptr(sigma), ptr(rgb), ptr(z), ptr(rays), ptr(sigma_noise), n, K, int(white_bkgd),
+         ptr(w), ptr(rgb_o), ptr(depth), ptr(acc), stream())
+    return w, rgb_o, depth, acc
+
+
+def composite_bwd(sigma, rgb, z, rays, g_rgb_out, g_depth, g_acc, white_bkgd=True, sigma_noise=None):
+    lead = z.shape[:-1]
+    K = z.shape[-1]
+    n = z.numel() // K
+    dev = z.device
+    g_sigma = torch.empty(*lead, K, device=dev)
+    g_rgb = torch.empty(*lead, K, 3, device=dev)
+    g_z = torch.empty(*lead, K, device=dev)
+    g_far = torch.empty(*lead, device=dev)
+    call("an_composite_bwd", ptr(sigma), ptr(rgb), ptr(z), ptr(rays), ptr(sigma_noise), n, K, int(white_bkgd),
+         ptr(_f32c(g_rgb_out)), ptr(_f32c(g_depth)), ptr(_f32c(g_acc)), ptr(g_sigma), ptr(g_rgb), ptr(g_z), ptr(g_far), stream())
+    return g_sigma, g_rgb, g_z, g_far
+
+
+# ------------------------------------------------------------------------- resampling
+def searchsorted_right(cdf, u):
+    cdf, u = _f32c(cdf), _f32c(u)
+    M, F = cdf.shape[-1], u.shape[-1]
+    n = cdf.numel() // M
+    inds = torch.empty(u.shape, device=u.device, dtype=torch.int32)
+    call("an_searchsorted_right", ptr(cdf), ptr(u), n, M, F, ptr(inds), stream())
+    return inds
+
+
+def sample_fine_merge(weights, z_coarse, n_fine, det, u=None, seed=0, want_src=True):
+    """A13/A14.  weights, z_coarse (...,Kc) -> z_fine (...,Kf), z_all (...,Kc+Kf) ascending, src uint8."""
+    lead = z_coarse.shape[:-1]
+    Kc = z_coarse.shape[-1]
+    n = z_coarse.numel() // Kc
+    dev = z_coarse.device
+    z_fine = torch.empty(*lead, n_fine, device=dev)
+    z_all = torch.empty(*lead, Kc + n_fine, device=dev)
+    src = torch.empty(*lead, Kc + n_fine, device=dev, dtype=torch.uint8) if want_src else None
+    if u is not None:
+        u = _f32c(u)
+    call("an_sample_fine_merge_fwd", ptr(_f32c(weights)), ptr(_f32c(z_coarse)), ptr(u), n, Kc, n_fine, int(det), int(seed),
+         ptr(z_fine), ptr(z_all), ptr(src), stream())
+    return z_fine, z_all, src

@@ -1,0 +1,154 @@
+/* animnerf_b200.h -- C ABI of the B200-native (sm_100a) Anim-NeRF rendering hot path.
+ *
+ * One shared library (libanimnerf_b200.so), plain pointers and sizes, no torch types.
+ * The reference (JanaldoChen/Anim-NeRF) is pure Python: its only native seam is the
+ * external KNN_CUDA wheel, every other boundary is a Python call signature.  Each entry
+ * point below cites the reference call it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *  - the caller owns every buffer including scratch; nothing is allocated inside;
+ *  - no global mutable state: calls are re-entrant per stream;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *  - return 0 on success, <0 for an argument error (AN_ERR_*), >0 = cudaError_t;
+ *  - nothing throws across the ABI;  there is NO CPU fallback.
+ *  - B = frames, R = rays per frame, K = samples per ray, N = R*K points per frame,
+ *    V = vertices (6890), J = joints (24), k = 4 neighbours.
+ */
+#ifndef ANIMNERF_B200_H
+#define ANIMNERF_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AN_OK 0
+#define AN_ERR_ARG (-1)       /* null pointer / non-positive extent                    */
+#define AN_ERR_UNSUPPORTED (-2) /* shape outside what the kernels were built for       */
+#define AN_ERR_ALIGN (-3)     /* pointer not aligned as documented                      */
+
+#define AN_KNN_K 4
+#define AN_MLP_W 256          /* trunk width (models/nerf.py:62)                        */
+#define AN_MLP_ENC 63         /* 3 + 3*2*10 positional-encoding channels                */
+#define AN_GRID_MAX_DIM 32    /* vertex hash grid is at most 32^3 cells                 */
+
+int an_version(void);
+const char* an_error_string(int code);
+
+/* ---- A1/A2: ray generation ------------------------------------------------------------
+ * replaces datasets/anim_nerf_dataset.py:56-85 gen_ray_directions/gen_rays (and the dead
+ * twin utils/ray_utils.py:74-121) fused with the ray part of
+ * models/anim_nerf.py:128-137 convert_to_body_model_space.
+ * c2w (B,3,4), focal (B,2), center (B,2) [cx,cy]; pix (B,R,2) int32 (row,col) or NULL for
+ * the full H*W grid in row-major order (then R must equal H*W); ginv (B,4,4) inverse root
+ * transform or NULL (world-space rays, near/far unclamped).  rays (B,R,8).               */
+int an_raygen_fwd(const float* c2w, const float* focal, const float* center, const int32_t* pix,
+                  const float* ginv, int B, int R, int H, int W, float near_, float far_,
+                  float* rays, void* stream);
+
+/* ---- A3: stratified sampling ------------------------------------------------------------
+ * replaces models/volume_rendering.py:29-56 VolumeRenderer.sample_coarse (lindisp=True,
+ * i.e. linear in depth).  rays (n_rays,8), z (n_rays,Kc).  perturb>0: noise_u (n_rays,Kc)
+ * U[0,1) draws if non-NULL (parity mode), else an in-kernel Philox stream (seed,offset).   */
+int an_sample_coarse_fwd(const float* rays, int64_t n_rays, int Kc, float perturb,
+                         const float* noise_u, uint64_t seed, float* z, void* stream);
+
+/* ---- A5-A8 (+A4): K-nearest-vertex search fused with inverse skinning --------------------
+ * replaces knn_cuda.KNN(k=4, transpose_mode=True).forward (call site
+ * models/anim_nerf.py:82-83,158-159) + get_neighbs (:153-178) + unpose (:180-192) +
+ * batch_index_select/batch_transform (:24-39) + the point generation in
+ * models/volume_rendering.py:117-120.
+ *
+ * an_vertex_grid_build: per-frame uniform hash grid over the posed vertices (cell >=
+ * dis_threshold) used for the exact pruned search.  ws must hold
+ * an_vertex_grid_bytes(B,V) bytes, 16-byte aligned.                                        */
+int64_t an_vertex_grid_bytes(int B, int V);
+int an_vertex_grid_build(const float* verts, int B, int V, float cell, void* ws, void* stream);
+
+/* Query points are either xyz (B,N,3) (rays,z NULL) or generated as o + z*d from rays
+ * (B,R,8), z (B,R,K) with N = R*K (xyz NULL).
+ * mode 0 = exhaustive shared-memory-tiled search; 1 = grid-pruned search (exact: falls back
+ * to the exhaustive scan per query when the pruning radius cannot prove the 4th neighbour).
+ * Outputs (any of idx/dist/qw/cidx may be NULL):
+ *   xyz_cano (B*N,3); valid (B*N) u8; idx (B*N,4) int32 ascending (d2,index); dist (B*N,4)
+ *   Euclidean; qw (B*N,4) normalised blend weights;  for invalid points sigma (B*N) := -1e5
+ *   and rgb (B*N,3) := 0 when those pointers are given;  cidx: compacted list of valid point
+ *   ids (global id b*N+n), *count incremented atomically (caller zeroes it).
+ * ober2cano (B,V,4,4) row-major (rows 0-2 used), lbs_weights (V,J).                        */
+int an_knn_unpose_fwd(const float* xyz, const float* rays, const float* z, int B, int R, int K,
+                      int64_t N, const float* verts, int V, const void* grid_ws,
+                      const float* ober2cano, const float* lbs_weights, int J,
+                      float dis_threshold, int mode,
+                      float* xyz_cano, uint8_t* valid, int32_t* idx, float* dist, float* qw,
+                      float* sigma, float* rgb, int32_t* cidx, int32_t* count, void* stream);
+
+/* backward of the blend + affine apply (autograd of models/anim_nerf.py:173-174,188; no
+ * gradient through dist/idx/valid, as under the reference's no_grad KNN).
+ * g_xyz_cano (B*N,3) is read at the `*count` compacted ids in cidx.  Accumulates (atomically)
+ * into g_ober2cano (B,V,4,4) and writes g_xyz (B*N,3) (zero for invalid points) when non-NULL. */
+int an_knn_unpose_bwd(const float* g_xyz_cano, const int32_t* cidx, const int32_t* count,
+                      const float* xyz, const float* rays, const float* z, int B, int R, int K,
+                      int64_t N, int V, const int32_t* idx, const float* qw, const float* ober2cano,
+                      float* g_ober2cano, float* g_xyz, void* stream);
+
+/* ---- A9-A11: positional encoding + 8x256 MLP (tcgen05/TMEM) -------------------------------
+ * replaces models/embedding.py:22-39 + models/nerf.py:129-175 (NeRF.forward/get_sigma) +
+ * the masking in models/anim_nerf.py:304-305.
+ *
+ * an_mlp_pack: fp32 nn.Linear (out,in) weights -> bf16 UMMA-ready swizzled images (+ fp32
+ * biases/heads).  w_host/b_host: HOST arrays of 12 DEVICE pointers in the order
+ * xyz_encoding_1..8, xyz_encoding_final, dir_encoding.0, sigma, rgb.0.
+ * packed must hold an_mlp_packed_bytes() bytes, 1024-byte aligned.                          */
+int64_t an_mlp_packed_bytes(void);
+int an_mlp_pack(const float* const* w_host, const float* const* b_host, void* packed, void* stream);
+
+/* forward over the compacted points: for p < *count: point id = cidx[p] (cidx NULL: id = p and
+ * the count is n_max), reads xyz_cano[id], writes sigma[id], rgb[id*3..].
+ * impl 0 = tcgen05 kernel (product), 1 = fp32 SIMT reference kernel (tests / bring-up only).
+ * stash: NULL for inference; else an_mlp_stash_bytes(n_max) bytes receiving the bf16
+ * activations the backward needs.                                                            */
+int64_t an_mlp_stash_bytes(int64_t n_max);
+int an_mlp_fwd(const void* packed, const float* xyz_cano, const int32_t* cidx, const int32_t* count,
+               int64_t n_max, float* sigma, float* rgb, void* stash, int impl, void* stream);
+
+/* backward: g_sigma (ids), g_rgb (ids,3) -> g_params (fp32, layout = an_mlp_grad_floats(),
+ * accumulated; caller zeroes) and g_xyz_cano (ids,3) when non-NULL.
+ * scratch: an_mlp_bwd_scratch_bytes(n_max).                                                  */
+int64_t an_mlp_grad_floats(void);
+int64_t an_mlp_bwd_scratch_bytes(int64_t n_max);
+int an_mlp_bwd(const void* packed, const void* stash, const float* xyz_cano, const int32_t* cidx,
+               const int32_t* count, int64_t n_max, const float* g_sigma, const float* g_rgb,
+               float* g_params, float* g_xyz_cano, void* scratch, void* stream);
+
+/* ---- A12: alpha compositing ------------------------------------------------------------
+ * replaces models/volume_rendering.py:128-160 (composite tail), far=True, white_bkgd flag.
+ * sigma (n_rays,K), rgb (n_rays,K,3), z (n_rays,K), rays (n_rays,8) (far = rays[:,7]);
+ * sigma_noise (n_rays,K) or NULL.  Outputs weights (n_rays,K) (may be NULL), rgb_out
+ * (n_rays,3), depth (n_rays), acc (n_rays).                                                  */
+int an_composite_fwd(const float* sigma, const float* rgb, const float* z, const float* rays,
+                     const float* sigma_noise, int64_t n_rays, int K, int white_bkgd,
+                     float* weights, float* rgb_out, float* depth, float* acc, void* stream);
+int an_composite_bwd(const float* sigma, const float* rgb, const float* z, const float* rays,
+                     const float* sigma_noise, int64_t n_rays, int K, int white_bkgd,
+                     const float* g_rgb_out, const float* g_depth, const float* g_acc,
+                     float* g_sigma, float* g_rgb, float* g_z, float* g_far, void* stream);
+
+/* ---- A13/A14: inverse-CDF resampling + sort-merge ---------------------------------------
+ * replaces models/volume_rendering.py:59-97 sample_fine and :199-207 (mid-points, cat, sort).
+ * an_searchsorted_right: the index stage alone (torch.searchsorted(cdf,u,right=True), :85),
+ * exposed for the bit-exact index check: cdf (n_rows,M), u (n_rows,F) -> inds int32.
+ * an_sample_fine_merge_fwd: weights (n_rays,Kc) coarse weights, z_coarse (n_rays,Kc);
+ * u (n_rays,Kf) explicit draws or NULL (det ? linspace(0,1,Kf) : Philox(seed));
+ * outputs z_fine (n_rays,Kf) (may be NULL), z_all (n_rays,Kc+Kf) ascending, src (n_rays,Kc+Kf)
+ * u8 = index into cat(z_coarse,z_fine) of each sorted entry (may be NULL).                   */
+int an_searchsorted_right(const float* cdf, const float* u, int64_t n_rows, int M, int F,
+                          int32_t* inds, void* stream);
+int an_sample_fine_merge_fwd(const float* weights, const float* z_coarse, const float* u,
+                             int64_t n_rays, int Kc, int Kf, int det, uint64_t seed,
+                             float* z_fine, float* z_all, uint8_t* src, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANIMNERF_B200_H */

@@ -1,0 +1,311 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ctypes) against the CPU oracle.
+Tolerances are stated per test; index outputs are compared bit for bit."""
+import numpy as np
+import pytest
+import torch
+
+from util import oracle, load_golden, nerf_params, body_model, golden_tables, synthetic
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def ops():
+    from anim_nerf_b200 import ops as o
+    return o
+
+
+@pytest.fixture(scope="module")
+def det():
+    return load_golden("render_det")
+
+
+@pytest.fixture(scope="module")
+def pert():
+    return load_golden("render_perturb")
+
+
+# ----------------------------------------------------------------------------- rays
+def test_raygen_full_frame_matches_reference_fixture():
+    fx = load_golden("gen_rays")
+    H, W = int(fx["H"]), int(fx["W"])
+    t = lambda a: torch.from_numpy(np.asarray(a)).to(DEV)[None]
+    rays = ops().raygen(t(fx["c2w"]), t(fx["focal"]), t(fx["c"]), H, W, 0.1, 10.0)
+    np.testing.assert_allclose(rays[0].cpu().numpy().reshape(H, W, 8), fx["rays"], atol=2e-6)
+
+
+def test_raygen_pixels_and_body_space():
+    rs = np.random.RandomState(0)
+    B, H, W, R = 3, 40, 56, 500
+    c2w = torch.from_numpy(rs.normal(size=(B, 3, 4)).astype(np.float32))
+    focal = torch.from_numpy(rs.uniform(40, 60, size=(B, 2)).astype(np.float32))
+    cen = torch.from_numpy(rs.uniform(15, 30, size=(B, 2)).astype(np.float32))
+    G = torch.eye(4).repeat(B, 1, 1)
+    G[:, :3, :] = torch.from_numpy(rs.normal(size=(B, 3, 4)).astype(np.float32))
+    pix = torch.from_numpy(np.stack([rs.randint(0, H, size=(B, R)), rs.randint(0, W, size=(B, R))], -1).astype(np.int32))
+    rays = ops().raygen(c2w.to(DEV), focal.to(DEV), cen.to(DEV), H, W, 0.1, 10.0, pix=pix.to(DEV),
+                        ginv=torch.inverse(G).to(DEV)).cpu()
+    for b in range(B):
+        full = oracle.gen_rays(c2w[b], H, W, focal[b], 0.1, 10.0, cen[b])
+        sel = full[pix[b, :, 0].long(), pix[b, :, 1].long()][None]
+        ref = oracle.rays_to_body_space(sel, G[b:b + 1])
+        np.testing.assert_allclose(rays[b].numpy(), ref[0].numpy(), atol=2e-5, rtol=1e-5)
+
+
+def test_sample_coarse(det, pert):
+    rays = torch.from_numpy(det["rays_body"])
+    z = ops().sample_coarse(rays.to(DEV), 64).cpu()
+    np.testing.assert_allclose(z.numpy(), det["z_coarse"], atol=1e-6)
+    rays = torch.from_numpy(pert["rays_body"])
+    z = ops().sample_coarse(rays.to(DEV), 64, perturb=1.0, noise_u=torch.from_numpy(pert["noise_coarse_u"]).to(DEV)).cpu()
+    np.testing.assert_allclose(z.numpy(), pert["z_coarse"], atol=1e-6)
+    # Philox mode: stratified property (each sample stays inside its stratum, ascending)
+    z = ops().sample_coarse(rays.to(DEV), 64, perturb=1.0, seed=123).cpu()
+    assert (z[..., 1:] >= z[..., :-1]).all()
+    assert (z >= rays[..., 6:7] - 1e-6).all() and (z <= rays[..., 7:8]).all()
+
+
+# ----------------------------------------------------------------------- KNN + unpose
+@pytest.mark.parametrize("mode", [0, 1])
+def test_knn_unpose_fixture(det, mode):
+    verts, o2c, lbs = golden_tables(det)
+    rays = torch.from_numpy(det["rays_body"]).to(DEV)
+    z = torch.from_numpy(det["z_coarse"]).to(DEV)
+    out = ops().knn_unpose(verts.to(DEV), o2c.to(DEV), lbs.to(DEV), 0.2, rays=rays, z=z, mode=mode,
+                           want_idx=True, want_dist=True, want_qw=True, compact=True)
+    idx = out["idx"].cpu().numpy()
+    ref_idx = det["knn_idx_coarse"].astype(np.int32)
+    valid = out["valid"].cpu().numpy()
+    ref_valid = det["valid_coarse"][..., 0]
+    assert (valid == ref_valid).mean() > 0.9999
+    found = (idx[..., 0] >= 0)
+    if mode == 0:
+        assert found.all()
+    assert found[ref_valid > 0].all()
+    # KNN indices bit-exact (golden = torch.cdist shim of the reference run; 1e-4 slack = cdist ties)
+    mism = (idx[found] != ref_idx[found]).any(-1).mean()
+    assert mism < 1e-4, mism
+    # ... and bit-exact vs the oracle contract on every found query
+    xyz = (rays[..., None, 0:3] + z[..., None] * rays[..., None, 3:6]).reshape(z.shape[0], -1, 3).cpu().numpy()
+    for b in range(verts.shape[0]):
+        d_o, i_o = oracle.knn(verts[b].numpy(), xyz[b], 4)
+        f = found[b]
+        assert (idx[b][f] == i_o[f]).all()
+        assert (out["dist"][b].cpu().numpy()[f] == d_o[f]).all()
+    v = ref_valid > 0
+    np.testing.assert_allclose(out["xyz_cano"].cpu().numpy()[v], det["xyz_cano_coarse"][v], atol=1e-5)
+    # compaction: the list holds exactly the valid ids
+    n = int(out["count"].item())
+    ids = np.sort(out["cidx"].cpu().numpy()[:n])
+    assert (ids == np.nonzero(valid.reshape(-1))[0]).all()
+
+
+def test_knn_million_queries_bit_exact():
+    """>= 1e6 synthetic queries: both search modes vs the C oracle, indices bit for bit."""
+    bm = body_model()
+    posed_np, tmpl_np = synthetic.make_body_params(2, seed=5)
+    t = lambda d: {k: torch.from_numpy(v) for k, v in d.items()}
+    posed, tmpl = bm(**t(posed_np)), bm(**t(tmpl_np))
+    verts, o2c = oracle.ober2cano_tables(posed, tmpl)
+    rs = np.random.RandomState(11)
+    N = 524288
+    lo, hi = verts.numpy().min((0, 1)) - 0.3, verts.numpy().max((0, 1)) + 0.3
+    xyz = torch.from_numpy(rs.uniform(lo, hi, size=(2, N, 3)).astype(np.float32))
+    lbs = bm.lbs_weights
+    outs = [ops().knn_unpose(verts.to(DEV), o2c.to(DEV), lbs.to(DEV), 0.2, xyz=xyz.to(DEV), mode=m,
+                             want_idx=True, want_dist=True) for m in (0, 1)]
+    for b in range(2):
+        d_o, i_o = oracle.knn(verts[b].numpy(), xyz[b].numpy(), 4)
+        i0 = outs[0]["idx"][b].cpu().numpy()
+        assert (i0 == i_o).all()
+        assert (outs[0]["dist"][b].cpu().numpy() == d_o).all()
+        i1 = outs[1]["idx"][b].cpu().numpy()
+        f = i1[:, 0] >= 0
+        assert (i1[f] == i_o[f]).all()
+        assert (d_o[~f, 0] >= 0.2).all()          # pruned queries are provably invalid
+    assert (outs[0]["valid"] == outs[1]["valid"]).all()
+    v = outs[0]["valid"].bool()
+    assert torch.equal(outs[0]["xyz_cano"][v], outs[1]["xyz_cano"][v])
+
+
+# ------------------------------------------------------------------------------ MLP
+def _packed(seed):
+    w = synthetic.make_nerf_weights(seed)
+    ws = [torch.from_numpy(w[n + ".weight"]).to(DEV) for n in synthetic.NERF_LAYER_NAMES]
+    bs = [torch.from_numpy(w[n + ".bias"]).to(DEV) for n in synthetic.NERF_LAYER_NAMES]
+    return ops().mlp_pack(ws, bs)
+
+
+def _unswizzle(img, rows):
+    """(rows*128 B uint8 image of one 64-column chunk) -> (rows,64) float32."""
+    raw = img.view(torch.int16).reshape(rows, 8, 8)       # (row, physical unit, 8 bf16)
+    r = torch.arange(rows, device=img.device)[:, None]
+    u = torch.arange(8, device=img.device)[None, :]
+    logical = torch.gather(raw, 1, ((u ^ (r & 7))[..., None]).expand(rows, 8, 8))
+    return logical.reshape(rows, 64).view(torch.bfloat16).float()
+
+
+def test_mlp_pack_images():
+    packed = _packed(10)
+    w = synthetic.make_nerf_weights(10)
+    W2 = torch.from_numpy(w["xyz_encoding_2.0.weight"]).to(DEV)
+    # fwd chunk (g=1, kc=2) starts after layer 0's single 32 KB chunk
+    off = 32768 + 2 * 32768
+    img = _unswizzle(packed[off:off + 32768], 256)
+    assert torch.equal(img, W2[:, 128:192].bfloat16().float())
+    W5 = torch.from_numpy(w["xyz_encoding_5.0.weight"]).to(DEV)
+    off = (1 + 12) * 32768
+    img = _unswizzle(packed[off:off + 32768], 256)
+    assert torch.equal(img[:, :63], W5[:, :63].bfloat16().float()) and (img[:, 63] == 0).all()
+    img = _unswizzle(packed[off + 32768:off + 65536], 256)
+    assert torch.equal(img, W5[:, 63:127].bfloat16().float())
+
+
+@pytest.mark.parametrize("impl,n", [(1, 3000), (0, 3000), (0, 70001)])
+def test_mlp_forward(impl, n):
+    """impl 1 (fp32 SIMT reference kernel): 2e-4.  impl 0 (tcgen05, bf16 operands, fp32 accumulate):
+    sigma within 3e-2 abs + 1e-2 rel, rgb within 1e-2 of the fp32 oracle."""
+    packed = _packed(10)
+    p = nerf_params(10)
+    rs = np.random.RandomState(3)
+    xc = torch.from_numpy(rs.uniform(-1.0, 1.0, size=(n, 3)).astype(np.float32))
+    rgb_ref, sig_ref = oracle.nerf_forward(p, xc)
+    sigma = torch.full((n,), -7.0, device=DEV)
+    rgb = torch.zeros(n, 3, device=DEV)
+    ops().mlp_fwd(packed, xc.to(DEV), sigma, rgb, impl=impl)
+    torch.cuda.synchronize()
+    ds = (sigma.cpu() - sig_ref[:, 0]).abs()
+    dr = (rgb.cpu() - rgb_ref).abs()
+    print("impl", impl, "n", n, "max|dsigma|", ds.max().item(), "max|drgb|", dr.max().item())
+    if impl == 1:
+        assert ds.max() < 2e-4 and dr.max() < 2e-5
+    else:
+        assert (ds <= 3e-2 + 1e-2 * sig_ref[:, 0].abs()).all(), ds.max()
+        assert dr.max() < 1e-2
+
+
+def test_mlp_forward_compacted_ids():
+    """scatter through cidx / device-side count: untouched ids keep their initial values."""
+    packed = _packed(11)
+    p = nerf_params(11)
+    rs = np.random.RandomState(4)
+    n_all, n_val = 5000, 1234
+    xc = torch.from_numpy(rs.uniform(-1, 1, size=(n_all, 3)).astype(np.float32))
+    ids = torch.from_numpy(rs.permutation(n_all)[:n_val].astype(np.int32))
+    cidx = torch.zeros(n_all, dtype=torch.int32)
+    cidx[:n_val] = ids
+    sigma = torch.full((n_all,), -1e5, device=DEV)
+    rgb = torch.zeros(n_all, 3, device=DEV)
+    count = torch.tensor([n_val], dtype=torch.int32, device=DEV)
+    ops().mlp_fwd(packed, xc.to(DEV), sigma, rgb, cidx=cidx.to(DEV), count=count, n_max=n_all)
+    rgb_ref, sig_ref = oracle.nerf_forward(p, xc[ids.long()])
+    s = sigma.cpu()
+    untouched = torch.ones(n_all, dtype=torch.bool)
+    untouched[ids.long()] = False
+    assert (s[untouched] == -1e5).all() and (rgb.cpu()[untouched] == 0).all()
+    assert ((s[ids.long()] - sig_ref[:, 0]).abs() <= 3e-2 + 1e-2 * sig_ref[:, 0].abs()).all()
+    assert (rgb.cpu()[ids.long()] - rgb_ref).abs().max() < 1e-2
+
+
+def test_mlp_stash_images_match_layerwise_oracle():
+    """training mode: every stashed activation image vs the fp32 oracle (bf16-level tolerance)."""
+    from anim_nerf_b200 import ops as o
+    packed = _packed(10)
+    p = nerf_params(10)
+    n = 700
+    rs = np.random.RandomState(5)
+    xc = torch.from_numpy(rs.uniform(-1, 1, size=(n, 3)).astype(np.float32))
+    sigma = torch.zeros(n, device=DEV)
+    rgb = torch.zeros(n, 3, device=DEV)
+    stash = o.mlp_stash(n, DEV)
+    stash.zero_()
+    o.mlp_fwd(packed, xc.to(DEV), sigma, rgb, stash=stash)
+    torch.cuda.synchronize()
+    e = oracle.embed(xc)
+    hs, h = [], e
+    for i in range(8):
+        if i == 4:
+            h = torch.cat([e, h], -1)
+        w, b = p["xyz_encoding_%d.0" % (i + 1)]
+        h = torch.relu(h @ w.T + b)
+        hs.append(h)
+    tile_bytes = 673792
+    for tile in range((n + 127) // 128):
+        base = tile * tile_bytes
+        rows = min(128, n - tile * 128)
+        sl = slice(tile * 128, tile * 128 + rows)
+        enc = _unswizzle(stash[base:base + 16384], 128)[:rows].cpu()
+        assert (enc[:, :63] - e[sl]).abs().max() < 1e-2, "enc tile %d" % tile
+        for l in range(8):
+            img = torch.cat([_unswizzle(stash[base + 16384 + l * 65536 + c * 16384:][:16384], 128) for c in range(4)], 1)[:rows].cpu()
+            err = (img - hs[l][sl]).abs().max().item()
+            assert err < 3e-2 * max(1.0, hs[l][sl].abs().max().item()), "h%d tile %d err %g" % (l + 1, tile, err)
+            m = stash[base + 16384 + 8 * 65536 + 65536 + 32768 + l * 4096:][:4096].view(torch.int32).reshape(128, 8)[:rows].cpu()
+            bits = ((m[:, :, None] >> torch.arange(32)) & 1).reshape(rows, 256).bool()
+            assert (bits == (img > 0)).all(), "mask h%d" % (l + 1)
+
+
+# ------------------------------------------------------------------------ compositing
+def _comp_inputs(seed, n, K):
+    rs = np.random.RandomState(seed)
+    sigma = torch.from_numpy(rs.normal(2.0, 6.0, size=(n, K)).astype(np.float32))
+    sigma[rs.uniform(size=(n, K)) < 0.4] = -1e5
+    rgb = torch.from_numpy(rs.uniform(size=(n, K, 3)).astype(np.float32))
+    z = torch.from_numpy(np.sort(rs.uniform(2.0, 4.0, size=(n, K)), -1).astype(np.float32))
+    rays = torch.zeros(n, 8)
+    rays[:, 7] = 4.0
+    return sigma, rgb, z, rays
+
+
+@pytest.mark.parametrize("K", [64, 96, 128])
+def test_composite_forward_backward(K):
+    n = 777
+    sigma, rgb, z, rays = _comp_inputs(K, n, K)
+    noise = torch.from_numpy(np.random.RandomState(1).normal(size=(n, K)).astype(np.float32))
+    for nz in (None, noise):
+        s, c, zz = sigma.clone().requires_grad_(True), rgb.clone().requires_grad_(True), z.clone().requires_grad_(True)
+        far = rays[:, 7:8].clone().requires_grad_(True)
+        w_r, rgb_r, dep_r, acc_r = oracle.composite(c[None], s[None], zz[None], far[None], True, None if nz is None else nz[None])
+        g = [o.to(DEV) for o in (sigma, rgb, z, rays)]
+        w, rgb_o, dep, acc = ops().composite(g[0], g[1], g[2], g[3], True, None if nz is None else nz.to(DEV))
+        np.testing.assert_allclose(w.cpu().numpy(), w_r[0].detach().numpy(), atol=2e-6)
+        np.testing.assert_allclose(rgb_o.cpu().numpy(), rgb_r[0].detach().numpy(), atol=5e-6)
+        np.testing.assert_allclose(dep.cpu().numpy(), dep_r[0].detach().numpy(), atol=2e-5)
+        np.testing.assert_allclose(acc.cpu().numpy(), acc_r[0].detach().numpy(), atol=5e-6)
+        rs = np.random.RandomState(9)
+        gr, gd, ga = [torch.from_numpy(rs.normal(size=s_).astype(np.float32)) for s_ in ((n, 3), (n, 1), (n, 1))]
+        ((rgb_r[0] * gr).sum() + (dep_r[0] * gd).sum() + (acc_r[0] * ga).sum()).backward()
+        g_sigma, g_rgb, g_z, g_far = ops().composite_bwd(g[0], g[1], g[2], g[3], gr.to(DEV), gd.to(DEV), ga.to(DEV), True,
+                                                         None if nz is None else nz.to(DEV))
+        np.testing.assert_allclose(g_rgb.cpu().numpy(), c.grad.numpy(), atol=1e-5)
+        np.testing.assert_allclose(g_sigma.cpu().numpy(), s.grad.numpy(), atol=1e-4, rtol=1e-3)
+        np.testing.assert_allclose(g_z.cpu().numpy(), zz.grad.numpy(), atol=2e-3, rtol=2e-3)
+        np.testing.assert_allclose(g_far.cpu().numpy(), far.grad.numpy()[:, 0], atol=1e-5)
+
+
+# ------------------------------------------------------------------------- resampling
+def test_searchsorted_bit_exact(det, pert):
+    for fx in (det, pert):
+        inds = ops().searchsorted_right(torch.from_numpy(fx["cdf"]).to(DEV), torch.from_numpy(fx["u"]).to(DEV))
+        assert (inds.cpu().numpy() == fx["inds"].astype(np.int32)).all()
+
+
+def test_sample_fine_merge(det, pert):
+    # deterministic u (in-kernel linspace) on the reference's captured coarse weights
+    w = torch.from_numpy(det["weights_coarse"]).to(DEV)
+    zc = torch.from_numpy(det["z_coarse"]).to(DEV)
+    z_fine, z_all, src = ops().sample_fine_merge(w, zc, 64, det=True)
+    ref_all = det["z_combine"]
+    za = z_all.cpu().numpy()
+    assert (np.diff(za, axis=-1) >= 0).all()
+    close = np.abs(za - ref_all) < 2e-4
+    assert close.mean() > 0.97, close.mean()     # re-derived cdf flips a few u==cdf ties
+    cat = torch.cat([zc, z_fine], -1)
+    assert torch.equal(torch.gather(cat, -1, src.long()), z_all)        # src is the sort permutation
+    assert (torch.sort(src.long(), -1)[0] == torch.arange(128, device=DEV)).all()
+    # explicit random u
+    w = torch.from_numpy(pert["weights_coarse"]).to(DEV)
+    zc = torch.from_numpy(pert["z_coarse"]).to(DEV)
+    _, z_all, _ = ops().sample_fine_merge(w, zc, 32, det=False, u=torch.from_numpy(pert["noise_fine_u"]).to(DEV))
+    np.testing.assert_allclose(z_all.cpu().numpy(), pert["z_combine"], atol=2e-4)
