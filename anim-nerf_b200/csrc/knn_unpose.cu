@@ -89,7 +89,8 @@ __device__ __forceinline__ void load_query(const float* __restrict__ xyz, const 
         const int64_t ray = gid / K;                 // rays are (B*R, 8), z is (B*R, K)
         const float4 r0 = __ldg((const float4*)rays + ray * 2), r1 = __ldg((const float4*)rays + ray * 2 + 1);
         const float zz = z[gid];
-        qx = r0.x + zz * r0.w; qy = r0.y + zz * r1.x; qz = r0.z + zz * r1.y;
+        // o + z*d with the product rounded first (torch evaluates mul and add separately; no FMA)
+        qx = __fadd_rn(r0.x, __fmul_rn(zz, r0.w)); qy = __fadd_rn(r0.y, __fmul_rn(zz, r1.x)); qz = __fadd_rn(r0.z, __fmul_rn(zz, r1.y));
     }
 }
 

@@ -1,6 +1,546 @@
-// placeholder: replaced by the tcgen05 backward (dgrad chain + wgrad)
+// A17 (MLP part): backward of the positional encoding + 8x256 MLP on tcgen05/TMEM.
+// Autograd of models/nerf.py:129-175 + models/embedding.py:22-39.  Three kernels:
+//
+//  1. mlp_bwd_dgrad_kernel -- same skeleton as the forward (persistent CTA, 2 x 128-row tiles,
+//     TMA-streamed W^T chunk images, accumulators in TMEM).  The activation-gradient image dY
+//     stays in shared memory as the next layer's A operand; ReLU masks come from the forward's
+//     1-bit stash; the sigma head's gradient is injected in the epilogue of the `final` layer;
+//     the encoding gradients (two N=64 GEMMs: layer 5's encoding part and layer 1) are folded
+//     to d(xyz) analytically in the epilogue.  Every pre-activation gradient image is also
+//     streamed to HBM scratch (TMA bulk store) for the weight-gradient kernel.
+//  2. mlp_bwd_wgrad_kernel -- dW_g = dY_g^T X_g as K-streaming GEMMs over the points: both
+//     operands are the row-major point images already in HBM, consumed as MN-major UMMA operands
+//     (no transposes).  One CTA owns one (layer, point-split) and keeps the full dW_g tile
+//     (2 x 128 x N fp32) in TMEM across its whole K loop; bias gradients are column sums of the
+//     dY image taken from shared memory by the otherwise idle warps.  HBM-bound by construction
+//     (128 FLOP/B < ridge 214 FLOP/B): ~9.6 KB read per point.
+//  3. mlp_bwd_heads_kernel -- sigma/rgb head weight gradients (dot-product heads, CUDA cores).
 #include "common.cuh"
 #include "mlp_layout.cuh"
-extern "C" int64_t an_mlp_bwd_scratch_bytes(int64_t n_max) { return n_max > 0 ? 16 : 0; }
-extern "C" int an_mlp_bwd(const void*, const void*, const float*, const int32_t*, const int32_t*, int64_t,
-                          const float*, const float*, float*, float*, void*, void*) { return AN_ERR_UNSUPPORTED; }
+#include "tc_common.cuh"
+
+namespace mlp {
+// forward stash layout (must match mlp_tc.cu)
+constexpr int64_t ST_ENC = 0;
+constexpr int64_t ST_H = 16384;
+constexpr int64_t ST_F = ST_H + 8 * 65536;
+constexpr int64_t ST_C = ST_F + 65536;
+constexpr int64_t ST_MASK = ST_C + 32768;
+constexpr int64_t ST_CMASK = ST_MASK + 8 * 4096;
+constexpr int64_t ST_TILE = ST_CMASK + 2048;
+// dY scratch layout per 128-row tile
+constexpr int64_t DY_G9 = 0;                        // dpre_c   (128 cols, 32 KB)
+constexpr int64_t DY_G8 = 32768;                    // df       (64 KB)
+constexpr int64_t DY_H = DY_G8 + 65536;             // dpre of layer g (0..7) at DY_H + g*64 KB
+constexpr int64_t DY_TILE = DY_H + 8 * 65536;       // 622 592
+}  // namespace mlp
+
+namespace {
+constexpr int THREADS = 320;
+constexpr int NSTAGE = 3;
+constexpr uint32_t SM_ACT = 0;                                   // [2][4][16 KB]
+constexpr uint32_t SM_WST = 131072;                              // [NSTAGE][32 KB]
+constexpr uint32_t SM_BAR = SM_WST + NSTAGE * 32768;
+constexpr uint32_t SM_BYTES = SM_BAR + 128;
+constexpr uint32_t SM_ALLOC = SM_BYTES + 1024;
+
+// order in which the backward consumes the W^T steps of mlp_layout.cuh (s6 = layer-5 encoding
+// part runs before s5 so both read the same dY image and share one accumulator region)
+__device__ __forceinline__ int step_of(int i) {
+    const int order[11] = {0, 1, 2, 3, 4, 6, 5, 7, 8, 9, 10};
+    return order[i];
+}
+}  // namespace
+
+__global__ void __launch_bounds__(THREADS, 1)
+mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ stash,
+                     const float* __restrict__ xyz_cano, const float* __restrict__ rgb,
+                     const int32_t* __restrict__ cidx, const int32_t* __restrict__ count, int64_t n_max,
+                     const float* __restrict__ g_sigma, const float* __restrict__ g_rgb,
+                     float* __restrict__ g_xyz, uint8_t* __restrict__ dy)
+{
+    using namespace mlp;
+    using namespace tc;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = sbase + SM_BAR, bar_empty = sbase + SM_BAR + 32;
+    const uint32_t bar_act = sbase + SM_BAR + 64, bar_acc = sbase + SM_BAR + 72, tmem_slot = sbase + SM_BAR + 80;
+    const bool want_gx = g_xyz != nullptr;
+
+    int64_t n = n_max;
+    if (cidx) { const int64_t c = *count; n = c < n_max ? c : n_max; }
+    const int64_t num_iters = (n + 255) / 256;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_act, 256);
+        mbar_init(bar_acc, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *(volatile uint32_t*)(sgen + SM_BAR + 80);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x)
+                for (int i = 0; i < 11; ++i) {
+                    const int s = step_of(i);
+                    if (!want_gx && (s == 6 || s == 10)) continue;
+                    const uint32_t bytes = bs_chunk_bytes(s);
+                    for (int kc = 0; kc < bs_chunks(s); ++kc, ++it) {
+                        const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+                        mbar_wait(bar_empty + 8 * st, ph ^ 1u);
+                        mbar_expect_tx(bar_full + 8 * st, bytes);
+                        bulk_g2s(sbase + SM_WST + st * 32768u, packed + bwd_chunk_off(s, kc), bytes, bar_full + 8 * st);
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t it = 0, act_phase = 0;
+            for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x)
+                for (int i = 0; i < 11; ++i) {
+                    const int s = step_of(i);
+                    if (!want_gx && (s == 6 || s == 10)) continue;
+                    mbar_wait(bar_act, act_phase); act_phase ^= 1u;
+                    tc_fence_after();
+                    const uint32_t idesc = make_idesc_bf16(128, bs_rows(s), 0, 0);
+                    for (int kc = 0; kc < bs_chunks(s); ++kc, ++it) {
+                        const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+                        mbar_wait(bar_full + 8 * st, ph);
+                        tc_fence_after();
+                        const uint32_t wb = sbase + SM_WST + st * 32768u;
+#pragma unroll
+                        for (int t = 0; t < 2; ++t) {
+                            const uint32_t ab = sbase + SM_ACT + t * 65536u + kc * 16384u;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma(tmem_base + t * 256u, make_desc(ab + k * 32u, 16, 1024),
+                                     make_desc(wb + k * 32u, 16, 1024), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit(bar_empty + 8 * st);
+                    }
+                    umma_commit(bar_acc);
+                }
+        }
+    } else {
+        const int e = threadIdx.x - 64;
+        const int t = e >> 7;
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t sw = (uint32_t)(row & 7);
+        uint8_t* act_row = sgen + SM_ACT + t * 65536 + row * 128;
+        const uint32_t act_s = sbase + SM_ACT + t * 65536u;
+        const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
+        const float* small = (const float*)(packed + SMALL_OFF);
+        const bool leader = (e & 127) == 0;
+        uint32_t acc_phase = 0;
+
+        for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x) {
+            const int64_t tile = iter * 2 + t;
+            const int64_t p = iter * 256 + t * 128 + row;
+            const bool in = p < n;
+            const int64_t id = in ? (cidx ? (int64_t)cidx[p] : p) : 0;
+            const uint8_t* st_tile = stash + tile * ST_TILE;
+            uint8_t* dy_tile = dy + tile * DY_TILE;
+            float gs = 0.f, dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
+            if (in) {
+                gs = g_sigma[id];
+                const float a0 = rgb[id * 3], a1 = rgb[id * 3 + 1], a2 = rgb[id * 3 + 2];
+                dp0 = g_rgb[id * 3] * a0 * (1.f - a0); dp1 = g_rgb[id * 3 + 1] * a1 * (1.f - a1); dp2 = g_rgb[id * 3 + 2] * a2 * (1.f - a2);
+            }
+            // previous iteration's bulk stores must have finished reading this tile's image
+            if (leader) bulk_wait_read0();
+            named_bar_sync(1 + t, 128);
+            {   // dpre_c = (Wr^T dpre_rgb) * [c > 0]  -> A image (2 chunks) = dY of the colour layer
+                const uint4 cm = *(const uint4*)(st_tile + ST_CMASK + row * 16);
+                const uint32_t cmw[4] = {cm.x, cm.y, cm.z, cm.w};
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) {
+                    float f[32];
+                    const float* wr = small + SM_WR + cb * 32;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float v = dp0 * __ldg(wr + c) + dp1 * __ldg(wr + 128 + c) + dp2 * __ldg(wr + 256 + c);
+                        f[c] = ((cmw[cb] >> c) & 1u) ? v : 0.f;
+                    }
+                    uint8_t* dst = act_row + (cb >> 1) * 16384;
+#pragma unroll
+                    for (uint32_t u = 0; u < 4; ++u) {
+                        uint4 o;
+                        o.x = pack_bf16(f[8 * u], f[8 * u + 1]); o.y = pack_bf16(f[8 * u + 2], f[8 * u + 3]);
+                        o.z = pack_bf16(f[8 * u + 4], f[8 * u + 5]); o.w = pack_bf16(f[8 * u + 6], f[8 * u + 7]);
+                        *(uint4*)(dst + ((((uint32_t)(cb & 1) * 4 + u) ^ sw) << 4)) = o;
+                    }
+                }
+            }
+            fence_proxy_async();
+            named_bar_sync(1 + t, 128);
+            if (leader) { bulk_s2g(dy_tile + DY_G9, act_s, 32768); bulk_commit(); }
+            mbar_arrive(bar_act);
+
+            // encoding derivative factors (same double-angle recurrence as the forward)
+            float gx[3] = {0.f, 0.f, 0.f};
+            float x[3] = {0.f, 0.f, 0.f};
+            if (want_gx && in) { x[0] = xyz_cano[id * 3]; x[1] = xyz_cano[id * 3 + 1]; x[2] = xyz_cano[id * 3 + 2]; }
+
+            for (int i = 0; i < 11; ++i) {
+                const int s = step_of(i);
+                if (!want_gx && (s == 6 || s == 10)) continue;
+                mbar_wait(bar_acc, acc_phase); acc_phase ^= 1u;
+                tc_fence_after();
+                if (s == 6 || s == 10) {
+                    // d(enc) (64 columns) -> d(xyz): enc = [x, sin(2^k x), cos(2^k x)]_k
+                    float de[64];
+                    {
+                        uint32_t v[32];
+                        tmem_ld32(tm, v); tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) de[c] = __uint_as_float(v[c]);
+                        tmem_ld32(tm + 32, v); tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) de[32 + c] = __uint_as_float(v[c]);
+                    }
+                    float sn[3], cs[3];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) { sincosf(x[a], &sn[a], &cs[a]); gx[a] += de[a]; }
+                    float f = 1.f;
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) {
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) {
+                            gx[a] += f * (de[3 + 6 * k + a] * cs[a] - de[6 + 6 * k + a] * sn[a]);
+                            const float s2 = 2.f * sn[a] * cs[a], c2 = 1.f - 2.f * sn[a] * sn[a];
+                            sn[a] = s2; cs[a] = c2;
+                        }
+                        f *= 2.f;
+                    }
+                    tc_fence_before();
+                    if (s == 10) {
+                        if (in) { g_xyz[id * 3] = gx[0]; g_xyz[id * 3 + 1] = gx[1]; g_xyz[id * 3 + 2] = gx[2]; }
+                    } else {
+                        mbar_arrive(bar_act);          // A image unchanged; accumulator region is free again
+                    }
+                    continue;
+                }
+                // wait until the previous image's bulk store has drained before overwriting it
+                if (leader) bulk_wait_read0();
+                named_bar_sync(1 + t, 128);
+                // which ReLU mask applies to this step's output, and where the dY image goes
+                int mask_layer = -1;            // index into the stash's h masks (0..7 = h1..h8)
+                int64_t dy_off = 0;
+                if (s == 0) { dy_off = DY_G8; }
+                else if (s >= 1 && s <= 4) { mask_layer = 8 - s; dy_off = DY_H + (int64_t)(8 - s) * 65536; }
+                else if (s == 5) { mask_layer = 3; dy_off = DY_H + 3 * 65536; }
+                else { mask_layer = 9 - s; dy_off = DY_H + (int64_t)(9 - s) * 65536; }     // s = 7,8,9 -> h3,h2,h1
+                uint32_t mw[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+                if (mask_layer >= 0) {
+                    const uint4* mp = (const uint4*)(st_tile + ST_MASK + mask_layer * 4096 + row * 32);
+                    const uint4 m0 = mp[0], m1 = mp[1];
+                    mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w; mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
+                }
+#pragma unroll
+                for (int cb = 0; cb < 8; ++cb) {
+                    uint32_t v[32];
+                    tmem_ld32(tm + cb * 32, v);
+                    tmem_ld_wait();
+                    float f[32];
+                    if (s == 1) {                 // + sigma head: d h8 += w_sigma * d sigma
+                        const float* ws = small + SM_WS + cb * 32;
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) f[c] = __uint_as_float(v[c]) + gs * __ldg(ws + c);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) f[c] = __uint_as_float(v[c]);
+                    }
+                    const uint32_t m = mw[cb];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) f[c] = ((m >> c) & 1u) ? f[c] : 0.f;
+                    uint8_t* dst = act_row + (cb >> 1) * 16384;
+#pragma unroll
+                    for (uint32_t u = 0; u < 4; ++u) {
+                        uint4 o;
+                        o.x = pack_bf16(f[8 * u], f[8 * u + 1]); o.y = pack_bf16(f[8 * u + 2], f[8 * u + 3]);
+                        o.z = pack_bf16(f[8 * u + 4], f[8 * u + 5]); o.w = pack_bf16(f[8 * u + 6], f[8 * u + 7]);
+                        *(uint4*)(dst + ((((uint32_t)(cb & 1) * 4 + u) ^ sw) << 4)) = o;
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                named_bar_sync(1 + t, 128);
+                if (leader) { bulk_s2g(dy_tile + dy_off, act_s, 65536); bulk_commit(); }
+                if (!(s == 9 && !want_gx)) mbar_arrive(bar_act);     // last step has no consumer MMA
+            }
+        }
+        if (leader) bulk_wait0();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------------------ wgrad
+namespace {
+// job table: (A = dY image offset in dy tile, out rows; B = X image offset in stash tile, N cols; flat weight offset / row stride / col offset)
+struct WJob { int64_t a_off; int a_chunks; int64_t b_off; int b_chunks; int lin; int col0; int ncol_valid; int bias; };
+__device__ __forceinline__ WJob wjob(int j) {
+    using namespace mlp;
+    WJob w;
+    switch (j) {
+        case 0:  w = {DY_H + 0 * 65536, 4, ST_ENC, 1, 0, 0, 63, 1}; break;                 // L1: X = enc
+        case 1:  w = {DY_H + 1 * 65536, 4, ST_H + 0 * 65536, 4, 1, 0, 256, 1}; break;     // L2: X = h1
+        case 2:  w = {DY_H + 2 * 65536, 4, ST_H + 1 * 65536, 4, 2, 0, 256, 1}; break;
+        case 3:  w = {DY_H + 3 * 65536, 4, ST_H + 2 * 65536, 4, 3, 0, 256, 1}; break;
+        case 4:  w = {DY_H + 4 * 65536, 4, ST_ENC, 1, 4, 0, 63, 0}; break;                 // L5 encoding columns
+        case 5:  w = {DY_H + 4 * 65536, 4, ST_H + 3 * 65536, 4, 4, 63, 256, 1}; break;    // L5 hidden columns: X = h4
+        case 6:  w = {DY_H + 5 * 65536, 4, ST_H + 4 * 65536, 4, 5, 0, 256, 1}; break;
+        case 7:  w = {DY_H + 6 * 65536, 4, ST_H + 5 * 65536, 4, 6, 0, 256, 1}; break;
+        case 8:  w = {DY_H + 7 * 65536, 4, ST_H + 6 * 65536, 4, 7, 0, 256, 1}; break;     // L8: X = h7
+        case 9:  w = {DY_G8, 4, ST_H + 7 * 65536, 4, 8, 0, 256, 1}; break;                 // final: X = h8
+        default: w = {DY_G9, 2, ST_F, 4, 9, 0, 256, 1}; break;                             // colour layer: X = f
+    }
+    return w;
+}
+constexpr int NJOBS = 11;
+constexpr int WG_THREADS = 320;
+constexpr int WG_STAGES = 3;
+constexpr uint32_t WG_STAGE_BYTES = 65536;               // A half (<=32 KB) + B half (<=32 KB): 64 points
+constexpr uint32_t WG_BAR = WG_STAGES * WG_STAGE_BYTES;
+constexpr uint32_t WG_ALLOC = WG_BAR + 128 + 1024;
+}  // namespace
+
+// grid = (splits, NJOBS).  CTA (sp, j) accumulates dW_j over tiles sp, sp+splits, ...
+__global__ void __launch_bounds__(WG_THREADS, 1)
+mlp_bwd_wgrad_kernel(const uint8_t* __restrict__ stash, const uint8_t* __restrict__ dy,
+                     const int32_t* __restrict__ count, int has_count, int64_t n_max,
+                     float* __restrict__ g_params)
+{
+    using namespace mlp;
+    using namespace tc;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = sbase + WG_BAR, bar_empty = sbase + WG_BAR + 32, bar_cs = sbase + WG_BAR + 64;
+    const uint32_t bar_done = sbase + WG_BAR + 96, tmem_slot = sbase + WG_BAR + 104;
+
+    int64_t n = n_max;
+    if (has_count) { const int64_t c = *count; n = c < n_max ? c : n_max; }
+    const int64_t n_tiles = ((n + 255) / 256) * 2;       // tiles written by the forward (zero rows beyond n)
+    const WJob job = wjob(blockIdx.y);
+    const int M_halves = job.a_chunks / 2;               // 128 output rows per half
+    const int N = job.b_chunks * 64;                      // accumulator columns per half
+    const uint32_t a_half_bytes = (uint32_t)job.a_chunks * 8192u, b_half_bytes = (uint32_t)job.b_chunks * 8192u;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < WG_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_cs + 8 * s, 256);
+        }
+        mbar_init(bar_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *(volatile uint32_t*)(sgen + WG_BAR + 104);
+
+    // stage layout: A chunks (a_chunks x 8 KB: 64 points x 128 B each) then B chunks at +32 KB
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (int half = 0; half < 2; ++half, ++it) {
+                    const uint32_t st = it % WG_STAGES, ph = (it / WG_STAGES) & 1u;
+                    mbar_wait(bar_empty + 8 * st, ph ^ 1u);
+                    mbar_wait(bar_cs + 8 * st, ph ^ 1u);          // column-sum readers are done with the stage too
+                    mbar_expect_tx(bar_full + 8 * st, a_half_bytes + b_half_bytes);
+                    const uint32_t dst = sbase + st * WG_STAGE_BYTES;
+                    const uint8_t* asrc = dy + tile * DY_TILE + job.a_off + half * 8192;
+                    const uint8_t* bsrc = stash + tile * ST_TILE + job.b_off + half * 8192;
+                    for (int c = 0; c < job.a_chunks; ++c) bulk_g2s(dst + c * 8192u, asrc + c * 16384, 8192, bar_full + 8 * st);
+                    for (int c = 0; c < job.b_chunks; ++c) bulk_g2s(dst + 32768u + c * 8192u, bsrc + c * 16384, 8192, bar_full + 8 * st);
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);           // both operands MN-major
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (int half = 0; half < 2; ++half, ++it) {
+                    const uint32_t st = it % WG_STAGES, ph = (it / WG_STAGES) & 1u;
+                    mbar_wait(bar_full + 8 * st, ph);
+                    tc_fence_after();
+                    const uint32_t ab = sbase + st * WG_STAGE_BYTES, bb = ab + 32768u;
+                    for (int h = 0; h < M_halves; ++h)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)      // 16 points per UMMA K-step = 2 x (8 rows x 128 B)
+                            umma(tmem_base + h * 256u,
+                                 make_desc(ab + h * 16384u + k * 2048u, 8192, 1024),
+                                 make_desc(bb + k * 2048u, 8192, 1024), idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(bar_empty + 8 * st);
+                }
+            umma_commit(bar_done);
+        }
+    } else {
+        // warps 2..9: bias gradient = column sums of the dY image (thread = output column), then the
+        // final TMEM -> global accumulation.
+        const int e = threadIdx.x - 64;                  // 0..255 = output feature
+        float bsum = 0.f;
+        const bool do_bias = job.bias && e < job.a_chunks * 64;
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+            for (int half = 0; half < 2; ++half, ++it) {
+                const uint32_t st = it % WG_STAGES, ph = (it / WG_STAGES) & 1u;
+                mbar_wait(bar_full + 8 * st, ph);
+                if (do_bias) {
+                    const uint8_t* img = sgen + st * WG_STAGE_BYTES + (e >> 6) * 8192;
+                    const int c = e & 63;
+#pragma unroll 8
+                    for (int r = 0; r < 64; ++r) {
+                        const uint16_t raw16 = *(const uint16_t*)(img + r * 128 + ((((c >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1)));
+                        bsum += __uint_as_float((uint32_t)raw16 << 16);
+                    }
+                }
+                mbar_arrive(bar_cs + 8 * st);
+            }
+        if (do_bias && n_tiles > blockIdx.x) atomicAdd(g_params + flat_b_off(job.lin) + e, bsum);
+        // drain the accumulators
+        if (n_tiles > (int64_t)blockIdx.x) {
+            mbar_wait(bar_done, 0);
+            tc_fence_after();
+            const int q = warp & 3;
+            const int grp = (warp - 2) >> 2;                         // 0: columns [0,N/2), 1: [N/2,N)
+            const int in_dim = lin_in(job.lin);
+            float* Wg = g_params + flat_w_off(job.lin);
+            for (int h = 0; h < M_halves; ++h) {
+                const int out_row = h * 128 + q * 32 + lane;
+                for (int cb = grp * (N / 64); cb < (grp + 1) * (N / 64); ++cb) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + h * 256u + cb * 32u, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int col = cb * 32 + c;
+                        if (col < job.ncol_valid)
+                            atomicAdd(Wg + (int64_t)out_row * in_dim + job.col0 + col, __uint_as_float(v[c]));
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ------------------------------------------------------------------------------ heads
+// sigma head: d ws[i] = sum_p dsigma_p * h8[p][i], d bs = sum dsigma;  rgb head: d Wr[j][i] = sum_p dpre_j * c[p][i].
+// block = 256 threads (thread = feature), tiles strided over the grid; partial sums in registers.
+__global__ void __launch_bounds__(256)
+mlp_bwd_heads_kernel(const uint8_t* __restrict__ stash, const float* __restrict__ rgb,
+                     const int32_t* __restrict__ cidx, const int32_t* __restrict__ count, int64_t n_max,
+                     const float* __restrict__ g_sigma, const float* __restrict__ g_rgb, float* __restrict__ g_params)
+{
+    using namespace mlp;
+    __shared__ float s_gs[128], s_dp[3][128];
+    int64_t n = n_max;
+    if (cidx) { const int64_t c = *count; n = c < n_max ? c : n_max; }
+    const int64_t n_tiles = (n + 127) / 128;
+    const int i = threadIdx.x;
+    float aws = 0.f, abs_ = 0.f, ar0 = 0.f, ar1 = 0.f, ar2 = 0.f, ab0 = 0.f, ab1 = 0.f, ab2 = 0.f;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        __syncthreads();
+        if (i < 128) {
+            const int64_t p = tile * 128 + i;
+            float gs = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
+            if (p < n) {
+                const int64_t id = cidx ? (int64_t)cidx[p] : p;
+                gs = g_sigma[id];
+                const float a0 = rgb[id * 3], a1 = rgb[id * 3 + 1], a2 = rgb[id * 3 + 2];
+                d0 = g_rgb[id * 3] * a0 * (1.f - a0); d1 = g_rgb[id * 3 + 1] * a1 * (1.f - a1); d2 = g_rgb[id * 3 + 2] * a2 * (1.f - a2);
+            }
+            s_gs[i] = gs; s_dp[0][i] = d0; s_dp[1][i] = d1; s_dp[2][i] = d2;
+        }
+        __syncthreads();
+        const uint8_t* st_tile = stash + tile * ST_TILE;
+        const uint8_t* h8 = st_tile + ST_H + 7 * 65536 + (i >> 6) * 16384;
+        const int c = i & 63;
+        for (int r = 0; r < 128; ++r) {
+            const uint16_t raw16 = *(const uint16_t*)(h8 + r * 128 + ((((c >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1)));
+            aws += s_gs[r] * __uint_as_float((uint32_t)raw16 << 16);
+        }
+        if (i < 128) {
+            const uint8_t* cimg = st_tile + ST_C + (i >> 6) * 16384;
+            for (int r = 0; r < 128; ++r) {
+                const uint16_t raw16 = *(const uint16_t*)(cimg + r * 128 + ((((c >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1)));
+                const float cv = __uint_as_float((uint32_t)raw16 << 16);
+                ar0 += s_dp[0][r] * cv; ar1 += s_dp[1][r] * cv; ar2 += s_dp[2][r] * cv;
+            }
+        }
+        if (i == 0) for (int r = 0; r < 128; ++r) { abs_ += s_gs[r]; ab0 += s_dp[0][r]; ab1 += s_dp[1][r]; ab2 += s_dp[2][r]; }
+    }
+    if ((int64_t)blockIdx.x < n_tiles) {
+        atomicAdd(g_params + flat_w_off(10) + i, aws);
+        if (i < 128) {
+            atomicAdd(g_params + flat_w_off(11) + i, ar0);
+            atomicAdd(g_params + flat_w_off(11) + 128 + i, ar1);
+            atomicAdd(g_params + flat_w_off(11) + 256 + i, ar2);
+        }
+        if (i == 0) {
+            atomicAdd(g_params + flat_b_off(10), abs_);
+            atomicAdd(g_params + flat_b_off(11), ab0); atomicAdd(g_params + flat_b_off(11) + 1, ab1); atomicAdd(g_params + flat_b_off(11) + 2, ab2);
+        }
+    }
+}
+
+extern "C" int64_t an_mlp_bwd_scratch_bytes(int64_t n_max)
+{
+    if (n_max <= 0) return 0;
+    return ((n_max + 255) / 256) * 2 * mlp::DY_TILE;
+}
+
+extern "C" int an_mlp_bwd(const void* packed, const void* stash, const float* xyz_cano, const float* rgb,
+                          const int32_t* cidx, const int32_t* count, int64_t n_max,
+                          const float* g_sigma, const float* g_rgb, float* g_params, float* g_xyz_cano,
+                          void* scratch, void* stream)
+{
+    if (!packed || !stash || !xyz_cano || !rgb || !g_sigma || !g_rgb || !g_params || !scratch || n_max <= 0) return AN_ERR_ARG;
+    if (cidx && !count) return AN_ERR_ARG;
+    if ((((uintptr_t)packed) & 1023) || (((uintptr_t)stash) & 127) || (((uintptr_t)scratch) & 127)) return AN_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaFuncSetAttribute(mlp_bwd_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(mlp_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_ALLOC);
+    if (e != cudaSuccess) return (int)e;
+    const int sms = an_num_sms();
+    const int64_t iters = (n_max + 255) / 256;
+    const int grid = (int)(iters < sms ? iters : sms);
+    mlp_bwd_dgrad_kernel<<<grid, THREADS, SM_ALLOC, st>>>(
+        (const uint8_t*)packed, (const uint8_t*)stash, xyz_cano, rgb, cidx, count, n_max, g_sigma, g_rgb,
+        g_xyz_cano, (uint8_t*)scratch);
+    AN_CHECK_LAUNCH();
+    int64_t splits = sms / NJOBS;                      // 13 on a 148-SM part -> 143 CTAs, one wave
+    if (splits > iters * 2) splits = iters * 2;
+    if (splits < 1) splits = 1;
+    dim3 wgrid((unsigned)splits, NJOBS);
+    mlp_bwd_wgrad_kernel<<<wgrid, WG_THREADS, WG_ALLOC, st>>>(
+        (const uint8_t*)stash, (const uint8_t*)scratch, count, cidx ? 1 : 0, n_max, g_params);
+    AN_CHECK_LAUNCH();
+    const int64_t tiles = (n_max + 127) / 128;
+    const int hgrid = (int)(tiles < sms * 2 ? tiles : sms * 2);
+    mlp_bwd_heads_kernel<<<hgrid, 256, 0, st>>>((const uint8_t*)stash, rgb, cidx, count, n_max, g_sigma, g_rgb, g_params);
+    AN_CHECK_LAUNCH();
+    return AN_OK;
+}
