@@ -1,0 +1,134 @@
+"""AnimNeRF: host-side mirror of reference `models/anim_nerf.py:AnimNeRF` (42-307).
+
+Same constructor keywords, same per-frame state setters (`set_body_model`,
+`convert_to_body_model_space`, `clac_ober2cano_transform`, `set_latent_code`) and the same
+`forward(xyz, viewdir, use_fine) -> (rgb, sigma)` / `query_canonical_space` contract; the work
+between the query points and (rgb, sigma) runs on the sm_100a kernels (KNN + unpose, MLP) --
+there is no torch fallback for it.  The per-frame table builder (SMPL LBS, 6890 4x4 inverses) is
+SURVEY §8 row A16 and stays in torch so autograd reaches the SMPL parameters.
+
+Only the shipped configuration is built (every reference yaml): use_unpose=True with k_neigh=4,
+use_view=False, use_deformation=False, no latent codes, query_inside=False.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops, synthetic
+from .autograd import PointQuery, RenderPass
+from .body_model import BodyModel
+from .nerf import NeRF
+
+
+def batch_transform(P, v, pad_ones=True):
+    """(P @ [v;1|0])[:3] for P (...,4,4), v (...,3)  (reference models/anim_nerf.py:31-39)."""
+    out = torch.matmul(P[..., :3, :3], v[..., None])[..., 0]
+    return out + P[..., :3, 3] if pad_ones else out
+
+
+class AnimNeRF(nn.Module):
+    def __init__(self, model_path="smplx/models", model_type="smpl", gender="male", freqs_xyz=10, freqs_dir=4,
+                 use_view=False, use_unpose=False, unpose_view=False, k_neigh=4, use_knn=False,
+                 use_deformation=False, deformation_dim=0, apperance_dim=0, use_fine=False, share_fine=False,
+                 dis_threshold=0.2, query_inside=False, body_model_data=None, **kwargs):
+        super().__init__()
+        if use_view or use_deformation or deformation_dim or apperance_dim or query_inside or k_neigh != 4:
+            raise NotImplementedError("only the shipped configuration is built: k_neigh=4, use_view=False, "
+                                      "no deformation/appearance codes, query_inside=False")
+        self.freqs_xyz, self.freqs_dir = freqs_xyz, freqs_dir
+        self.use_view, self.use_unpose, self.unpose_view = use_view, use_unpose, unpose_view
+        self.k_neigh, self.use_knn = k_neigh, use_knn
+        self.use_deformation, self.deformation_dim, self.apperance_dim = use_deformation, deformation_dim, apperance_dim
+        self.use_fine, self.share_fine = use_fine, share_fine
+        self.dis_threshold, self.query_inside = dis_threshold, query_inside
+        self.weight_std = 0.1
+        self.knn_mode = 1          # 1 = grid-pruned exact search (default), 0 = exhaustive
+        self.mlp_impl = 0          # 0 = tcgen05 kernel; 1 = fp32 SIMT reference (tests only)
+        if body_model_data is None:
+            import os
+            path = os.path.join(model_path, model_type, "%s_%s.pkl" % (model_type.upper(), gender.upper()))
+            body_model_data = path if os.path.exists(path) else synthetic.make_smpl_dict(0)
+        self.body_model = BodyModel(body_model_data)
+        self.lbs_dim = self.body_model.lbs_weights.shape[1]
+        self.nerf = NeRF(freqs_xyz=freqs_xyz, freqs_dir=freqs_dir, use_view=use_view)
+        if use_fine:
+            self.nerf_fine = self.nerf if share_fine else NeRF(freqs_xyz=freqs_xyz, freqs_dir=freqs_dir, use_view=use_view)
+        self._grid = None
+
+    def set_latent_code(self, latent_code):
+        pass    # no latent codes in the shipped configuration (deformation_dim = apperance_dim = 0)
+
+    # ------------------------------------------------------------------ per-frame state (A16, A2)
+    def set_body_model(self, body_model_params, body_model_params_template=None):
+        out = self.body_model(**body_model_params)
+        self.verts = out["vertices"]
+        self.joints = out["joints"][:, :self.lbs_dim]
+        self.verts_transform = out["vertices_transform"]
+        self.joints_transform = out["joints_transform"]
+        self.shape_offsets, self.pose_offsets = out["shape_offsets"], out["pose_offsets"]
+        self.global_transform = out["joints_transform"][:, 0, :, :].clone()
+        if body_model_params_template is not None:
+            t = self.body_model(**body_model_params_template)
+            self.verts_template = t["vertices"]
+            self.joints_template = t["joints"][:, :self.lbs_dim]
+            self.verts_transform_template = t["vertices_transform"]
+            self.joints_transform_template = t["joints_transform"]
+            self.shape_offsets_template, self.pose_offsets_template = t["shape_offsets"], t["pose_offsets"]
+        self._grid = None
+
+    def convert_to_body_model_space(self, rays):
+        ginv = torch.inverse(self.global_transform).unsqueeze(1)            # (bs,1,4,4)
+        rays_o = batch_transform(ginv, rays[:, :, 0:3], True)
+        rays_d = batch_transform(ginv, rays[:, :, 3:6], False)
+        cam_dist = torch.norm(rays_o, dim=-1, keepdim=True)
+        near = torch.max(rays[:, :, 6:7], cam_dist - 1.0)
+        far = torch.min(rays[:, :, 7:8], cam_dist + 1.0)
+        self.verts = batch_transform(ginv, self.verts, True)
+        self.joints = batch_transform(ginv, self.joints, True)
+        self.global_transform = torch.matmul(ginv.squeeze(1), self.global_transform)
+        self.verts_transform = torch.matmul(ginv, self.verts_transform)
+        self._grid = None
+        return torch.cat((rays_o, rays_d, near, far), dim=-1)
+
+    def clac_ober2cano_transform(self):
+        inv = torch.inverse(self.verts_transform)
+        shift = (self.shape_offsets_template - self.shape_offsets) + (self.pose_offsets_template - self.pose_offsets)
+        inv = torch.cat([inv[..., :3], torch.cat([inv[..., :3, 3:] + shift[..., None], inv[..., 3:, 3:]], dim=-2)], dim=-1)
+        self.ober2cano_transform = torch.matmul(self.verts_transform_template, inv)
+
+    # ------------------------------------------------------------------ kernel configuration
+    def _cfg(self, use_fine):
+        verts = self.verts.detach().contiguous()
+        if self._grid is None or self._grid[1] != self.dis_threshold:
+            self._grid = (ops.vertex_grid(verts, self.dis_threshold) if self.knn_mode == 1 else None, self.dis_threshold)
+        net = self.nerf_fine if use_fine else self.nerf
+        return dict(verts=verts, lbs=self.body_model.lbs_weights, grid=self._grid[0], thr=float(self.dis_threshold),
+                    net=net, knn_mode=self.knn_mode, mlp_impl=self.mlp_impl, unpose=self.use_unpose)
+
+    def render_pass(self, rays, z, use_fine=False, sigma_noise=None, white_bkgd=True):
+        """Fused composite pass used by VolumeRenderer: -> (weights, rgb, depth, acc)."""
+        if not self.use_unpose:
+            raise NotImplementedError("render_pass is built for use_unpose=True (every shipped config)")
+        cfg = self._cfg(use_fine)
+        cfg["white"] = bool(white_bkgd)
+        rgb, depth, acc, w = RenderPass.apply(rays, z, self.ober2cano_transform, sigma_noise, cfg, *cfg["net"].param_list())
+        return w, rgb, depth, acc
+
+    # ------------------------------------------------------------------ point queries (B2)
+    def unpose(self, xyz, viewdir=None):
+        cfg = self._cfg(False)
+        out = ops.knn_unpose(cfg["verts"], self.ober2cano_transform.detach(), cfg["lbs"], cfg["thr"], xyz=xyz.detach(),
+                             grid=cfg["grid"], mode=self.knn_mode)
+        return out["xyz_cano"], viewdir, out["valid"].float().unsqueeze(-1)
+
+    def query_canonical_space(self, xyz, viewdir=None, use_fine=False, only_sigma=False, only_normal=False):
+        net = self.nerf_fine if use_fine else self.nerf
+        if only_sigma:
+            return net.get_sigma(xyz, only_sigma=True)         # torch path: regularisers
+        if only_normal:
+            return net.get_normal(xyz)
+        return net(xyz)
+
+    def forward(self, xyz, viewdir=None, use_fine=False):
+        cfg = self._cfg(use_fine)
+        o2c = self.ober2cano_transform if self.use_unpose else None
+        return PointQuery.apply(xyz, o2c, cfg, *cfg["net"].param_list())

@@ -1,0 +1,163 @@
+"""torch.autograd glue: the CUDA kernels as differentiable functions.
+
+`RenderPass` is one composite pass of the reference (`VolumeRenderer.composite`,
+models/volume_rendering.py:113-160) with everything between the ray samples and the per-ray
+outputs on kernels: point generation + KNN + unpose -> compaction of valid points -> MLP ->
+compositing.  Its backward chains composite_bwd -> mlp_bwd -> knn_unpose_bwd and returns
+gradients for the MLP parameters, the per-vertex observation->canonical table, the rays and the
+sample depths (the three routes to the SMPL parameters, SURVEY §7 traps).  As in the reference
+there is no gradient through KNN distances/indices, `valid`, or z_fine.
+"""
+import torch
+
+from . import ops
+
+
+class RenderPass(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rays, z, ober2cano, sigma_noise, cfg, *params):
+        """rays (B,R,8) body space, z (B,R,K); cfg = dict(verts, lbs, grid, thr, net, white, knn_mode, mlp_impl)."""
+        net = cfg["net"]
+        B, R, K = z.shape
+        dev = z.device
+        need_grad = any(ctx.needs_input_grad)
+        rays_c, z_c, o2c_c = rays.contiguous(), z.contiguous(), ober2cano.contiguous()
+        sigma = torch.empty(B, R, K, device=dev)
+        rgb = torch.empty(B, R, K, 3, device=dev)
+        out = ops.knn_unpose(cfg["verts"], o2c_c, cfg["lbs"], cfg["thr"], rays=rays_c, z=z_c, grid=cfg["grid"],
+                             mode=cfg.get("knn_mode", 1), want_idx=need_grad, want_qw=need_grad,
+                             sigma=sigma, rgb=rgb, compact=True)
+        packed = net.packed()
+        stash = ops.mlp_stash(B * R * K, dev) if need_grad else None
+        ops.mlp_fwd(packed, out["xyz_cano"], sigma, rgb, cidx=out["cidx"], count=out["count"], n_max=B * R * K,
+                    stash=stash, impl=cfg.get("mlp_impl", 0))
+        w, rgb_o, depth, acc = ops.composite(sigma, rgb, z_c, rays_c, cfg["white"], sigma_noise)
+        if need_grad:
+            ctx.cfg = cfg
+            ctx.packed, ctx.stash, ctx.aux = packed, stash, out
+            ctx.save_for_backward(rays_c, z_c, o2c_c, sigma, rgb, sigma_noise if sigma_noise is not None else torch.empty(0))
+        ctx.mark_non_differentiable(w)
+        return rgb_o, depth, acc, w
+
+    @staticmethod
+    def backward(ctx, g_rgb_o, g_depth, g_acc, _gw):
+        rays, z, o2c, sigma, rgb, noise = ctx.saved_tensors
+        noise = noise if noise.numel() else None
+        cfg, aux = ctx.cfg, ctx.aux
+        net = cfg["net"]
+        B, R, K = z.shape
+        g_sigma, g_rgb, g_z, g_far = ops.composite_bwd(sigma, rgb, z, rays, g_rgb_o, g_depth, g_acc, cfg["white"], noise)
+        need_geo = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        g_flat, g_xc = ops.mlp_bwd(ctx.packed, ctx.stash, aux["xyz_cano"], rgb, g_sigma, g_rgb, cidx=aux["cidx"],
+                                   count=aux["count"], n_max=B * R * K, want_g_xyz=need_geo)
+        g_rays = g_zz = g_o2c = None
+        if need_geo:
+            g_o2c, g_xyz = ops.knn_unpose_bwd(g_xc, aux["cidx"], aux["count"], aux["idx"], aux["qw"], o2c, rays=rays, z=z)
+            g_xyz = g_xyz.view(B, R, K, 3)
+            if ctx.needs_input_grad[0]:
+                g_rays = torch.zeros_like(rays)
+                g_rays[..., 0:3] = g_xyz.sum(2)
+                g_rays[..., 3:6] = (g_xyz * z[..., None]).sum(2)
+                g_rays[..., 7] = g_far
+            if ctx.needs_input_grad[1]:
+                g_zz = g_z + (g_xyz * rays[:, :, None, 3:6]).sum(-1)
+            if not ctx.needs_input_grad[2]:
+                g_o2c = None
+        g_params = net.split_flat_grad(g_flat)
+        ctx.stash = ctx.aux = None
+        return (g_rays, g_zz, g_o2c, None, None) + tuple(g_params)
+
+
+class PointQuery(torch.autograd.Function):
+    """AnimNeRF.forward / NeRF.forward on explicit points: (optional unpose) -> MLP -> mask."""
+
+    @staticmethod
+    def forward(ctx, xyz, ober2cano, cfg, *params):
+        net = cfg["net"]
+        B, N = xyz.shape[:2]
+        dev = xyz.device
+        need_grad = any(ctx.needs_input_grad)
+        xyz_c = xyz.contiguous()
+        sigma = torch.empty(B, N, device=dev)
+        rgb = torch.empty(B, N, 3, device=dev)
+        packed = net.packed()
+        stash = ops.mlp_stash(B * N, dev) if need_grad else None
+        if cfg.get("unpose", True):
+            o2c_c = ober2cano.contiguous()
+            out = ops.knn_unpose(cfg["verts"], o2c_c, cfg["lbs"], cfg["thr"], xyz=xyz_c, grid=cfg["grid"],
+                                 mode=cfg.get("knn_mode", 1), want_idx=need_grad, want_qw=need_grad,
+                                 sigma=sigma, rgb=rgb, compact=True)
+            ops.mlp_fwd(packed, out["xyz_cano"], sigma, rgb, cidx=out["cidx"], count=out["count"], n_max=B * N,
+                        stash=stash, impl=cfg.get("mlp_impl", 0))
+        else:
+            o2c_c, out = None, dict(xyz_cano=xyz_c, cidx=None, count=None)
+            ops.mlp_fwd(packed, xyz_c, sigma, rgb, n_max=B * N, stash=stash, impl=cfg.get("mlp_impl", 0))
+        if need_grad:
+            ctx.cfg, ctx.packed, ctx.stash, ctx.aux = cfg, packed, stash, out
+            ctx.save_for_backward(xyz_c, o2c_c if o2c_c is not None else torch.empty(0), rgb)
+        return rgb, sigma.unsqueeze(-1)
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_sigma):
+        xyz, o2c, rgb = ctx.saved_tensors
+        cfg, aux = ctx.cfg, ctx.aux
+        B, N = xyz.shape[:2]
+        need_geo = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        g_flat, g_xc = ops.mlp_bwd(ctx.packed, ctx.stash, aux["xyz_cano"], rgb, g_sigma.contiguous().view(B, N),
+                                   g_rgb.contiguous(), cidx=aux["cidx"], count=aux["count"], n_max=B * N,
+                                   want_g_xyz=need_geo)
+        g_xyz = g_o2c = None
+        if need_geo:
+            if cfg.get("unpose", True):
+                g_o2c, g_xyz = ops.knn_unpose_bwd(g_xc, aux["cidx"], aux["count"], aux["idx"], aux["qw"], o2c, xyz=xyz)
+                if not ctx.needs_input_grad[1]:
+                    g_o2c = None
+            else:
+                g_xyz = g_xc.view_as(xyz)
+        ctx.stash = ctx.aux = None
+        return (g_xyz, g_o2c, None) + tuple(cfg["net"].split_flat_grad(g_flat))
+
+
+def mlp_query(net, xyz):
+    """Canonical-space NeRF query (no unposing): xyz (B,N,3) -> rgb (B,N,3), sigma (B,N,1)."""
+    cfg = dict(net=net, unpose=False)
+    return PointQuery.apply(xyz, None, cfg, *net.param_list())
+
+
+class SampleCoarse(torch.autograd.Function):
+    """models/volume_rendering.py:29-56.  z is affine in (near, far): z = near + s*(far-near)."""
+
+    @staticmethod
+    def forward(ctx, rays, n_coarse, perturb, noise_u, seed):
+        z = ops.sample_coarse(rays, n_coarse, perturb, noise_u, seed)
+        ctx.save_for_backward(rays, z)
+        return z
+
+    @staticmethod
+    def backward(ctx, g_z):
+        rays, z = ctx.saved_tensors
+        near, far = rays[..., 6:7], rays[..., 7:8]
+        s = (z - near) / (far - near)
+        g = torch.zeros_like(rays)
+        g[..., 6] = (g_z * (1 - s)).sum(-1)
+        g[..., 7] = (g_z * s).sum(-1)
+        return g, None, None, None, None
+
+
+class SampleFineMerge(torch.autograd.Function):
+    """models/volume_rendering.py:59-97 + :199-207.  z_fine is detached in the reference; the sorted
+    union carries the coarse depths' gradient through the sort permutation."""
+
+    @staticmethod
+    def forward(ctx, weights, z_coarse, n_fine, det, u, seed):
+        z_fine, z_all, src = ops.sample_fine_merge(weights, z_coarse, n_fine, det, u, seed)
+        ctx.save_for_backward(src)
+        ctx.kc = z_coarse.shape[-1]
+        ctx.mark_non_differentiable(z_fine)
+        return z_all, z_fine
+
+    @staticmethod
+    def backward(ctx, g_all, _g_fine):
+        (src,) = ctx.saved_tensors
+        g_cat = torch.zeros_like(g_all).scatter_(-1, src.long(), g_all)
+        return None, g_cat[..., :ctx.kc].contiguous(), None, None, None, None

@@ -142,7 +142,7 @@ def mlp_stash(n_max, device):
     return buf[off:off + nbytes]
 
 
-def mlp_bwd(packed, stash, xyz_cano, g_sigma, g_rgb, cidx=None, count=None, n_max=None, want_g_xyz=True):
+def mlp_bwd(packed, stash, xyz_cano, rgb, g_sigma, g_rgb, cidx=None, count=None, n_max=None, want_g_xyz=True):
     if n_max is None:
         n_max = xyz_cano.numel() // 3
     dev = xyz_cano.device
@@ -151,9 +151,14 @@ def mlp_bwd(packed, stash, xyz_cano, g_sigma, g_rgb, cidx=None, count=None, n_ma
     nscr = _lib.load().an_mlp_bwd_scratch_bytes(int(n_max))
     scratch = torch.empty(nscr + 128, device=dev, dtype=torch.uint8)
     off = (-scratch.data_ptr()) % 128
-    call("an_mlp_bwd", ptr(packed), ptr(stash), ptr(xyz_cano), ptr(cidx), ptr(count), int(n_max), ptr(g_sigma),
-         ptr(g_rgb), ptr(g_params), ptr(g_xyz), ptr(scratch[off:off + nscr]), stream())
+    global _last_bwd_scratch
+    _last_bwd_scratch = scratch[off:off + nscr]      # kept alive until the next call (tests inspect the dY images)
+    call("an_mlp_bwd", ptr(packed), ptr(stash), ptr(xyz_cano), ptr(rgb), ptr(cidx), ptr(count), int(n_max), ptr(g_sigma),
+         ptr(g_rgb), ptr(g_params), ptr(g_xyz), ptr(_last_bwd_scratch), stream())
     return g_params, g_xyz
+
+
+_last_bwd_scratch = None
 
 
 # ------------------------------------------------------------------------ compositing

@@ -1,0 +1,133 @@
+"""AnimNeRFSystem: host-side mirror of reference `train.py:AnimNeRFSystem` (103-424), duck-type
+compatible with a LightningModule (`forward`, `training_step`, `configure_optimizers`,
+`compute_loss`, `decode_batch`) but importable without pytorch-lightning (absent here).
+
+`forward(rays (B,h,w,8), body_model_params, body_model_params_template, latent_code, perturb)`
+follows train.py:189-215: per-frame tables -> rays to body space -> render -> dict of (B,h,w,.).
+The reference's `chunk` loop (train.py:205-210) exists to bound the memory of its materialised
+gathers; the fused kernels need no chunking, so `chunk` only caps the rays per launch
+(default: all rays of the call at once).
+
+Losses (train.py:228-322): rgb MSE + 0.1 * alpha L1 on coarse and fine run on the render outputs;
+the foreground/background density and the normal-smoothness regularisers query the MLP through
+the reference's torch formulation (`NeRF.get_sigma/get_normal`, double backward) -- SURVEY §8(f)#2
+marks moving them onto the kernels as the next step.  They share the same nn.Parameters.
+"""
+from collections import defaultdict
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .anim_nerf import AnimNeRF
+from .volume_rendering import VolumeRenderer
+
+
+def default_hparams(**over):
+    """The hot-path-relevant keys of reference config.py / male-3-casual.yaml."""
+    hp = dict(model_path="smplx/models", model_type="smpl", gender="male", freqs_xyz=10, freqs_dir=0,
+              use_view=False, k_neigh=4, use_knn=True, use_unpose=True, unpose_view=False, use_deformation=False,
+              deformation_dim=0, apperance_dim=0, latent_dim=0, use_fine=True, share_fine=False, dis_threshold=0.2,
+              query_inside=False, n_samples=64, n_importance=32, n_depth=0, chunk=None, white_bkgd=True,
+              optim_body_params=False, num_frames=1,
+              train=SimpleNamespace(lr=5e-4, lambda_alphas=0.1, lambda_foreground=0.01, lambda_background=0.01,
+                                    lambda_normals=0.01, epsilon=0.02, optimizer="adam", weight_decay=0.0))
+    hp.update(over)
+    return SimpleNamespace(**hp)
+
+
+class AnimNeRFSystem(nn.Module):
+    def __init__(self, hparams=None, body_model_data=None, **over):
+        super().__init__()
+        self.hparams = hparams if hparams is not None else default_hparams(**over)
+        hp = self.hparams
+        self.anim_nerf = AnimNeRF(model_path=hp.model_path, model_type=hp.model_type, gender=hp.gender,
+                                  freqs_xyz=hp.freqs_xyz, freqs_dir=hp.freqs_dir, use_view=hp.use_view,
+                                  k_neigh=hp.k_neigh, use_knn=hp.use_knn, use_unpose=hp.use_unpose,
+                                  unpose_view=hp.unpose_view, use_deformation=hp.use_deformation,
+                                  deformation_dim=hp.deformation_dim, apperance_dim=hp.apperance_dim,
+                                  use_fine=hp.n_importance > 0 or hp.n_depth > 0, share_fine=hp.share_fine,
+                                  dis_threshold=hp.dis_threshold, query_inside=hp.query_inside,
+                                  body_model_data=body_model_data)
+        self.volume_renderer = VolumeRenderer(n_coarse=hp.n_samples, n_fine=hp.n_importance, n_fine_depth=hp.n_depth,
+                                              share_fine=hp.share_fine, white_bkgd=hp.white_bkgd)
+
+    def forward(self, rays, body_model_params, body_model_params_template, latent_code=None, perturb=1.0, noise=None):
+        bs, h, w = rays.shape[:3]
+        n_rays = h * w
+        rays = rays.view(bs, n_rays, -1)
+        self.anim_nerf.set_body_model(body_model_params, body_model_params_template)
+        rays = self.anim_nerf.convert_to_body_model_space(rays)
+        self.anim_nerf.clac_ober2cano_transform()
+        chunk = getattr(self.hparams, "chunk", None) or n_rays
+        results = defaultdict(list)
+        for i in range(0, n_rays, chunk):
+            out = self.volume_renderer(self.anim_nerf, rays[:, i:i + chunk, :], perturb=perturb, noise=noise)
+            for k, v in out.items():
+                results[k].append(v)
+        return {k: torch.cat(v, 1).view(bs, h, w, -1) for k, v in results.items()}
+
+    def configure_optimizers(self):
+        hp = self.hparams
+        groups = [{"params": self.anim_nerf.parameters(), "lr": hp.train.lr}]
+        self.optimizer = torch.optim.Adam(groups, lr=hp.train.lr, eps=1e-8, weight_decay=hp.train.weight_decay)
+        return [self.optimizer], []
+
+    def compute_loss(self, rgbs, alphas, results, frame_idx=None, latent_code=None, fg_points=None, bg_points=None,
+                     with_regularizers=True):
+        hp = self.hparams
+        fine = hp.n_importance > 0 and not hp.share_fine
+        loss, det = 0, {}
+
+        def add(name, value, weight=1.0):
+            nonlocal loss
+            loss = loss + weight * value
+            det[name] = value
+        add("loss_rgb", F.mse_loss(results["rgbs"], rgbs))
+        if fine:
+            add("loss_rgb_fine", F.mse_loss(results["rgbs_fine"], rgbs))
+        add("loss_alphas", F.l1_loss(results["alphas"], alphas), hp.train.lambda_alphas)
+        if fine:
+            add("loss_alphas_fine", F.l1_loss(results["alphas_fine"], alphas), hp.train.lambda_alphas)
+        if not with_regularizers:
+            return loss, det
+        k = -2.0 / hp.n_samples
+        q = self.anim_nerf.query_canonical_space
+        if hp.use_unpose and fg_points is not None:
+            add("loss_foreground", torch.mean(torch.exp(k * torch.relu(q(fg_points, use_fine=False, only_sigma=True)))),
+                hp.train.lambda_foreground)
+            if fine:
+                add("loss_foreground_fine", torch.mean(torch.exp(k * torch.relu(q(fg_points, use_fine=True, only_sigma=True)))),
+                    hp.train.lambda_foreground)
+        if hp.use_unpose and bg_points is not None:
+            add("loss_background", torch.mean(1 - torch.exp(k * torch.relu(q(bg_points, use_fine=False, only_sigma=True)))),
+                hp.train.lambda_background)
+            if fine:
+                add("loss_background_fine", torch.mean(1 - torch.exp(k * torch.relu(q(bg_points, use_fine=True, only_sigma=True)))),
+                    hp.train.lambda_background)
+        points = self.anim_nerf.verts_template.detach().clone()
+        points = points + torch.randn_like(points) * hp.dis_threshold * 0.5
+        neighbs = points + torch.randn_like(points) * hp.train.epsilon
+
+        def unit(v):
+            return v / (torch.norm(v, p=2, dim=-1, keepdim=True) + 1e-5)
+        add("loss_normals", F.mse_loss(unit(q(points, use_fine=False, only_normal=True)),
+                                       unit(q(neighbs, use_fine=False, only_normal=True))), hp.train.lambda_normals)
+        if fine:
+            add("loss_normals_fine", F.mse_loss(unit(q(points, use_fine=True, only_normal=True)),
+                                                unit(q(neighbs, use_fine=True, only_normal=True))), hp.train.lambda_normals)
+        return loss, det
+
+    def decode_batch(self, batch):
+        g = batch.get
+        return (g("frame_id"), g("cam_id"), g("frame_idx"), batch["rays"], batch["rgbs"], batch["alphas"],
+                batch["body_model_params"], batch["body_model_params_template"], g("fg_points"), g("bg_points"))
+
+    def training_step(self, batch, batch_idx=0, with_regularizers=True):
+        (_, _, frame_idx, rays, rgbs, alphas, params, params_t, fg, bg) = self.decode_batch(batch)
+        results = self(rays, params, params_t)
+        loss, details = self.compute_loss(rgbs, alphas, results, frame_idx=frame_idx, fg_points=fg, bg_points=bg,
+                                          with_regularizers=with_regularizers)
+        self.last_details = details
+        return loss

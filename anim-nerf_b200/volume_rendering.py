@@ -1,0 +1,84 @@
+"""VolumeRenderer: host-side mirror of reference `models/volume_rendering.py` (8-232).
+
+Same constructor, same `forward(model, rays, perturb=0., **kw) -> dict` keys and shapes
+('rgbs','alphas','depths'[,'rgbs_fine','alphas_fine','depths_fine']).  The stages run on the
+sm_100a kernels: stratified sampling, (model.render_pass =) point generation + KNN/unpose + MLP +
+alpha compositing, inverse-CDF resampling + sort-merge.  Randomness: `perturb>0` draws come from
+an in-kernel Philox stream seeded per call from torch's generator; pass `noise=dict(coarse_u,
+fine_u, sigma_c, sigma_f)` to use explicit draws instead (parity tests).
+
+A `model` without `render_pass` (any callable with the reference's
+`model(xyz, viewdir, use_fine=...) -> (rgb, sigma)` contract) goes through the generic path:
+torch point generation, the callable, then the compositing kernel -- forward only.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .autograd import SampleCoarse, SampleFineMerge
+
+
+class VolumeRenderer(nn.Module):
+    def __init__(self, n_coarse=64, n_fine=0, n_fine_depth=0, share_fine=False, noise_std=1.0, depth_std=0.02,
+                 white_bkgd=True, lindisp=True):
+        super().__init__()
+        if not lindisp:
+            raise NotImplementedError("lindisp=False (sampling linear in disparity) is unused by every reference config")
+        if n_fine_depth > 0:
+            raise NotImplementedError("n_fine_depth > 0 is unused by every reference config (n_depth=0)")
+        self.n_coarse, self.n_fine, self.n_fine_depth = n_coarse, n_fine, n_fine_depth
+        self.share_fine, self.noise_std, self.depth_std = share_fine, noise_std, depth_std
+        self.lindisp, self.white_bkgd = lindisp, white_bkgd
+
+    @staticmethod
+    def _seed():
+        return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+    def sample_coarse(self, rays, perturb=0., noise_u=None):
+        rays = rays[..., :8].contiguous()
+        return SampleCoarse.apply(rays, self.n_coarse, float(perturb), noise_u,
+                                  self._seed() if (perturb > 0 and noise_u is None) else 0)
+
+    def sample_fine_merge(self, z_coarse, weights, det=False, u=None):
+        """Fused `sample_fine` + cat + sort (reference :199-207): takes the coarse depths and the full
+        coarse weights (the kernel forms the mid-point bins and the w[1:-1] slice itself); returns
+        (z_combine sorted, z_fine)."""
+        return SampleFineMerge.apply(weights.detach(), z_coarse, self.n_fine, bool(det), u,
+                                     self._seed() if (not det and u is None) else 0)
+
+    def composite(self, model, rays, z_samp, coarse=True, far=True, perturb=0., sigma_noise=None, **kwargs):
+        if not far:
+            raise NotImplementedError("far=False is never used by the reference's callers")
+        bs, n_rays, K = z_samp.shape
+        if self.noise_std > 0.0 and perturb > 0 and sigma_noise is None:
+            sigma_noise = torch.randn(bs, n_rays, K, device=z_samp.device) * self.noise_std
+        if hasattr(model, "render_pass"):
+            return model.render_pass(rays[..., :8].contiguous(), z_samp, use_fine=not coarse,
+                                     sigma_noise=sigma_noise, white_bkgd=self.white_bkgd)
+        # generic callable: reference semantics, compositing on the kernel (forward only)
+        xyz = (rays[..., None, :3] + z_samp.unsqueeze(-1) * rays[..., None, 3:6]).reshape(bs, -1, 3)
+        viewdir = rays[..., None, 3:6].expand(-1, -1, K, -1).reshape(bs, -1, 3)
+        rgbs, sigmas = model(xyz, viewdir, use_fine=not coarse, **kwargs)
+        w, rgb, depth, acc = ops.composite(sigmas.reshape(bs, n_rays, K).contiguous().float(),
+                                           rgbs.reshape(bs, n_rays, K, 3).contiguous().float(),
+                                           z_samp.contiguous(), rays[..., :8].contiguous(), self.white_bkgd, sigma_noise)
+        return w, rgb, depth, acc
+
+    def forward(self, model, rays, perturb=0., noise=None, **kwargs):
+        noise = noise or {}
+        rays = rays[..., :8].contiguous()
+        z_coarse = self.sample_coarse(rays, perturb=perturb, noise_u=noise.get("coarse_u"))
+        no_grad_coarse = self.n_fine > 0 and self.share_fine
+        with torch.set_grad_enabled(torch.is_grad_enabled() and not no_grad_coarse):
+            weights, rgbs, depths, alphas = self.composite(model, rays, z_coarse, coarse=True, far=True, perturb=perturb,
+                                                           sigma_noise=noise.get("sigma_c"), **kwargs)
+        output = {"rgbs": rgbs, "alphas": alphas, "depths": depths}
+        if self.n_fine > 0:
+            z_combine, _ = self.sample_fine_merge(z_coarse, weights, det=(perturb == 0), u=noise.get("fine_u"))
+            _, rgbs_f, depths_f, alphas_f = self.composite(model, rays, z_combine, coarse=False, far=True, perturb=perturb,
+                                                           sigma_noise=noise.get("sigma_f"), **kwargs)
+            if self.share_fine:
+                output = {"rgbs": rgbs_f, "alphas": alphas_f, "depths": depths_f}
+            else:
+                output.update({"rgbs_fine": rgbs_f, "alphas_fine": alphas_f, "depths_fine": depths_f})
+        return output

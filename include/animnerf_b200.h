@@ -112,13 +112,15 @@ int64_t an_mlp_stash_bytes(int64_t n_max);
 int an_mlp_fwd(const void* packed, const float* xyz_cano, const int32_t* cidx, const int32_t* count,
                int64_t n_max, float* sigma, float* rgb, void* stash, int impl, void* stream);
 
-/* backward: g_sigma (ids), g_rgb (ids,3) -> g_params (fp32, layout = an_mlp_grad_floats(),
- * accumulated; caller zeroes) and g_xyz_cano (ids,3) when non-NULL.
+/* backward: g_sigma (ids), g_rgb (ids,3), rgb = the forward's output (ids,3) -> g_params (fp32 flat
+ * vector of an_mlp_grad_floats() = 592 388 floats: per nn.Linear weight then bias, in an_mlp_pack's
+ * order; accumulated, caller zeroes) and g_xyz_cano (ids,3) when non-NULL (caller zeroes).
  * scratch: an_mlp_bwd_scratch_bytes(n_max).                                                  */
 int64_t an_mlp_grad_floats(void);
 int64_t an_mlp_bwd_scratch_bytes(int64_t n_max);
-int an_mlp_bwd(const void* packed, const void* stash, const float* xyz_cano, const int32_t* cidx,
-               const int32_t* count, int64_t n_max, const float* g_sigma, const float* g_rgb,
+int an_mlp_bwd(const void* packed, const void* stash, const float* xyz_cano, const float* rgb,
+               const int32_t* cidx, const int32_t* count, int64_t n_max,
+               const float* g_sigma, const float* g_rgb,
                float* g_params, float* g_xyz_cano, void* scratch, void* stream);
 
 /* ---- A12: alpha compositing ------------------------------------------------------------
