@@ -242,3 +242,61 @@ def make_nerf_weights(seed, sigma_bias=5.0):
         out[name + ".weight"] = w
         out[name + ".bias"] = b
     return out
+
+
+# ----------------------------------------------------------------- synthetic training frames
+def project_points(pts, cam):
+    """world points (n,3) -> (row, col) float pixel coordinates under `make_camera`'s convention
+    (world dir of pixel (row j, col i) is ((i-cx)/fx, (j-cy)/fy, 1), camera at the origin)."""
+    fx, fy = cam["focal"]
+    cx, cy = cam["c"]
+    col = cx + fx * pts[:, 0] / pts[:, 2]
+    row = cy + fy * pts[:, 1] / pts[:, 2]
+    return row, col
+
+
+def camera_rays(cam, rows, cols, near=0.1, far=10.0):
+    """world-space rays (n,8) of the given pixels (numpy restatement of gen_rays for fixtures;
+    the timed path uses the an_raygen_fwd kernel)."""
+    fx, fy = cam["focal"]
+    cx, cy = cam["c"]
+    d = np.stack([(cols - cx) / fx, -(rows - cy) / fy, -np.ones_like(cols, dtype=np.float64)], -1)
+    d = d / np.linalg.norm(d, axis=-1, keepdims=True)
+    dw = d @ cam["c2w"][:, :3].T.astype(np.float64)
+    o = np.broadcast_to(cam["c2w"][:, 3].astype(np.float64), dw.shape)
+    return np.concatenate([o, dw, np.full_like(dw[:, :1], near), np.full_like(dw[:, :1], far)], -1).astype(np.float32)
+
+
+def make_training_batch(verts_world, n_side=32, W=512, H=512, seed=3, fg_frac=0.9, band=64):
+    """cfg2-style batch: per frame n_side^2 pixels, 90 % on the body silhouette and
+    10 % within a `band`-pixel ring outside it (mimics the reference's foreground_pixel sampling,
+    datasets/anim_nerf_dataset.py:30-48), random colour targets, alphas in {0,1}.
+    verts_world (B,V,3) numpy.  Returns dict of numpy arrays."""
+    from scipy import ndimage
+    rs = np.random.RandomState(seed)
+    cam = make_camera(W, H)
+    B = verts_world.shape[0]
+    n = n_side * n_side
+    rays = np.zeros((B, n, 8), np.float32)
+    pix = np.zeros((B, n, 2), np.int32)
+    alphas = np.zeros((B, n, 1), np.float32)
+    for b in range(B):
+        row, col = project_points(verts_world[b].astype(np.float64), cam)
+        mask = np.zeros((H, W), bool)
+        r = np.clip(np.round(row).astype(int), 0, H - 1)
+        c = np.clip(np.round(col).astype(int), 0, W - 1)
+        mask[r, c] = True
+        mask = ndimage.binary_closing(ndimage.binary_dilation(mask, iterations=3), iterations=2)
+        ring = ndimage.binary_dilation(mask, iterations=band) & ~mask
+        fg = np.argwhere(mask)
+        bg = np.argwhere(ring)
+        n_fg = int(round(fg_frac * n))
+        sel = np.concatenate([fg[rs.randint(0, len(fg), n_fg)], bg[rs.randint(0, len(bg), n - n_fg)]], 0)
+        perm = rs.permutation(n)
+        sel = sel[perm]
+        pix[b] = sel
+        alphas[b, :, 0] = (np.arange(n) < n_fg)[perm]
+        rays[b] = camera_rays(cam, sel[:, 0].astype(np.float64), sel[:, 1].astype(np.float64))
+    rgbs = rs.uniform(size=(B, n, 3)).astype(np.float32)
+    return dict(rays=rays.reshape(B, n_side, n_side, 8), pix=pix, rgbs=rgbs.reshape(B, n_side, n_side, 3),
+                alphas=alphas.reshape(B, n_side, n_side, 1), cam=cam)
