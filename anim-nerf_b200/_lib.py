@@ -32,6 +32,9 @@ SIGNATURES = {
     "an_mlp_grad_floats": (_i64, []),
     "an_mlp_bwd_scratch_bytes": (_i64, [_i64]),
     "an_mlp_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "an_mlp_bwd_dgrad": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "an_mlp_bwd_wgrad": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "an_mlp_bwd_heads": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "an_composite_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "an_composite_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "an_searchsorted_right": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
@@ -80,5 +83,28 @@ def check(code, what):
         raise AnimNerfB200Error("%s failed: %d (%s)" % (what, code, msg.decode() if msg else "?"))
 
 
+# kernels launched per entry point (for bench.py's gpu_launches claim)
+KERNELS_PER_CALL = {"an_mlp_bwd": 3}
+launch_count = 0
+_timing = None          # bench.py: dict name -> list of (start_event, stop_event) on the launching stream
+
+
+def enable_timing(on=True):
+    """Record a CUDA-event pair around every kernel-launching call (on the current stream)."""
+    global _timing
+    _timing = {} if on else None
+    return _timing
+
+
 def call(name, *args):
+    global launch_count
+    launch_count += KERNELS_PER_CALL.get(name, 1)
+    if _timing is None:
+        check(getattr(load(), name)(*args), name)
+        return
+    s = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(s)
     check(getattr(load(), name)(*args), name)
+    e1.record(s)
+    _timing.setdefault(name, []).append((e0, e1))

@@ -511,36 +511,76 @@ extern "C" int64_t an_mlp_bwd_scratch_bytes(int64_t n_max)
     return ((n_max + 255) / 256) * 2 * mlp::DY_TILE;
 }
 
+static int bwd_check(const void* packed, const void* stash, const void* scratch, int64_t n_max,
+                     const int32_t* cidx, const int32_t* count)
+{
+    if (!stash || !scratch || n_max <= 0) return AN_ERR_ARG;
+    if (cidx && !count) return AN_ERR_ARG;
+    if ((packed && (((uintptr_t)packed) & 1023)) || (((uintptr_t)stash) & 127) || (((uintptr_t)scratch) & 127)) return AN_ERR_ALIGN;
+    return AN_OK;
+}
+
+extern "C" int an_mlp_bwd_dgrad(const void* packed, const void* stash, const float* xyz_cano, const float* rgb,
+                                const int32_t* cidx, const int32_t* count, int64_t n_max,
+                                const float* g_sigma, const float* g_rgb, float* g_xyz_cano,
+                                void* scratch, void* stream)
+{
+    if (!packed || !xyz_cano || !rgb || !g_sigma || !g_rgb) return AN_ERR_ARG;
+    int rc = bwd_check(packed, stash, scratch, n_max, cidx, count);
+    if (rc) return rc;
+    cudaError_t e = cudaFuncSetAttribute(mlp_bwd_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);
+    if (e != cudaSuccess) return (int)e;
+    const int sms = an_num_sms();
+    const int64_t iters = (n_max + 255) / 256;
+    const int grid = (int)(iters < sms ? iters : sms);
+    mlp_bwd_dgrad_kernel<<<grid, THREADS, SM_ALLOC, (cudaStream_t)stream>>>(
+        (const uint8_t*)packed, (const uint8_t*)stash, xyz_cano, rgb, cidx, count, n_max, g_sigma, g_rgb,
+        g_xyz_cano, (uint8_t*)scratch);
+    AN_CHECK_LAUNCH();
+    return AN_OK;
+}
+
+extern "C" int an_mlp_bwd_wgrad(const void* stash, const void* scratch, const int32_t* cidx, const int32_t* count,
+                                int64_t n_max, float* g_params, void* stream)
+{
+    if (!g_params) return AN_ERR_ARG;
+    int rc = bwd_check(nullptr, stash, scratch, n_max, cidx, count);
+    if (rc) return rc;
+    cudaError_t e = cudaFuncSetAttribute(mlp_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_ALLOC);
+    if (e != cudaSuccess) return (int)e;
+    const int sms = an_num_sms();
+    const int64_t iters = (n_max + 255) / 256;
+    int64_t splits = sms / NJOBS;                      // 13 on a 148-SM part -> 143 CTAs, one wave
+    if (splits > iters * 2) splits = iters * 2;
+    if (splits < 1) splits = 1;
+    dim3 wgrid((unsigned)splits, NJOBS);
+    mlp_bwd_wgrad_kernel<<<wgrid, WG_THREADS, WG_ALLOC, (cudaStream_t)stream>>>(
+        (const uint8_t*)stash, (const uint8_t*)scratch, count, cidx ? 1 : 0, n_max, g_params);
+    AN_CHECK_LAUNCH();
+    return AN_OK;
+}
+
+extern "C" int an_mlp_bwd_heads(const void* stash, const float* rgb, const int32_t* cidx, const int32_t* count,
+                                int64_t n_max, const float* g_sigma, const float* g_rgb, float* g_params, void* stream)
+{
+    if (!stash || !rgb || !g_sigma || !g_rgb || !g_params || n_max <= 0) return AN_ERR_ARG;
+    if (cidx && !count) return AN_ERR_ARG;
+    const int sms = an_num_sms();
+    const int64_t tiles = (n_max + 127) / 128;
+    const int hgrid = (int)(tiles < sms * 2 ? tiles : sms * 2);
+    mlp_bwd_heads_kernel<<<hgrid, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)stash, rgb, cidx, count, n_max, g_sigma, g_rgb, g_params);
+    AN_CHECK_LAUNCH();
+    return AN_OK;
+}
+
 extern "C" int an_mlp_bwd(const void* packed, const void* stash, const float* xyz_cano, const float* rgb,
                           const int32_t* cidx, const int32_t* count, int64_t n_max,
                           const float* g_sigma, const float* g_rgb, float* g_params, float* g_xyz_cano,
                           void* scratch, void* stream)
 {
-    if (!packed || !stash || !xyz_cano || !rgb || !g_sigma || !g_rgb || !g_params || !scratch || n_max <= 0) return AN_ERR_ARG;
-    if (cidx && !count) return AN_ERR_ARG;
-    if ((((uintptr_t)packed) & 1023) || (((uintptr_t)stash) & 127) || (((uintptr_t)scratch) & 127)) return AN_ERR_ALIGN;
-    cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaFuncSetAttribute(mlp_bwd_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(mlp_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_ALLOC);
-    if (e != cudaSuccess) return (int)e;
-    const int sms = an_num_sms();
-    const int64_t iters = (n_max + 255) / 256;
-    const int grid = (int)(iters < sms ? iters : sms);
-    mlp_bwd_dgrad_kernel<<<grid, THREADS, SM_ALLOC, st>>>(
-        (const uint8_t*)packed, (const uint8_t*)stash, xyz_cano, rgb, cidx, count, n_max, g_sigma, g_rgb,
-        g_xyz_cano, (uint8_t*)scratch);
-    AN_CHECK_LAUNCH();
-    int64_t splits = sms / NJOBS;                      // 13 on a 148-SM part -> 143 CTAs, one wave
-    if (splits > iters * 2) splits = iters * 2;
-    if (splits < 1) splits = 1;
-    dim3 wgrid((unsigned)splits, NJOBS);
-    mlp_bwd_wgrad_kernel<<<wgrid, WG_THREADS, WG_ALLOC, st>>>(
-        (const uint8_t*)stash, (const uint8_t*)scratch, count, cidx ? 1 : 0, n_max, g_params);
-    AN_CHECK_LAUNCH();
-    const int64_t tiles = (n_max + 127) / 128;
-    const int hgrid = (int)(tiles < sms * 2 ? tiles : sms * 2);
-    mlp_bwd_heads_kernel<<<hgrid, 256, 0, st>>>((const uint8_t*)stash, rgb, cidx, count, n_max, g_sigma, g_rgb, g_params);
-    AN_CHECK_LAUNCH();
-    return AN_OK;
+    int rc = an_mlp_bwd_dgrad(packed, stash, xyz_cano, rgb, cidx, count, n_max, g_sigma, g_rgb, g_xyz_cano, scratch, stream);
+    if (rc) return rc;
+    rc = an_mlp_bwd_wgrad(stash, scratch, cidx, count, n_max, g_params, stream);
+    if (rc) return rc;
+    return an_mlp_bwd_heads(stash, rgb, cidx, count, n_max, g_sigma, g_rgb, g_params, stream);
 }

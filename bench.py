@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- rays/s of the Anim-NeRF render_rays forward+backward (+Adam) training step.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # reference algorithm on host cores
+
+Workload (BASELINE.json configs[1], "cfg2"): one training step at the People-Snapshot
+male-3-casual shape -- 16 frames x 1024 rays (32x32 pixels each), 64 coarse + 64 fine samples
+(192 point queries per ray), forward + backward + Adam, synthetic frames: seeded synthetic
+SMPL-topology body, random poses, random-init MLP weights (sigma bias +5), 90 % of the pixels on
+the body silhouette.  A "step" = per-frame tables (torch SMPL LBS) -> rays to body space ->
+coarse pass -> inverse-CDF resampling -> fine pass -> rgb MSE + 0.1*alpha L1 (coarse+fine) ->
+backward -> Adam -> weight repack.  The training regularisers (fg/bg density, normal smoothness;
+torch double-backward in the reference) are outside the path the metric names and
+are NOT included; stated in config.
+
+N>1: one process per GPU (torchrun), each rank owns its own 16-frame batch (weak scaling, the
+global batch is N x 16 384 rays), one NCCL all-reduce of the flat MLP gradient bucket per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "rays/sec render_rays fwd+bwd (64+64 samples)"
+FLOP_PER_POINT_FWD = 1179904
+N_FRAMES, N_SIDE, KC, KF = 16, 32, 64, 64
+
+
+# ----------------------------------------------------------------------------- scene
+def build_batch(rank, device=None):
+    import anim_nerf_b200  # noqa: F401
+    from anim_nerf_b200 import synthetic
+    from anim_nerf_b200.body_model import BodyModel
+    data = synthetic.make_smpl_dict(0)
+    bm = BodyModel(data)
+    posed_np, tmpl_np = synthetic.make_body_params(N_FRAMES, seed=1 + 100 * rank)
+    with torch.no_grad():
+        verts = bm(**{k: torch.from_numpy(v) for k, v in posed_np.items()})["vertices"].numpy()
+    batch = synthetic.make_training_batch(verts, n_side=N_SIDE, seed=3 + rank)
+    host = dict(rays=torch.from_numpy(batch["rays"]), rgbs=torch.from_numpy(batch["rgbs"]),
+                alphas=torch.from_numpy(batch["alphas"]))
+    params = {k: torch.from_numpy(v) for k, v in posed_np.items()}
+    tmpl = {k: torch.from_numpy(v) for k, v in tmpl_np.items()}
+    return data, host, params, tmpl
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch.distributed as dist
+    import anim_nerf_b200  # noqa: F401
+    from anim_nerf_b200 import _lib, synthetic
+    from anim_nerf_b200.system import AnimNeRFSystem
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the rendering path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    data, host, params, tmpl = build_batch(rank)
+    sysm = AnimNeRFSystem(body_model_data=data, n_samples=KC, n_importance=KF).to(dev)
+    for name, seed in (("nerf", 10), ("nerf_fine", 11)):      # same init on every rank
+        sd = {k: torch.from_numpy(v) for k, v in synthetic.make_nerf_weights(seed).items()}
+        getattr(sysm.anim_nerf, name).load_state_dict(sd, strict=True)
+    mlp_params = [p for n in ("nerf", "nerf_fine") for p in getattr(sysm.anim_nerf, n).parameters()]
+    opt = torch.optim.Adam(mlp_params, lr=5e-4, eps=1e-8, fused=True)
+    pin = {k: v.pin_memory() for k, v in host.items()}
+    params_d = {k: v.to(dev) for k, v in params.items()}
+    tmpl_d = {k: v.to(dev) for k, v in tmpl.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    lam = sysm.hparams.train.lambda_alphas
+    n_rays = N_FRAMES * N_SIDE * N_SIDE
+
+    def step(batch_dev):
+        out = sysm(batch_dev["rays"], params_d, tmpl_d, perturb=1.0)
+        mse = torch.nn.functional.mse_loss
+        l1 = torch.nn.functional.l1_loss
+        loss = (mse(out["rgbs"], batch_dev["rgbs"]) + mse(out["rgbs_fine"], batch_dev["rgbs"])
+                + lam * (l1(out["alphas"], batch_dev["alphas"]) + l1(out["alphas_fine"], batch_dev["alphas"])))
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if world > 1:
+            bucket = torch.cat([p.grad.reshape(-1) for p in mlp_params])
+            dist.all_reduce(bucket)
+            bucket /= world
+            o = 0
+            for p in mlp_params:
+                p.grad.copy_(bucket[o:o + p.numel()].view_as(p)); o += p.numel()
+        opt.step()
+        return loss
+
+    def step_e2e():
+        batch_dev = {k: v.to(dev, non_blocking=True) for k, v in pin.items()}
+        return float(step(batch_dev).item())           # D2H read of the loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm
+    for _ in range(args.warmup):
+        step(resident)
+    barrier()
+    timing = _lib.enable_timing(True)
+    launches0 = _lib.launch_count
+    clocks = ClockSampler(local)
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step(resident)
+    ev1.record()
+    barrier()
+    clk = clocks.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count - launches0
+    _lib.enable_timing(False)
+    per_kernel = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in timing.items()}
+    calls_per_step = {k: len(v) / args.steps for k, v in timing.items()}
+    share = {k: per_kernel[k] * calls_per_step[k] for k in per_kernel}
+    step_ms = ms / args.steps
+
+    # valid-point counts (useful MLP work) from one extra instrumented forward
+    with torch.no_grad():
+        sysm.anim_nerf.set_body_model(params_d, tmpl_d)
+        rb = sysm.anim_nerf.convert_to_body_model_space(resident["rays"].view(N_FRAMES, -1, 8))
+        sysm.anim_nerf.clac_ober2cano_transform()
+        from anim_nerf_b200 import ops
+        zc = ops.sample_coarse(rb, KC)
+        cfg = sysm.anim_nerf._cfg(False)
+        o = ops.knn_unpose(cfg["verts"], sysm.anim_nerf.ober2cano_transform, cfg["lbs"], cfg["thr"], rays=rb, z=zc,
+                           grid=cfg["grid"], compact=True)
+        valid_frac_coarse = float(o["count"].item()) / (n_rays * KC)
+
+    # ---- end-to-end arm (host buffers, H2D + D2H inside the timed region)
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+        step_ms = ms / args.steps
+    total_rays = n_rays * world * args.steps
+    value = total_rays / (ms * 1e-3)
+    e2e_value = total_rays / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (tensor-bound MLP kernels; measured peaks)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    dom = max(share, key=share.get) if share else None
+    roofline = None
+    if dom is not None:
+        # algorithmic FLOP per launch of each MLP kernel = valid points of that pass x 1 179 904 (fwd, dgrad, wgrad alike)
+        n_calls = calls_per_step.get(dom, 1)
+        mlp_kernels = ("an_mlp_fwd", "an_mlp_bwd_dgrad", "an_mlp_bwd_wgrad")
+        k = dom if dom in mlp_kernels else "an_mlp_fwd"
+        # mean valid points per launch over the coarse (64) and fine (128) pass
+        pts_per_launch = valid_frac_coarse * n_rays * (KC + (KC + KF)) / 2.0
+        flops = pts_per_launch * FLOP_PER_POINT_FWD
+        achieved = flops / (per_kernel[k] * 1e-3) / 1e12
+        roofline = {"kernel": k, "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                    "avg_launch_ms": per_kernel[k], "share_of_step": share[k] / step_ms,
+                    "note": "useful FLOP = valid (non-culled) points x 1 179 904; valid fraction (coarse pass) %.3f; "
+                            "mean of the coarse (64/ray) and fine (128/ray) launches" % valid_frac_coarse}
+
+    line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "cfg2: training step, 16 frames x 1024 rays, 64+64 samples, fwd+bwd+Adam, per GPU",
+                       "rays_per_step_per_gpu": n_rays, "points_per_ray": KC + KC + KF, "perturb": 1.0,
+                       "regularizers": "not included (outside the named path; torch double-backward in the reference)",
+                       "parallelism": "dp%d (rays sharded by frame, NCCL all-reduce of MLP grads)" % world,
+                       "valid_point_fraction_coarse": valid_frac_coarse,
+                       "l2": "per-step working set (bf16 activation stash + dY scratch, > 5 GB) exceeds the 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in pin.values())),
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
+            "clocks": clk, "roofline": roofline}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(sample_rays=args.cpu_rays)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- reference / CPU
+def _oracle_step(n_rays_sample, with_grad=True, seed_offset=0):
+    """One bounded sample of the workload through the oracle port (torch CPU + C KNN)."""
+    import anim_nerf_b200  # noqa: F401
+    from anim_nerf_b200 import synthetic
+    from anim_nerf_b200.body_model import BodyModel
+    from oracle import animnerf_oracle as oracle
+    st = _oracle_step.__dict__.setdefault("state", {})
+    if not st:
+        data = synthetic.make_smpl_dict(0)
+        st["bm"] = BodyModel(data)
+        posed_np, tmpl_np = synthetic.make_body_params(N_FRAMES, seed=1)
+        st["posed"] = {k: torch.from_numpy(v) for k, v in posed_np.items()}
+        st["tmpl"] = {k: torch.from_numpy(v) for k, v in tmpl_np.items()}
+        with torch.no_grad():
+            verts = st["bm"](**st["posed"])["vertices"].numpy()
+        st["batch"] = synthetic.make_training_batch(verts, n_side=N_SIDE, seed=3)
+        st["p"] = []
+        for seed in (10, 11):
+            w = synthetic.make_nerf_weights(seed)
+            st["p"].append({n: (torch.from_numpy(w[n + ".weight"]).requires_grad_(True),
+                                torch.from_numpy(w[n + ".bias"]).requires_grad_(True)) for n in synthetic.NERF_LAYER_NAMES})
+    bm = st["bm"]
+    # sample: whole frames first (1024 rays each), then a slice of one frame
+    nf = max(1, min(N_FRAMES, n_rays_sample // (N_SIDE * N_SIDE)))
+    per = min(N_SIDE * N_SIDE, n_rays_sample)
+    sl = slice(0, nf)
+    posed = bm(**{k: v[sl] for k, v in st["posed"].items()})
+    tmpl = bm(**{k: v[sl] for k, v in st["tmpl"].items()})
+    rays = torch.from_numpy(st["batch"]["rays"][sl]).reshape(nf, -1, 8)[:, :per]
+    tgt = torch.from_numpy(st["batch"]["rgbs"][sl]).reshape(nf, -1, 3)[:, :per]
+    tga = torch.from_numpy(st["batch"]["alphas"][sl]).reshape(nf, -1, 1)[:, :per]
+    g = torch.Generator().manual_seed(5)
+    noise = dict(coarse_u=torch.rand(nf, per, KC, generator=g), fine_u=torch.rand(nf, per, KF, generator=g),
+                 sigma_c=torch.randn(nf, per, KC, generator=g), sigma_f=torch.randn(nf, per, KC + KF, generator=g))
+    with torch.set_grad_enabled(with_grad):
+        out, _, _ = oracle.system_forward(st["p"][0], st["p"][1], rays, posed, tmpl, bm.lbs_weights,
+                                          n_coarse=KC, n_fine=KF, perturb=1.0, noise=noise)
+        mse, l1 = torch.nn.functional.mse_loss, torch.nn.functional.l1_loss
+        loss = mse(out["rgbs"], tgt) + mse(out["rgbs_fine"], tgt) + 0.1 * (l1(out["alphas"], tga) + l1(out["alphas_fine"], tga))
+        if with_grad:
+            loss.backward()
+    return nf * per
+
+
+def cpu_baseline(sample_rays=512):
+    """Oracle port (reference algorithm, torch CPU + OpenMP C KNN) on the box's host cores."""
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    _oracle_step(64)                                    # warm-up (builds state)
+    t0 = time.time()
+    n = _oracle_step(sample_rays)
+    dt = time.time() - t0
+    return {"value": n / dt, "unit": "rays/s", "cores": threads, "kind": "port",
+            "sample": "%d rays of the same workload (64+64 samples, fwd+bwd, no Adam), 1 repetition after warm-up, %.1f s" % (n, dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    t0 = time.time()
+    n0 = _oracle_step(64)
+    rate = n0 / (time.time() - t0)                      # first estimate incl. setup: conservative
+    budget_s = 150.0
+    per_step = int(min(1024, max(32, rate * budget_s / max(1, args.steps + args.warmup))))
+    per_step = max(32, per_step // 32 * 32)
+    for _ in range(args.warmup):
+        _oracle_step(per_step)
+    t0 = time.time()
+    n = 0
+    for _ in range(args.steps):
+        n += _oracle_step(per_step)
+    dt = time.time() - t0
+    value = n / dt
+    sample = "%d rays/step of cfg2 (64+64 samples, fwd+bwd, no Adam) through the oracle port of the reference algorithm" % per_step
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg2: training step, 16 frames x 1024 rays, 64+64 samples (bounded sample per step)"},
+            "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-rays", type=int, default=512)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

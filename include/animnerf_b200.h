@@ -122,6 +122,18 @@ int an_mlp_bwd(const void* packed, const void* stash, const float* xyz_cano, con
                const int32_t* cidx, const int32_t* count, int64_t n_max,
                const float* g_sigma, const float* g_rgb,
                float* g_params, float* g_xyz_cano, void* scratch, void* stream);
+/* the three stages of an_mlp_bwd, callable separately (same arguments):
+ *   dgrad  activation-gradient chain (writes the dY images to scratch, g_xyz_cano)
+ *   wgrad  dW/db of the ten tensor-core layers from stash (X) and scratch (dY)
+ *   heads  dW/db of the sigma and rgb heads                                                 */
+int an_mlp_bwd_dgrad(const void* packed, const void* stash, const float* xyz_cano, const float* rgb,
+                     const int32_t* cidx, const int32_t* count, int64_t n_max,
+                     const float* g_sigma, const float* g_rgb, float* g_xyz_cano,
+                     void* scratch, void* stream);
+int an_mlp_bwd_wgrad(const void* stash, const void* scratch, const int32_t* cidx, const int32_t* count,
+                     int64_t n_max, float* g_params, void* stream);
+int an_mlp_bwd_heads(const void* stash, const float* rgb, const int32_t* cidx, const int32_t* count,
+                     int64_t n_max, const float* g_sigma, const float* g_rgb, float* g_params, void* stream);
 
 /* ---- A12: alpha compositing ------------------------------------------------------------
  * replaces models/volume_rendering.py:128-160 (composite tail), far=True, white_bkgd flag.
