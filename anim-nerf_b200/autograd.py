@@ -13,6 +13,9 @@ import torch
 from . import ops
 
 
+COUNT_LOG = None      # bench.py sets this to a list to collect (K, device count tensor) per pass
+
+
 class RenderPass(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rays, z, ober2cano, sigma_noise, cfg, *params):
@@ -27,6 +30,8 @@ class RenderPass(torch.autograd.Function):
         out = ops.knn_unpose(cfg["verts"], o2c_c, cfg["lbs"], cfg["thr"], rays=rays_c, z=z_c, grid=cfg["grid"],
                              mode=cfg.get("knn_mode", 1), want_idx=need_grad, want_qw=need_grad,
                              sigma=sigma, rgb=rgb, compact=True)
+        if COUNT_LOG is not None:
+            COUNT_LOG.append((K, out["count"]))
         packed = net.packed()
         stash = ops.mlp_stash(B * R * K, dev) if need_grad else None
         ops.mlp_fwd(packed, out["xyz_cano"], sigma, rgb, cidx=out["cidx"], count=out["count"], n_max=B * R * K,

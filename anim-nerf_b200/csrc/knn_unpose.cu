@@ -11,13 +11,13 @@
 // Two search kernels share one epilogue:
 //   mode 0  exhaustive: the frame's vertex table (6890 x float4 = 110 KB) is staged once per
 //           CTA in shared memory and every thread scans it with warp-broadcast LDS.128 reads.
-//   mode 1  grid-pruned: a per-frame uniform grid (cell slightly larger than dis_threshold)
-//           built by an_vertex_grid_build.  A query whose 3x3x3 cell block holds no vertex
-//           closer than dis_threshold is invalid *exactly* (valid needs d_min < threshold,
-//           SURVEY App. A) and skips everything; otherwise the block scan is exact whenever
-//           the 4th neighbour lies within one cell width, else the thread falls back to an
-//           exhaustive scan of the global table.  The (d2,index) order key makes the result
-//           independent of the scan order, so both modes return identical bits.
+//   mode 1  grid-pruned: a per-frame uniform grid (cell ~ dis_threshold/3) built by
+//           an_vertex_grid_build, with a dilated occupancy flag per cell.  A query with no vertex
+//           within dis_threshold is invalid *exactly* (valid needs d_min < threshold, SURVEY
+//           App. A) and skips everything; otherwise a ball-pruned row scan of the 7^3 cell box
+//           returns the exact 4-NN whenever the 4th neighbour lies within the threshold, else the
+//           thread falls back to an exhaustive scan of the global table.  The (d2,index) order
+//           key makes the result independent of the scan order: both modes return identical bits.
 // The epilogue (confidence from skinning-weight L1 distance, exp(-dist) weights, blend of the
 // 4 neighbours' 3x4 observation->canonical transforms, affine apply, validity) reads the
 // L2-resident tables (lbs 661 KB, ober2cano 441 KB per frame) with 128-bit loads.
@@ -27,18 +27,23 @@
 #include <math_constants.h>
 
 #define KNN_THREADS 256
+#define KNN_B0_SCALE 1.25f   // must match the cell the host passes: 3*cell >= KNN_B0_SCALE * dis_threshold
 #define GRID_MAXC (AN_GRID_MAX_DIM * AN_GRID_MAX_DIM * AN_GRID_MAX_DIM)
 
 struct GridHeader { float ox, oy, oz, cell; int nx, ny, nz, pad; };
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+#define GRID_R 3                                    // search box radius in cells: GRID_R * cell >= dis_threshold
+#define GRID_EXT (AN_GRID_MAX_DIM + 2 * GRID_R)     // occupancy flags cover the grid dilated by GRID_R cells
+#define GRID_FLAG_BYTES ((GRID_EXT * GRID_EXT * GRID_EXT + 15) / 16 * 16)
 static inline int64_t grid_frame_bytes(int V) {
     return align_up(sizeof(GridHeader), 16) + align_up((int64_t)(GRID_MAXC + 1) * 4, 16) +
-           align_up((int64_t)GRID_MAXC * 4, 16) + align_up((int64_t)V * 16, 16);
+           align_up((int64_t)GRID_MAXC * 4, 16) + GRID_FLAG_BYTES + align_up((int64_t)V * 16, 16);
 }
 #define GRID_OFF_START 32
 #define GRID_OFF_COUNT (GRID_OFF_START + ((GRID_MAXC + 1) * 4 + 15) / 16 * 16)
-#define GRID_OFF_SORTED (GRID_OFF_COUNT + GRID_MAXC * 4)
+#define GRID_OFF_FLAGS (GRID_OFF_COUNT + GRID_MAXC * 4)
+#define GRID_OFF_SORTED (GRID_OFF_FLAGS + GRID_FLAG_BYTES)
 
 struct Best4 { float d[4]; int i[4]; };
 
@@ -280,6 +285,24 @@ vertex_grid_build_kernel(const float* __restrict__ verts, int V, float cell_in, 
     for (int c = tid * per; c < min(ncell, (tid + 1) * per); ++c) { cell_start[c] = run; run += counts[c]; }
     if (tid == 0) cell_start[ncell] = V;
     __syncthreads();
+    {   // occupancy of the GRID_R-dilated neighbourhood for every cell of the extended grid
+        uint8_t* flags = (uint8_t*)(base + GRID_OFF_FLAGS);
+        const int ex_n = h.nx + 2 * GRID_R, ey_n = h.ny + 2 * GRID_R, ez_n = h.nz + 2 * GRID_R;
+        for (int e = tid; e < ex_n * ey_n * ez_n; e += blockDim.x) {
+            const int ex = e % ex_n, ey = (e / ex_n) % ey_n, ez = e / (ex_n * ey_n);
+            // extended index = grid index + GRID_R; neighbourhood of grid cell g is [g-R, g+R] = [e-2R, e]
+            const int x0 = max(ex - 2 * GRID_R, 0), x1 = min(ex, h.nx - 1);
+            int any = 0;
+            if (x0 <= x1)
+                for (int gz = max(ez - 2 * GRID_R, 0); gz <= min(ez, h.nz - 1) && !any; ++gz)
+                    for (int gy = max(ey - 2 * GRID_R, 0); gy <= min(ey, h.ny - 1); ++gy) {
+                        const int row = (gz * h.ny + gy) * h.nx;
+                        if (cell_start[row + x1 + 1] > cell_start[row + x0]) { any = 1; break; }
+                    }
+            flags[e] = (uint8_t)any;
+        }
+    }
+    __syncthreads();
     for (int v = tid; v < V; v += blockDim.x) {
         const float x = vb[v * 3], y = vb[v * 3 + 1], zc = vb[v * 3 + 2];
         const int cx = min(h.nx - 1, max(0, (int)floorf((x - h.ox) / h.cell)));
@@ -292,6 +315,38 @@ vertex_grid_build_kernel(const float* __restrict__ verts, int V, float cell_in, 
 }
 
 // ------------------------------------------------------------------ mode 1: grid-pruned
+// Warp-cooperative ball-pruned search.  A warp owns 32 consecutive queries (consecutive samples
+// of one ray) and resolves them one at a time with all 32 lanes:
+//   * the cell is ~dis_threshold/3 and the search box is 7x7x7 cells around the query's cell
+//     (covers radius >= dis_threshold); a dilated occupancy flag rejects far queries in one load;
+//   * lanes 0..48 (two batches) each own one (y,z) row of the box: rows whose slab is farther
+//     than the bound B are dropped and the x-range is trimmed to the ball of radius sqrt(B); the
+//     cells of a row are contiguous in the sorted vertex list, so a row is one [s,e) range;
+//   * the non-empty ranges are walked with the 32 lanes striding over the candidates (coalesced
+//     128-bit loads), each lane keeping a private top-4 keyed by (d2, index);
+//   * four REDUX (min) rounds merge the private lists into the exact global top-4.
+// B comes from the previous query of the same warp by the triangle inequality
+// (d4(q') <= d4(q) + |q - q'|: consecutive ray samples are centimetres apart), else
+// B = dis_threshold^2.  Exactness: everything skipped is provably farther than the final 4th
+// neighbour whenever that neighbour lies within sqrt(B) and the box (margins absorb fp32
+// rounding); otherwise the lane rescans the whole table.  Afterwards the 32 lanes run the blend
+// epilogue for their own query in parallel.
+__device__ __forceinline__ void warp_merge4(Best4& lb, Best4& g)
+{
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const unsigned kd = __float_as_uint(lb.d[0]);                  // d2 >= 0: uint order == float order
+        const unsigned mn = __reduce_min_sync(0xffffffffu, kd);
+        const unsigned ci = (kd == mn) ? (unsigned)lb.i[0] : 0xffffffffu;
+        const unsigned mi = __reduce_min_sync(0xffffffffu, ci);
+        g.d[k] = __uint_as_float(mn); g.i[k] = (int)mi;
+        if (kd == mn && (unsigned)lb.i[0] == mi) {
+            lb.d[0] = lb.d[1]; lb.i[0] = lb.i[1]; lb.d[1] = lb.d[2]; lb.i[1] = lb.i[2];
+            lb.d[2] = lb.d[3]; lb.i[2] = lb.i[3]; lb.d[3] = CUDART_INF_F; lb.i[3] = 0x7fffffff;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_unpose_grid_kernel(const float* __restrict__ xyz, const float* __restrict__ rays,
                        const float* __restrict__ z, int K, int64_t N,
@@ -300,52 +355,111 @@ knn_unpose_grid_kernel(const float* __restrict__ xyz, const float* __restrict__ 
                        const float* __restrict__ lbsw, int J, float thr, UnposeOut o)
 {
     const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
     const char* base = ws + (int64_t)b * frame_bytes;
     const GridHeader h = *(const GridHeader*)base;
     const int* __restrict__ cell_start = (const int*)(base + GRID_OFF_START);
+    const uint8_t* __restrict__ flags = (const uint8_t*)(base + GRID_OFF_FLAGS);
     const float4* __restrict__ sorted = (const float4*)(base + GRID_OFF_SORTED);
-    const float* vb = verts + (int64_t)b * V * 3;
     const float thr2 = thr * thr * (1.0f + 1e-5f);   // prune only what is invalid beyond rounding doubt
-    const float rs = h.cell * (1.0f - 1e-4f);
-    const float safe2 = rs * rs;
-    const int64_t per = (int64_t)gridDim.x * blockDim.x;
-    const int64_t rounds = (N + per - 1) / per;
-    for (int64_t it = 0; it < rounds; ++it) {
-        const int64_t n = it * per + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const float inv_cell = 1.0f / h.cell;
+    const float box_r = GRID_R * h.cell * (1.0f - 1e-4f);
+    const float box_r2 = box_r * box_r;
+    // first bound of a run: slightly beyond the threshold so that a 4th neighbour a little farther
+    // than a valid nearest one (d0 < thr <= d4) is still found without the exhaustive fallback
+    const float b0 = fminf(box_r2, thr * thr * (KNN_B0_SCALE * KNN_B0_SCALE));
+    const int ex_n = h.nx + 2 * GRID_R, ey_n = h.ny + 2 * GRID_R, ez_n = h.nz + 2 * GRID_R;
+    const int64_t n_chunks = (N + 31) / 32;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t chunk = warp0; chunk < n_chunks; chunk += n_warps) {
+        const int64_t n = chunk * 32 + lane;
         const bool active = n < N;
         const int64_t gid = (int64_t)b * N + (active ? n : 0);
         float qx = 0.f, qy = 0.f, qz = 0.f;
-        Best4 best; best_init(best);
-        bool found = false;
-        if (active) {
-            load_query(xyz, rays, z, gid, K, qx, qy, qz);
-            const int cx = (int)floorf((qx - h.ox) / h.cell);
-            const int cy = (int)floorf((qy - h.oy) / h.cell);
-            const int cz = (int)floorf((qz - h.oz) / h.cell);
-            if (cx >= -1 && cx <= h.nx && cy >= -1 && cy <= h.ny && cz >= -1 && cz <= h.nz) {
-                const int x0 = max(cx - 1, 0), x1 = min(cx + 1, h.nx - 1);
-                for (int gz = max(cz - 1, 0); gz <= min(cz + 1, h.nz - 1); ++gz)
-                    for (int gy = max(cy - 1, 0); gy <= min(cy + 1, h.ny - 1); ++gy) {
-                        if (x0 > x1) continue;
-                        const int row = (gz * h.ny + gy) * h.nx;
-                        const int s = __ldg(cell_start + row + x0), e = __ldg(cell_start + row + x1 + 1);
-                        for (int p = s; p < e; ++p) {             // x-adjacent cells are contiguous
-                            const float4 v = __ldg(sorted + p);
-                            best_push_any(best, dist2_rn(qx, qy, qz, v.x, v.y, v.z), __float_as_int(v.w));
+        if (active) load_query(xyz, rays, z, gid, K, qx, qy, qz);
+        Best4 mine; best_init(mine);
+        float myB = 0.f;
+        float hint = CUDART_INF_F, hx = 0.f, hy = 0.f, hz = 0.f;      // warp-uniform
+        const unsigned act_mask = __ballot_sync(0xffffffffu, active);
+        for (int qi = 0; qi < 32; ++qi) {
+            if (!((act_mask >> qi) & 1u)) continue;
+            const float ux = __shfl_sync(0xffffffffu, qx, qi), uy = __shfl_sync(0xffffffffu, qy, qi), uz = __shfl_sync(0xffffffffu, qz, qi);
+            const int cx = (int)floorf((ux - h.ox) * inv_cell);
+            const int cy = (int)floorf((uy - h.oy) * inv_cell);
+            const int cz = (int)floorf((uz - h.oz) * inv_cell);
+            const int ex = cx + GRID_R, ey = cy + GRID_R, ez = cz + GRID_R;
+            bool maybe = ex >= 0 && ex < ex_n && ey >= 0 && ey < ey_n && ez >= 0 && ez < ez_n;
+            if (maybe) maybe = __ldg(flags + ((int64_t)ez * ey_n + ey) * ex_n + ex) != 0;
+            if (!maybe) { hint = CUDART_INF_F; continue; }
+            float B = b0;
+            if (hint < 1e30f) {
+                const float sx = ux - hx, sy = uy - hy, sz = uz - hz;
+                const float r = hint + sqrtf(sx * sx + sy * sy + sz * sz);
+                B = r * r * (1.0f + 1e-4f);
+            }
+            const float Bm = fminf(B * 1.001f, box_r2 * 1.01f);
+            Best4 lb; best_init(lb);
+#pragma unroll
+            for (int batch = 0; batch < 2; ++batch) {
+                const int r = lane + 32 * batch;
+                int s = 0, e = 0;
+                if (r < (2 * GRID_R + 1) * (2 * GRID_R + 1)) {
+                    const int dz = r / (2 * GRID_R + 1) - GRID_R, dy = r % (2 * GRID_R + 1) - GRID_R;
+                    const int gz = cz + dz, gy = cy + dy;
+                    if (gz >= 0 && gz < h.nz && gy >= 0 && gy < h.ny) {
+                        const float gapz = dz == 0 ? 0.f : (dz > 0 ? (h.oz + gz * h.cell) - uz : uz - (h.oz + (gz + 1) * h.cell));
+                        const float gapy = dy == 0 ? 0.f : (dy > 0 ? (h.oy + gy * h.cell) - uy : uy - (h.oy + (gy + 1) * h.cell));
+                        const float g2 = (gapz > 0.f ? gapz * gapz : 0.f) + (gapy > 0.f ? gapy * gapy : 0.f);
+                        if (g2 <= Bm) {
+                            const float w = sqrtf(Bm - g2) + 1e-3f * h.cell;
+                            int x0 = max(cx - GRID_R, (int)floorf((ux - w - h.ox) * inv_cell));
+                            int x1 = min(cx + GRID_R, (int)floorf((ux + w - h.ox) * inv_cell));
+                            x0 = max(x0, 0); x1 = min(x1, h.nx - 1);
+                            if (x0 <= x1) {
+                                const int row = (gz * h.ny + gy) * h.nx;
+                                s = __ldg(cell_start + row + x0); e = __ldg(cell_start + row + x1 + 1);
+                            }
                         }
                     }
-            }
-            if (best.d[0] < thr2) {              // may be valid: need the exact 4-NN
-                if (best.d[3] <= safe2) found = true;
-                else {                           // rare: 4th neighbour not provably inside the block
-                    best_init(best);
-                    for (int v = 0; v < V; ++v)
-                        best_push_ordered(best, dist2_rn(qx, qy, qz, __ldg(vb + v * 3), __ldg(vb + v * 3 + 1), __ldg(vb + v * 3 + 2)), v);
-                    found = true;
+                }
+                unsigned m = __ballot_sync(0xffffffffu, e > s);
+                while (m) {
+                    const int rr = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int s_r = __shfl_sync(0xffffffffu, s, rr), e_r = __shfl_sync(0xffffffffu, e, rr);
+                    for (int p = s_r + lane; p < e_r; p += 32) {
+                        const float4 v = __ldg(sorted + p);
+                        best_push_any(lb, dist2_rn(ux, uy, uz, v.x, v.y, v.z), __float_as_int(v.w));
+                    }
                 }
             }
+            Best4 g;
+            warp_merge4(lb, g);
+            if (g.d[0] < thr2 && g.d[3] < 1e30f) { hint = sqrtf(g.d[3]); hx = ux; hy = uy; hz = uz; }
+            else hint = CUDART_INF_F;
+            if (lane == qi) { mine = g; myB = B; }
         }
-        unpose_epilogue(best, found, qx, qy, qz, gid, b, V, J, ober2cano, lbsw, thr, o, active);
+        bool found = false, redo = false;
+        if (active && mine.d[0] < thr2) {              // may be valid: need the exact 4-NN
+            if (mine.d[3] <= myB && mine.d[3] <= box_r2) found = true;
+            else redo = true;                          // rare: 4th neighbour not provably inside the scanned ball
+        }
+        unsigned redo_mask = __ballot_sync(0xffffffffu, redo);
+        while (redo_mask) {                            // exhaustive rescan, still warp-cooperative
+            const int qi = __ffs(redo_mask) - 1;
+            redo_mask &= redo_mask - 1;
+            const float ux = __shfl_sync(0xffffffffu, qx, qi), uy = __shfl_sync(0xffffffffu, qy, qi), uz = __shfl_sync(0xffffffffu, qz, qi);
+            Best4 lb; best_init(lb);
+            for (int p = lane; p < V; p += 32) {
+                const float4 v = __ldg(sorted + p);
+                best_push_any(lb, dist2_rn(ux, uy, uz, v.x, v.y, v.z), __float_as_int(v.w));
+            }
+            Best4 g;
+            warp_merge4(lb, g);
+            if (lane == qi) { mine = g; found = true; }
+        }
+        unpose_epilogue(mine, found, qx, qy, qz, gid, b, V, J, ober2cano, lbsw, thr, o, active);
     }
 }
 
@@ -430,7 +544,7 @@ extern "C" int an_knn_unpose_fwd(const float* xyz, const float* rays, const floa
             xyz, rays, z, K, N, verts, V, ober2cano, lbs_weights, J, dis_threshold, o);
     } else if (mode == 1) {
         if (!grid_ws) return AN_ERR_ARG;
-        const int64_t cap = ((int64_t)sms * 32 + B - 1) / B;
+        const int64_t cap = ((int64_t)sms * 16 + B - 1) / B;
         if (bx > cap) bx = cap;
         dim3 grid((unsigned)bx, (unsigned)B);
         knn_unpose_grid_kernel<<<grid, KNN_THREADS, 0, (cudaStream_t)stream>>>(

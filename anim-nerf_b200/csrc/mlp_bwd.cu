@@ -67,7 +67,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
     uint8_t* sgen = smem_raw + (sbase - raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar_full = sbase + SM_BAR, bar_empty = sbase + SM_BAR + 32;
-    const uint32_t bar_act = sbase + SM_BAR + 64, bar_acc = sbase + SM_BAR + 72, tmem_slot = sbase + SM_BAR + 80;
+    const uint32_t bar_act = sbase + SM_BAR + 64, bar_acc = sbase + SM_BAR + 80, tmem_slot = sbase + SM_BAR + 96;
     const bool want_gx = g_xyz != nullptr;
 
     int64_t n = n_max;
@@ -76,16 +76,16 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        mbar_init(bar_act, 256);
-        mbar_init(bar_acc, 1);
+        for (int t = 0; t < 2; ++t) { mbar_init(bar_act + 8 * t, 128); mbar_init(bar_acc + 8 * t, 1); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *(volatile uint32_t*)(sgen + SM_BAR + 80);
+    const uint32_t tmem_base = *(volatile uint32_t*)(sgen + SM_BAR + 96);
 
+    // tiles ping-pong exactly as in the forward: MMAs of one tile overlap the other tile's epilogue
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
@@ -94,12 +94,13 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                     const int s = step_of(i);
                     if (!want_gx && (s == 6 || s == 10)) continue;
                     const uint32_t bytes = bs_chunk_bytes(s);
-                    for (int kc = 0; kc < bs_chunks(s); ++kc, ++it) {
-                        const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1u;
-                        mbar_wait(bar_empty + 8 * st, ph ^ 1u);
-                        mbar_expect_tx(bar_full + 8 * st, bytes);
-                        bulk_g2s(sbase + SM_WST + st * 32768u, packed + bwd_chunk_off(s, kc), bytes, bar_full + 8 * st);
-                    }
+                    for (int t = 0; t < 2; ++t)
+                        for (int kc = 0; kc < bs_chunks(s); ++kc, ++it) {
+                            const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+                            mbar_wait(bar_empty + 8 * st, ph ^ 1u);
+                            mbar_expect_tx(bar_full + 8 * st, bytes);
+                            bulk_g2s(sbase + SM_WST + st * 32768u, packed + bwd_chunk_off(s, kc), bytes, bar_full + 8 * st);
+                        }
                 }
         }
     } else if (warp == 1) {
@@ -109,25 +110,25 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                 for (int i = 0; i < 11; ++i) {
                     const int s = step_of(i);
                     if (!want_gx && (s == 6 || s == 10)) continue;
-                    mbar_wait(bar_act, act_phase); act_phase ^= 1u;
-                    tc_fence_after();
                     const uint32_t idesc = make_idesc_bf16(128, bs_rows(s), 0, 0);
-                    for (int kc = 0; kc < bs_chunks(s); ++kc, ++it) {
-                        const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1u;
-                        mbar_wait(bar_full + 8 * st, ph);
+                    for (int t = 0; t < 2; ++t) {
+                        mbar_wait(bar_act + 8 * t, act_phase);
                         tc_fence_after();
-                        const uint32_t wb = sbase + SM_WST + st * 32768u;
-#pragma unroll
-                        for (int t = 0; t < 2; ++t) {
+                        for (int kc = 0; kc < bs_chunks(s); ++kc, ++it) {
+                            const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+                            mbar_wait(bar_full + 8 * st, ph);
+                            tc_fence_after();
+                            const uint32_t wb = sbase + SM_WST + st * 32768u;
                             const uint32_t ab = sbase + SM_ACT + t * 65536u + kc * 16384u;
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
                                 umma(tmem_base + t * 256u, make_desc(ab + k * 32u, 16, 1024),
                                      make_desc(wb + k * 32u, 16, 1024), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                            umma_commit(bar_empty + 8 * st);
                         }
-                        umma_commit(bar_empty + 8 * st);
+                        umma_commit(bar_acc + 8 * t);
                     }
-                    umma_commit(bar_acc);
+                    act_phase ^= 1u;
                 }
         }
     } else {
@@ -141,6 +142,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
         const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
         const float* small = (const float*)(packed + SMALL_OFF);
         const bool leader = (e & 127) == 0;
+        const uint32_t my_act = bar_act + 8 * t, my_acc = bar_acc + 8 * t;
         uint32_t acc_phase = 0;
 
         for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x) {
@@ -184,7 +186,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
             fence_proxy_async();
             named_bar_sync(1 + t, 128);
             if (leader) { bulk_s2g(dy_tile + DY_G9, act_s, 32768); bulk_commit(); }
-            mbar_arrive(bar_act);
+            mbar_arrive(my_act);
 
             // encoding derivative factors (same double-angle recurrence as the forward)
             float gx[3] = {0.f, 0.f, 0.f};
@@ -194,7 +196,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
             for (int i = 0; i < 11; ++i) {
                 const int s = step_of(i);
                 if (!want_gx && (s == 6 || s == 10)) continue;
-                mbar_wait(bar_acc, acc_phase); acc_phase ^= 1u;
+                mbar_wait(my_acc, acc_phase); acc_phase ^= 1u;
                 tc_fence_after();
                 if (s == 6 || s == 10) {
                     // d(enc) (64 columns) -> d(xyz): enc = [x, sin(2^k x), cos(2^k x)]_k
@@ -226,7 +228,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                     if (s == 10) {
                         if (in) { g_xyz[id * 3] = gx[0]; g_xyz[id * 3 + 1] = gx[1]; g_xyz[id * 3 + 2] = gx[2]; }
                     } else {
-                        mbar_arrive(bar_act);          // A image unchanged; accumulator region is free again
+                        mbar_arrive(my_act);           // A image unchanged; accumulator region is free again
                     }
                     continue;
                 }
@@ -246,16 +248,22 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                     const uint4 m0 = mp[0], m1 = mp[1];
                     mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w; mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
                 }
+                uint32_t va[32], vb[32];
+                tmem_ld32(tm, va);
 #pragma unroll
                 for (int cb = 0; cb < 8; ++cb) {
-                    uint32_t v[32];
-                    tmem_ld32(tm + cb * 32, v);
+                    uint32_t (&v)[32] = (cb & 1) ? vb : va;
                     tmem_ld_wait();
+                    if (cb + 1 < 8) tmem_ld32(tm + (cb + 1) * 32, (cb & 1) ? va : vb);     // prefetch the next block
                     float f[32];
                     if (s == 1) {                 // + sigma head: d h8 += w_sigma * d sigma
                         const float* ws = small + SM_WS + cb * 32;
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) f[c] = __uint_as_float(v[c]) + gs * __ldg(ws + c);
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            const float4 w4 = __ldg((const float4*)ws + c4);
+                            f[4 * c4] = __uint_as_float(v[4 * c4]) + gs * w4.x; f[4 * c4 + 1] = __uint_as_float(v[4 * c4 + 1]) + gs * w4.y;
+                            f[4 * c4 + 2] = __uint_as_float(v[4 * c4 + 2]) + gs * w4.z; f[4 * c4 + 3] = __uint_as_float(v[4 * c4 + 3]) + gs * w4.w;
+                        }
                     } else {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) f[c] = __uint_as_float(v[c]);
@@ -276,7 +284,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                 fence_proxy_async();
                 named_bar_sync(1 + t, 128);
                 if (leader) { bulk_s2g(dy_tile + dy_off, act_s, 65536); bulk_commit(); }
-                if (!(s == 9 && !want_gx)) mbar_arrive(bar_act);     // last step has no consumer MMA
+                if (!(s == 9 && !want_gx)) mbar_arrive(my_act);      // last step has no consumer MMA
             }
         }
         if (leader) bulk_wait0();
@@ -447,7 +455,9 @@ mlp_bwd_wgrad_kernel(const uint8_t* __restrict__ stash, const uint8_t* __restric
 
 // ------------------------------------------------------------------------------ heads
 // sigma head: d ws[i] = sum_p dsigma_p * h8[p][i], d bs = sum dsigma;  rgb head: d Wr[j][i] = sum_p dpre_j * c[p][i].
-// block = 256 threads (thread = feature), tiles strided over the grid; partial sums in registers.
+// HBM-bound read of the h8 and c images (768 B/point) with 16-byte loads: thread (rg, unit) owns
+// the 8 columns of one 16-byte unit for the rows r == rg (mod 8) -- the swizzle (unit ^ (r&7)) is
+// then constant per thread -- partial sums stay in registers across tiles and are reduced once.
 __global__ void __launch_bounds__(256)
 mlp_bwd_heads_kernel(const uint8_t* __restrict__ stash, const float* __restrict__ rgb,
                      const int32_t* __restrict__ cidx, const int32_t* __restrict__ count, int64_t n_max,
@@ -455,15 +465,25 @@ mlp_bwd_heads_kernel(const uint8_t* __restrict__ stash, const float* __restrict_
 {
     using namespace mlp;
     __shared__ float s_gs[128], s_dp[3][128];
+    __shared__ float s_ws[256], s_wr[3][128], s_b[4];
     int64_t n = n_max;
     if (cidx) { const int64_t c = *count; n = c < n_max ? c : n_max; }
     const int64_t n_tiles = (n + 127) / 128;
-    const int i = threadIdx.x;
-    float aws = 0.f, abs_ = 0.f, ar0 = 0.f, ar1 = 0.f, ar2 = 0.f, ab0 = 0.f, ab1 = 0.f, ab2 = 0.f;
+    const int tid = threadIdx.x;
+    const int rg = tid >> 5, unit = tid & 31;            // h8: 32 units of 16 B per row, 8 row groups
+    const int h_chunk = unit >> 3, h_lu = (unit & 7) ^ rg;
+    const int c_rg = tid >> 4, c_unit = tid & 15;         // c: 16 units per row, 16 row groups
+    const int c_chunk = c_unit >> 3, c_lu = (c_unit & 7) ^ (c_rg & 7);
+    float aw[8], ar[3][8], ab[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { aw[k] = 0.f; ar[0][k] = 0.f; ar[1][k] = 0.f; ar[2][k] = 0.f; }
+    for (int e = tid; e < 256; e += 256) s_ws[e] = 0.f;
+    for (int e = tid; e < 384; e += 256) s_wr[e / 128][e % 128] = 0.f;
+    if (tid < 4) s_b[tid] = 0.f;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         __syncthreads();
-        if (i < 128) {
-            const int64_t p = tile * 128 + i;
+        if (tid < 128) {
+            const int64_t p = tile * 128 + tid;
             float gs = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
             if (p < n) {
                 const int64_t id = cidx ? (int64_t)cidx[p] : p;
@@ -471,38 +491,58 @@ mlp_bwd_heads_kernel(const uint8_t* __restrict__ stash, const float* __restrict_
                 const float a0 = rgb[id * 3], a1 = rgb[id * 3 + 1], a2 = rgb[id * 3 + 2];
                 d0 = g_rgb[id * 3] * a0 * (1.f - a0); d1 = g_rgb[id * 3 + 1] * a1 * (1.f - a1); d2 = g_rgb[id * 3 + 2] * a2 * (1.f - a2);
             }
-            s_gs[i] = gs; s_dp[0][i] = d0; s_dp[1][i] = d1; s_dp[2][i] = d2;
+            s_gs[tid] = gs; s_dp[0][tid] = d0; s_dp[1][tid] = d1; s_dp[2][tid] = d2;
         }
         __syncthreads();
         const uint8_t* st_tile = stash + tile * ST_TILE;
-        const uint8_t* h8 = st_tile + ST_H + 7 * 65536 + (i >> 6) * 16384;
-        const int c = i & 63;
-        for (int r = 0; r < 128; ++r) {
-            const uint16_t raw16 = *(const uint16_t*)(h8 + r * 128 + ((((c >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1)));
-            aws += s_gs[r] * __uint_as_float((uint32_t)raw16 << 16);
-        }
-        if (i < 128) {
-            const uint8_t* cimg = st_tile + ST_C + (i >> 6) * 16384;
-            for (int r = 0; r < 128; ++r) {
-                const uint16_t raw16 = *(const uint16_t*)(cimg + r * 128 + ((((c >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1)));
-                const float cv = __uint_as_float((uint32_t)raw16 << 16);
-                ar0 += s_dp[0][r] * cv; ar1 += s_dp[1][r] * cv; ar2 += s_dp[2][r] * cv;
+        const uint8_t* h8 = st_tile + ST_H + 7 * 65536 + h_chunk * 16384 + (unit & 7) * 16;
+#pragma unroll 4
+        for (int r = rg; r < 128; r += 8) {
+            const uint4 v = __ldg((const uint4*)(h8 + r * 128));
+            const float g = s_gs[r];
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                aw[2 * k] += g * __uint_as_float(w[k] << 16);
+                aw[2 * k + 1] += g * __uint_as_float(w[k] & 0xffff0000u);
             }
         }
-        if (i == 0) for (int r = 0; r < 128; ++r) { abs_ += s_gs[r]; ab0 += s_dp[0][r]; ab1 += s_dp[1][r]; ab2 += s_dp[2][r]; }
-    }
-    if ((int64_t)blockIdx.x < n_tiles) {
-        atomicAdd(g_params + flat_w_off(10) + i, aws);
-        if (i < 128) {
-            atomicAdd(g_params + flat_w_off(11) + i, ar0);
-            atomicAdd(g_params + flat_w_off(11) + 128 + i, ar1);
-            atomicAdd(g_params + flat_w_off(11) + 256 + i, ar2);
+        const uint8_t* cimg = st_tile + ST_C + c_chunk * 16384 + (c_unit & 7) * 16;
+#pragma unroll 2
+        for (int r = c_rg; r < 128; r += 16) {
+            const uint4 v = __ldg((const uint4*)(cimg + r * 128));
+            const float d0 = s_dp[0][r], d1 = s_dp[1][r], d2 = s_dp[2][r];
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float lo = __uint_as_float(w[k] << 16), hi = __uint_as_float(w[k] & 0xffff0000u);
+                ar[0][2 * k] += d0 * lo; ar[0][2 * k + 1] += d0 * hi;
+                ar[1][2 * k] += d1 * lo; ar[1][2 * k + 1] += d1 * hi;
+                ar[2][2 * k] += d2 * lo; ar[2][2 * k + 1] += d2 * hi;
+            }
         }
-        if (i == 0) {
-            atomicAdd(g_params + flat_b_off(10), abs_);
-            atomicAdd(g_params + flat_b_off(11), ab0); atomicAdd(g_params + flat_b_off(11) + 1, ab1); atomicAdd(g_params + flat_b_off(11) + 2, ab2);
+        if (tid < 128) { ab[0] += s_gs[tid]; ab[1] += s_dp[0][tid]; ab[2] += s_dp[1][tid]; ab[3] += s_dp[2][tid]; }
+    }
+    if ((int64_t)blockIdx.x >= n_tiles) return;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        atomicAdd(&s_ws[h_chunk * 64 + h_lu * 8 + k], aw[k]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) atomicAdd(&s_wr[j][c_chunk * 64 + c_lu * 8 + k], ar[j][k]);
+    }
+    if (tid < 128) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v = warp_sum(ab[j]);
+            if ((tid & 31) == 0) atomicAdd(&s_b[j], v);
         }
     }
+    __syncthreads();
+    atomicAdd(g_params + flat_w_off(10) + tid, s_ws[tid]);
+    for (int e = tid; e < 384; e += 256) atomicAdd(g_params + flat_w_off(11) + e, s_wr[e / 128][e % 128]);
+    if (tid == 0) atomicAdd(g_params + flat_b_off(10), s_b[0]);
+    if (tid < 3) atomicAdd(g_params + flat_b_off(11) + tid, s_b[1 + tid]);
 }
 
 extern "C" int64_t an_mlp_bwd_scratch_bytes(int64_t n_max)

@@ -3,12 +3,13 @@
 // leave the SM).  Reference: models/embedding.py:22-39 + models/nerf.py:129-175.
 //
 // One persistent CTA per SM; each loop iteration owns 256 compacted (valid) points = two
-// 128-row tiles that share every weight chunk (weights cross L2->smem once per 256 rows).
+// 128-row tiles that ping-pong: the tensor core runs layer g of one tile while the other tile's
+// epilogue runs on the CUDA cores (each tile streams its own copy of the weight chunks from L2).
 //   warp 0      weight producer: cp.async.bulk of pre-swizzled 64-wide K-chunk images into a
 //               2-stage ring (full/empty mbarriers); runs ahead across layers and tiles.
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=256|128, K=16),
-//               2 tiles x 4 K-steps per chunk; tcgen05.commit releases the stage / publishes
-//               the accumulators.  Also owns the TMEM allocation (512 columns = 2 x 128x256 fp32).
+//               4 K-steps per chunk; tcgen05.commit releases the stage / publishes the tile's
+//               accumulators.  Also owns the TMEM allocation (512 columns = 2 x 128x256 fp32).
 //   warps 2-9   epilogue, one thread per row: tcgen05.ld 32 columns at a time, +bias, ReLU,
 //               bf16 pack, st.shared into the K-major SWIZZLE_128B image that is the next
 //               layer's A operand (in place: the layer's MMAs have completed).  The sigma head
@@ -48,6 +49,7 @@ constexpr int64_t ST_CMASK = ST_MASK + 8 * 4096;   // 128 rows x 16 B
 constexpr int64_t ST_TILE = ST_CMASK + 2048;       // 673 792
 }  // namespace mlp
 
+template <bool TRAIN>
 __global__ void __launch_bounds__(THREADS, 1)
 mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ xyz_cano,
                   const int32_t* __restrict__ cidx, const int32_t* __restrict__ count, int64_t n_max,
@@ -61,11 +63,11 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     uint8_t* sgen = smem_raw + (sbase - raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    const uint32_t bar_full = sbase + SM_BAR;            // [NSTAGE]
-    const uint32_t bar_empty = sbase + SM_BAR + 16;      // [NSTAGE]
-    const uint32_t bar_act = sbase + SM_BAR + 32;        // epilogue -> MMA (256 arrivals)
-    const uint32_t bar_acc = sbase + SM_BAR + 40;        // MMA -> epilogue (tcgen05.commit)
-    const uint32_t tmem_slot = sbase + SM_BAR + 48;
+    const uint32_t bar_full = sbase + SM_BAR;            // [NSTAGE]  TMA -> MMA
+    const uint32_t bar_empty = sbase + SM_BAR + 16;      // [NSTAGE]  MMA -> TMA
+    const uint32_t bar_act = sbase + SM_BAR + 32;        // [2 tiles] epilogue -> MMA (128 arrivals)
+    const uint32_t bar_acc = sbase + SM_BAR + 48;        // [2 tiles] MMA -> epilogue (tcgen05.commit)
+    const uint32_t tmem_slot = sbase + SM_BAR + 64;
 
     int64_t n = n_max;
     if (cidx) { const int64_t c = *count; n = c < n_max ? c : n_max; }
@@ -73,62 +75,63 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        mbar_init(bar_act, 256);
-        mbar_init(bar_acc, 1);
+        for (int t = 0; t < 2; ++t) { mbar_init(bar_act + 8 * t, 128); mbar_init(bar_acc + 8 * t, 1); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *(volatile uint32_t*)(sgen + SM_BAR + 48);
+    const uint32_t tmem_base = *(volatile uint32_t*)(sgen + SM_BAR + 64);
 
+    // The two 128-row tiles ping-pong: while the tensor core runs layer g of one tile, the other
+    // tile's epilogue (TMEM -> bias/ReLU -> bf16 image) runs on the CUDA cores.  Each tile streams
+    // its own copy of the layer's weight chunks (L2 hits).
     if (warp == 0) {
         // ------------------------------------------------------------ weight producer
         if (lane == 0) {
             uint32_t it = 0;
-            for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x) {
+            for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x)
                 for (int g = 0; g < NG; ++g) {
                     const uint32_t bytes = g_chunk_bytes(g);
-                    for (int kc = 0; kc < g_chunks(g); ++kc, ++it) {
-                        const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
-                        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                        mbar_expect_tx(bar_full + 8 * s, bytes);
-                        bulk_g2s(sbase + SM_WST + s * 32768u, packed + fwd_chunk_off(g, kc), bytes, bar_full + 8 * s);
-                    }
+                    for (int t = 0; t < 2; ++t)
+                        for (int kc = 0; kc < g_chunks(g); ++kc, ++it) {
+                            const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+                            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                            mbar_expect_tx(bar_full + 8 * s, bytes);
+                            bulk_g2s(sbase + SM_WST + s * 32768u, packed + fwd_chunk_off(g, kc), bytes, bar_full + 8 * s);
+                        }
                 }
-            }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             uint32_t it = 0, act_phase = 0;
-            for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x) {
+            for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x)
                 for (int g = 0; g < NG; ++g) {
-                    mbar_wait(bar_act, act_phase); act_phase ^= 1u;
-                    tc_fence_after();
                     const uint32_t idesc = make_idesc_bf16(128, g_N(g), 0, 0);
-                    for (int kc = 0; kc < g_chunks(g); ++kc, ++it) {
-                        const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
-                        mbar_wait(bar_full + 8 * s, ph);
+                    for (int t = 0; t < 2; ++t) {
+                        mbar_wait(bar_act + 8 * t, act_phase);
                         tc_fence_after();
-                        const uint32_t wb = sbase + SM_WST + s * 32768u;
-                        const bool from_enc = (g == 0) || (g == 4 && kc == 0);
-                        const int ac = (g == 4) ? kc - 1 : kc;
-#pragma unroll
-                        for (int t = 0; t < 2; ++t) {
+                        for (int kc = 0; kc < g_chunks(g); ++kc, ++it) {
+                            const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+                            mbar_wait(bar_full + 8 * s, ph);
+                            tc_fence_after();
+                            const uint32_t wb = sbase + SM_WST + s * 32768u;
+                            const bool from_enc = (g == 0) || (g == 4 && kc == 0);
+                            const int ac = (g == 4) ? kc - 1 : kc;
                             const uint32_t ab = from_enc ? (sbase + SM_ENC + t * 16384u)
                                                          : (sbase + SM_ACT + t * 65536u + ac * 16384u);
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
                                 umma(tmem_base + t * 256u, make_desc(ab + k * 32u, 16, 1024),
                                      make_desc(wb + k * 32u, 16, 1024), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                            umma_commit(bar_empty + 8 * s);       // stage free once these MMAs retire
                         }
-                        umma_commit(bar_empty + 8 * s);       // stage free once these MMAs retire
+                        umma_commit(bar_acc + 8 * t);              // accumulators of (layer g, tile t) complete
                     }
-                    umma_commit(bar_acc);                      // accumulators of layer g complete
+                    act_phase ^= 1u;
                 }
-            }
         }
     } else {
         // ------------------------------------------------------------ epilogue (1 thread = 1 row)
@@ -142,6 +145,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
         const uint32_t act_s = sbase + SM_ACT + t * 65536u;
         const uint32_t enc_s = sbase + SM_ENC + t * 16384u;
         const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
+        const uint32_t my_act = bar_act + 8 * t, my_acc = bar_acc + 8 * t;
         const float* small = (const float*)(packed + SMALL_OFF);
         const bool leader = (e & 127) == 0;          // issues the tile's TMA stores
         uint32_t acc_phase = 0;
@@ -150,7 +154,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             const int64_t p = iter * 256 + t * 128 + row;
             const bool in = p < n;
             const int64_t id = in ? (cidx ? (int64_t)cidx[p] : p) : 0;
-            uint8_t* st_tile = stash ? stash + (iter * 2 + t) * ST_TILE : nullptr;
+            uint8_t* st_tile = TRAIN ? stash + (iter * 2 + t) * ST_TILE : nullptr;
             float x[3] = {0.f, 0.f, 0.f};
             if (in) { x[0] = xyz_cano[id * 3]; x[1] = xyz_cano[id * 3 + 1]; x[2] = xyz_cano[id * 3 + 2]; }
             {   // positional encoding -> bf16 K-major image (64 columns, last one zero)
@@ -168,7 +172,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                     }
                 }
                 ev[63] = 0.f;
-                if (stash) {      // previous iteration's TMA stores must have drained this tile's smem
+                if (TRAIN) {      // previous iteration's TMA stores must have drained this tile's smem
                     if (leader) bulk_wait_read0();
                     named_bar_sync(1 + t, 128);
                 }
@@ -181,67 +185,99 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 }
             }
             fence_proxy_async();
-            if (stash) {
+            if (TRAIN) {
                 named_bar_sync(1 + t, 128);
                 if (leader) { bulk_s2g(st_tile + ST_ENC, enc_s, 16384); bulk_commit(); }
             }
-            mbar_arrive(bar_act);
+            mbar_arrive(my_act);
 
             float sig = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
             for (int g = 0; g < NG; ++g) {
-                mbar_wait(bar_acc, acc_phase); acc_phase ^= 1u;
+                const float* bias = small + SM_BIAS + g * 256;
+                const int nblk = g_N(g) / 32;
+                // bias of the first block is fetched before the accumulator wait (hides the L2 latency)
+                float4 bq[8];
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) bq[c4] = __ldg((const float4*)bias + c4);
+                mbar_wait(my_acc, acc_phase); acc_phase ^= 1u;
                 tc_fence_after();
-                if (stash && g > 0) {     // act image of layer g-1 is being stored: wait before overwriting it
+                if (TRAIN && g > 0) {     // act image of layer g-1 is being stored: wait before overwriting it
                     if (leader) bulk_wait_read0();
                     named_bar_sync(1 + t, 128);
                 }
-                const float* bias = small + SM_BIAS + g * 256;
-                const int nblk = g_N(g) / 32;
                 uint32_t mask_words[8];
-                for (int cb = 0; cb < nblk; ++cb) {
-                    uint32_t v[32];
-                    tmem_ld32(tm + cb * 32, v);
-                    tmem_ld_wait();
+                uint32_t va[32], vb[32];
+                tmem_ld32(tm, va);
+                for (int cb = 0; cb < nblk; cb += 2) {
+                    // ---- even block: data in va; prefetch the odd block into vb and its bias
                     float f[32];
-                    uint32_t mw = 0;
+                    tmem_ld_wait();
+                    tmem_ld32(tm + (cb + 1) * 32, vb);
 #pragma unroll
                     for (int c4 = 0; c4 < 8; ++c4) {
-                        const float4 b4 = __ldg((const float4*)(bias + cb * 32) + c4);
-                        f[4 * c4] = __uint_as_float(v[4 * c4]) + b4.x; f[4 * c4 + 1] = __uint_as_float(v[4 * c4 + 1]) + b4.y;
-                        f[4 * c4 + 2] = __uint_as_float(v[4 * c4 + 2]) + b4.z; f[4 * c4 + 3] = __uint_as_float(v[4 * c4 + 3]) + b4.w;
+                        f[4 * c4] = __uint_as_float(va[4 * c4]) + bq[c4].x; f[4 * c4 + 1] = __uint_as_float(va[4 * c4 + 1]) + bq[c4].y;
+                        f[4 * c4 + 2] = __uint_as_float(va[4 * c4 + 2]) + bq[c4].z; f[4 * c4 + 3] = __uint_as_float(va[4 * c4 + 3]) + bq[c4].w;
                     }
-                    if (g != 8) {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) { mw |= (f[c] > 0.f ? 1u : 0u) << c; f[c] = fmaxf(f[c], 0.f); }
-                    }
-                    mask_words[cb & 7] = mw;
-                    if (g == 7) {
-                        const float* ws = small + SM_WS + cb * 32;
+                    for (int c4 = 0; c4 < 8; ++c4) bq[c4] = __ldg((const float4*)(bias + (cb + 1) * 32) + c4);
 #pragma unroll
-                        for (int c4 = 0; c4 < 8; ++c4) {
-                            const float4 w4 = __ldg((const float4*)ws + c4);
-                            sig += f[4 * c4] * w4.x + f[4 * c4 + 1] * w4.y + f[4 * c4 + 2] * w4.z + f[4 * c4 + 3] * w4.w;
+                    for (int half = 0; half < 2; ++half) {
+                        const int blk = cb + half;
+                        if (half == 1) {
+                            tmem_ld_wait();
+                            if (blk + 1 < nblk) tmem_ld32(tm + (blk + 1) * 32, va);
+#pragma unroll
+                            for (int c4 = 0; c4 < 8; ++c4) {
+                                f[4 * c4] = __uint_as_float(vb[4 * c4]) + bq[c4].x; f[4 * c4 + 1] = __uint_as_float(vb[4 * c4 + 1]) + bq[c4].y;
+                                f[4 * c4 + 2] = __uint_as_float(vb[4 * c4 + 2]) + bq[c4].z; f[4 * c4 + 3] = __uint_as_float(vb[4 * c4 + 3]) + bq[c4].w;
+                            }
+                            if (blk + 1 < nblk) {
+#pragma unroll
+                                for (int c4 = 0; c4 < 8; ++c4) bq[c4] = __ldg((const float4*)(bias + (blk + 1) * 32) + c4);
+                            }
                         }
-                    }
-                    if (g == 9) {
-                        const float* wr = small + SM_WR + cb * 32;
+                        if (g != 8) {
+                            if (TRAIN) {
+                                uint32_t mw = 0;
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            r0 += f[c] * __ldg(wr + c); r1 += f[c] * __ldg(wr + 128 + c); r2 += f[c] * __ldg(wr + 256 + c);
+                                for (int c = 0; c < 32; ++c) mw |= (f[c] > 0.f ? 1u : 0u) << c;
+                                mask_words[blk & 7] = mw;
+                            }
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) f[c] = fmaxf(f[c], 0.f);
                         }
-                    }
-                    if (g < 9 || stash) {
-                        uint8_t* dst = act_row + (cb >> 1) * 16384;
+                        if (g == 7) {
+                            const float* ws = small + SM_WS + blk * 32;
 #pragma unroll
-                        for (uint32_t u = 0; u < 4; ++u) {
-                            uint4 o;
-                            o.x = pack_bf16(f[8 * u], f[8 * u + 1]); o.y = pack_bf16(f[8 * u + 2], f[8 * u + 3]);
-                            o.z = pack_bf16(f[8 * u + 4], f[8 * u + 5]); o.w = pack_bf16(f[8 * u + 6], f[8 * u + 7]);
-                            *(uint4*)(dst + ((((uint32_t)(cb & 1) * 4 + u) ^ sw) << 4)) = o;
+                            for (int c4 = 0; c4 < 8; ++c4) {
+                                const float4 w4 = __ldg((const float4*)ws + c4);
+                                sig += f[4 * c4] * w4.x + f[4 * c4 + 1] * w4.y + f[4 * c4 + 2] * w4.z + f[4 * c4 + 3] * w4.w;
+                            }
+                        }
+                        if (g == 9) {
+                            const float* wr = small + SM_WR + blk * 32;
+#pragma unroll
+                            for (int c4 = 0; c4 < 8; ++c4) {
+                                const float4 a4 = __ldg((const float4*)wr + c4), b4 = __ldg((const float4*)(wr + 128) + c4),
+                                             d4 = __ldg((const float4*)(wr + 256) + c4);
+                                r0 += f[4 * c4] * a4.x + f[4 * c4 + 1] * a4.y + f[4 * c4 + 2] * a4.z + f[4 * c4 + 3] * a4.w;
+                                r1 += f[4 * c4] * b4.x + f[4 * c4 + 1] * b4.y + f[4 * c4 + 2] * b4.z + f[4 * c4 + 3] * b4.w;
+                                r2 += f[4 * c4] * d4.x + f[4 * c4 + 1] * d4.y + f[4 * c4 + 2] * d4.z + f[4 * c4 + 3] * d4.w;
+                            }
+                        }
+                        if (g < 9 || TRAIN) {
+                            uint8_t* dst = act_row + (blk >> 1) * 16384;
+#pragma unroll
+                            for (uint32_t u = 0; u < 4; ++u) {
+                                uint4 o;
+                                o.x = pack_bf16(f[8 * u], f[8 * u + 1]); o.y = pack_bf16(f[8 * u + 2], f[8 * u + 3]);
+                                o.z = pack_bf16(f[8 * u + 4], f[8 * u + 5]); o.w = pack_bf16(f[8 * u + 6], f[8 * u + 7]);
+                                *(uint4*)(dst + ((((uint32_t)(blk & 1) * 4 + u) ^ sw) << 4)) = o;
+                            }
                         }
                     }
                 }
-                if (stash) {
+                if (TRAIN) {
                     if (g <= 7) {
                         uint4* m = (uint4*)(st_tile + ST_MASK + g * 4096 + row * 32);
                         m[0] = make_uint4(mask_words[0], mask_words[1], mask_words[2], mask_words[3]);
@@ -258,7 +294,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                         rgb_out[id * 3 + 2] = 1.f / (1.f + __expf(-(r2 + __ldg(small + SM_BR + 2))));
                     }
                     tc_fence_before();            // TMEM reads done before the next iteration's MMAs
-                    if (stash) {
+                    if (TRAIN) {
                         fence_proxy_async();
                         named_bar_sync(1 + t, 128);
                         if (leader) { bulk_s2g(st_tile + ST_C, act_s, 32768); bulk_commit(); }
@@ -266,22 +302,22 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 } else {
                     tc_fence_before();
                     fence_proxy_async();
-                    if (stash) {
+                    if (TRAIN) {
                         named_bar_sync(1 + t, 128);
                         if (leader) {
                             bulk_s2g(st_tile + (g == 8 ? ST_F : ST_H + (int64_t)g * 65536), act_s, 65536);
                             bulk_commit();
                         }
                     }
-                    mbar_arrive(bar_act);
+                    mbar_arrive(my_act);
                 }
             }
         }
-        if (stash && leader) bulk_wait0();
+        if (TRAIN && leader) bulk_wait0();
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
 }
 
 int mlp_fwd_ref_launch(const void* packed, const float* xyz_cano, const int32_t* cidx, const int32_t* count,
@@ -302,13 +338,19 @@ extern "C" int an_mlp_fwd(const void* packed, const float* xyz_cano, const int32
     if (stash && (((uintptr_t)stash) & 127)) return AN_ERR_ALIGN;
     if (impl == 1) return mlp_fwd_ref_launch(packed, xyz_cano, cidx, count, n_max, sigma, rgb, (cudaStream_t)stream);
     if (impl != 0) return AN_ERR_ARG;
-    cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);
+    cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
     const int64_t iters = (n_max + 255) / 256;
     const int sms = an_num_sms();
     const int grid = (int)(iters < sms ? iters : sms);
-    mlp_fwd_tc_kernel<<<grid, THREADS, SM_ALLOC, (cudaStream_t)stream>>>(
-        (const uint8_t*)packed, xyz_cano, cidx, count, n_max, sigma, rgb, (uint8_t*)stash);
+    if (stash)
+        mlp_fwd_tc_kernel<true><<<grid, THREADS, SM_ALLOC, (cudaStream_t)stream>>>(
+            (const uint8_t*)packed, xyz_cano, cidx, count, n_max, sigma, rgb, (uint8_t*)stash);
+    else
+        mlp_fwd_tc_kernel<false><<<grid, THREADS, SM_ALLOC, (cudaStream_t)stream>>>(
+            (const uint8_t*)packed, xyz_cano, cidx, count, n_max, sigma, rgb, nullptr);
     AN_CHECK_LAUNCH();
     return AN_OK;
 }

@@ -48,13 +48,14 @@ def sample_coarse(rays, n_coarse, perturb=0.0, noise_u=None, seed=0):
 
 # ------------------------------------------------------------------------ KNN + unpose
 def vertex_grid(verts, dis_threshold):
-    """Per-frame vertex grid for the pruned search.  The cell is 0.1 % larger than the threshold so
-    that 'no vertex in the 3x3x3 block' proves d_min > threshold beyond fp32 rounding."""
+    """Per-frame vertex grid for the pruned search.  cell = 1.25*threshold/3 (+0.1 %): the kernel's
+    7^3-cell search box then covers radius >= 1.25*threshold, so 'nothing found' proves
+    d_min > threshold and a 4th neighbour up to 25 % beyond the threshold needs no exhaustive rescan."""
     verts = _f32c(verts)
     B, V = verts.shape[:2]
     nbytes = _lib.load().an_vertex_grid_bytes(B, V)
     ws = torch.empty(nbytes, device=verts.device, dtype=torch.uint8)
-    call("an_vertex_grid_build", ptr(verts), B, V, float(dis_threshold) * 1.001, ptr(ws), stream())
+    call("an_vertex_grid_build", ptr(verts), B, V, float(dis_threshold) * 1.25 / 3.0 * 1.001, ptr(ws), stream())
     return ws
 
 

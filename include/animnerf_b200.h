@@ -60,9 +60,10 @@ int an_sample_coarse_fwd(const float* rays, int64_t n_rays, int Kc, float pertur
  * batch_index_select/batch_transform (:24-39) + the point generation in
  * models/volume_rendering.py:117-120.
  *
- * an_vertex_grid_build: per-frame uniform hash grid over the posed vertices (cell >=
- * dis_threshold) used for the exact pruned search.  ws must hold
- * an_vertex_grid_bytes(B,V) bytes, 16-byte aligned.                                        */
+ * an_vertex_grid_build: per-frame uniform grid over the posed vertices used by the exact pruned
+ * search.  REQUIRED: 3*cell >= dis_threshold of the later queries (the kernel scans a 7^3-cell box);
+ * pass cell = 1.25 * dis_threshold/3 * 1.001 (a smaller cell only triggers more exhaustive rescans).  The cell grows automatically if the body would need more
+ * than AN_GRID_MAX_DIM cells per axis.  ws: an_vertex_grid_bytes(B,V) bytes, 16-byte aligned.    */
 int64_t an_vertex_grid_bytes(int B, int V);
 int an_vertex_grid_build(const float* verts, int B, int V, float cell, void* ws, void* stream);
 
