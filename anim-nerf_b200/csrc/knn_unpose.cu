@@ -400,10 +400,11 @@ knn_unpose_grid_kernel(const float* __restrict__ xyz, const float* __restrict__ 
             }
             const float Bm = fminf(B * 1.001f, box_r2 * 1.01f);
             Best4 lb; best_init(lb);
+            // each lane owns rows `lane` and `lane+32` of the 49-row box: [s,e) ranges in the sorted list
+            int rs[2] = {0, 0}, rc[2] = {0, 0};
 #pragma unroll
             for (int batch = 0; batch < 2; ++batch) {
                 const int r = lane + 32 * batch;
-                int s = 0, e = 0;
                 if (r < (2 * GRID_R + 1) * (2 * GRID_R + 1)) {
                     const int dz = r / (2 * GRID_R + 1) - GRID_R, dy = r % (2 * GRID_R + 1) - GRID_R;
                     const int gz = cz + dz, gy = cy + dy;
@@ -418,20 +419,40 @@ knn_unpose_grid_kernel(const float* __restrict__ xyz, const float* __restrict__ 
                             x0 = max(x0, 0); x1 = min(x1, h.nx - 1);
                             if (x0 <= x1) {
                                 const int row = (gz * h.ny + gy) * h.nx;
-                                s = __ldg(cell_start + row + x0); e = __ldg(cell_start + row + x1 + 1);
+                                rs[batch] = __ldg(cell_start + row + x0);
+                                rc[batch] = __ldg(cell_start + row + x1 + 1) - rs[batch];
                             }
                         }
                     }
                 }
-                unsigned m = __ballot_sync(0xffffffffu, e > s);
-                while (m) {
-                    const int rr = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int s_r = __shfl_sync(0xffffffffu, s, rr), e_r = __shfl_sync(0xffffffffu, e, rr);
-                    for (int p = s_r + lane; p < e_r; p += 32) {
-                        const float4 v = __ldg(sorted + p);
-                        best_push_any(lb, dist2_rn(ux, uy, uz, v.x, v.y, v.z), __float_as_int(v.w));
-                    }
+            }
+            // flatten all candidates of the 49 ranges over the 32 lanes: inclusive scan of the per-lane
+            // counts, then every lane maps its flat index back to (owner lane, offset) by a shuffle search
+            const int cnt = rc[0] + rc[1];
+            int pre = cnt;
+#pragma unroll
+            for (int ofs = 1; ofs < 32; ofs <<= 1) {
+                const int nb = __shfl_up_sync(0xffffffffu, pre, ofs);
+                if (lane >= ofs) pre += nb;
+            }
+            const int total = __shfl_sync(0xffffffffu, pre, 31);
+            for (int j0 = 0; j0 < total; j0 += 32) {
+                const int j = j0 + lane;
+                int rr = 0;
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const int t = __shfl_sync(0xffffffffu, pre, rr + step - 1);
+                    if (t <= j) rr += step;
+                }
+                rr = min(rr, 31);
+                const int pre_r = __shfl_sync(0xffffffffu, pre, rr), cnt_r = __shfl_sync(0xffffffffu, cnt, rr);
+                const int c0_r = __shfl_sync(0xffffffffu, rc[0], rr);
+                const int s0_r = __shfl_sync(0xffffffffu, rs[0], rr), s1_r = __shfl_sync(0xffffffffu, rs[1], rr);
+                if (j < total) {
+                    const int off = j - (pre_r - cnt_r);
+                    const int p = off < c0_r ? s0_r + off : s1_r + (off - c0_r);
+                    const float4 v = __ldg(sorted + p);
+                    best_push_any(lb, dist2_rn(ux, uy, uz, v.x, v.y, v.z), __float_as_int(v.w));
                 }
             }
             Best4 g;

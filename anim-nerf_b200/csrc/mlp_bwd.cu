@@ -171,7 +171,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         const float v = dp0 * __ldg(wr + c) + dp1 * __ldg(wr + 128 + c) + dp2 * __ldg(wr + 256 + c);
-                        f[c] = ((cmw[cb] >> c) & 1u) ? v : 0.f;
+                        f[c] = ((cmw[cb] >> mask_bit_of_col(c)) & 1u) ? v : 0.f;
                     }
                     uint8_t* dst = act_row + (cb >> 1) * 16384;
 #pragma unroll
@@ -270,7 +270,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                     }
                     const uint32_t m = mw[cb];
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) f[c] = ((m >> c) & 1u) ? f[c] : 0.f;
+                    for (int c = 0; c < 32; ++c) f[c] = ((m >> mask_bit_of_col(c)) & 1u) ? f[c] : 0.f;
                     uint8_t* dst = act_row + (cb >> 1) * 16384;
 #pragma unroll
                     for (uint32_t u = 0; u < 4; ++u) {

@@ -236,13 +236,8 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                                 for (int c4 = 0; c4 < 8; ++c4) bq[c4] = __ldg((const float4*)(bias + (blk + 1) * 32) + c4);
                             }
                         }
-                        if (g != 8) {
-                            if (TRAIN) {
-                                uint32_t mw = 0;
-#pragma unroll
-                                for (int c = 0; c < 32; ++c) mw |= (f[c] > 0.f ? 1u : 0u) << c;
-                                mask_words[blk & 7] = mw;
-                            }
+                        // fp32 ReLU only where an fp32 head consumes the activations (sigma: layer 8, rgb: colour layer)
+                        if (g == 7 || g == 9) {
 #pragma unroll
                             for (int c = 0; c < 32; ++c) f[c] = fmaxf(f[c], 0.f);
                         }
@@ -266,14 +261,27 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                             }
                         }
                         if (g < 9 || TRAIN) {
+                            // pack to bf16x2, ReLU on the packed pairs, 1-bit mask from the packed pairs:
+                            // word k holds columns (2k, 2k+1); mask bit k <-> column 2k, bit 16+k <-> column 2k+1
+                            uint32_t w[16];
+                            uint32_t mw = 0;
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) {
+                                w[k] = pack_bf16(f[2 * k], f[2 * k + 1]);
+                                if (g != 8) {
+                                    if (g != 7 && g != 9) w[k] = relu_bf16x2(w[k]);
+                                    if (TRAIN) {      // halves are >= +0 here: h + 0x7fff sets bit 15 iff h > 0 (no carry)
+                                        const uint32_t t = w[k] + 0x7fff7fffu;
+                                        mw |= (k <= 15 ? (t >> (15 - k)) : 0u) & (0x00010001u << k);
+                                    }
+                                }
+                            }
+                            if (TRAIN) mask_words[blk & 7] = mw;
                             uint8_t* dst = act_row + (blk >> 1) * 16384;
 #pragma unroll
-                            for (uint32_t u = 0; u < 4; ++u) {
-                                uint4 o;
-                                o.x = pack_bf16(f[8 * u], f[8 * u + 1]); o.y = pack_bf16(f[8 * u + 2], f[8 * u + 3]);
-                                o.z = pack_bf16(f[8 * u + 4], f[8 * u + 5]); o.w = pack_bf16(f[8 * u + 6], f[8 * u + 7]);
-                                *(uint4*)(dst + ((((uint32_t)(blk & 1) * 4 + u) ^ sw) << 4)) = o;
-                            }
+                            for (uint32_t u = 0; u < 4; ++u)
+                                *(uint4*)(dst + ((((uint32_t)(blk & 1) * 4 + u) ^ sw) << 4)) =
+                                    make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
                         }
                     }
                 }

@@ -109,4 +109,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return r;
 }
 
+// ReLU on a packed bf16 pair (max with +0; PTX max orders -0 < +0)
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
+    uint32_t r;
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(0u));
+    return r;
+}
+// mask layout shared by the forward (writer) and dgrad (reader): for a 32-column block,
+// bit k (k < 16) <-> column 2k, bit 16+k <-> column 2k+1
+__device__ __forceinline__ uint32_t mask_bit_of_col(int c) { return (uint32_t)((c & 1) * 16 + (c >> 1)); }
+
 }  // namespace tc

@@ -1,0 +1,59 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: frame/ray sharding, the single flat
+gradient all-reduce of the training step, and slab gathering for sharded inference."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from util import ROOT  # noqa: F401  (puts the repo on sys.path)
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import anim_nerf_b200  # noqa: F401
+    from anim_nerf_b200 import dist_utils as du
+    from anim_nerf_b200.nerf import NeRF
+    torch.manual_seed(0)
+    net = NeRF(freqs_dir=0)                      # same init on both ranks
+    for i, p in enumerate(net.parameters()):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    du.allreduce_grads(list(net.parameters()))
+    ok_grad = all(torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1))) for i, p in enumerate(net.parameters()))
+    a, b = du.shard_range(17, rank, world)
+    local = torch.arange(a, b, dtype=torch.float32)[:, None].repeat(1, 3)
+    full = du.gather_slabs(local, 17)
+    ok_gather = torch.equal(full[:, 0], torch.arange(17, dtype=torch.float32))
+    q.put((rank, ok_grad, (a, b), ok_gather))
+    dist.destroy_process_group()
+
+
+def test_two_rank_allreduce_and_sharding():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert all(r[1] for r in res), res
+    assert [r[2] for r in res] == [(0, 9), (9, 17)]
+    assert all(r[3] for r in res), res
+
+
+def test_shard_range_partitions_everything():
+    from anim_nerf_b200 import dist_utils as du
+    for n in (1, 7, 16, 120, 262144):
+        for w in (1, 2, 4, 8):
+            spans = [du.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
