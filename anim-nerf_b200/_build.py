@@ -10,6 +10,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libanimnerf_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+if os.environ.get("AN_MLP_TRACE"):      # debug timeline build (tools/trace_mlp.py); never the shipped library
+    NVCC_FLAGS.append("-DAN_MLP_TRACE")
 
 
 def _newer(target, sources):

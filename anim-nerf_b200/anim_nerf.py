@@ -25,6 +25,24 @@ def batch_transform(P, v, pad_ones=True):
     return out + P[..., :3, 3] if pad_ones else out
 
 
+def affine_inverse(T):
+    """Inverse of affine 4x4 transforms (last row [0,0,0,1]) in closed form: adjugate of the 3x3
+    block over its determinant, then -R^-1 t.  Replaces the reference's `torch.inverse`
+    (models/anim_nerf.py:131,148): same result to fp32 round-off, but no batched-LU launch chain
+    and no host synchronisation (`linalg.inv` reads its `info` back), so the per-frame table
+    builder can be captured in a CUDA graph.  Differentiable."""
+    R, t = T[..., :3, :3], T[..., :3, 3]
+    c0, c1, c2 = R[..., :, 0], R[..., :, 1], R[..., :, 2]
+    r0, r1, r2 = torch.cross(c1, c2, dim=-1), torch.cross(c2, c0, dim=-1), torch.cross(c0, c1, dim=-1)
+    det = (c0 * r0).sum(-1, keepdim=True)
+    Rinv = torch.stack([r0 / det, r1 / det, r2 / det], dim=-2)
+    tinv = -torch.matmul(Rinv, t[..., None])
+    top = torch.cat([Rinv, tinv], dim=-1)
+    bottom = torch.zeros_like(top[..., :1, :])
+    bottom[..., 0, 3] = 1.0
+    return torch.cat([top, bottom], dim=-2)
+
+
 class AnimNeRF(nn.Module):
     def __init__(self, model_path="smplx/models", model_type="smpl", gender="male", freqs_xyz=10, freqs_dir=4,
                  use_view=False, use_unpose=False, unpose_view=False, k_neigh=4, use_knn=False,
@@ -76,7 +94,7 @@ class AnimNeRF(nn.Module):
         self._grid = None
 
     def convert_to_body_model_space(self, rays):
-        ginv = torch.inverse(self.global_transform).unsqueeze(1)            # (bs,1,4,4)
+        ginv = affine_inverse(self.global_transform).unsqueeze(1)            # (bs,1,4,4)
         rays_o = batch_transform(ginv, rays[:, :, 0:3], True)
         rays_d = batch_transform(ginv, rays[:, :, 3:6], False)
         cam_dist = torch.norm(rays_o, dim=-1, keepdim=True)
@@ -90,7 +108,7 @@ class AnimNeRF(nn.Module):
         return torch.cat((rays_o, rays_d, near, far), dim=-1)
 
     def clac_ober2cano_transform(self):
-        inv = torch.inverse(self.verts_transform)
+        inv = affine_inverse(self.verts_transform)
         shift = (self.shape_offsets_template - self.shape_offsets) + (self.pose_offsets_template - self.pose_offsets)
         inv = torch.cat([inv[..., :3], torch.cat([inv[..., :3, 3:] + shift[..., None], inv[..., 3:, 3:]], dim=-2)], dim=-1)
         self.ober2cano_transform = torch.matmul(self.verts_transform_template, inv)

@@ -31,19 +31,22 @@ def rodrigues(rvec):
     return eye + s * K + (1 - c) * torch.bmm(K, K)
 
 
-def rigid_chain(rot, joints, parents):
+def rigid_chain(rot, joints, parents, parent_idx=None):
     """rot (B,J,3,3), rest joints (B,J,3) -> posed joints (B,J,3) and the relative
     transforms A (B,J,4,4) that map rest-pose points to posed points."""
     B, J = joints.shape[:2]
+    parents = [int(p) for p in parents]               # host list: no device read-back inside the chain
     rel = joints.clone()
-    rel[:, 1:] = joints[:, 1:] - joints[:, parents[1:]]
+    if parent_idx is None:
+        parent_idx = torch.as_tensor(parents[1:], dtype=torch.long, device=joints.device)
+    rel[:, 1:] = joints[:, 1:] - joints.index_select(1, parent_idx)
     local = torch.zeros(B, J, 4, 4, dtype=rot.dtype, device=rot.device)
     local[:, :, :3, :3] = rot
     local[:, :, :3, 3] = rel
     local[:, :, 3, 3] = 1.0
     chain = [local[:, 0]]
     for j in range(1, J):
-        chain.append(torch.matmul(chain[int(parents[j])], local[:, j]))
+        chain.append(torch.matmul(chain[parents[j]], local[:, j]))
     G = torch.stack(chain, dim=1)                      # world transform of each joint
     posed = G[:, :, :3, 3]
     # subtract G @ [rest joint; 0] from the translation column
@@ -73,6 +76,8 @@ class BodyModel(nn.Module):
         parents = torch.as_tensor(np.asarray(data["kintree_table"])[0]).long().clone()
         parents[0] = -1
         self.register_buffer("parents", parents)
+        self.parents_host = [int(p) for p in parents]   # the kinematic tree is static: keep it on the host
+        self.register_buffer("parent_idx", parents[1:].clone())
         self.register_buffer("lbs_weights", t(data["weights"]))
 
     def forward(self, betas, body_pose, global_orient, transl=None, **_):
@@ -88,7 +93,7 @@ class BodyModel(nn.Module):
         feat = (rot[:, 1:] - eye).reshape(B, -1)
         pose_offsets = torch.matmul(feat, self.posedirs).view(B, -1, 3)
         v_posed = pose_offsets + v_shaped
-        joints, A = rigid_chain(rot, J, self.parents)
+        joints, A = rigid_chain(rot, J, self.parents_host, self.parent_idx)
         nj = self.J_regressor.shape[0]
         T = torch.matmul(self.lbs_weights[None].expand(B, -1, -1), A.view(B, nj, 16)).view(B, -1, 4, 4)
         vh = torch.cat([v_posed, torch.ones_like(v_posed[..., :1])], dim=2)

@@ -36,6 +36,20 @@ constexpr uint32_t SM_BAR = SM_WST + NSTAGE * 32768;   // 229376
 constexpr uint32_t SM_BYTES = SM_BAR + 128;
 constexpr uint32_t SM_ALLOC = SM_BYTES + 1024;     // slack for manual 1024-B alignment
 
+#ifdef AN_MLP_TRACE
+// debug timeline (tools/trace_mlp.py): CTA 0 appends (clock << 24 | role << 20 | ev << 16 | a << 8 | b)
+__device__ unsigned long long* g_trace = nullptr;
+__device__ __forceinline__ void trace(int role, int ev, int a, int b) {
+    if (blockIdx.x == 0 && g_trace) {
+        const unsigned long long i = atomicAdd(g_trace, 1ull);
+        if (i < (1u << 20) - 1) g_trace[1 + i] = ((unsigned long long)clock64() << 24) | ((unsigned long long)role << 20) | (ev << 16) | (a << 8) | b;
+    }
+}
+#define TRACE(role, ev, a, b) trace(role, ev, a, b)
+#else
+#define TRACE(role, ev, a, b)
+#endif
+
 }  // namespace
 
 namespace mlp {
@@ -98,6 +112,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                         for (int kc = 0; kc < g_chunks(g); ++kc, ++it) {
                             const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
                             mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                            TRACE(0, 0, g, t * 8 + kc);
                             mbar_expect_tx(bar_full + 8 * s, bytes);
                             bulk_g2s(sbase + SM_WST + s * 32768u, packed + fwd_chunk_off(g, kc), bytes, bar_full + 8 * s);
                         }
@@ -111,11 +126,14 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 for (int g = 0; g < NG; ++g) {
                     const uint32_t idesc = make_idesc_bf16(128, g_N(g), 0, 0);
                     for (int t = 0; t < 2; ++t) {
+                        TRACE(1, 0, g, t);
                         mbar_wait(bar_act + 8 * t, act_phase);
+                        TRACE(1, 1, g, t);
                         tc_fence_after();
                         for (int kc = 0; kc < g_chunks(g); ++kc, ++it) {
                             const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
                             mbar_wait(bar_full + 8 * s, ph);
+                            TRACE(1, 2, g, t * 8 + kc);
                             tc_fence_after();
                             const uint32_t wb = sbase + SM_WST + s * 32768u;
                             const bool from_enc = (g == 0) || (g == 4 && kc == 0);
@@ -199,12 +217,15 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 float4 bq[8];
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) bq[c4] = __ldg((const float4*)bias + c4);
+                if (leader) TRACE(2 + t, 0, g, 0);
                 mbar_wait(my_acc, acc_phase); acc_phase ^= 1u;
+                if (leader) TRACE(2 + t, 1, g, 0);
                 tc_fence_after();
                 if (TRAIN && g > 0) {     // act image of layer g-1 is being stored: wait before overwriting it
                     if (leader) bulk_wait_read0();
                     named_bar_sync(1 + t, 128);
                 }
+                if (leader) TRACE(2 + t, 2, g, 0);
                 uint32_t mask_words[8];
                 uint32_t va[32], vb[32];
                 tmem_ld32(tm, va);
@@ -319,6 +340,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                     }
                     mbar_arrive(my_act);
                 }
+                if (leader) TRACE(2 + t, 3, g, 0);
             }
         }
         if (TRAIN && leader) bulk_wait0();
@@ -330,6 +352,12 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
 
 int mlp_fwd_ref_launch(const void* packed, const float* xyz_cano, const int32_t* cidx, const int32_t* count,
                        int64_t n_max, float* sigma, float* rgb, cudaStream_t stream);
+
+#ifdef AN_MLP_TRACE
+extern "C" int an_debug_trace_fwd(void* buf) {
+    return (int)cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf));
+}
+#endif
 
 extern "C" int64_t an_mlp_stash_bytes(int64_t n_max)
 {

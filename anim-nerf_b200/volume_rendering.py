@@ -29,6 +29,10 @@ class VolumeRenderer(nn.Module):
         self.n_coarse, self.n_fine, self.n_fine_depth = n_coarse, n_fine, n_fine_depth
         self.share_fine, self.noise_std, self.depth_std = share_fine, noise_std, depth_std
         self.lindisp, self.white_bkgd = lindisp, white_bkgd
+        # False: in-kernel Philox streams seeded per call from torch's CPU generator (a host value, so it
+        # would be frozen into a captured CUDA graph).  True: draws come from torch's device generator
+        # (graph-safe: its Philox offset advances on every replay) and reach the kernels as explicit tensors.
+        self.device_rng = False
 
     @staticmethod
     def _seed():
@@ -36,6 +40,8 @@ class VolumeRenderer(nn.Module):
 
     def sample_coarse(self, rays, perturb=0., noise_u=None):
         rays = rays[..., :8].contiguous()
+        if self.device_rng and perturb > 0 and noise_u is None:
+            noise_u = torch.rand(*rays.shape[:-1], self.n_coarse, device=rays.device)
         return SampleCoarse.apply(rays, self.n_coarse, float(perturb), noise_u,
                                   self._seed() if (perturb > 0 and noise_u is None) else 0)
 
@@ -43,6 +49,8 @@ class VolumeRenderer(nn.Module):
         """Fused `sample_fine` + cat + sort (reference :199-207): takes the coarse depths and the full
         coarse weights (the kernel forms the mid-point bins and the w[1:-1] slice itself); returns
         (z_combine sorted, z_fine)."""
+        if self.device_rng and not det and u is None:
+            u = torch.rand(*z_coarse.shape[:-1], self.n_fine, device=z_coarse.device)
         return SampleFineMerge.apply(weights.detach(), z_coarse, self.n_fine, bool(det), u,
                                      self._seed() if (not det and u is None) else 0)
 

@@ -119,20 +119,23 @@ def run_ours(args):
         sd = {k: torch.from_numpy(v) for k, v in synthetic.make_nerf_weights(seed).items()}
         getattr(sysm.anim_nerf, name).load_state_dict(sd, strict=True)
     mlp_params = [p for n in ("nerf", "nerf_fine") for p in getattr(sysm.anim_nerf, n).parameters()]
-    opt = torch.optim.Adam(mlp_params, lr=5e-4, eps=1e-8, fused=True)
+    opt = torch.optim.Adam(mlp_params, lr=5e-4, eps=1e-8, fused=True, capturable=True)
+    sysm.volume_renderer.device_rng = True            # graph-safe randomness (torch device generator)
     pin = {k: v.pin_memory() for k, v in host.items()}
     params_d = {k: v.to(dev) for k, v in params.items()}
     tmpl_d = {k: v.to(dev) for k, v in tmpl.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
     lam = sysm.hparams.train.lambda_alphas
     n_rays = N_FRAMES * N_SIDE * N_SIDE
+    mse, l1 = torch.nn.functional.mse_loss, torch.nn.functional.l1_loss
 
-    def step(batch_dev):
+    def loss_fn(batch_dev):
         out = sysm(batch_dev["rays"], params_d, tmpl_d, perturb=1.0)
-        mse = torch.nn.functional.mse_loss
-        l1 = torch.nn.functional.l1_loss
-        loss = (mse(out["rgbs"], batch_dev["rgbs"]) + mse(out["rgbs_fine"], batch_dev["rgbs"])
+        return (mse(out["rgbs"], batch_dev["rgbs"]) + mse(out["rgbs_fine"], batch_dev["rgbs"])
                 + lam * (l1(out["alphas"], batch_dev["alphas"]) + l1(out["alphas_fine"], batch_dev["alphas"])))
+
+    def step_eager(batch_dev):
+        loss = loss_fn(batch_dev)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         if world > 1:
@@ -140,42 +143,32 @@ def run_ours(args):
         opt.step()
         return loss
 
-    def step_e2e():
-        batch_dev = {k: v.to(dev, non_blocking=True) for k, v in pin.items()}
-        return float(step(batch_dev).item())           # D2H read of the loss
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm
+    # ---- eager pass: per-kernel CUDA-event timing on the launching stream + launch / valid-point counts
+    from anim_nerf_b200 import autograd as _ag
     for _ in range(args.warmup):
-        step(resident)
+        step_eager(resident)
     barrier()
     timing = _lib.enable_timing(True)
-    from anim_nerf_b200 import autograd as _ag
     _ag.COUNT_LOG = []
     launches0 = _lib.launch_count
-    clocks = ClockSampler(local)
-    clocks.start()
+    n_eager = max(2, min(args.steps, 5))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     ev0.record()
-    for _ in range(args.steps):
-        step(resident)
+    for _ in range(n_eager):
+        step_eager(resident)
     ev1.record()
     barrier()
-    clk = clocks.stop()
-    ms = ev0.elapsed_time(ev1)
-    launches = _lib.launch_count - launches0
+    eager_ms = ev0.elapsed_time(ev1) / n_eager
+    launches_per_step = (_lib.launch_count - launches0) // n_eager
     _lib.enable_timing(False)
     per_kernel = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in timing.items()}
-    calls_per_step = {k: len(v) / args.steps for k, v in timing.items()}
+    calls_per_step = {k: len(v) / n_eager for k, v in timing.items()}
     share = {k: per_kernel[k] * calls_per_step[k] for k in per_kernel}
-    step_ms = ms / args.steps
-
-    # valid (non-culled) points per pass, read back from the device-side compaction counters
     counts = _ag.COUNT_LOG
     _ag.COUNT_LOG = None
     pts_coarse = float(np.mean([c.item() for k, c in counts if k == KC]))
@@ -183,7 +176,30 @@ def run_ours(args):
     valid_frac_coarse = pts_coarse / (n_rays * KC)
     valid_frac_fine = pts_fine / (n_rays * (KC + KF))
 
-    # ---- end-to-end arm (host buffers, H2D + D2H inside the timed region)
+    # ---- headline: the same step replayed from CUDA graphs (inputs resident in HBM)
+    from anim_nerf_b200.graph_step import GraphedTrainStep
+    gstep = GraphedTrainStep(loss_fn, opt, mlp_params, resident, world=world, warmup=args.warmup)
+    for _ in range(args.warmup):
+        gstep()
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        gstep()
+    ev1.record()
+    barrier()
+    clk = clocks.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = launches_per_step * args.steps
+    step_ms = ms / args.steps
+
+    # ---- end-to-end arm (pinned host buffers; H2D of the batch + D2H of the loss inside the timed region)
+    def step_e2e():
+        return float(gstep(pin).item())
+
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
     barrier()
@@ -236,6 +252,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "cfg2: training step, 16 frames x 1024 rays, 64+64 samples, fwd+bwd+Adam, per GPU",
+                       "launch": "whole step replayed from CUDA graphs (GraphedTrainStep); eager launch: %.3f ms/step" % eager_ms,
                        "rays_per_step_per_gpu": n_rays, "points_per_ray": KC + KC + KF, "perturb": 1.0,
                        "regularizers": "not included (outside the named path; torch double-backward in the reference)",
                        "parallelism": "dp%d (rays sharded by frame, NCCL all-reduce of MLP grads)" % world,

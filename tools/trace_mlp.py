@@ -1,0 +1,70 @@
+"""In-kernel timeline of the MLP forward kernel (needs a library built with AN_MLP_TRACE=1).
+    AN_MLP_TRACE=1 python -m anim_nerf_b200._build --force ; python tools/trace_mlp.py [n] [--train]"""
+import sys, os, ctypes
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+import anim_nerf_b200  # noqa
+from anim_nerf_b200 import ops, synthetic, _lib
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 148 * 256 * 8
+train = "--train" in sys.argv
+dev = "cuda"
+w = synthetic.make_nerf_weights(10)
+ws = [torch.from_numpy(w[k + ".weight"]).to(dev) for k in synthetic.NERF_LAYER_NAMES]
+bs = [torch.from_numpy(w[k + ".bias"]).to(dev) for k in synthetic.NERF_LAYER_NAMES]
+packed = ops.mlp_pack(ws, bs)
+xc = torch.rand(n, 3, device=dev) * 2 - 1
+sigma = torch.empty(n, device=dev); rgb = torch.empty(n, 3, device=dev)
+stash = ops.mlp_stash(n, dev) if train else None
+lib = _lib.load()
+buf = torch.zeros(1 << 20, dtype=torch.int64, device=dev)
+for _ in range(2):
+    ops.mlp_fwd(packed, xc, sigma, rgb, stash=stash)
+torch.cuda.synchronize()
+lib.an_debug_trace_fwd.argtypes = [ctypes.c_void_p]
+assert lib.an_debug_trace_fwd(ctypes.c_void_p(buf.data_ptr())) == 0
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); ops.mlp_fwd(packed, xc, sigma, rgb, stash=stash); e1.record()
+torch.cuda.synchronize()
+print("kernel ms", e0.elapsed_time(e1), "n", n, "train", train)
+h = buf.cpu().numpy().astype(np.uint64)
+cnt = int(h[0]); ev = h[1:1 + cnt]
+clk = (ev >> np.uint64(24)).astype(np.int64); role = ((ev >> np.uint64(20)) & np.uint64(15)).astype(int)
+e = ((ev >> np.uint64(16)) & np.uint64(15)).astype(int); a = ((ev >> np.uint64(8)) & np.uint64(255)).astype(int); b = (ev & np.uint64(255)).astype(int)
+t0 = clk.min(); clk -= t0
+print("events", cnt, "span clk", clk.max())
+# epilogue tiles: per layer g: wait-for-acc (ev0->ev1), store drain (ev1->ev2), body (ev2->ev3)
+for t in (0, 1):
+    m = role == 2 + t
+    c, ee, aa = clk[m], e[m], a[m]
+    o = np.argsort(c, kind="stable"); c, ee, aa = c[o], ee[o], aa[o]
+    wait = {}; drain = {}; body = {}; gap = {}
+    last = {}; prev_end = None
+    for ci, ei, gi in zip(c, ee, aa):
+        if ei == 0:
+            if prev_end is not None: gap.setdefault(gi, []).append(ci - prev_end)
+            last[0] = ci
+        elif ei == 1: wait.setdefault(gi, []).append(ci - last[0]); last[1] = ci
+        elif ei == 2: drain.setdefault(gi, []).append(ci - last[1]); last[2] = ci
+        elif ei == 3: body.setdefault(gi, []).append(ci - last[2]); prev_end = ci
+    print("tile %d  layer: wait_acc / store_drain / epilogue_body / gap-before(prologue at g=0)   [median clk]" % t)
+    for g in range(10):
+        print("   g=%d  %8.0f %8.0f %8.0f %8.0f" % (g, np.median(wait.get(g, [0])), np.median(drain.get(g, [0])),
+                                                   np.median(body.get(g, [0])), np.median(gap.get(g, [0]))))
+# MMA issuer: wait for act (ev0->ev1), per-chunk full waits
+m = role == 1
+c, ee, aa, bb = clk[m], e[m], a[m], b[m]
+o = np.argsort(c, kind="stable"); c, ee, aa, bb = c[o], ee[o], aa[o], bb[o]
+wact = {}; wfull = {}
+prev = None
+for ci, ei, gi, bi in zip(c, ee, aa, bb):
+    if ei == 1: wact.setdefault((gi, bi), []).append(ci - prev)
+    if ei == 2: wfull.setdefault((gi, bi >> 3), []).append(ci - prev)
+    prev = ci
+print("MMA issuer: median clk waiting for act[g,t]; per-chunk issue interval (full wait + issue) [g,t]")
+for g in range(10):
+    print("   g=%d  act: %7.0f %7.0f   chunk: %7.0f %7.0f" % (g, np.median(wact[(g, 0)]), np.median(wact[(g, 1)]),
+                                                              np.median(wfull[(g, 0)]), np.median(wfull[(g, 1)])))
+tot_iter = len(wact[(0, 0)])
+print("iterations traced:", tot_iter, " clk/iteration:", clk.max() / tot_iter)
