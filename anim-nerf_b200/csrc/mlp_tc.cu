@@ -37,16 +37,19 @@ constexpr uint32_t SM_BYTES = SM_BAR + 128;
 constexpr uint32_t SM_ALLOC = SM_BYTES + 1024;     // slack for manual 1024-B alignment
 
 #ifdef AN_MLP_TRACE
-// debug timeline (tools/trace_mlp.py): CTA 0 appends (clock << 24 | role << 20 | ev << 16 | a << 8 | b)
+// debug timeline (tools/trace_mlp.py): CTA 0, one region of 64 Ki entries per role, plain stores
+// (clock << 24 | role << 20 | ev << 16 | a << 8 | b); entry 0 of a region = its event count
 __device__ unsigned long long* g_trace = nullptr;
-__device__ __forceinline__ void trace(int role, int ev, int a, int b) {
-    if (blockIdx.x == 0 && g_trace) {
-        const unsigned long long i = atomicAdd(g_trace, 1ull);
-        if (i < (1u << 20) - 1) g_trace[1 + i] = ((unsigned long long)clock64() << 24) | ((unsigned long long)role << 20) | (ev << 16) | (a << 8) | b;
-    }
-}
-#define TRACE(role, ev, a, b) trace(role, ev, a, b)
+#define TRACE_DECL unsigned int tr_n = 0
+#define TRACE(role, ev, a, b)                                                                                      \
+    do {                                                                                                           \
+        if (blockIdx.x == 0 && g_trace && tr_n < 65535u) {                                                         \
+            g_trace[(role) * 65536 + 1 + tr_n] = ((unsigned long long)clock64() << 24) | ((unsigned long long)(role) << 20) | ((ev) << 16) | ((a) << 8) | (b); \
+            g_trace[(role) * 65536] = ++tr_n;                                                                      \
+        }                                                                                                          \
+    } while (0)
 #else
+#define TRACE_DECL
 #define TRACE(role, ev, a, b)
 #endif
 
@@ -86,7 +89,6 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     int64_t n = n_max;
     if (cidx) { const int64_t c = *count; n = c < n_max ? c : n_max; }
     const int64_t num_iters = (n + 255) / 256;
-
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int t = 0; t < 2; ++t) { mbar_init(bar_act + 8 * t, 128); mbar_init(bar_acc + 8 * t, 1); }
@@ -104,6 +106,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     if (warp == 0) {
         // ------------------------------------------------------------ weight producer
         if (lane == 0) {
+            TRACE_DECL;
             uint32_t it = 0;
             for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x)
                 for (int g = 0; g < NG; ++g) {
@@ -121,6 +124,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
+            TRACE_DECL;
             uint32_t it = 0, act_phase = 0;
             for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x)
                 for (int g = 0; g < NG; ++g) {
@@ -143,7 +147,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
                                 umma(tmem_base + t * 256u, make_desc(ab + k * 32u, 16, 1024),
-                                     make_desc(wb + k * 32u, 16, 1024), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                                     make_desc(wb + k * 32u, 16, 1024), idesc, 1u);   // accumulators start from the bias
                             umma_commit(bar_empty + 8 * s);       // stage free once these MMAs retire
                         }
                         umma_commit(bar_acc + 8 * t);              // accumulators of (layer g, tile t) complete
@@ -167,6 +171,22 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
         const float* small = (const float*)(packed + SMALL_OFF);
         const bool leader = (e & 127) == 0;          // issues the tile's TMA stores
         uint32_t acc_phase = 0;
+        TRACE_DECL;
+
+        {   // layer 0's accumulators start from its bias (later layers: re-initialised while draining, see below)
+            uint32_t b0[32];
+#pragma unroll 1
+            for (int blk = 0; blk < 8; ++blk) {
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const uint4 b4 = __ldg((const uint4*)(small + SM_BIAS + blk * 32) + c4);
+                    b0[4 * c4] = b4.x; b0[4 * c4 + 1] = b4.y; b0[4 * c4 + 2] = b4.z; b0[4 * c4 + 3] = b4.w;
+                }
+                tmem_st32(tm + blk * 32, b0);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+        }
 
         for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x) {
             const int64_t p = iter * 256 + t * 128 + row;
@@ -211,12 +231,21 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
 
             float sig = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
             for (int g = 0; g < NG; ++g) {
-                const float* bias = small + SM_BIAS + g * 256;
                 const int nblk = g_N(g) / 32;
-                // bias of the first block is fetched before the accumulator wait (hides the L2 latency)
-                float4 bq[8];
+                // The accumulators start from the bias: while draining layer g, every drained block of
+                // TMEM columns is re-initialised (tcgen05.st) with the bias of the layer that writes
+                // it next -- layer g+1, or layer 0 of the next iteration for the columns the 128-wide
+                // colour layer leaves alone.  The MMAs always accumulate; no bias add in the epilogue.
+                const int nb_lo = g < 8 ? g + 1 : (g == 8 ? 9 : 0);       // bias layer for blocks 0..3
+                const int nb_hi = g < 8 ? g + 1 : 0;                      // bias layer for blocks 4..7
+                const float* bias_lo = small + SM_BIAS + nb_lo * 256;
+                const float* bias_hi = small + SM_BIAS + nb_hi * 256;
+                uint32_t bq[32];
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) bq[c4] = __ldg((const float4*)bias + c4);
+                for (int c4 = 0; c4 < 8; ++c4) {   // first block's bias is fetched before the accumulator wait
+                    const uint4 b4 = __ldg((const uint4*)bias_lo + c4);
+                    bq[4 * c4] = b4.x; bq[4 * c4 + 1] = b4.y; bq[4 * c4 + 2] = b4.z; bq[4 * c4 + 3] = b4.w;
+                }
                 if (leader) TRACE(2 + t, 0, g, 0);
                 mbar_wait(my_acc, acc_phase); acc_phase ^= 1u;
                 if (leader) TRACE(2 + t, 1, g, 0);
@@ -226,48 +255,33 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                     named_bar_sync(1 + t, 128);
                 }
                 if (leader) TRACE(2 + t, 2, g, 0);
-                uint32_t mask_words[8];
                 uint32_t va[32], vb[32];
                 tmem_ld32(tm, va);
+#pragma unroll 1
                 for (int cb = 0; cb < nblk; cb += 2) {
-                    // ---- even block: data in va; prefetch the odd block into vb and its bias
-                    float f[32];
-                    tmem_ld_wait();
-                    tmem_ld32(tm + (cb + 1) * 32, vb);
-#pragma unroll
-                    for (int c4 = 0; c4 < 8; ++c4) {
-                        f[4 * c4] = __uint_as_float(va[4 * c4]) + bq[c4].x; f[4 * c4 + 1] = __uint_as_float(va[4 * c4 + 1]) + bq[c4].y;
-                        f[4 * c4 + 2] = __uint_as_float(va[4 * c4 + 2]) + bq[c4].z; f[4 * c4 + 3] = __uint_as_float(va[4 * c4 + 3]) + bq[c4].w;
-                    }
-#pragma unroll
-                    for (int c4 = 0; c4 < 8; ++c4) bq[c4] = __ldg((const float4*)(bias + (cb + 1) * 32) + c4);
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         const int blk = cb + half;
-                        if (half == 1) {
-                            tmem_ld_wait();
-                            if (blk + 1 < nblk) tmem_ld32(tm + (blk + 1) * 32, va);
+                        uint32_t (&v)[32] = half ? vb : va;
+                        tmem_ld_wait();
+                        if (blk + 1 < nblk) tmem_ld32(tm + (blk + 1) * 32, half ? va : vb);   // prefetch the next block
+                        tmem_st32(tm + blk * 32, bq);                                          // bias for the next writer
+                        if (blk + 1 < nblk) {
+                            const float* bn = ((blk + 1) < 4 ? bias_lo : bias_hi) + (blk + 1) * 32;
 #pragma unroll
                             for (int c4 = 0; c4 < 8; ++c4) {
-                                f[4 * c4] = __uint_as_float(vb[4 * c4]) + bq[c4].x; f[4 * c4 + 1] = __uint_as_float(vb[4 * c4 + 1]) + bq[c4].y;
-                                f[4 * c4 + 2] = __uint_as_float(vb[4 * c4 + 2]) + bq[c4].z; f[4 * c4 + 3] = __uint_as_float(vb[4 * c4 + 3]) + bq[c4].w;
-                            }
-                            if (blk + 1 < nblk) {
-#pragma unroll
-                                for (int c4 = 0; c4 < 8; ++c4) bq[c4] = __ldg((const float4*)(bias + (blk + 1) * 32) + c4);
+                                const uint4 b4 = __ldg((const uint4*)bn + c4);
+                                bq[4 * c4] = b4.x; bq[4 * c4 + 1] = b4.y; bq[4 * c4 + 2] = b4.z; bq[4 * c4 + 3] = b4.w;
                             }
                         }
-                        // fp32 ReLU only where an fp32 head consumes the activations (sigma: layer 8, rgb: colour layer)
-                        if (g == 7 || g == 9) {
-#pragma unroll
-                            for (int c = 0; c < 32; ++c) f[c] = fmaxf(f[c], 0.f);
-                        }
+                        // fp32 heads (sigma from h8 = relu(layer 8), rgb from c = relu(colour layer))
                         if (g == 7) {
                             const float* ws = small + SM_WS + blk * 32;
 #pragma unroll
                             for (int c4 = 0; c4 < 8; ++c4) {
                                 const float4 w4 = __ldg((const float4*)ws + c4);
-                                sig += f[4 * c4] * w4.x + f[4 * c4 + 1] * w4.y + f[4 * c4 + 2] * w4.z + f[4 * c4 + 3] * w4.w;
+                                sig += fmaxf(__uint_as_float(v[4 * c4]), 0.f) * w4.x + fmaxf(__uint_as_float(v[4 * c4 + 1]), 0.f) * w4.y +
+                                       fmaxf(__uint_as_float(v[4 * c4 + 2]), 0.f) * w4.z + fmaxf(__uint_as_float(v[4 * c4 + 3]), 0.f) * w4.w;
                             }
                         }
                         if (g == 9) {
@@ -276,28 +290,31 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                             for (int c4 = 0; c4 < 8; ++c4) {
                                 const float4 a4 = __ldg((const float4*)wr + c4), b4 = __ldg((const float4*)(wr + 128) + c4),
                                              d4 = __ldg((const float4*)(wr + 256) + c4);
-                                r0 += f[4 * c4] * a4.x + f[4 * c4 + 1] * a4.y + f[4 * c4 + 2] * a4.z + f[4 * c4 + 3] * a4.w;
-                                r1 += f[4 * c4] * b4.x + f[4 * c4 + 1] * b4.y + f[4 * c4 + 2] * b4.z + f[4 * c4 + 3] * b4.w;
-                                r2 += f[4 * c4] * d4.x + f[4 * c4 + 1] * d4.y + f[4 * c4 + 2] * d4.z + f[4 * c4 + 3] * d4.w;
+                                const float f0 = fmaxf(__uint_as_float(v[4 * c4]), 0.f), f1 = fmaxf(__uint_as_float(v[4 * c4 + 1]), 0.f),
+                                            f2 = fmaxf(__uint_as_float(v[4 * c4 + 2]), 0.f), f3 = fmaxf(__uint_as_float(v[4 * c4 + 3]), 0.f);
+                                r0 += f0 * a4.x + f1 * a4.y + f2 * a4.z + f3 * a4.w;
+                                r1 += f0 * b4.x + f1 * b4.y + f2 * b4.z + f3 * b4.w;
+                                r2 += f0 * d4.x + f1 * d4.y + f2 * d4.z + f3 * d4.w;
                             }
                         }
                         if (g < 9 || TRAIN) {
-                            // pack to bf16x2, ReLU on the packed pairs, 1-bit mask from the packed pairs:
-                            // word k holds columns (2k, 2k+1); mask bit k <-> column 2k, bit 16+k <-> column 2k+1
-                            uint32_t w[16];
-                            uint32_t mw = 0;
+                            if (TRAIN && g != 8) {
+                                // 1-bit ReLU mask from the sign bits: one funnel shift per column; bit (31-c) of the
+                                // word <-> column c of the block (tc::mask_bit_of_col)
+                                uint32_t neg = 0;
 #pragma unroll
-                            for (int k = 0; k < 16; ++k) {
-                                w[k] = pack_bf16(f[2 * k], f[2 * k + 1]);
-                                if (g != 8) {
-                                    if (g != 7 && g != 9) w[k] = relu_bf16x2(w[k]);
-                                    if (TRAIN) {      // halves are >= +0 here: h + 0x7fff sets bit 15 iff h > 0 (no carry)
-                                        const uint32_t t = w[k] + 0x7fff7fffu;
-                                        mw |= (k <= 15 ? (t >> (15 - k)) : 0u) & (0x00010001u << k);
-                                    }
-                                }
+                                for (int c = 0; c < 32; ++c) neg = __funnelshift_l(v[c], neg, 1);
+                                if (g <= 7) *(uint32_t*)(st_tile + ST_MASK + g * 4096 + row * 32 + blk * 4) = ~neg;
+                                else *(uint32_t*)(st_tile + ST_CMASK + row * 16 + blk * 4) = ~neg;
                             }
-                            if (TRAIN) mask_words[blk & 7] = mw;
+                            uint32_t w[16];
+                            if (g == 8) {
+#pragma unroll
+                                for (int k = 0; k < 16; ++k) w[k] = pack_bf16(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 16; ++k) w[k] = pack_relu_bf16(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
+                            }
                             uint8_t* dst = act_row + (blk >> 1) * 16384;
 #pragma unroll
                             for (uint32_t u = 0; u < 4; ++u)
@@ -306,15 +323,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                         }
                     }
                 }
-                if (TRAIN) {
-                    if (g <= 7) {
-                        uint4* m = (uint4*)(st_tile + ST_MASK + g * 4096 + row * 32);
-                        m[0] = make_uint4(mask_words[0], mask_words[1], mask_words[2], mask_words[3]);
-                        m[1] = make_uint4(mask_words[4], mask_words[5], mask_words[6], mask_words[7]);
-                    } else if (g == 9) {
-                        *(uint4*)(st_tile + ST_CMASK + row * 16) = make_uint4(mask_words[0], mask_words[1], mask_words[2], mask_words[3]);
-                    }
-                }
+                tmem_st_wait();
                 if (g == 9) {
                     if (in) {
                         sigma_out[id] = sig + __ldg(small + SM_BS);
@@ -322,7 +331,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                         rgb_out[id * 3 + 1] = 1.f / (1.f + __expf(-(r1 + __ldg(small + SM_BR + 1))));
                         rgb_out[id * 3 + 2] = 1.f / (1.f + __expf(-(r2 + __ldg(small + SM_BR + 2))));
                     }
-                    tc_fence_before();            // TMEM reads done before the next iteration's MMAs
+                    tc_fence_before();            // TMEM reads/writes done before the next iteration's MMAs
                     if (TRAIN) {
                         fence_proxy_async();
                         named_bar_sync(1 + t, 128);

@@ -242,9 +242,9 @@ def test_mlp_stash_images_match_layerwise_oracle():
             err = (img - hs[l][sl]).abs().max().item()
             assert err < 3e-2 * max(1.0, hs[l][sl].abs().max().item()), "h%d tile %d err %g" % (l + 1, tile, err)
             m = stash[base + 16384 + 8 * 65536 + 65536 + 32768 + l * 4096:][:4096].view(torch.int32).reshape(128, 8)[:rows].cpu()
-            # mask bit layout per 32-column block: bit k <-> column 2k, bit 16+k <-> column 2k+1
+            # mask bit layout per 32-column block: bit (31-c) <-> column c
             col = torch.arange(32)
-            bits = ((m[:, :, None] >> ((col & 1) * 16 + (col >> 1))) & 1).reshape(rows, 256).bool()
+            bits = ((m[:, :, None] >> (31 - col)) & 1).reshape(rows, 256).bool()
             assert (bits == (img > 0)).all(), "mask h%d" % (l + 1)
 
 
