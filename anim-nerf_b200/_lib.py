@@ -22,7 +22,8 @@ SIGNATURES = {
     "an_sample_coarse_fwd": (_i32, [_vp, _i64, _i32, _f32, _vp, _u64, _vp, _vp]),
     "an_vertex_grid_bytes": (_i64, [_i32, _i32]),
     "an_vertex_grid_build": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp]),
-    "an_knn_unpose_fwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _f32, _i32,
+    "an_knn_query_ws_bytes": (_i64, [_i32, _i64]),
+    "an_knn_unpose_fwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _i32,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "an_knn_unpose_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "an_mlp_packed_bytes": (_i64, []),
@@ -84,7 +85,7 @@ def check(code, what):
 
 
 # kernels launched per entry point (for bench.py's gpu_launches claim)
-KERNELS_PER_CALL = {"an_mlp_bwd": 3}
+KERNELS_PER_CALL = {"an_mlp_bwd": 3, "an_knn_unpose_fwd": 2}
 launch_count = 0
 _timing = None          # bench.py: dict name -> list of (start_event, stop_event) on the launching stream
 

@@ -120,10 +120,21 @@ __device__ __forceinline__ void unpose_epilogue(const Best4& best, bool found, f
         // confidence: skinning rows of neighbour j vs neighbour 0
         const float* w0 = lbsw + (int64_t)best.i[0] * J;
         float l1[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int c = 0; c < J; ++c) {
-            const float a = __ldg(w0 + c);
+        if ((J & 3) == 0 && (((uintptr_t)lbsw) & 15) == 0) {      // 16-byte rows: 128-bit loads
+            for (int c = 0; c < J; c += 4) {
+                const float4 a = __ldg((const float4*)(w0 + c));
 #pragma unroll
-            for (int j = 1; j < 4; ++j) l1[j] += fabsf(__ldg(lbsw + (int64_t)best.i[j] * J + c) - a);
+                for (int j = 1; j < 4; ++j) {
+                    const float4 v = __ldg((const float4*)(lbsw + (int64_t)best.i[j] * J + c));
+                    l1[j] += fabsf(v.x - a.x); l1[j] += fabsf(v.y - a.y); l1[j] += fabsf(v.z - a.z); l1[j] += fabsf(v.w - a.w);
+                }
+            }
+        } else {
+            for (int c = 0; c < J; ++c) {
+                const float a = __ldg(w0 + c);
+#pragma unroll
+                for (int j = 1; j < 4; ++j) l1[j] += fabsf(__ldg(lbsw + (int64_t)best.i[j] * J + c) - a);
+            }
         }
         float qs = 0.f;
 #pragma unroll
@@ -315,22 +326,27 @@ vertex_grid_build_kernel(const float* __restrict__ verts, int V, float cell_in, 
 }
 
 // ------------------------------------------------------------------ mode 1: grid-pruned
-// Warp-cooperative ball-pruned search.  A warp owns 32 consecutive queries (consecutive samples
-// of one ray) and resolves them one at a time with all 32 lanes:
-//   * the cell is ~dis_threshold/3 and the search box is 7x7x7 cells around the query's cell
-//     (covers radius >= dis_threshold); a dilated occupancy flag rejects far queries in one load;
-//   * lanes 0..48 (two batches) each own one (y,z) row of the box: rows whose slab is farther
-//     than the bound B are dropped and the x-range is trimmed to the ball of radius sqrt(B); the
-//     cells of a row are contiguous in the sorted vertex list, so a row is one [s,e) range;
-//   * the non-empty ranges are walked with the 32 lanes striding over the candidates (coalesced
-//     128-bit loads), each lane keeping a private top-4 keyed by (d2, index);
-//   * four REDUX (min) rounds merge the private lists into the exact global top-4.
-// B comes from the previous query of the same warp by the triangle inequality
-// (d4(q') <= d4(q) + |q - q'|: consecutive ray samples are centimetres apart), else
-// B = dis_threshold^2.  Exactness: everything skipped is provably farther than the final 4th
-// neighbour whenever that neighbour lies within sqrt(B) and the box (margins absorb fp32
-// rounding); otherwise the lane rescans the whole table.  Afterwards the 32 lanes run the blend
-// epilogue for their own query in parallel.
+// Two kernels.
+//  knn_classify_kernel  one thread per query: generate the point, look up the dilated occupancy
+//      flag of its cell (cell ~ 1.25*dis_threshold/3, search box 7x7x7 cells).  A query with no
+//      vertex within the box radius is invalid *exactly* (valid needs d_min < threshold, SURVEY
+//      App. A): it gets its final outputs here.  Every other query is appended (x,y,z,id) to a
+//      compact work list, 32 consecutive queries per warp-aggregated append, so consecutive list
+//      entries are (almost always) consecutive samples of one ray.
+//  knn_search_kernel    one thread per listed query, a warp pulling 32 consecutive entries at a time,
+//      so every lane has work and neighbouring lanes walk nearly the same cells (L1 hits).  The
+//      search is a shrinking-ball walk of the cell box: own cell first; the bound is then tightened
+//      from the neighbouring lanes by the triangle inequality (d4(q) <= d4(q') + |q - q'|:
+//      consecutive ray samples are centimetres apart); then the rows (dy,dz) nearest ring first; a
+//      row is skipped when its slab is farther than the bound B, its x-range is trimmed to the
+//      ball of radius sqrt(B), and B drops to the current 4th-best distance as soon as four
+//      candidates are in hand.
+// Exactness: everything skipped is provably farther than the final 4th neighbour whenever that
+// neighbour lies within the query's initial bound and the box (margins absorb fp32 rounding);
+// otherwise the warp rescans the whole table cooperatively.  The (d2,index) order key makes the
+// result independent of the scan order: both modes return identical bits.
+struct QueryWs { unsigned int n_work; unsigned int next_chunk; unsigned int pad[2]; };   // then float4 work[B*N]
+
 __device__ __forceinline__ void warp_merge4(Best4& lb, Best4& g)
 {
 #pragma unroll
@@ -347,133 +363,175 @@ __device__ __forceinline__ void warp_merge4(Best4& lb, Best4& g)
     }
 }
 
+// Rows (dy,dz) of the 7x7 cell box, nearest ring first: ring k = max(|dy|,|dz|).
+__constant__ int8_t c_row_dy[49] = {0, -1, 0, 1, -1, 1, -1, 0, 1, -2, -1, 0, 1, 2, -2, 2, -2, 2, -2, 2, -2, -1, 0, 1, 2, -3, -2, -1, 0, 1, 2, 3, -3, 3, -3, 3, -3, 3, -3, 3, -3, 3, -3, -2, -1, 0, 1, 2, 3};
+__constant__ int8_t c_row_dz[49] = {0, -1, -1, -1, 0, 0, 1, 1, 1, -2, -2, -2, -2, -2, -1, -1, 0, 0, 1, 1, 2, 2, 2, 2, 2, -3, -3, -3, -3, -3, -3, -3, -2, -2, -1, -1, 0, 0, 1, 1, 2, 2, 3, 3, 3, 3, 3, 3, 3};
+__constant__ int8_t c_row_ring[49] = {0, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3};
+static_assert(GRID_R == 3, "row tables are generated for a 7x7 box");
+
 __global__ void __launch_bounds__(KNN_THREADS)
-knn_unpose_grid_kernel(const float* __restrict__ xyz, const float* __restrict__ rays,
-                       const float* __restrict__ z, int K, int64_t N,
-                       const float* __restrict__ verts, int V, const char* __restrict__ ws,
-                       int64_t frame_bytes, const float* __restrict__ ober2cano,
-                       const float* __restrict__ lbsw, int J, float thr, UnposeOut o)
+knn_classify_kernel(const float* __restrict__ xyz, const float* __restrict__ rays, const float* __restrict__ z,
+                    int K, int64_t N, int64_t total, const char* __restrict__ ws, int64_t frame_bytes,
+                    QueryWs* __restrict__ qws, UnposeOut o)
 {
-    const int b = blockIdx.y;
+    float4* __restrict__ work = (float4*)(qws + 1);
     const int lane = threadIdx.x & 31;
-    const char* base = ws + (int64_t)b * frame_bytes;
-    const GridHeader h = *(const GridHeader*)base;
-    const int* __restrict__ cell_start = (const int*)(base + GRID_OFF_START);
-    const uint8_t* __restrict__ flags = (const uint8_t*)(base + GRID_OFF_FLAGS);
-    const float4* __restrict__ sorted = (const float4*)(base + GRID_OFF_SORTED);
-    const float thr2 = thr * thr * (1.0f + 1e-5f);   // prune only what is invalid beyond rounding doubt
-    const float inv_cell = 1.0f / h.cell;
-    const float box_r = GRID_R * h.cell * (1.0f - 1e-4f);
-    const float box_r2 = box_r * box_r;
-    // first bound of a run: slightly beyond the threshold so that a 4th neighbour a little farther
-    // than a valid nearest one (d0 < thr <= d4) is still found without the exhaustive fallback
-    const float b0 = fminf(box_r2, thr * thr * (KNN_B0_SCALE * KNN_B0_SCALE));
-    const int ex_n = h.nx + 2 * GRID_R, ey_n = h.ny + 2 * GRID_R, ez_n = h.nz + 2 * GRID_R;
-    const int64_t n_chunks = (N + 31) / 32;
-    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t chunk = warp0; chunk < n_chunks; chunk += n_warps) {
-        const int64_t n = chunk * 32 + lane;
-        const bool active = n < N;
-        const int64_t gid = (int64_t)b * N + (active ? n : 0);
+    for (int64_t g0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) & ~31ll; g0 < total; g0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t gid = g0 + lane;
+        const bool active = gid < total;
+        bool maybe = false;
         float qx = 0.f, qy = 0.f, qz = 0.f;
-        if (active) load_query(xyz, rays, z, gid, K, qx, qy, qz);
-        Best4 mine; best_init(mine);
-        float myB = 0.f;
-        float hint = CUDART_INF_F, hx = 0.f, hy = 0.f, hz = 0.f;      // warp-uniform
-        const unsigned act_mask = __ballot_sync(0xffffffffu, active);
-        for (int qi = 0; qi < 32; ++qi) {
-            if (!((act_mask >> qi) & 1u)) continue;
-            const float ux = __shfl_sync(0xffffffffu, qx, qi), uy = __shfl_sync(0xffffffffu, qy, qi), uz = __shfl_sync(0xffffffffu, qz, qi);
-            const int cx = (int)floorf((ux - h.ox) * inv_cell);
-            const int cy = (int)floorf((uy - h.oy) * inv_cell);
-            const int cz = (int)floorf((uz - h.oz) * inv_cell);
-            const int ex = cx + GRID_R, ey = cy + GRID_R, ez = cz + GRID_R;
-            bool maybe = ex >= 0 && ex < ex_n && ey >= 0 && ey < ey_n && ez >= 0 && ez < ez_n;
+        if (active) {
+            const int b = (int)(gid / N);
+            const GridHeader h = *(const GridHeader*)(ws + (int64_t)b * frame_bytes);
+            const uint8_t* __restrict__ flags = (const uint8_t*)(ws + (int64_t)b * frame_bytes + GRID_OFF_FLAGS);
+            load_query(xyz, rays, z, gid, K, qx, qy, qz);
+            const float inv_cell = 1.0f / h.cell;
+            const int ex = (int)floorf((qx - h.ox) * inv_cell) + GRID_R, ey = (int)floorf((qy - h.oy) * inv_cell) + GRID_R,
+                      ez = (int)floorf((qz - h.oz) * inv_cell) + GRID_R;
+            const int ex_n = h.nx + 2 * GRID_R, ey_n = h.ny + 2 * GRID_R, ez_n = h.nz + 2 * GRID_R;
+            maybe = ex >= 0 && ex < ex_n && ey >= 0 && ey < ey_n && ez >= 0 && ez < ez_n;
             if (maybe) maybe = __ldg(flags + ((int64_t)ez * ey_n + ey) * ex_n + ex) != 0;
-            if (!maybe) { hint = CUDART_INF_F; continue; }
-            float B = b0;
-            if (hint < 1e30f) {
-                const float sx = ux - hx, sy = uy - hy, sz = uz - hz;
-                const float r = hint + sqrtf(sx * sx + sy * sy + sz * sz);
-                B = r * r * (1.0f + 1e-4f);
+            if (!maybe) {            // no vertex within the box radius (>= threshold): final outputs of an invalid point
+                o.xyz_cano[gid * 3] = 0.f; o.xyz_cano[gid * 3 + 1] = 0.f; o.xyz_cano[gid * 3 + 2] = 0.f;
+                o.valid[gid] = 0;
+                if (o.idx) ((int4*)o.idx)[gid] = make_int4(-1, -1, -1, -1);
+                if (o.dist) ((float4*)o.dist)[gid] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (o.qw) ((float4*)o.qw)[gid] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (o.sigma) o.sigma[gid] = -1e5f;
+                if (o.rgb) { o.rgb[gid * 3] = 0.f; o.rgb[gid * 3 + 1] = 0.f; o.rgb[gid * 3 + 2] = 0.f; }
             }
-            const float Bm = fminf(B * 1.001f, box_r2 * 1.01f);
-            Best4 lb; best_init(lb);
-            // each lane owns rows `lane` and `lane+32` of the 49-row box: [s,e) ranges in the sorted list
-            int rs[2] = {0, 0}, rc[2] = {0, 0};
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, maybe);
+        if (mask) {
+            const int leader = __ffs(mask) - 1;
+            unsigned base = 0;
+            if (lane == leader) base = atomicAdd(&qws->n_work, (unsigned)__popc(mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (maybe) work[base + __popc(mask & ((1u << lane) - 1))] = make_float4(qx, qy, qz, __int_as_float((int)gid));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_search_kernel(int64_t N, const float* __restrict__ verts, int V, const char* __restrict__ ws,
+                  int64_t frame_bytes, QueryWs* __restrict__ qws, const float* __restrict__ ober2cano,
+                  const float* __restrict__ lbsw, int J, float thr, UnposeOut o)
+{
+    const float4* __restrict__ work = (const float4*)(qws + 1);
+    const int lane = threadIdx.x & 31;
+    const unsigned n_work = qws->n_work;
+    const unsigned n_chunks = (n_work + 31) / 32;
+    const float thr2 = thr * thr * (1.0f + 1e-5f);   // prune only what is invalid beyond rounding doubt
+    for (;;) {
+        unsigned chunk = 0;
+        if (lane == 0) chunk = atomicAdd(&qws->next_chunk, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= n_chunks) break;
+        const unsigned e = chunk * 32 + lane;
+        const bool active = e < n_work;
+        float qx = 0.f, qy = 0.f, qz = 0.f;
+        int64_t gid = 0;
+        if (active) { const float4 w = __ldg(work + e); qx = w.x; qy = w.y; qz = w.z; gid = (int64_t)__float_as_int(w.w); }
+        const int b = (int)(gid / N);
+        const char* base = ws + (int64_t)b * frame_bytes;
+        const GridHeader h = *(const GridHeader*)base;
+        const int* __restrict__ cell_start = (const int*)(base + GRID_OFF_START);
+        const float4* __restrict__ sorted = (const float4*)(base + GRID_OFF_SORTED);
+        const float inv_cell = 1.0f / h.cell;
+        const float box_r = GRID_R * h.cell * (1.0f - 1e-4f);
+        const float box_r2 = box_r * box_r;
+        // cold bound: slightly beyond the threshold so that a 4th neighbour a little farther than a
+        // valid nearest one (d0 < thr <= d4) is still found without the exhaustive fallback
+        float B = fminf(box_r2, thr * thr * (KNN_B0_SCALE * KNN_B0_SCALE));
+        const int cx = (int)floorf((qx - h.ox) * inv_cell), cy = (int)floorf((qy - h.oy) * inv_cell),
+                  cz = (int)floorf((qz - h.oz) * inv_cell);
+        const bool own = active && cx >= 0 && cx < h.nx && cy >= 0 && cy < h.ny && cz >= 0 && cz < h.nz;
+        Best4 mine; best_init(mine);
+        if (own) {                                // own cell first: usually yields four candidates and a tight bound
+            const int c = (cz * h.ny + cy) * h.nx + cx;
+            const int s = __ldg(cell_start + c), e1 = __ldg(cell_start + c + 1);
+            for (int p = s; p < e1; ++p) {
+                const float4 v = __ldg(sorted + p);
+                const float d2 = dist2_rn(qx, qy, qz, v.x, v.y, v.z);
+                if (key_less(d2, __float_as_int(v.w), mine.d[3], mine.i[3])) best_push_any(mine, d2, __float_as_int(v.w));
+            }
+        }
+        {   // neighbouring lanes are neighbouring samples of a ray: d4(q) <= d4(q') + |q - q'| tightens the
+            // bound of the lanes whose own cell held fewer than four vertices
+            float u = active ? sqrtf(fminf(mine.d[3], B)) : CUDART_INF_F;
 #pragma unroll
-            for (int batch = 0; batch < 2; ++batch) {
-                const int r = lane + 32 * batch;
-                if (r < (2 * GRID_R + 1) * (2 * GRID_R + 1)) {
-                    const int dz = r / (2 * GRID_R + 1) - GRID_R, dy = r % (2 * GRID_R + 1) - GRID_R;
-                    const int gz = cz + dz, gy = cy + dy;
-                    if (gz >= 0 && gz < h.nz && gy >= 0 && gy < h.ny) {
-                        const float gapz = dz == 0 ? 0.f : (dz > 0 ? (h.oz + gz * h.cell) - uz : uz - (h.oz + (gz + 1) * h.cell));
-                        const float gapy = dy == 0 ? 0.f : (dy > 0 ? (h.oy + gy * h.cell) - uy : uy - (h.oy + (gy + 1) * h.cell));
-                        const float g2 = (gapz > 0.f ? gapz * gapz : 0.f) + (gapy > 0.f ? gapy * gapy : 0.f);
-                        if (g2 <= Bm) {
-                            const float w = sqrtf(Bm - g2) + 1e-3f * h.cell;
-                            int x0 = max(cx - GRID_R, (int)floorf((ux - w - h.ox) * inv_cell));
-                            int x1 = min(cx + GRID_R, (int)floorf((ux + w - h.ox) * inv_cell));
-                            x0 = max(x0, 0); x1 = min(x1, h.nx - 1);
-                            if (x0 <= x1) {
-                                const int row = (gz * h.ny + gy) * h.nx;
-                                rs[batch] = __ldg(cell_start + row + x0);
-                                rc[batch] = __ldg(cell_start + row + x1 + 1) - rs[batch];
-                            }
+            for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+                for (int dl = -1; dl <= 1; dl += 2) {
+                    const int src = min(31, max(0, lane + dl));
+                    const float ou = __shfl_sync(0xffffffffu, u, src);
+                    const float ox = __shfl_sync(0xffffffffu, qx, src), oy = __shfl_sync(0xffffffffu, qy, src), oz = __shfl_sync(0xffffffffu, qz, src);
+                    const int ob = __shfl_sync(0xffffffffu, b, src);
+                    const bool oact = __shfl_sync(0xffffffffu, (int)active, src) != 0;
+                    if (oact && ob == b) {
+                        const float sx = qx - ox, sy = qy - oy, sz = qz - oz;
+                        u = fminf(u, (ou + sqrtf(sx * sx + sy * sy + sz * sz)) * (1.0f + 1e-4f));
+                    }
+                }
+            }
+            B = fminf(B, u * u * (1.0f + 1e-4f));
+        }
+        if (active) {
+            float Bm = fminf(fminf(B, mine.d[3]) * 1.001f, box_r2 * 1.01f);
+            // position of the query inside its cell -> exact slab gaps per row
+            const float fy = qy - (h.oy + cy * h.cell), fz = qz - (h.oz + cz * h.cell);
+            for (int r = 0; r < (2 * GRID_R + 1) * (2 * GRID_R + 1); ++r) {
+                const int ring = c_row_ring[r];
+                if (ring >= 2) {                  // nearest row of ring k is at least (k-1) cells away
+                    const float rg = (float)(ring - 1) * h.cell;
+                    if (rg * rg > Bm) break;
+                }
+                const int dy = c_row_dy[r], dz = c_row_dz[r];
+                const int gy = cy + dy, gz = cz + dz;
+                if (gz < 0 || gz >= h.nz || gy < 0 || gy >= h.ny) continue;
+                const float gapy = dy == 0 ? 0.f : (dy > 0 ? (float)dy * h.cell - fy : fy - (float)(dy + 1) * h.cell);
+                const float gapz = dz == 0 ? 0.f : (dz > 0 ? (float)dz * h.cell - fz : fz - (float)(dz + 1) * h.cell);
+                const float g2 = (gapy > 0.f ? gapy * gapy : 0.f) + (gapz > 0.f ? gapz * gapz : 0.f);
+                if (g2 > Bm) continue;
+                const float w = sqrtf(Bm - g2) + 1e-3f * h.cell;
+                int x0 = max(cx - GRID_R, (int)floorf((qx - w - h.ox) * inv_cell));
+                int x1 = min(cx + GRID_R, (int)floorf((qx + w - h.ox) * inv_cell));
+                x0 = max(x0, 0); x1 = min(x1, h.nx - 1);
+                if (x0 > x1) continue;
+                const int row = (gz * h.ny + gy) * h.nx;
+                // candidate ranges of the row; the own cell (row 0) was scanned above: skip it
+                int s0 = __ldg(cell_start + row + x0), e0r = 0, s1 = 0, e1 = __ldg(cell_start + row + x1 + 1);
+                if (r == 0 && own && cx >= x0 && cx <= x1) { e0r = __ldg(cell_start + row + cx); s1 = __ldg(cell_start + row + cx + 1); }
+                else { e0r = e1; s1 = e1; }
+                for (int part = 0; part < 2; ++part) {
+                    const int ps = part ? s1 : s0, pe = part ? e1 : e0r;
+                    for (int p = ps; p < pe; ++p) {
+                        const float4 v = __ldg(sorted + p);
+                        const float d2 = dist2_rn(qx, qy, qz, v.x, v.y, v.z);
+                        if (key_less(d2, __float_as_int(v.w), mine.d[3], mine.i[3])) {
+                            best_push_any(mine, d2, __float_as_int(v.w));
+                            Bm = fminf(Bm, mine.d[3] * 1.001f);
                         }
                     }
                 }
             }
-            // flatten all candidates of the 49 ranges over the 32 lanes: inclusive scan of the per-lane
-            // counts, then every lane maps its flat index back to (owner lane, offset) by a shuffle search
-            const int cnt = rc[0] + rc[1];
-            int pre = cnt;
-#pragma unroll
-            for (int ofs = 1; ofs < 32; ofs <<= 1) {
-                const int nb = __shfl_up_sync(0xffffffffu, pre, ofs);
-                if (lane >= ofs) pre += nb;
-            }
-            const int total = __shfl_sync(0xffffffffu, pre, 31);
-            for (int j0 = 0; j0 < total; j0 += 32) {
-                const int j = j0 + lane;
-                int rr = 0;
-#pragma unroll
-                for (int step = 16; step >= 1; step >>= 1) {
-                    const int t = __shfl_sync(0xffffffffu, pre, rr + step - 1);
-                    if (t <= j) rr += step;
-                }
-                rr = min(rr, 31);
-                const int pre_r = __shfl_sync(0xffffffffu, pre, rr), cnt_r = __shfl_sync(0xffffffffu, cnt, rr);
-                const int c0_r = __shfl_sync(0xffffffffu, rc[0], rr);
-                const int s0_r = __shfl_sync(0xffffffffu, rs[0], rr), s1_r = __shfl_sync(0xffffffffu, rs[1], rr);
-                if (j < total) {
-                    const int off = j - (pre_r - cnt_r);
-                    const int p = off < c0_r ? s0_r + off : s1_r + (off - c0_r);
-                    const float4 v = __ldg(sorted + p);
-                    best_push_any(lb, dist2_rn(ux, uy, uz, v.x, v.y, v.z), __float_as_int(v.w));
-                }
-            }
-            Best4 g;
-            warp_merge4(lb, g);
-            if (g.d[0] < thr2 && g.d[3] < 1e30f) { hint = sqrtf(g.d[3]); hx = ux; hy = uy; hz = uz; }
-            else hint = CUDART_INF_F;
-            if (lane == qi) { mine = g; myB = B; }
         }
-        bool found = false, redo = false;
-        if (active && mine.d[0] < thr2) {              // may be valid: need the exact 4-NN
-            if (mine.d[3] <= myB && mine.d[3] <= box_r2) found = true;
-            else redo = true;                          // rare: 4th neighbour not provably inside the scanned ball
-        }
+        // the walk saw every vertex within sqrt(min(B, box_r2)): four of them => the 4-NN are exact
+        const bool exact4 = active && mine.d[3] <= B && mine.d[3] <= box_r2;
+        const bool near_ = active && mine.d[0] < thr2;          // may be valid: needs the exact 4-NN
+        bool found = near_ && exact4;
+        const bool redo = near_ && !exact4;            // rare: 4th neighbour not provably inside the scanned ball
         unsigned redo_mask = __ballot_sync(0xffffffffu, redo);
-        while (redo_mask) {                            // exhaustive rescan, still warp-cooperative
+        while (redo_mask) {                            // exhaustive rescan, warp-cooperative
             const int qi = __ffs(redo_mask) - 1;
             redo_mask &= redo_mask - 1;
             const float ux = __shfl_sync(0xffffffffu, qx, qi), uy = __shfl_sync(0xffffffffu, qy, qi), uz = __shfl_sync(0xffffffffu, qz, qi);
+            const int ub = __shfl_sync(0xffffffffu, b, qi);
+            const float4* __restrict__ srt = (const float4*)(ws + (int64_t)ub * frame_bytes + GRID_OFF_SORTED);
             Best4 lb; best_init(lb);
             for (int p = lane; p < V; p += 32) {
-                const float4 v = __ldg(sorted + p);
+                const float4 v = __ldg(srt + p);
                 best_push_any(lb, dist2_rn(ux, uy, uz, v.x, v.y, v.z), __float_as_int(v.w));
             }
             Best4 g;
@@ -538,8 +596,13 @@ extern "C" int an_vertex_grid_build(const float* verts, int B, int V, float cell
     return AN_OK;
 }
 
+extern "C" int64_t an_knn_query_ws_bytes(int B, int64_t N)
+{
+    return (B > 0 && N > 0) ? (int64_t)sizeof(QueryWs) + (int64_t)B * N * (int64_t)sizeof(float4) : 0;
+}
+
 extern "C" int an_knn_unpose_fwd(const float* xyz, const float* rays, const float* z, int B, int R, int K,
-                                 int64_t N, const float* verts, int V, const void* grid_ws,
+                                 int64_t N, const float* verts, int V, const void* grid_ws, void* query_ws,
                                  const float* ober2cano, const float* lbs_weights, int J,
                                  float dis_threshold, int mode,
                                  float* xyz_cano, uint8_t* valid, int32_t* idx, float* dist, float* qw,
@@ -564,13 +627,22 @@ extern "C" int an_knn_unpose_fwd(const float* xyz, const float* rays, const floa
         knn_unpose_brute_kernel<<<grid, KNN_THREADS, smem, (cudaStream_t)stream>>>(
             xyz, rays, z, K, N, verts, V, ober2cano, lbs_weights, J, dis_threshold, o);
     } else if (mode == 1) {
-        if (!grid_ws) return AN_ERR_ARG;
-        const int64_t cap = ((int64_t)sms * 16 + B - 1) / B;
-        if (bx > cap) bx = cap;
-        dim3 grid((unsigned)bx, (unsigned)B);
-        knn_unpose_grid_kernel<<<grid, KNN_THREADS, 0, (cudaStream_t)stream>>>(
-            xyz, rays, z, K, N, verts, V, (const char*)grid_ws, grid_frame_bytes(V), ober2cano, lbs_weights, J,
-            dis_threshold, o);
+        if (!grid_ws || !query_ws) return AN_ERR_ARG;
+        if (((uintptr_t)query_ws) & 15) return AN_ERR_ALIGN;
+        QueryWs* qws = (QueryWs*)query_ws;
+        cudaError_t e = cudaMemsetAsync(qws, 0, sizeof(QueryWs), (cudaStream_t)stream);
+        if (e != cudaSuccess) return (int)e;
+        const int64_t total = (int64_t)B * N;
+        int64_t cb = (total + KNN_THREADS - 1) / KNN_THREADS;
+        if (cb > (int64_t)sms * 32) cb = (int64_t)sms * 32;
+        knn_classify_kernel<<<(unsigned)cb, KNN_THREADS, 0, (cudaStream_t)stream>>>(
+            xyz, rays, z, K, N, total, (const char*)grid_ws, grid_frame_bytes(V), qws, o);
+        AN_CHECK_LAUNCH();
+        // persistent search CTAs pull 32-query chunks from the work list (its length is device-side)
+        int64_t sb = (total + KNN_THREADS - 1) / KNN_THREADS;
+        if (sb > (int64_t)sms * 8) sb = (int64_t)sms * 8;
+        knn_search_kernel<<<(unsigned)sb, KNN_THREADS, 0, (cudaStream_t)stream>>>(
+            N, verts, V, (const char*)grid_ws, grid_frame_bytes(V), qws, ober2cano, lbs_weights, J, dis_threshold, o);
     } else return AN_ERR_ARG;
     AN_CHECK_LAUNCH();
     return AN_OK;

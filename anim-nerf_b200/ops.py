@@ -81,7 +81,10 @@ def knn_unpose(verts, ober2cano, lbs_weights, dis_threshold, xyz=None, rays=None
     out["count"] = torch.zeros(1, device=dev, dtype=torch.int32) if compact else None
     if mode == 1 and grid is None:
         grid = vertex_grid(verts, dis_threshold)
-    call("an_knn_unpose_fwd", ptr(xyz), ptr(rays), ptr(z), B, R, K, N, ptr(verts), V, ptr(grid),
+    qws = None
+    if mode == 1:       # work list of the queries that survive the occupancy test (scratch, freed on return)
+        qws = torch.empty(_lib.load().an_knn_query_ws_bytes(B, N), device=dev, dtype=torch.uint8)
+    call("an_knn_unpose_fwd", ptr(xyz), ptr(rays), ptr(z), B, R, K, N, ptr(verts), V, ptr(grid), ptr(qws),
          ptr(ober2cano), ptr(lbs_weights), lbs_weights.shape[1], float(dis_threshold), int(mode),
          ptr(out["xyz_cano"]), ptr(out["valid"]), ptr(out["idx"]), ptr(out["dist"]), ptr(out["qw"]),
          ptr(sigma), ptr(rgb), ptr(out["cidx"]), ptr(out["count"]), stream())

@@ -76,9 +76,12 @@ int an_vertex_grid_build(const float* verts, int B, int V, float cell, void* ws,
  *   Euclidean; qw (B*N,4) normalised blend weights;  for invalid points sigma (B*N) := -1e5
  *   and rgb (B*N,3) := 0 when those pointers are given;  cidx: compacted list of valid point
  *   ids (global id b*N+n), *count incremented atomically (caller zeroes it).
- * ober2cano (B,V,4,4) row-major (rows 0-2 used), lbs_weights (V,J).                        */
+ * ober2cano (B,V,4,4) row-major (rows 0-2 used), lbs_weights (V,J).
+ * query_ws (mode 1 only, else NULL): scratch of an_knn_query_ws_bytes(B,N) bytes, 16-byte
+ * aligned, holding the work list of the queries that survive the occupancy test.           */
+int64_t an_knn_query_ws_bytes(int B, int64_t N);
 int an_knn_unpose_fwd(const float* xyz, const float* rays, const float* z, int B, int R, int K,
-                      int64_t N, const float* verts, int V, const void* grid_ws,
+                      int64_t N, const float* verts, int V, const void* grid_ws, void* query_ws,
                       const float* ober2cano, const float* lbs_weights, int J,
                       float dis_threshold, int mode,
                       float* xyz_cano, uint8_t* valid, int32_t* idx, float* dist, float* qw,
