@@ -162,8 +162,9 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
             if (leader) bulk_wait_read0();
             named_bar_sync(1 + t, 128);
             {   // dpre_c = (Wr^T dpre_rgb) * [c > 0]  -> A image (2 chunks) = dY of the colour layer
-                const uint4 cm = *(const uint4*)(st_tile + ST_CMASK + row * 16);
-                const uint32_t cmw[4] = {cm.x, cm.y, cm.z, cm.w};
+                uint32_t cmw[4];
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) cmw[cb] = *(const uint32_t*)(st_tile + ST_CMASK + cb * 512 + row * 4);
 #pragma unroll
                 for (int cb = 0; cb < 4; ++cb) {
                     float f[32];
@@ -244,9 +245,9 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                 else { mask_layer = 9 - s; dy_off = DY_H + (int64_t)(9 - s) * 65536; }     // s = 7,8,9 -> h3,h2,h1
                 uint32_t mw[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
                 if (mask_layer >= 0) {
-                    const uint4* mp = (const uint4*)(st_tile + ST_MASK + mask_layer * 4096 + row * 32);
-                    const uint4 m0 = mp[0], m1 = mp[1];
-                    mw[0] = m0.x; mw[1] = m0.y; mw[2] = m0.z; mw[3] = m0.w; mw[4] = m1.x; mw[5] = m1.y; mw[6] = m1.z; mw[7] = m1.w;
+                    const uint8_t* mp = st_tile + ST_MASK + mask_layer * 4096 + row * 4;     // [block][row] words
+#pragma unroll
+                    for (int cb = 0; cb < 8; ++cb) mw[cb] = *(const uint32_t*)(mp + cb * 512);
                 }
                 uint32_t va[32], vb[32];
                 tmem_ld32(tm, va);

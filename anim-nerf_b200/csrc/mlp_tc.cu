@@ -33,8 +33,10 @@ constexpr uint32_t SM_ACT = 0;                     // [2 tiles][4 chunks][128 ro
 constexpr uint32_t SM_ENC = 131072;                // [2 tiles][128 rows x 128 B]
 constexpr uint32_t SM_WST = 163840;                // [NSTAGE][32 KB]
 constexpr uint32_t SM_BAR = SM_WST + NSTAGE * 32768;   // 229376
-constexpr uint32_t SM_BYTES = SM_BAR + 128;
-constexpr uint32_t SM_ALLOC = SM_BYTES + 1024;     // slack for manual 1024-B alignment
+constexpr uint32_t SM_BIASBUF = SM_BAR + 128;      // [2 tiles][256 fp32]: bias of the layer that writes the accumulators next
+constexpr uint32_t SM_BYTES = SM_BIASBUF + 2048;
+constexpr uint32_t SM_ALLOC = SM_BYTES + 896;      // slack for manual 1024-B alignment (the base is at least 128-B aligned)
+static_assert(SM_ALLOC <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
 
 #ifdef AN_MLP_TRACE
 // debug timeline (tools/trace_mlp.py): CTA 0, one region of 64 Ki entries per role, plain stores
@@ -61,8 +63,8 @@ constexpr int64_t ST_ENC = 0;                      // 16 KB image
 constexpr int64_t ST_H = 16384;                    // h1..h8: 8 x 64 KB images
 constexpr int64_t ST_F = ST_H + 8 * 65536;         // 64 KB
 constexpr int64_t ST_C = ST_F + 65536;             // 32 KB (2 chunks)
-constexpr int64_t ST_MASK = ST_C + 32768;          // h1..h8 masks: 8 x (128 rows x 32 B)
-constexpr int64_t ST_CMASK = ST_MASK + 8 * 4096;   // 128 rows x 16 B
+constexpr int64_t ST_MASK = ST_C + 32768;          // h1..h8 masks: 8 x [8 blocks][128 rows] x 4 B
+constexpr int64_t ST_CMASK = ST_MASK + 8 * 4096;   // [4 blocks][128 rows] x 4 B
 constexpr int64_t ST_TILE = ST_CMASK + 2048;       // 673 792
 }  // namespace mlp
 
@@ -74,7 +76,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
 {
     using namespace mlp;
     using namespace tc;
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sbase - raw);
@@ -169,6 +171,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
         const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
         const uint32_t my_act = bar_act + 8 * t, my_acc = bar_acc + 8 * t;
         const float* small = (const float*)(packed + SMALL_OFF);
+        uint8_t* bias_s = sgen + SM_BIASBUF + t * 1024;
         const bool leader = (e & 127) == 0;          // issues the tile's TMA stores
         uint32_t acc_phase = 0;
         TRACE_DECL;
@@ -238,22 +241,17 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 // colour layer leaves alone.  The MMAs always accumulate; no bias add in the epilogue.
                 const int nb_lo = g < 8 ? g + 1 : (g == 8 ? 9 : 0);       // bias layer for blocks 0..3
                 const int nb_hi = g < 8 ? g + 1 : 0;                      // bias layer for blocks 4..7
-                const float* bias_lo = small + SM_BIAS + nb_lo * 256;
-                const float* bias_hi = small + SM_BIAS + nb_hi * 256;
-                uint32_t bq[32];
-#pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {   // first block's bias is fetched before the accumulator wait
-                    const uint4 b4 = __ldg((const uint4*)bias_lo + c4);
-                    bq[4 * c4] = b4.x; bq[4 * c4 + 1] = b4.y; bq[4 * c4 + 2] = b4.z; bq[4 * c4 + 3] = b4.w;
-                }
+                // each thread fetches two of the 256 values now (latency hidden behind the accumulator wait);
+                // they are staged in shared memory and read back as broadcast 128-bit loads per block
+                const int bl = (2 * (e & 127) < 128) ? nb_lo : nb_hi;
+                const float2 bmine = __ldg((const float2*)(small + SM_BIAS + bl * 256) + (e & 127));
                 if (leader) TRACE(2 + t, 0, g, 0);
                 mbar_wait(my_acc, acc_phase); acc_phase ^= 1u;
                 if (leader) TRACE(2 + t, 1, g, 0);
                 tc_fence_after();
-                if (TRAIN && g > 0) {     // act image of layer g-1 is being stored: wait before overwriting it
-                    if (leader) bulk_wait_read0();
-                    named_bar_sync(1 + t, 128);
-                }
+                if (TRAIN && g > 0 && leader) bulk_wait_read0();   // act image of layer g-1 is being stored: wait before overwriting it
+                ((float2*)bias_s)[e & 127] = bmine;
+                named_bar_sync(1 + t, 128);
                 if (leader) TRACE(2 + t, 2, g, 0);
                 uint32_t va[32], vb[32];
                 tmem_ld32(tm, va);
@@ -265,14 +263,14 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                         uint32_t (&v)[32] = half ? vb : va;
                         tmem_ld_wait();
                         if (blk + 1 < nblk) tmem_ld32(tm + (blk + 1) * 32, half ? va : vb);   // prefetch the next block
-                        tmem_st32(tm + blk * 32, bq);                                          // bias for the next writer
-                        if (blk + 1 < nblk) {
-                            const float* bn = ((blk + 1) < 4 ? bias_lo : bias_hi) + (blk + 1) * 32;
+                        {   // bias for the next writer of these columns
+                            uint32_t bq[32];
 #pragma unroll
                             for (int c4 = 0; c4 < 8; ++c4) {
-                                const uint4 b4 = __ldg((const uint4*)bn + c4);
+                                const uint4 b4 = *((const uint4*)(bias_s + blk * 128) + c4);
                                 bq[4 * c4] = b4.x; bq[4 * c4 + 1] = b4.y; bq[4 * c4 + 2] = b4.z; bq[4 * c4 + 3] = b4.w;
                             }
+                            tmem_st32(tm + blk * 32, bq);
                         }
                         // fp32 heads (sigma from h8 = relu(layer 8), rgb from c = relu(colour layer))
                         if (g == 7) {
@@ -301,11 +299,16 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                             if (TRAIN && g != 8) {
                                 // 1-bit ReLU mask from the sign bits: one funnel shift per column; bit (31-c) of the
                                 // word <-> column c of the block (tc::mask_bit_of_col)
-                                uint32_t neg = 0;
+                                // (four independent 8-column chains, then merged, so the shifts are not one serial chain)
+                                uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;
 #pragma unroll
-                                for (int c = 0; c < 32; ++c) neg = __funnelshift_l(v[c], neg, 1);
-                                if (g <= 7) *(uint32_t*)(st_tile + ST_MASK + g * 4096 + row * 32 + blk * 4) = ~neg;
-                                else *(uint32_t*)(st_tile + ST_CMASK + row * 16 + blk * 4) = ~neg;
+                                for (int c = 0; c < 8; ++c) {
+                                    n0 = __funnelshift_l(v[c], n0, 1); n1 = __funnelshift_l(v[8 + c], n1, 1);
+                                    n2 = __funnelshift_l(v[16 + c], n2, 1); n3 = __funnelshift_l(v[24 + c], n3, 1);
+                                }
+                                const uint32_t neg = (((n0 * 256u + n1) * 256u + n2) * 256u) + n3;
+                                if (g <= 7) *(uint32_t*)(st_tile + ST_MASK + g * 4096 + blk * 512 + row * 4) = ~neg;     // [block][row]: coalesced
+                                else *(uint32_t*)(st_tile + ST_CMASK + blk * 512 + row * 4) = ~neg;
                             }
                             uint32_t w[16];
                             if (g == 8) {
@@ -323,7 +326,9 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                         }
                     }
                 }
+                if (leader) TRACE(2 + t, 4, g, 0);
                 tmem_st_wait();
+                if (leader) TRACE(2 + t, 5, g, 0);
                 if (g == 9) {
                     if (in) {
                         sigma_out[id] = sig + __ldg(small + SM_BS);
@@ -342,6 +347,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                     fence_proxy_async();
                     if (TRAIN) {
                         named_bar_sync(1 + t, 128);
+                        if (leader) TRACE(2 + t, 6, g, 0);
                         if (leader) {
                             bulk_s2g(st_tile + (g == 8 ? ST_F : ST_H + (int64_t)g * 65536), act_s, 65536);
                             bulk_commit();

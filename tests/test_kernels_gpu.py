@@ -241,8 +241,8 @@ def test_mlp_stash_images_match_layerwise_oracle():
             img = torch.cat([_unswizzle(stash[base + 16384 + l * 65536 + c * 16384:][:16384], 128) for c in range(4)], 1)[:rows].cpu()
             err = (img - hs[l][sl]).abs().max().item()
             assert err < 3e-2 * max(1.0, hs[l][sl].abs().max().item()), "h%d tile %d err %g" % (l + 1, tile, err)
-            m = stash[base + 16384 + 8 * 65536 + 65536 + 32768 + l * 4096:][:4096].view(torch.int32).reshape(128, 8)[:rows].cpu()
-            # mask bit layout per 32-column block: bit (31-c) <-> column c
+            m = stash[base + 16384 + 8 * 65536 + 65536 + 32768 + l * 4096:][:4096].view(torch.int32).reshape(8, 128).T[:rows].cpu()
+            # mask words are stored [block][row]; bit layout per 32-column block: bit (31-c) <-> column c
             col = torch.arange(32)
             bits = ((m[:, :, None] >> (31 - col)) & 1).reshape(rows, 256).bool()
             assert (bits == (img > 0)).all(), "mask h%d" % (l + 1)

@@ -39,7 +39,7 @@ for t in (0, 1):
     m = role == 2 + t
     c, ee, aa = clk[m], e[m], a[m]
     o = np.argsort(c, kind="stable"); c, ee, aa = c[o], ee[o], aa[o]
-    wait = {}; drain = {}; body = {}; gap = {}
+    wait = {}; drain = {}; body = {}; gap = {}; loop = {}; stw = {}; nbar = {}
     last = {}; prev_end = None
     for ci, ei, gi in zip(c, ee, aa):
         if ei == 0:
@@ -48,10 +48,14 @@ for t in (0, 1):
         elif ei == 1: wait.setdefault(gi, []).append(ci - last[0]); last[1] = ci
         elif ei == 2: drain.setdefault(gi, []).append(ci - last[1]); last[2] = ci
         elif ei == 3: body.setdefault(gi, []).append(ci - last[2]); prev_end = ci
+        elif ei == 4: loop.setdefault(gi, []).append(ci - last[2]); last[4] = ci
+        elif ei == 5: stw.setdefault(gi, []).append(ci - last[4]); last[5] = ci
+        elif ei == 6: nbar.setdefault(gi, []).append(ci - last[5])
     print("tile %d  layer: wait_acc / store_drain / epilogue_body / gap-before(prologue at g=0)   [median clk]" % t)
     for g in range(10):
-        print("   g=%d  %8.0f %8.0f %8.0f %8.0f" % (g, np.median(wait.get(g, [0])), np.median(drain.get(g, [0])),
-                                                   np.median(body.get(g, [0])), np.median(gap.get(g, [0]))))
+        print("   g=%d  %8.0f %8.0f %8.0f %8.0f   | block loop %6.0f  st-wait %5.0f  fence+named-bar %5.0f" % (
+            g, np.median(wait.get(g, [0])), np.median(drain.get(g, [0])), np.median(body.get(g, [0])), np.median(gap.get(g, [0])),
+            np.median(loop.get(g, [0])), np.median(stw.get(g, [0])), np.median(nbar.get(g, [0]))))
 # MMA issuer: wait for act (ev0->ev1), per-chunk full waits
 m = role == 1
 c, ee, aa, bb = clk[m], e[m], a[m], b[m]
