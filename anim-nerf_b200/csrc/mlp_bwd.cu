@@ -4,8 +4,9 @@
 //  1. mlp_bwd_dgrad_kernel -- same skeleton as the forward (persistent CTA, 2 x 128-row tiles,
 //     TMA-streamed W^T chunk images, accumulators in TMEM).  The activation-gradient image dY
 //     stays in shared memory as the next layer's A operand; ReLU masks come from the forward's
-//     1-bit stash; the sigma head's gradient is injected in the epilogue of the `final` layer;
-//     the encoding gradients (two N=64 GEMMs: layer 5's encoding part and layer 1) are folded
+//     1-bit stash.  Both heads run on the tensor cores (mlp_layout.cuh): step 0 is the rgb head
+//     (K = 16: d rgb_pre -> d c), step 1 the fused head layer (K = 144: [d c_pre | d sigma] -> d h8).
+//     The encoding gradients (two N=64 GEMMs: layer 5's encoding part and layer 1) are folded
 //     to d(xyz) analytically in the epilogue.  Every pre-activation gradient image is also
 //     streamed to HBM scratch (TMA bulk store) for the weight-gradient kernel.
 //  2. mlp_bwd_wgrad_kernel -- dW_g = dY_g^T X_g as K-streaming GEMMs over the points: both
@@ -13,27 +14,13 @@
 //     (no transposes).  One CTA owns one (layer, point-split) and keeps the full dW_g tile
 //     (2 x 128 x N fp32) in TMEM across its whole K loop; bias gradients are column sums of the
 //     dY image taken from shared memory by the otherwise idle warps.  HBM-bound by construction
-//     (128 FLOP/B < ridge 214 FLOP/B): ~9.6 KB read per point.
-//  3. mlp_bwd_heads_kernel -- sigma/rgb head weight gradients (dot-product heads, CUDA cores).
+//     (128 FLOP/B < ridge 214 FLOP/B): ~9.4 KB read per point.  The head-layer and rgb jobs run
+//     transposed (A = X, B = dY) because their dY is narrower than one UMMA M.
+//  3. mlp_unfuse_grad_kernel (mlp_pack.cu) -- chain rule from the fused head layer's dW', db' to
+//     xyz_encoding_final / dir_encoding.
 #include "common.cuh"
 #include "mlp_layout.cuh"
 #include "tc_common.cuh"
-
-namespace mlp {
-// forward stash layout (must match mlp_tc.cu)
-constexpr int64_t ST_ENC = 0;
-constexpr int64_t ST_H = 16384;
-constexpr int64_t ST_F = ST_H + 8 * 65536;
-constexpr int64_t ST_C = ST_F + 65536;
-constexpr int64_t ST_MASK = ST_C + 32768;
-constexpr int64_t ST_CMASK = ST_MASK + 8 * 4096;
-constexpr int64_t ST_TILE = ST_CMASK + 2048;
-// dY scratch layout per 128-row tile
-constexpr int64_t DY_G9 = 0;                        // dpre_c   (128 cols, 32 KB)
-constexpr int64_t DY_G8 = 32768;                    // df       (64 KB)
-constexpr int64_t DY_H = DY_G8 + 65536;             // dpre of layer g (0..7) at DY_H + g*64 KB
-constexpr int64_t DY_TILE = DY_H + 8 * 65536;       // 622 592
-}  // namespace mlp
 
 namespace {
 constexpr int THREADS = 320;
@@ -120,8 +107,8 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                             tc_fence_after();
                             const uint32_t wb = sbase + SM_WST + st * 32768u;
                             const uint32_t ab = sbase + SM_ACT + t * 65536u + kc * 16384u;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
+                            const int nk = bs_ksteps(s, kc);
+                            for (int k = 0; k < nk; ++k)
                                 umma(tmem_base + t * 256u, make_desc(ab + k * 32u, 16, 1024),
                                      make_desc(wb + k * 32u, 16, 1024), idesc, (kc > 0 || k > 0) ? 1u : 0u);
                             umma_commit(bar_empty + 8 * st);
@@ -161,32 +148,13 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
             // previous iteration's bulk stores must have finished reading this tile's image
             if (leader) bulk_wait_read0();
             named_bar_sync(1 + t, 128);
-            {   // dpre_c = (Wr^T dpre_rgb) * [c > 0]  -> A image (2 chunks) = dY of the colour layer
-                uint32_t cmw[4];
-#pragma unroll
-                for (int cb = 0; cb < 4; ++cb) cmw[cb] = *(const uint32_t*)(st_tile + ST_CMASK + cb * 512 + row * 4);
-#pragma unroll
-                for (int cb = 0; cb < 4; ++cb) {
-                    float f[32];
-                    const float* wr = small + SM_WR + cb * 32;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float v = dp0 * __ldg(wr + c) + dp1 * __ldg(wr + 128 + c) + dp2 * __ldg(wr + 256 + c);
-                        f[c] = ((cmw[cb] >> mask_bit_of_col(c)) & 1u) ? v : 0.f;
-                    }
-                    uint8_t* dst = act_row + (cb >> 1) * 16384;
-#pragma unroll
-                    for (uint32_t u = 0; u < 4; ++u) {
-                        uint4 o;
-                        o.x = pack_bf16(f[8 * u], f[8 * u + 1]); o.y = pack_bf16(f[8 * u + 2], f[8 * u + 3]);
-                        o.z = pack_bf16(f[8 * u + 4], f[8 * u + 5]); o.w = pack_bf16(f[8 * u + 6], f[8 * u + 7]);
-                        *(uint4*)(dst + ((((uint32_t)(cb & 1) * 4 + u) ^ sw) << 4)) = o;
-                    }
-                }
+            {   // d rgb_pre -> A image of step 0 (K = 16: units 0,1 of chunk 0; columns 0..2 carry data)
+                *(uint4*)(act_row + ((0u ^ sw) << 4)) = make_uint4(pack_bf16(dp0, dp1), pack_bf16(dp2, 0.f), 0u, 0u);
+                *(uint4*)(act_row + ((1u ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
             }
             fence_proxy_async();
             named_bar_sync(1 + t, 128);
-            if (leader) { bulk_s2g(dy_tile + DY_G9, act_s, 32768); bulk_commit(); }
+            if (leader) { bulk_s2g(dy_tile + DY_RGB, act_s, 16384); bulk_commit(); }
             mbar_arrive(my_act);
 
             // encoding derivative factors (same double-angle recurrence as the forward)
@@ -237,9 +205,9 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                 if (leader) bulk_wait_read0();
                 named_bar_sync(1 + t, 128);
                 // which ReLU mask applies to this step's output, and where the dY image goes
-                int mask_layer = -1;            // index into the stash's h masks (0..7 = h1..h8)
+                int mask_layer = -1;            // index into the stash's h masks (0..7 = h1..h8); step 0 uses the c mask
                 int64_t dy_off = 0;
-                if (s == 0) { dy_off = DY_G8; }
+                if (s == 0) { dy_off = DY_HEAD; }
                 else if (s >= 1 && s <= 4) { mask_layer = 8 - s; dy_off = DY_H + (int64_t)(8 - s) * 65536; }
                 else if (s == 5) { mask_layer = 3; dy_off = DY_H + 3 * 65536; }
                 else { mask_layer = 9 - s; dy_off = DY_H + (int64_t)(9 - s) * 65536; }     // s = 7,8,9 -> h3,h2,h1
@@ -248,27 +216,22 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                     const uint8_t* mp = st_tile + ST_MASK + mask_layer * 4096 + row * 4;     // [block][row] words
 #pragma unroll
                     for (int cb = 0; cb < 8; ++cb) mw[cb] = *(const uint32_t*)(mp + cb * 512);
+                } else {                        // step 0: d c (128 columns) masked by [c > 0]
+#pragma unroll
+                    for (int cb = 0; cb < 4; ++cb) mw[cb] = *(const uint32_t*)(st_tile + ST_CMASK + cb * 512 + row * 4);
                 }
+                const int ncb = s == 0 ? 4 : 8;
                 uint32_t va[32], vb[32];
                 tmem_ld32(tm, va);
 #pragma unroll
                 for (int cb = 0; cb < 8; ++cb) {
+                    if (cb >= ncb) break;
                     uint32_t (&v)[32] = (cb & 1) ? vb : va;
                     tmem_ld_wait();
-                    if (cb + 1 < 8) tmem_ld32(tm + (cb + 1) * 32, (cb & 1) ? va : vb);     // prefetch the next block
+                    if (cb + 1 < ncb) tmem_ld32(tm + (cb + 1) * 32, (cb & 1) ? va : vb);     // prefetch the next block
                     float f[32];
-                    if (s == 1) {                 // + sigma head: d h8 += w_sigma * d sigma
-                        const float* ws = small + SM_WS + cb * 32;
 #pragma unroll
-                        for (int c4 = 0; c4 < 8; ++c4) {
-                            const float4 w4 = __ldg((const float4*)ws + c4);
-                            f[4 * c4] = __uint_as_float(v[4 * c4]) + gs * w4.x; f[4 * c4 + 1] = __uint_as_float(v[4 * c4 + 1]) + gs * w4.y;
-                            f[4 * c4 + 2] = __uint_as_float(v[4 * c4 + 2]) + gs * w4.z; f[4 * c4 + 3] = __uint_as_float(v[4 * c4 + 3]) + gs * w4.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) f[c] = __uint_as_float(v[c]);
-                    }
+                    for (int c = 0; c < 32; ++c) f[c] = __uint_as_float(v[c]);
                     const uint32_t m = mw[cb];
 #pragma unroll
                     for (int c = 0; c < 32; ++c) f[c] = ((m >> mask_bit_of_col(c)) & 1u) ? f[c] : 0.f;
@@ -281,10 +244,14 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                         *(uint4*)(dst + ((((uint32_t)(cb & 1) * 4 + u) ^ sw) << 4)) = o;
                     }
                 }
+                if (s == 0) {   // third chunk of the head layer's dY: column 0 = d sigma (K-step 0 = units 0,1)
+                    *(uint4*)(act_row + 2 * 16384 + ((0u ^ sw) << 4)) = make_uint4(pack_bf16(gs, 0.f), 0u, 0u, 0u);
+                    *(uint4*)(act_row + 2 * 16384 + ((1u ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+                }
                 tc_fence_before();
                 fence_proxy_async();
                 named_bar_sync(1 + t, 128);
-                if (leader) { bulk_s2g(dy_tile + dy_off, act_s, 65536); bulk_commit(); }
+                if (leader) { bulk_s2g(dy_tile + dy_off, act_s, s == 0 ? 49152u : 65536u); bulk_commit(); }
                 if (!(s == 9 && !want_gx)) mbar_arrive(my_act);      // last step has no consumer MMA
             }
         }
@@ -297,23 +264,32 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
 
 // ------------------------------------------------------------------------------ wgrad
 namespace {
-// job table: (A = dY image offset in dy tile, out rows; B = X image offset in stash tile, N cols; flat weight offset / row stride / col offset)
-struct WJob { int64_t a_off; int a_chunks; int64_t b_off; int b_chunks; int lin; int col0; int ncol_valid; int bias; };
+// Job table.  Normal job:  dW (out x in) = dY^T X:  A = dY image (M = out features, from the dY scratch),
+// B = X image (N = in features, from the forward stash); accumulator lane = out feature, column = in feature.
+// Transposed job (swap = 1, the two head layers, whose dY is narrower than one UMMA M):  dW^T = X^T dY:
+// A = X image (stash), B = dY image (scratch, N = head width); lane = in feature, column = out feature.
+struct WJob {
+    int64_t a_off; int a_chunks;        // A operand: image offset inside its tile, 64-column chunks
+    int64_t b_off; int b_chunks; int N; // B operand, UMMA N
+    int swap;                           // 0: A = dY (scratch), B = X (stash);  1: A = X (stash), B = dY (scratch)
+    int kind;                           // 0: trunk linear `lin` (columns col0..col0+ncol_valid), 1: fused head layer, 2: rgb head
+    int lin; int col0; int ncol_valid; int bias;
+};
 __device__ __forceinline__ WJob wjob(int j) {
     using namespace mlp;
     WJob w;
     switch (j) {
-        case 0:  w = {DY_H + 0 * 65536, 4, ST_ENC, 1, 0, 0, 63, 1}; break;                 // L1: X = enc
-        case 1:  w = {DY_H + 1 * 65536, 4, ST_H + 0 * 65536, 4, 1, 0, 256, 1}; break;     // L2: X = h1
-        case 2:  w = {DY_H + 2 * 65536, 4, ST_H + 1 * 65536, 4, 2, 0, 256, 1}; break;
-        case 3:  w = {DY_H + 3 * 65536, 4, ST_H + 2 * 65536, 4, 3, 0, 256, 1}; break;
-        case 4:  w = {DY_H + 4 * 65536, 4, ST_ENC, 1, 4, 0, 63, 0}; break;                 // L5 encoding columns
-        case 5:  w = {DY_H + 4 * 65536, 4, ST_H + 3 * 65536, 4, 4, 63, 256, 1}; break;    // L5 hidden columns: X = h4
-        case 6:  w = {DY_H + 5 * 65536, 4, ST_H + 4 * 65536, 4, 5, 0, 256, 1}; break;
-        case 7:  w = {DY_H + 6 * 65536, 4, ST_H + 5 * 65536, 4, 6, 0, 256, 1}; break;
-        case 8:  w = {DY_H + 7 * 65536, 4, ST_H + 6 * 65536, 4, 7, 0, 256, 1}; break;     // L8: X = h7
-        case 9:  w = {DY_G8, 4, ST_H + 7 * 65536, 4, 8, 0, 256, 1}; break;                 // final: X = h8
-        default: w = {DY_G9, 2, ST_F, 4, 9, 0, 256, 1}; break;                             // colour layer: X = f
+        case 0:  w = {DY_H + 0 * 65536, 4, ST_ENC, 1, 64, 0, 0, 0, 0, 63, 1}; break;                 // L1: X = enc
+        case 1:  w = {DY_H + 1 * 65536, 4, ST_H + 0 * 65536, 4, 256, 0, 0, 1, 0, 256, 1}; break;    // L2: X = h1
+        case 2:  w = {DY_H + 2 * 65536, 4, ST_H + 1 * 65536, 4, 256, 0, 0, 2, 0, 256, 1}; break;
+        case 3:  w = {DY_H + 3 * 65536, 4, ST_H + 2 * 65536, 4, 256, 0, 0, 3, 0, 256, 1}; break;
+        case 4:  w = {DY_H + 4 * 65536, 4, ST_ENC, 1, 64, 0, 0, 4, 0, 63, 0}; break;                 // L5 encoding columns
+        case 5:  w = {DY_H + 4 * 65536, 4, ST_H + 3 * 65536, 4, 256, 0, 0, 4, 63, 256, 1}; break;   // L5 hidden columns: X = h4
+        case 6:  w = {DY_H + 5 * 65536, 4, ST_H + 4 * 65536, 4, 256, 0, 0, 5, 0, 256, 1}; break;
+        case 7:  w = {DY_H + 6 * 65536, 4, ST_H + 5 * 65536, 4, 256, 0, 0, 6, 0, 256, 1}; break;
+        case 8:  w = {DY_H + 7 * 65536, 4, ST_H + 6 * 65536, 4, 256, 0, 0, 7, 0, 256, 1}; break;    // L8: X = h7
+        case 9:  w = {ST_H + 7 * 65536, 4, DY_HEAD, 3, HEAD_N, 1, 1, 8, 0, 129, 1}; break;           // head layer: X = h8, dY = [d c_pre | d sigma]
+        default: w = {ST_C, 2, DY_RGB, 1, RGB_N, 1, 2, 11, 0, 3, 1}; break;                          // rgb head: X = c
     }
     return w;
 }
@@ -345,9 +321,12 @@ mlp_bwd_wgrad_kernel(const uint8_t* __restrict__ stash, const uint8_t* __restric
     if (has_count) { const int64_t c = *count; n = c < n_max ? c : n_max; }
     const int64_t n_tiles = ((n + 255) / 256) * 2;       // tiles written by the forward (zero rows beyond n)
     const WJob job = wjob(blockIdx.y);
-    const int M_halves = job.a_chunks / 2;               // 128 output rows per half
-    const int N = job.b_chunks * 64;                      // accumulator columns per half
+    const int M_halves = (job.a_chunks + 1) / 2;          // 128 accumulator lanes per half
+    const int N = job.N;                                  // accumulator columns per half
     const uint32_t a_half_bytes = (uint32_t)job.a_chunks * 8192u, b_half_bytes = (uint32_t)job.b_chunks * 8192u;
+    const uint8_t* a_base = job.swap ? stash : dy;
+    const uint8_t* b_base = job.swap ? dy : stash;
+    const int64_t a_tile = job.swap ? ST_TILE : DY_TILE, b_tile = job.swap ? DY_TILE : ST_TILE;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < WG_STAGES; ++s) {
@@ -375,8 +354,8 @@ mlp_bwd_wgrad_kernel(const uint8_t* __restrict__ stash, const uint8_t* __restric
                     mbar_wait(bar_cs + 8 * st, ph ^ 1u);          // column-sum readers are done with the stage too
                     mbar_expect_tx(bar_full + 8 * st, a_half_bytes + b_half_bytes);
                     const uint32_t dst = sbase + st * WG_STAGE_BYTES;
-                    const uint8_t* asrc = dy + tile * DY_TILE + job.a_off + half * 8192;
-                    const uint8_t* bsrc = stash + tile * ST_TILE + job.b_off + half * 8192;
+                    const uint8_t* asrc = a_base + tile * a_tile + job.a_off + half * 8192;
+                    const uint8_t* bsrc = b_base + tile * b_tile + job.b_off + half * 8192;
                     for (int c = 0; c < job.a_chunks; ++c) bulk_g2s(dst + c * 8192u, asrc + c * 16384, 8192, bar_full + 8 * st);
                     for (int c = 0; c < job.b_chunks; ++c) bulk_g2s(dst + 32768u + c * 8192u, bsrc + c * 16384, 8192, bar_full + 8 * st);
                 }
@@ -402,18 +381,20 @@ mlp_bwd_wgrad_kernel(const uint8_t* __restrict__ stash, const uint8_t* __restric
             umma_commit(bar_done);
         }
     } else {
-        // warps 2..9: bias gradient = column sums of the dY image (thread = output column), then the
+        // warps 2..9: bias gradient = column sums of the dY image (thread = dY column), then the
         // final TMEM -> global accumulation.
-        const int e = threadIdx.x - 64;                  // 0..255 = output feature
+        const int e = threadIdx.x - 64;                  // 0..255 = dY column
         float bsum = 0.f;
-        const bool do_bias = job.bias && e < job.a_chunks * 64;
+        const int dy_cols = job.swap ? job.ncol_valid : job.a_chunks * 64;
+        const bool do_bias = job.bias && e < dy_cols;
+        const uint32_t dy_img = job.swap ? 32768u : 0u;   // the dY image is the B operand of a transposed job
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
             for (int half = 0; half < 2; ++half, ++it) {
                 const uint32_t st = it % WG_STAGES, ph = (it / WG_STAGES) & 1u;
                 mbar_wait(bar_full + 8 * st, ph);
                 if (do_bias) {
-                    const uint8_t* img = sgen + st * WG_STAGE_BYTES + (e >> 6) * 8192;
+                    const uint8_t* img = sgen + st * WG_STAGE_BYTES + dy_img + (e >> 6) * 8192;
                     const int c = e & 63;
 #pragma unroll 8
                     for (int r = 0; r < 64; ++r) {
@@ -423,26 +404,38 @@ mlp_bwd_wgrad_kernel(const uint8_t* __restrict__ stash, const uint8_t* __restric
                 }
                 mbar_arrive(bar_cs + 8 * st);
             }
-        if (do_bias && n_tiles > blockIdx.x) atomicAdd(g_params + flat_b_off(job.lin) + e, bsum);
+        if (do_bias && n_tiles > blockIdx.x) {
+            float* dst;
+            if (job.kind == 0) dst = g_params + flat_b_off(job.lin) + e;
+            else if (job.kind == 1) dst = e < 128 ? g_params + GRAD_FUSED_B + e : g_params + flat_b_off(10);   // db', d b_sigma
+            else dst = g_params + flat_b_off(11) + e;
+            atomicAdd(dst, bsum);
+        }
         // drain the accumulators
         if (n_tiles > (int64_t)blockIdx.x) {
             mbar_wait(bar_done, 0);
             tc_fence_after();
             const int q = warp & 3;
-            const int grp = (warp - 2) >> 2;                         // 0: columns [0,N/2), 1: [N/2,N)
+            const int grp = (warp - 2) >> 2;                         // two warp groups split the column blocks
+            const int nblk = (N + 31) / 32;
             const int in_dim = lin_in(job.lin);
             float* Wg = g_params + flat_w_off(job.lin);
             for (int h = 0; h < M_halves; ++h) {
-                const int out_row = h * 128 + q * 32 + lane;
-                for (int cb = grp * (N / 64); cb < (grp + 1) * (N / 64); ++cb) {
+                const int lane_row = h * 128 + q * 32 + lane;
+                for (int cb = grp; cb < nblk; cb += 2) {
                     uint32_t v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + h * 256u + cb * 32u, v);
                     tmem_ld_wait();
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         const int col = cb * 32 + c;
-                        if (col < job.ncol_valid)
-                            atomicAdd(Wg + (int64_t)out_row * in_dim + job.col0 + col, __uint_as_float(v[c]));
+                        if (col >= job.ncol_valid) continue;
+                        float* dst;
+                        if (job.kind == 0) dst = Wg + (int64_t)lane_row * in_dim + job.col0 + col;          // lane = out, col = in
+                        else if (job.kind == 1)                                                              // lane = in (h8), col = out
+                            dst = col < 128 ? g_params + GRAD_FUSED_W + col * 256 + lane_row : g_params + flat_w_off(10) + lane_row;
+                        else dst = g_params + flat_w_off(11) + col * 128 + lane_row;                         // lane = in (c), col = rgb channel
+                        atomicAdd(dst, __uint_as_float(v[c]));
                     }
                 }
             }
@@ -454,97 +447,7 @@ mlp_bwd_wgrad_kernel(const uint8_t* __restrict__ stash, const uint8_t* __restric
     if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
 }
 
-// ------------------------------------------------------------------------------ heads
-// sigma head: d ws[i] = sum_p dsigma_p * h8[p][i], d bs = sum dsigma;  rgb head: d Wr[j][i] = sum_p dpre_j * c[p][i].
-// HBM-bound read of the h8 and c images (768 B/point) with 16-byte loads: thread (rg, unit) owns
-// the 8 columns of one 16-byte unit for the rows r == rg (mod 8) -- the swizzle (unit ^ (r&7)) is
-// then constant per thread -- partial sums stay in registers across tiles and are reduced once.
-__global__ void __launch_bounds__(256)
-mlp_bwd_heads_kernel(const uint8_t* __restrict__ stash, const float* __restrict__ rgb,
-                     const int32_t* __restrict__ cidx, const int32_t* __restrict__ count, int64_t n_max,
-                     const float* __restrict__ g_sigma, const float* __restrict__ g_rgb, float* __restrict__ g_params)
-{
-    using namespace mlp;
-    __shared__ float s_gs[128], s_dp[3][128];
-    __shared__ float s_ws[256], s_wr[3][128], s_b[4];
-    int64_t n = n_max;
-    if (cidx) { const int64_t c = *count; n = c < n_max ? c : n_max; }
-    const int64_t n_tiles = (n + 127) / 128;
-    const int tid = threadIdx.x;
-    const int rg = tid >> 5, unit = tid & 31;            // h8: 32 units of 16 B per row, 8 row groups
-    const int h_chunk = unit >> 3, h_lu = (unit & 7) ^ rg;
-    const int c_rg = tid >> 4, c_unit = tid & 15;         // c: 16 units per row, 16 row groups
-    const int c_chunk = c_unit >> 3, c_lu = (c_unit & 7) ^ (c_rg & 7);
-    float aw[8], ar[3][8], ab[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { aw[k] = 0.f; ar[0][k] = 0.f; ar[1][k] = 0.f; ar[2][k] = 0.f; }
-    for (int e = tid; e < 256; e += 256) s_ws[e] = 0.f;
-    for (int e = tid; e < 384; e += 256) s_wr[e / 128][e % 128] = 0.f;
-    if (tid < 4) s_b[tid] = 0.f;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        __syncthreads();
-        if (tid < 128) {
-            const int64_t p = tile * 128 + tid;
-            float gs = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
-            if (p < n) {
-                const int64_t id = cidx ? (int64_t)cidx[p] : p;
-                gs = g_sigma[id];
-                const float a0 = rgb[id * 3], a1 = rgb[id * 3 + 1], a2 = rgb[id * 3 + 2];
-                d0 = g_rgb[id * 3] * a0 * (1.f - a0); d1 = g_rgb[id * 3 + 1] * a1 * (1.f - a1); d2 = g_rgb[id * 3 + 2] * a2 * (1.f - a2);
-            }
-            s_gs[tid] = gs; s_dp[0][tid] = d0; s_dp[1][tid] = d1; s_dp[2][tid] = d2;
-        }
-        __syncthreads();
-        const uint8_t* st_tile = stash + tile * ST_TILE;
-        const uint8_t* h8 = st_tile + ST_H + 7 * 65536 + h_chunk * 16384 + (unit & 7) * 16;
-#pragma unroll 4
-        for (int r = rg; r < 128; r += 8) {
-            const uint4 v = __ldg((const uint4*)(h8 + r * 128));
-            const float g = s_gs[r];
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                aw[2 * k] += g * __uint_as_float(w[k] << 16);
-                aw[2 * k + 1] += g * __uint_as_float(w[k] & 0xffff0000u);
-            }
-        }
-        const uint8_t* cimg = st_tile + ST_C + c_chunk * 16384 + (c_unit & 7) * 16;
-#pragma unroll 2
-        for (int r = c_rg; r < 128; r += 16) {
-            const uint4 v = __ldg((const uint4*)(cimg + r * 128));
-            const float d0 = s_dp[0][r], d1 = s_dp[1][r], d2 = s_dp[2][r];
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float lo = __uint_as_float(w[k] << 16), hi = __uint_as_float(w[k] & 0xffff0000u);
-                ar[0][2 * k] += d0 * lo; ar[0][2 * k + 1] += d0 * hi;
-                ar[1][2 * k] += d1 * lo; ar[1][2 * k + 1] += d1 * hi;
-                ar[2][2 * k] += d2 * lo; ar[2][2 * k + 1] += d2 * hi;
-            }
-        }
-        if (tid < 128) { ab[0] += s_gs[tid]; ab[1] += s_dp[0][tid]; ab[2] += s_dp[1][tid]; ab[3] += s_dp[2][tid]; }
-    }
-    if ((int64_t)blockIdx.x >= n_tiles) return;
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        atomicAdd(&s_ws[h_chunk * 64 + h_lu * 8 + k], aw[k]);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) atomicAdd(&s_wr[j][c_chunk * 64 + c_lu * 8 + k], ar[j][k]);
-    }
-    if (tid < 128) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float v = warp_sum(ab[j]);
-            if ((tid & 31) == 0) atomicAdd(&s_b[j], v);
-        }
-    }
-    __syncthreads();
-    atomicAdd(g_params + flat_w_off(10) + tid, s_ws[tid]);
-    for (int e = tid; e < 384; e += 256) atomicAdd(g_params + flat_w_off(11) + e, s_wr[e / 128][e % 128]);
-    if (tid == 0) atomicAdd(g_params + flat_b_off(10), s_b[0]);
-    if (tid < 3) atomicAdd(g_params + flat_b_off(11) + tid, s_b[1 + tid]);
-}
+int mlp_unfuse_grad_launch(const void* packed, float* g_params, cudaStream_t stream);
 
 extern "C" int64_t an_mlp_bwd_scratch_bytes(int64_t n_max)
 {
@@ -581,11 +484,11 @@ extern "C" int an_mlp_bwd_dgrad(const void* packed, const void* stash, const flo
     return AN_OK;
 }
 
-extern "C" int an_mlp_bwd_wgrad(const void* stash, const void* scratch, const int32_t* cidx, const int32_t* count,
-                                int64_t n_max, float* g_params, void* stream)
+extern "C" int an_mlp_bwd_wgrad(const void* packed, const void* stash, const void* scratch, const int32_t* cidx,
+                                const int32_t* count, int64_t n_max, float* g_params, void* stream)
 {
-    if (!g_params) return AN_ERR_ARG;
-    int rc = bwd_check(nullptr, stash, scratch, n_max, cidx, count);
+    if (!g_params || !packed) return AN_ERR_ARG;
+    int rc = bwd_check(packed, stash, scratch, n_max, cidx, count);
     if (rc) return rc;
     cudaError_t e = cudaFuncSetAttribute(mlp_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_ALLOC);
     if (e != cudaSuccess) return (int)e;
@@ -598,20 +501,8 @@ extern "C" int an_mlp_bwd_wgrad(const void* stash, const void* scratch, const in
     mlp_bwd_wgrad_kernel<<<wgrid, WG_THREADS, WG_ALLOC, (cudaStream_t)stream>>>(
         (const uint8_t*)stash, (const uint8_t*)scratch, count, cidx ? 1 : 0, n_max, g_params);
     AN_CHECK_LAUNCH();
-    return AN_OK;
-}
-
-extern "C" int an_mlp_bwd_heads(const void* stash, const float* rgb, const int32_t* cidx, const int32_t* count,
-                                int64_t n_max, const float* g_sigma, const float* g_rgb, float* g_params, void* stream)
-{
-    if (!stash || !rgb || !g_sigma || !g_rgb || !g_params || n_max <= 0) return AN_ERR_ARG;
-    if (cidx && !count) return AN_ERR_ARG;
-    const int sms = an_num_sms();
-    const int64_t tiles = (n_max + 127) / 128;
-    const int hgrid = (int)(tiles < sms * 2 ? tiles : sms * 2);
-    mlp_bwd_heads_kernel<<<hgrid, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)stash, rgb, cidx, count, n_max, g_sigma, g_rgb, g_params);
-    AN_CHECK_LAUNCH();
-    return AN_OK;
+    // chain rule through the fused head layer: dW', db' -> xyz_encoding_final / dir_encoding gradients
+    return mlp_unfuse_grad_launch(packed, g_params, (cudaStream_t)stream);
 }
 
 extern "C" int an_mlp_bwd(const void* packed, const void* stash, const float* xyz_cano, const float* rgb,
@@ -621,7 +512,5 @@ extern "C" int an_mlp_bwd(const void* packed, const void* stash, const float* xy
 {
     int rc = an_mlp_bwd_dgrad(packed, stash, xyz_cano, rgb, cidx, count, n_max, g_sigma, g_rgb, g_xyz_cano, scratch, stream);
     if (rc) return rc;
-    rc = an_mlp_bwd_wgrad(stash, scratch, cidx, count, n_max, g_params, stream);
-    if (rc) return rc;
-    return an_mlp_bwd_heads(stash, rgb, cidx, count, n_max, g_sigma, g_rgb, g_params, stream);
+    return an_mlp_bwd_wgrad(packed, stash, scratch, cidx, count, n_max, g_params, stream);
 }

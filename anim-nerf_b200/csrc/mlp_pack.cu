@@ -1,33 +1,69 @@
 // Weight repack: fp32 nn.Linear (out,in) tensors -> bf16 UMMA-ready swizzled chunk images
-// (forward W and backward W^T), fp32 bias/head block, flat fp32 copy.  Runs once per
-// optimiser step (2.4 MB read, 4.8 MB written per net); checkpoints keep the reference's
+// (forward W and backward W^T), fp32 bias block, fused head-layer block, flat fp32 copy.  Runs once
+// per optimiser step (2.4 MB read, ~5 MB written per net); checkpoints keep the reference's
 // state-dict layout because the fp32 nn.Parameters stay the source of truth.
+//
+// mlp_fuse_kernel forms the head layer of mlp_layout.cuh in fp32: W' = W_dir . W_final (128x256),
+// b' = W_dir . b_final + b_dir (reference models/nerf.py:173 then :150: no activation in between).
 #include "common.cuh"
 #include "mlp_layout.cuh"
 #include <cuda_bf16.h>
 
 struct PackPtrs { const float* w[mlp::NLIN]; const float* b[mlp::NLIN]; };
 
-// one CTA per chunk image (fwd: 38, bwd: 42), then CTAs for the fp32 blocks
+// grid 129 x 256 threads: CTA i < 128 -> row i of W' (thread j: sum_k Wd[i][k] Wf[k][j]); CTA 128 -> b'
+__global__ void __launch_bounds__(256)
+mlp_fuse_kernel(PackPtrs P, uint8_t* __restrict__ packed)
+{
+    using namespace mlp;
+    float* fused = (float*)(packed + FUSED_OFF);
+    const float* Wf = P.w[8];
+    const float* Wd = P.w[9];
+    __shared__ float s_row[256];
+    const int i = blockIdx.x, j = threadIdx.x;
+    if (i < 128) {
+        s_row[j] = Wd[i * 256 + j];
+        __syncthreads();
+        float acc = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < 256; ++k) acc += s_row[k] * Wf[k * 256 + j];     // coalesced over j
+        fused[i * 256 + j] = acc;
+    } else if (j < 128) {
+        float acc = P.b[9][j];
+        for (int k = 0; k < 256; ++k) acc += Wd[j * 256 + k] * P.b[8][k];
+        fused[128 * 256 + j] = acc;
+    }
+}
+
+// value of the forward B operand of GEMM layer g at (output row r, input column c)
+__device__ __forceinline__ float fwd_weight(const PackPtrs& P, const float* fused, int g, int r, int c)
+{
+    using namespace mlp;
+    if (g < 8) return P.w[g][(int64_t)r * lin_in(g) + c];
+    if (g == 8) return r < 128 ? fused[r * 256 + c] : (r == 128 ? P.w[10][c] : 0.f);
+    return r < 3 ? P.w[11][r * 128 + c] : 0.f;
+}
+
+// one CTA per chunk image (fwd: 36, bwd: 40), then CTAs for the fp32 blocks
 __global__ void __launch_bounds__(256)
 mlp_pack_kernel(PackPtrs P, uint8_t* __restrict__ packed)
 {
     using namespace mlp;
+    const float* fused = (const float*)(packed + FUSED_OFF);
     int job = blockIdx.x;
     if (job < FWD_CHUNKS) {
         int g = 0, kc = job;
         while (kc >= g_chunks(g)) { kc -= g_chunks(g); ++g; }
-        const int N = g_N(g), in = lin_in(g);
+        const int N = g_N(g);
         // source column range of this chunk
         int c0, ncol;
         if (g == 0) { c0 = 0; ncol = 63; }
         else if (g == 4) { if (kc == 0) { c0 = 0; ncol = 63; } else { c0 = 63 + 64 * (kc - 1); ncol = 64; } }
         else { c0 = 64 * kc; ncol = 64; }
         uint8_t* dst = packed + fwd_chunk_off(g, kc);
-        const float* Wg = P.w[g];
         for (int e = threadIdx.x; e < N * 64; e += blockDim.x) {
             const int r = e >> 6, c = e & 63;
-            const float v = (c < ncol) ? Wg[(int64_t)r * in + c0 + c] : 0.0f;
+            const float v = (c < ncol) ? fwd_weight(P, fused, g, r, c0 + c) : 0.0f;
             *(__nv_bfloat16*)(dst + img_off(r, c)) = __float2bfloat16_rn(v);
         }
         return;
@@ -36,14 +72,20 @@ mlp_pack_kernel(PackPtrs P, uint8_t* __restrict__ packed)
     if (job < BWD_CHUNKS) {
         int s = 0, kc = job;
         while (kc >= bs_chunks(s)) { kc -= bs_chunks(s); ++s; }
-        const int g = bs_layer(s), rows = bs_rows(s), in = lin_in(g), out = lin_out(g);
-        const int in0 = bs_in0(s), nvalid = bs_in_valid(s);
+        const int rows = bs_rows(s);
         uint8_t* dst = packed + bwd_chunk_off(s, kc);
-        const float* Wg = P.w[g];
         for (int e = threadIdx.x; e < rows * 64; e += blockDim.x) {
             const int r = e >> 6, c = e & 63;          // r = input feature (row of W^T), c = output feature in chunk
-            const int o = kc * 64 + c;
-            const float v = (r < nvalid && o < out) ? Wg[(int64_t)o * in + in0 + r] : 0.0f;
+            float v = 0.f;
+            if (s == 0) { if (c < 3) v = P.w[11][c * 128 + r]; }                     // rgb^T
+            else if (s == 1) {                                                        // head^T
+                const int o = kc * 64 + c;
+                if (o < 128) v = fused[o * 256 + r]; else if (o == 128) v = P.w[10][r];
+            } else {
+                const int g = bs_layer(s), in = lin_in(g), out = lin_out(g);
+                const int o = kc * 64 + c;
+                if (r < bs_in_valid(s) && o < out) v = P.w[g][(int64_t)o * in + bs_in0(s) + r];
+            }
             *(__nv_bfloat16*)(dst + img_off(r, c)) = __float2bfloat16_rn(v);
         }
         return;
@@ -52,12 +94,11 @@ mlp_pack_kernel(PackPtrs P, uint8_t* __restrict__ packed)
     if (job == 0) {
         float* sm = (float*)(packed + SMALL_OFF);
         for (int e = threadIdx.x; e < SMALL_FLOATS; e += blockDim.x) {
+            const int g = e >> 8, c = e & 255;
             float v = 0.f;
-            if (e < SM_WS) { const int g = e >> 8, c = e & 255; v = (c < lin_out(g)) ? P.b[g][c] : 0.f; }
-            else if (e < SM_BS) v = P.w[10][e - SM_WS];
-            else if (e < SM_WR) v = (e == SM_BS) ? P.b[10][0] : 0.f;
-            else if (e < SM_BR) v = P.w[11][e - SM_WR];
-            else v = (e - SM_BR < 3) ? P.b[11][e - SM_BR] : 0.f;
+            if (g < 8) v = P.b[g][c];
+            else if (g == 8) v = c < 128 ? fused[128 * 256 + c] : (c == 128 ? P.b[10][0] : 0.f);
+            else v = c < 3 ? P.b[11][c] : 0.f;
             sm[e] = v;
         }
         return;
@@ -74,8 +115,55 @@ mlp_pack_kernel(PackPtrs P, uint8_t* __restrict__ packed)
     }
 }
 
+// Chain rule through the fused head layer, once per backward call: from dW' (128x256), db' (128) in the
+// scratch tail of the gradient vector to  dW_final = W_dir^T dW',  dW_dir = dW' W_final^T + db' b_final^T,
+// db_final = W_dir^T db',  db_dir = db'.   grid (256 + 128 + 1) x 256 threads; reads the flat fp32 copy.
+__global__ void __launch_bounds__(256)
+mlp_unfuse_grad_kernel(const uint8_t* __restrict__ packed, float* __restrict__ g)
+{
+    using namespace mlp;
+    const float* flat = (const float*)(packed + FLAT_OFF);
+    const float* Wf = flat + flat_w_off(8);
+    const float* bf = flat + flat_b_off(8);
+    const float* Wd = flat + flat_w_off(9);
+    const float* dWp = g + GRAD_FUSED_W;
+    const float* dbp = g + GRAD_FUSED_B;
+    __shared__ float s_v[256];
+    const int blk = blockIdx.x, j = threadIdx.x;
+    if (blk < 256) {                     // dW_final[k = blk][j] = sum_i Wd[i][k] dW'[i][j]
+        const int k = blk;
+        if (j < 128) s_v[j] = Wd[j * 256 + k];
+        __syncthreads();
+        float acc = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < 128; ++i) acc += s_v[i] * dWp[i * 256 + j];
+        g[flat_w_off(8) + k * 256 + j] += acc;
+    } else if (blk < 384) {              // dW_dir[i][k = j] = sum_jj dW'[i][jj] Wf[k][jj] + db'[i] bf[k]
+        const int i = blk - 256;
+        s_v[j] = dWp[i * 256 + j];
+        __syncthreads();
+        float acc = dbp[i] * bf[j];
+        const float* wrow = Wf + (int64_t)j * 256;
+#pragma unroll 8
+        for (int jj = 0; jj < 256; ++jj) acc += s_v[jj] * wrow[jj];
+        g[flat_w_off(9) + i * 256 + j] += acc;
+    } else {                             // db_final[k = j] = sum_i Wd[i][k] db'[i];  db_dir = db'
+        float acc = 0.f;
+        for (int i = 0; i < 128; ++i) acc += Wd[i * 256 + j] * dbp[i];
+        g[flat_b_off(8) + j] += acc;
+        if (j < 128) g[flat_b_off(9) + j] += dbp[j];
+    }
+}
+
+int mlp_unfuse_grad_launch(const void* packed, float* g_params, cudaStream_t stream)
+{
+    mlp_unfuse_grad_kernel<<<385, 256, 0, stream>>>((const uint8_t*)packed, g_params);
+    AN_CHECK_LAUNCH();
+    return AN_OK;
+}
+
 extern "C" int64_t an_mlp_packed_bytes(void) { return mlp::PACKED_BYTES; }
-extern "C" int64_t an_mlp_grad_floats(void) { return mlp::FLAT_FLOATS; }
+extern "C" int64_t an_mlp_grad_floats(void) { return mlp::GRAD_FLOATS; }
 
 extern "C" int an_mlp_pack(const float* const* w_host, const float* const* b_host, void* packed, void* stream)
 {
@@ -86,6 +174,8 @@ extern "C" int an_mlp_pack(const float* const* w_host, const float* const* b_hos
         if (!w_host[i] || !b_host[i]) return AN_ERR_ARG;
         P.w[i] = w_host[i]; P.b[i] = b_host[i];
     }
+    mlp_fuse_kernel<<<129, 256, 0, (cudaStream_t)stream>>>(P, (uint8_t*)packed);
+    AN_CHECK_LAUNCH();
     const int blocks = mlp::FWD_CHUNKS + mlp::BWD_CHUNKS + 1 + 64;
     mlp_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(P, (uint8_t*)packed);
     AN_CHECK_LAUNCH();

@@ -10,17 +10,20 @@
 //   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=256|128, K=16),
 //               4 K-steps per chunk; tcgen05.commit releases the stage / publishes the tile's
 //               accumulators.  Also owns the TMEM allocation (512 columns = 2 x 128x256 fp32).
-//   warps 2-9   epilogue, one thread per row: tcgen05.ld 32 columns at a time, +bias, ReLU,
-//               bf16 pack, st.shared into the K-major SWIZZLE_128B image that is the next
-//               layer's A operand (in place: the layer's MMAs have completed).  The sigma head
-//               is a dot product folded into layer 8's epilogue, the rgb head into the colour
-//               layer's; the encoding (sin/cos by double-angle recurrence from one sincosf per
+//   warps 2-9   epilogue, one thread per row: tcgen05.ld 32 columns at a time, ReLU + bf16 pack
+//               in one cvt, st.shared into the K-major SWIZZLE_128B image that is the next
+//               layer's A operand (in place: the layer's MMAs have completed).  Biases are not
+//               added here: the accumulators start from them (tcgen05.st while draining).  Both
+//               heads run on the tensor cores too (mlp_layout.cuh): the density is one more
+//               output column of the fused final+colour layer, the rgb head a 16-wide GEMM.
+//               The encoding (sin/cos by double-angle recurrence from one sincosf per
 //               coordinate; inputs stay fp32 until after the encoding) is the prologue.
 // Training mode (stash != NULL) additionally streams every activation image to HBM with TMA
 // bulk stores plus 1-bit ReLU masks; the backward kernels consume them (mlp_bwd.cu).
 //
-// Roofline: tensor-bound.  1 179 904 FLOP per point; per 256-point iteration the kernel issues
-// 38 chunks x 2 tiles x 4 MMAs.  Algorithmic HBM bytes per point: 16 B in (id + xyz), 16 B out.
+// Roofline: tensor-bound.  1 179 904 algorithmic FLOP per point (the reference's 12 linears; the
+// fused head layer executes 1 118 208 of them); per 256-point iteration the kernel issues
+// 36 chunks x 2 tiles x 4 MMAs.  Algorithmic HBM bytes per point: 16 B in (id + xyz), 16 B out.
 #include "common.cuh"
 #include "mlp_layout.cuh"
 #include "tc_common.cuh"
@@ -56,17 +59,6 @@ __device__ unsigned long long* g_trace = nullptr;
 #endif
 
 }  // namespace
-
-namespace mlp {
-// stash layout per 128-row tile (bytes)
-constexpr int64_t ST_ENC = 0;                      // 16 KB image
-constexpr int64_t ST_H = 16384;                    // h1..h8: 8 x 64 KB images
-constexpr int64_t ST_F = ST_H + 8 * 65536;         // 64 KB
-constexpr int64_t ST_C = ST_F + 65536;             // 32 KB (2 chunks)
-constexpr int64_t ST_MASK = ST_C + 32768;          // h1..h8 masks: 8 x [8 blocks][128 rows] x 4 B
-constexpr int64_t ST_CMASK = ST_MASK + 8 * 4096;   // [4 blocks][128 rows] x 4 B
-constexpr int64_t ST_TILE = ST_CMASK + 2048;       // 673 792
-}  // namespace mlp
 
 template <bool TRAIN>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -232,19 +224,19 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             }
             mbar_arrive(my_act);
 
-            float sig = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
             for (int g = 0; g < NG; ++g) {
-                const int nblk = g_N(g) / 32;
-                // The accumulators start from the bias: while draining layer g, every drained block of
-                // TMEM columns is re-initialised (tcgen05.st) with the bias of the layer that writes
-                // it next -- layer g+1, or layer 0 of the next iteration for the columns the 128-wide
-                // colour layer leaves alone.  The MMAs always accumulate; no bias add in the epilogue.
-                const int nb_lo = g < 8 ? g + 1 : (g == 8 ? 9 : 0);       // bias layer for blocks 0..3
-                const int nb_hi = g < 8 ? g + 1 : 0;                      // bias layer for blocks 4..7
-                // each thread fetches two of the 256 values now (latency hidden behind the accumulator wait);
-                // they are staged in shared memory and read back as broadcast 128-bit loads per block
-                const int bl = (2 * (e & 127) < 128) ? nb_lo : nb_hi;
-                const float2 bmine = __ldg((const float2*)(small + SM_BIAS + bl * 256) + (e & 127));
+                // accumulator blocks (32 columns) to drain, and blocks whose bias is re-initialised: the
+                // accumulators start from the bias -- while draining layer g, every block of TMEM columns is
+                // rewritten (tcgen05.st) with the bias of the layer that writes it next: layer g+1, or layer 0
+                // of the next iteration for the columns the narrow head layers leave alone.  The MMAs always
+                // accumulate; there is no bias add in the epilogue.
+                const int nld = g < 8 ? 8 : (g == 8 ? 5 : 1);
+                const int nst = g < 9 ? 8 : 1;
+                // each thread fetches two of the (up to) 256 values now (latency hidden behind the accumulator
+                // wait); they are staged in shared memory and read back as broadcast 128-bit loads per block
+                const int c2 = 2 * (e & 127);
+                const int bl = g < 8 ? g + 1 : (g == 8 ? (c2 < 32 ? 9 : 0) : 0);
+                const float2 bmine = __ldg((const float2*)(small + SM_BIAS + bl * 256 + c2));
                 if (leader) TRACE(2 + t, 0, g, 0);
                 mbar_wait(my_acc, acc_phase); acc_phase ^= 1u;
                 if (leader) TRACE(2 + t, 1, g, 0);
@@ -256,13 +248,16 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 uint32_t va[32], vb[32];
                 tmem_ld32(tm, va);
 #pragma unroll 1
-                for (int cb = 0; cb < nblk; cb += 2) {
+                for (int cb = 0; cb < nst; cb += 2) {
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         const int blk = cb + half;
+                        if (blk >= nst) break;
                         uint32_t (&v)[32] = half ? vb : va;
-                        tmem_ld_wait();
-                        if (blk + 1 < nblk) tmem_ld32(tm + (blk + 1) * 32, half ? va : vb);   // prefetch the next block
+                        if (blk < nld) {
+                            tmem_ld_wait();
+                            if (blk + 1 < nld) tmem_ld32(tm + (blk + 1) * 32, half ? va : vb);   // prefetch the next block
+                        }
                         {   // bias for the next writer of these columns
                             uint32_t bq[32];
 #pragma unroll
@@ -272,84 +267,54 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                             }
                             tmem_st32(tm + blk * 32, bq);
                         }
-                        // fp32 heads (sigma from h8 = relu(layer 8), rgb from c = relu(colour layer))
-                        if (g == 7) {
-                            const float* ws = small + SM_WS + blk * 32;
-#pragma unroll
-                            for (int c4 = 0; c4 < 8; ++c4) {
-                                const float4 w4 = __ldg((const float4*)ws + c4);
-                                sig += fmaxf(__uint_as_float(v[4 * c4]), 0.f) * w4.x + fmaxf(__uint_as_float(v[4 * c4 + 1]), 0.f) * w4.y +
-                                       fmaxf(__uint_as_float(v[4 * c4 + 2]), 0.f) * w4.z + fmaxf(__uint_as_float(v[4 * c4 + 3]), 0.f) * w4.w;
+                        if (blk >= nld) continue;
+                        if (g == 9) {                 // rgb head: columns 0..2 (bias already in the accumulator)
+                            if (in) {
+                                rgb_out[id * 3] = 1.f / (1.f + __expf(-__uint_as_float(v[0])));
+                                rgb_out[id * 3 + 1] = 1.f / (1.f + __expf(-__uint_as_float(v[1])));
+                                rgb_out[id * 3 + 2] = 1.f / (1.f + __expf(-__uint_as_float(v[2])));
                             }
+                            continue;
                         }
-                        if (g == 9) {
-                            const float* wr = small + SM_WR + blk * 32;
-#pragma unroll
-                            for (int c4 = 0; c4 < 8; ++c4) {
-                                const float4 a4 = __ldg((const float4*)wr + c4), b4 = __ldg((const float4*)(wr + 128) + c4),
-                                             d4 = __ldg((const float4*)(wr + 256) + c4);
-                                const float f0 = fmaxf(__uint_as_float(v[4 * c4]), 0.f), f1 = fmaxf(__uint_as_float(v[4 * c4 + 1]), 0.f),
-                                            f2 = fmaxf(__uint_as_float(v[4 * c4 + 2]), 0.f), f3 = fmaxf(__uint_as_float(v[4 * c4 + 3]), 0.f);
-                                r0 += f0 * a4.x + f1 * a4.y + f2 * a4.z + f3 * a4.w;
-                                r1 += f0 * b4.x + f1 * b4.y + f2 * b4.z + f3 * b4.w;
-                                r2 += f0 * d4.x + f1 * d4.y + f2 * d4.z + f3 * d4.w;
-                            }
+                        if (g == 8 && blk == 4) {     // density head: column 128 of the head layer, raw
+                            if (in) sigma_out[id] = __uint_as_float(v[0]);
+                            continue;
                         }
-                        if (g < 9 || TRAIN) {
-                            if (TRAIN && g != 8) {
-                                // 1-bit ReLU mask from the sign bits: one funnel shift per column; bit (31-c) of the
-                                // word <-> column c of the block (tc::mask_bit_of_col)
-                                // (four independent 8-column chains, then merged, so the shifts are not one serial chain)
-                                uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+                        if (TRAIN) {
+                            // 1-bit ReLU mask from the sign bits: one funnel shift per column; bit (31-c) of the
+                            // word <-> column c of the block (tc::mask_bit_of_col)
+                            // (four independent 8-column chains, then merged, so the shifts are not one serial chain)
+                            uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;
 #pragma unroll
-                                for (int c = 0; c < 8; ++c) {
-                                    n0 = __funnelshift_l(v[c], n0, 1); n1 = __funnelshift_l(v[8 + c], n1, 1);
-                                    n2 = __funnelshift_l(v[16 + c], n2, 1); n3 = __funnelshift_l(v[24 + c], n3, 1);
-                                }
-                                const uint32_t neg = (((n0 * 256u + n1) * 256u + n2) * 256u) + n3;
-                                if (g <= 7) *(uint32_t*)(st_tile + ST_MASK + g * 4096 + blk * 512 + row * 4) = ~neg;     // [block][row]: coalesced
-                                else *(uint32_t*)(st_tile + ST_CMASK + blk * 512 + row * 4) = ~neg;
+                            for (int c = 0; c < 8; ++c) {
+                                n0 = __funnelshift_l(v[c], n0, 1); n1 = __funnelshift_l(v[8 + c], n1, 1);
+                                n2 = __funnelshift_l(v[16 + c], n2, 1); n3 = __funnelshift_l(v[24 + c], n3, 1);
                             }
-                            uint32_t w[16];
-                            if (g == 8) {
-#pragma unroll
-                                for (int k = 0; k < 16; ++k) w[k] = pack_bf16(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
-                            } else {
-#pragma unroll
-                                for (int k = 0; k < 16; ++k) w[k] = pack_relu_bf16(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
-                            }
-                            uint8_t* dst = act_row + (blk >> 1) * 16384;
-#pragma unroll
-                            for (uint32_t u = 0; u < 4; ++u)
-                                *(uint4*)(dst + ((((uint32_t)(blk & 1) * 4 + u) ^ sw) << 4)) =
-                                    make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+                            const uint32_t neg = (((n0 * 256u + n1) * 256u + n2) * 256u) + n3;
+                            if (g <= 7) *(uint32_t*)(st_tile + ST_MASK + g * 4096 + blk * 512 + row * 4) = ~neg;     // [block][row]: coalesced
+                            else *(uint32_t*)(st_tile + ST_CMASK + blk * 512 + row * 4) = ~neg;
                         }
+                        uint32_t w[16];
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) w[k] = pack_relu_bf16(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
+                        uint8_t* dst = act_row + (blk >> 1) * 16384;
+#pragma unroll
+                        for (uint32_t u = 0; u < 4; ++u)
+                            *(uint4*)(dst + ((((uint32_t)(blk & 1) * 4 + u) ^ sw) << 4)) =
+                                make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
                     }
                 }
                 if (leader) TRACE(2 + t, 4, g, 0);
                 tmem_st_wait();
                 if (leader) TRACE(2 + t, 5, g, 0);
-                if (g == 9) {
-                    if (in) {
-                        sigma_out[id] = sig + __ldg(small + SM_BS);
-                        rgb_out[id * 3] = 1.f / (1.f + __expf(-(r0 + __ldg(small + SM_BR))));
-                        rgb_out[id * 3 + 1] = 1.f / (1.f + __expf(-(r1 + __ldg(small + SM_BR + 1))));
-                        rgb_out[id * 3 + 2] = 1.f / (1.f + __expf(-(r2 + __ldg(small + SM_BR + 2))));
-                    }
-                    tc_fence_before();            // TMEM reads/writes done before the next iteration's MMAs
-                    if (TRAIN) {
-                        fence_proxy_async();
-                        named_bar_sync(1 + t, 128);
-                        if (leader) { bulk_s2g(st_tile + ST_C, act_s, 32768); bulk_commit(); }
-                    }
-                } else {
-                    tc_fence_before();
+                tc_fence_before();                // TMEM reads/writes done before the MMAs that follow the arrive
+                if (g < 9) {
                     fence_proxy_async();
                     if (TRAIN) {
                         named_bar_sync(1 + t, 128);
                         if (leader) TRACE(2 + t, 6, g, 0);
-                        if (leader) {
-                            bulk_s2g(st_tile + (g == 8 ? ST_F : ST_H + (int64_t)g * 65536), act_s, 65536);
+                        if (leader) {             // h_{g+1} (64 KB), or c (32 KB) after the head layer
+                            bulk_s2g(st_tile + (g == 8 ? ST_C : ST_H + (int64_t)g * 65536), act_s, g == 8 ? 32768u : 65536u);
                             bulk_commit();
                         }
                     }

@@ -160,9 +160,7 @@ def mlp_bwd(packed, stash, xyz_cano, rgb, g_sigma, g_rgb, cidx=None, count=None,
     scr = ptr(_last_bwd_scratch)
     call("an_mlp_bwd_dgrad", ptr(packed), ptr(stash), ptr(xyz_cano), ptr(rgb), ptr(cidx), ptr(count), int(n_max),
          ptr(g_sigma), ptr(g_rgb), ptr(g_xyz), scr, stream())
-    call("an_mlp_bwd_wgrad", ptr(stash), scr, ptr(cidx), ptr(count), int(n_max), ptr(g_params), stream())
-    call("an_mlp_bwd_heads", ptr(stash), ptr(rgb), ptr(cidx), ptr(count), int(n_max), ptr(g_sigma), ptr(g_rgb),
-         ptr(g_params), stream())
+    call("an_mlp_bwd_wgrad", ptr(packed), ptr(stash), scr, ptr(cidx), ptr(count), int(n_max), ptr(g_params), stream())
     return g_params, g_xyz
 
 

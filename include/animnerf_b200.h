@@ -116,9 +116,10 @@ int64_t an_mlp_stash_bytes(int64_t n_max);
 int an_mlp_fwd(const void* packed, const float* xyz_cano, const int32_t* cidx, const int32_t* count,
                int64_t n_max, float* sigma, float* rgb, void* stash, int impl, void* stream);
 
-/* backward: g_sigma (ids), g_rgb (ids,3), rgb = the forward's output (ids,3) -> g_params (fp32 flat
- * vector of an_mlp_grad_floats() = 592 388 floats: per nn.Linear weight then bias, in an_mlp_pack's
- * order; accumulated, caller zeroes) and g_xyz_cano (ids,3) when non-NULL (caller zeroes).
+/* backward: g_sigma (ids), g_rgb (ids,3), rgb = the forward's output (ids,3) -> g_params (fp32 vector
+ * of an_mlp_grad_floats() floats: the first 592 388 are the gradient, per nn.Linear weight then
+ * bias, in an_mlp_pack's order; the tail is scratch for the fused head layer; accumulated, caller
+ * zeroes the whole vector) and g_xyz_cano (ids,3) when non-NULL (caller zeroes).
  * scratch: an_mlp_bwd_scratch_bytes(n_max).                                                  */
 int64_t an_mlp_grad_floats(void);
 int64_t an_mlp_bwd_scratch_bytes(int64_t n_max);
@@ -126,18 +127,16 @@ int an_mlp_bwd(const void* packed, const void* stash, const float* xyz_cano, con
                const int32_t* cidx, const int32_t* count, int64_t n_max,
                const float* g_sigma, const float* g_rgb,
                float* g_params, float* g_xyz_cano, void* scratch, void* stream);
-/* the three stages of an_mlp_bwd, callable separately (same arguments):
+/* the two stages of an_mlp_bwd, callable separately:
  *   dgrad  activation-gradient chain (writes the dY images to scratch, g_xyz_cano)
- *   wgrad  dW/db of the ten tensor-core layers from stash (X) and scratch (dY)
- *   heads  dW/db of the sigma and rgb heads                                                 */
+ *   wgrad  dW/db of every layer (both heads included) from stash (X) and scratch (dY) on the tensor
+ *          cores, then the chain rule from the fused final+colour layer to the two nn.Linear       */
 int an_mlp_bwd_dgrad(const void* packed, const void* stash, const float* xyz_cano, const float* rgb,
                      const int32_t* cidx, const int32_t* count, int64_t n_max,
                      const float* g_sigma, const float* g_rgb, float* g_xyz_cano,
                      void* scratch, void* stream);
-int an_mlp_bwd_wgrad(const void* stash, const void* scratch, const int32_t* cidx, const int32_t* count,
-                     int64_t n_max, float* g_params, void* stream);
-int an_mlp_bwd_heads(const void* stash, const float* rgb, const int32_t* cidx, const int32_t* count,
-                     int64_t n_max, const float* g_sigma, const float* g_rgb, float* g_params, void* stream);
+int an_mlp_bwd_wgrad(const void* packed, const void* stash, const void* scratch, const int32_t* cidx,
+                     const int32_t* count, int64_t n_max, float* g_params, void* stream);
 
 /* ---- A12: alpha compositing ------------------------------------------------------------
  * replaces models/volume_rendering.py:128-160 (composite tail), far=True, white_bkgd flag.

@@ -230,7 +230,7 @@ def test_mlp_stash_images_match_layerwise_oracle():
         w, b = p["xyz_encoding_%d.0" % (i + 1)]
         h = torch.relu(h @ w.T + b)
         hs.append(h)
-    tile_bytes = 673792
+    tile_bytes = 608256                      # mlp_layout.cuh ST_TILE: enc 16K + 8 x 64K (h1..h8) + c 32K + masks
     for tile in range((n + 127) // 128):
         base = tile * tile_bytes
         rows = min(128, n - tile * 128)
@@ -241,7 +241,7 @@ def test_mlp_stash_images_match_layerwise_oracle():
             img = torch.cat([_unswizzle(stash[base + 16384 + l * 65536 + c * 16384:][:16384], 128) for c in range(4)], 1)[:rows].cpu()
             err = (img - hs[l][sl]).abs().max().item()
             assert err < 3e-2 * max(1.0, hs[l][sl].abs().max().item()), "h%d tile %d err %g" % (l + 1, tile, err)
-            m = stash[base + 16384 + 8 * 65536 + 65536 + 32768 + l * 4096:][:4096].view(torch.int32).reshape(8, 128).T[:rows].cpu()
+            m = stash[base + 16384 + 8 * 65536 + 32768 + l * 4096:][:4096].view(torch.int32).reshape(8, 128).T[:rows].cpu()
             # mask words are stored [block][row]; bit layout per 32-column block: bit (31-c) <-> column c
             col = torch.arange(32)
             bits = ((m[:, :, None] >> (31 - col)) & 1).reshape(rows, 256).bool()
@@ -341,12 +341,16 @@ def _mlp_bwd_case(n, seed=10, with_gx=True, emulate_bf16=True):
         a.retain_grad(); pre.append(a)
         h32 = torch.relu(a)
         h = rd(h32)
-    sig = (h32 @ p["sigma"][0].T + p["sigma"][1])[:, 0]
-    f = h @ rd(p["xyz_encoding_final"][0]).T + p["xyz_encoding_final"][1]
-    f.retain_grad()
-    cpre = rd(f) @ rd(p["dir_encoding.0"][0]).T + p["dir_encoding.0"][1]
+    # the kernels run final+colour as ONE layer W' = W_dir W_final (formed in fp32, rounded once to bf16),
+    # with the density head as one more output column of it, and the rgb head as a bf16 GEMM on c
+    Wf, bf = p["xyz_encoding_final"]
+    Wd, bd = p["dir_encoding.0"]
+    sig = (h @ rd(p["sigma"][0]).T + p["sigma"][1])[:, 0]
+    cpre = h @ rd(Wd @ Wf).T + (Wd @ bf + bd)
     cpre.retain_grad()
-    rgb_ref = torch.sigmoid(torch.relu(cpre) @ p["rgb.0"][0].T + p["rgb.0"][1])
+    rgbpre = rd(torch.relu(cpre)) @ rd(p["rgb.0"][0]).T + p["rgb.0"][1]
+    rgbpre.retain_grad()
+    rgb_ref = torch.sigmoid(rgbpre)
     ((sig * gs).sum() + (rgb_ref * grgb).sum()).backward()
     sigma = torch.zeros(n, device=DEV)
     rgb = torch.zeros(n, 3, device=DEV)
@@ -354,7 +358,7 @@ def _mlp_bwd_case(n, seed=10, with_gx=True, emulate_bf16=True):
     o.mlp_fwd(packed, xc.detach().to(DEV), sigma, rgb, stash=stash)
     g_params, g_xyz = o.mlp_bwd(packed, stash, xc.detach().to(DEV), rgb, gs.to(DEV), grgb.to(DEV), want_g_xyz=with_gx)
     torch.cuda.synchronize()
-    return dict(p=p, xc=xc, pre=pre, f=f, cpre=cpre, g_params=g_params.cpu(), g_xyz=None if g_xyz is None else g_xyz.cpu(),
+    return dict(p=p, xc=xc, pre=pre, cpre=cpre, rgbpre=rgbpre, gs=gs, g_params=g_params.cpu(), g_xyz=None if g_xyz is None else g_xyz.cpu(),
                 scratch=o._last_bwd_scratch)
 
 
@@ -373,18 +377,20 @@ def test_mlp_backward(n, with_gx, emu):
     r = _mlp_bwd_case(n, with_gx=with_gx, emulate_bf16=emu)
     tol = 5e-2 if emu else 0.25
     # dgrad diagnostics: every pre-activation gradient image vs autograd
-    DY_TILE, dy_err = 622592, {}
+    DY_TILE, DY_HEAD, DY_H, dy_err = 589824, 16384, 65536, {}       # mlp_layout.cuh
     for tile in range((n + 127) // 128):
         rows = min(128, n - tile * 128)
         sl = slice(tile * 128, tile * 128 + rows)
         base = tile * DY_TILE
         sc = r["scratch"]
-        img = torch.cat([_unswizzle(sc[base + c * 16384:][:16384], 128) for c in range(2)], 1)[:rows].cpu()
+        img = _unswizzle(sc[base:][:16384], 128)[:rows, :3].cpu()                       # d rgb_pre (columns 0..2)
+        dy_err.setdefault("rgbpre", []).append(_rel(img, r["rgbpre"].grad[sl]))
+        img = torch.cat([_unswizzle(sc[base + DY_HEAD + c * 16384:][:16384], 128) for c in range(2)], 1)[:rows].cpu()
         dy_err.setdefault("cpre", []).append(_rel(img, r["cpre"].grad[sl]))
-        img = torch.cat([_unswizzle(sc[base + 32768 + c * 16384:][:16384], 128) for c in range(4)], 1)[:rows].cpu()
-        dy_err.setdefault("f", []).append(_rel(img, r["f"].grad[sl]))
+        img = _unswizzle(sc[base + DY_HEAD + 2 * 16384:][:16384], 128)[:rows, 0].cpu()  # d sigma rides in the head layer's third chunk
+        dy_err.setdefault("dsigma", []).append(_rel(img, r["gs"][sl]))
         for g in range(8):
-            img = torch.cat([_unswizzle(sc[base + 98304 + g * 65536 + c * 16384:][:16384], 128) for c in range(4)], 1)[:rows].cpu()
+            img = torch.cat([_unswizzle(sc[base + DY_H + g * 65536 + c * 16384:][:16384], 128) for c in range(4)], 1)[:rows].cpu()
             dy_err.setdefault("pre%d" % (g + 1), []).append(_rel(img, r["pre"][g].grad[sl]))
     print("dY rel err (max over tiles):", {k: round(max(v), 4) for k, v in dy_err.items()})
     names = synthetic.NERF_LAYER_NAMES
