@@ -92,19 +92,28 @@ class AnimNeRF(nn.Module):
             self.joints_transform_template = t["joints_transform"]
             self.shape_offsets_template, self.pose_offsets_template = t["shape_offsets"], t["pose_offsets"]
         self._grid = None
+        if torch.is_grad_enabled():         # a training step: the optimiser may have moved the weights
+            self.nerf.mark_dirty()
+            if self.use_fine:
+                self.nerf_fine.mark_dirty()
 
     def convert_to_body_model_space(self, rays):
+        """rays=None re-expresses only the per-frame tables (the rays then come from `an_raygen_fwd`,
+        which applies the same root-frame transform and near/far clamp while generating them)."""
         ginv = affine_inverse(self.global_transform).unsqueeze(1)            # (bs,1,4,4)
-        rays_o = batch_transform(ginv, rays[:, :, 0:3], True)
-        rays_d = batch_transform(ginv, rays[:, :, 3:6], False)
-        cam_dist = torch.norm(rays_o, dim=-1, keepdim=True)
-        near = torch.max(rays[:, :, 6:7], cam_dist - 1.0)
-        far = torch.min(rays[:, :, 7:8], cam_dist + 1.0)
+        if rays is not None:
+            rays_o = batch_transform(ginv, rays[:, :, 0:3], True)
+            rays_d = batch_transform(ginv, rays[:, :, 3:6], False)
+            cam_dist = torch.norm(rays_o, dim=-1, keepdim=True)
+            near = torch.max(rays[:, :, 6:7], cam_dist - 1.0)
+            far = torch.min(rays[:, :, 7:8], cam_dist + 1.0)
         self.verts = batch_transform(ginv, self.verts, True)
         self.joints = batch_transform(ginv, self.joints, True)
         self.global_transform = torch.matmul(ginv.squeeze(1), self.global_transform)
         self.verts_transform = torch.matmul(ginv, self.verts_transform)
         self._grid = None
+        if rays is None:
+            return None
         return torch.cat((rays_o, rays_d, near, far), dim=-1)
 
     def clac_ober2cano_transform(self):

@@ -34,15 +34,17 @@ def allreduce_grads(params, world=None, average=True):
 
 
 def gather_slabs(local, n_total, dim=0):
-    """Inference: all_gather equally-sized per-rank slabs along `dim` (pads the last rank)."""
+    """Inference: all_gather the per-rank slabs of a `shard_range(n_total, rank, world)` partition along
+    `dim` (slabs are padded to the largest one for the collective, the padding is dropped afterwards)."""
     world = dist.get_world_size() if dist.is_initialized() else 1
     if world == 1:
         return local
-    per = (n_total + world - 1) // world
+    sizes = [b - a for a, b in (shard_range(n_total, r, world) for r in range(world))]
+    per = max(sizes)
     pad = per - local.shape[dim]
     if pad:
         shape = list(local.shape); shape[dim] = pad
         local = torch.cat([local, local.new_zeros(shape)], dim)
     out = [torch.empty_like(local) for _ in range(world)]
     dist.all_gather(out, local.contiguous())
-    return torch.cat(out, dim).narrow(dim, 0, n_total)
+    return torch.cat([o.narrow(dim, 0, n) for o, n in zip(out, sizes)], dim)

@@ -56,6 +56,8 @@ class NeRF(nn.Module):
         self.rgb = nn.Sequential(nn.Linear(W // 2, 3), nn.Sigmoid())
         self._packed = None
         self._packed_key = None
+        self._packed_buf = None
+        self._dirty = False
 
     # ---- kernel-side view of the parameters
     def linears(self):
@@ -67,12 +69,24 @@ class NeRF(nn.Module):
         ls = self.linears()
         return [l.weight for l in ls] + [l.bias for l in ls]
 
+    def mark_dirty(self):
+        """Force a repack on the next `packed()` call.  The training path calls this once per step
+        (`AnimNeRF.set_body_model` under grad mode): an optimiser step is not reliably visible from the
+        host -- fused/capturable Adam does not bump `Tensor._version`, and a replayed CUDA graph never
+        re-runs this Python -- so the repack must be an unconditional part of every training step."""
+        self._dirty = True
+
     def packed(self):
         ps = self.param_list()
         key = tuple((p.data_ptr(), p._version) for p in ps)
-        if self._packed is None or key != self._packed_key or self._packed.device != ps[0].device:
-            self._packed = ops.mlp_pack(ps[:12], ps[12:])
+        if (self._packed is None or self._dirty or key != self._packed_key
+                or self._packed.device != ps[0].device):
+            if self._packed_buf is None or self._packed_buf.device != ps[0].device:
+                self._packed_buf = torch.empty(ops.mlp_packed_bytes() + 1024, device=ps[0].device, dtype=torch.uint8)
+            # always the same storage: kernels captured in a CUDA graph keep reading the refreshed images
+            self._packed = ops.mlp_pack(ps[:12], ps[12:], packed=self._packed_buf)
             self._packed_key = key
+            self._dirty = False
         return self._packed
 
     def split_flat_grad(self, flat):

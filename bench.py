@@ -211,10 +211,46 @@ def run_ours(args):
     barrier()
     ms_e2e = e0.elapsed_time(e1)
 
+    # ---- BASELINE metric, second half: ms per 512x512 frame (cfg3: inference, coarse+fine, perturb=0).  The
+    # frame's rows are sharded over the ranks (no data-path collective); timed through the public call
+    # (camera parameters in, per-frame tables + fused ray generation + render), with the D2H read of the
+    # finished rgb/alpha/depth slabs into pinned host memory inside the timed region.
+    from anim_nerf_b200 import inference
+    del gstep
+    torch.cuda.empty_cache()
+    FH = FW = 512
+    cam = synthetic.make_camera(FW, FH)
+    cam_d = [torch.from_numpy(cam[k])[None].to(dev) for k in ("c2w", "focal", "c")]
+    p1 = {k: v[:1] for k, v in params_d.items()}
+    t1 = {k: v[:1] for k, v in tmpl_d.items()}
+    rows = dist_utils.shard_range(FH, rank, world)
+    host_img = {k: torch.empty(1, rows[1] - rows[0], FW, c, pin_memory=True)
+                for k, c in (("rgbs_fine", 3), ("alphas_fine", 1), ("depths_fine", 1))}
+
+    def frame():
+        out = inference.render_frame_sharded(sysm.volume_renderer, sysm.anim_nerf, cam_d[0], cam_d[1], cam_d[2], FH, FW,
+                                             p1, t1, rank=rank, world=world, gather=False)
+        for k, h in host_img.items():
+            h.copy_(out[k], non_blocking=True)
+        return out
+
+    for _ in range(args.warmup):
+        out_f = frame()
+    barrier()
+    n_frames_timed = max(3, min(args.steps, 10))
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(n_frames_timed):
+        out_f = frame()
+    f1.record()
+    barrier()
+    ms_frame = f0.elapsed_time(f1) / n_frames_timed
+    frame_cov = float((out_f["alphas_fine"] > 0.5).float().mean())
+
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, ms_frame], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+        ms, ms_e2e, ms_frame = float(t[0]), float(t[1]), float(t[2])
         step_ms = ms / args.steps
     total_rays = n_rays * world * args.steps
     value = total_rays / (ms * 1e-3)
@@ -261,6 +297,11 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in pin.values())),
                     "d2h_bytes_per_step": 4},
+            "frame_512": {"ms": ms_frame, "rays_per_s": FH * FW / (ms_frame * 1e-3), "frames_timed": n_frames_timed,
+                          "workload": "cfg3: 512x512 novel-view frame, inference, 64+64 samples, perturb=0, rows sharded over "
+                                      "%d GPU(s); per-frame tables + ray generation + render + D2H of rgb/alpha/depth" % world,
+                          "d2h_bytes_per_frame": int(sum(h.numel() * 4 for h in host_img.values())) * world,
+                          "foreground_pixel_fraction": frame_cov},
             "gpu_launches": int(launches),
             "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
             "clocks": clk, "roofline": roofline}

@@ -147,3 +147,52 @@ def test_point_query_matches_oracle_and_masks_invalid():
     ref = fx["sigma_pts_coarse"][..., 0]
     assert np.abs(s[valid] - ref[valid]).max() < 5e-2
     assert np.abs(rgb.cpu().numpy()[valid] - fx["rgb_pts_coarse"].astype(np.float32)[valid]).max() < 1e-2
+
+
+def _train_setup(B=2, n_side=8):
+    from anim_nerf_b200.system import AnimNeRFSystem
+    data = synthetic.make_smpl_dict(0)
+    posed_np, tmpl_np = synthetic.make_body_params(B, seed=1)
+    with torch.no_grad():
+        verts = body_model()(**{k: torch.from_numpy(v) for k, v in posed_np.items()})["vertices"].numpy()
+    batch = synthetic.make_training_batch(verts, n_side=n_side, seed=3)
+    sysm = AnimNeRFSystem(body_model_data=data, n_samples=64, n_importance=64).to(DEV)
+    for name, seed in (("nerf", 10), ("nerf_fine", 11)):
+        sd = {k: torch.from_numpy(v) for k, v in synthetic.make_nerf_weights(seed).items()}
+        getattr(sysm.anim_nerf, name).load_state_dict(sd, strict=True)
+    dev_batch = {k: torch.from_numpy(batch[k]).to(DEV) for k in ("rays", "rgbs", "alphas")}
+    posed = {k: torch.from_numpy(v).to(DEV) for k, v in posed_np.items()}
+    tmpl = {k: torch.from_numpy(v).to(DEV) for k, v in tmpl_np.items()}
+    params = [p for n in ("nerf", "nerf_fine") for p in getattr(sysm.anim_nerf, n).parameters()]
+    opt = torch.optim.Adam(params, lr=5e-4, eps=1e-8, fused=True, capturable=True)
+    mse, l1 = torch.nn.functional.mse_loss, torch.nn.functional.l1_loss
+
+    def loss_fn(b):
+        out = sysm(b["rays"], posed, tmpl, perturb=0.0)
+        return (mse(out["rgbs"], b["rgbs"]) + mse(out["rgbs_fine"], b["rgbs"])
+                + 0.1 * (l1(out["alphas"], b["alphas"]) + l1(out["alphas_fine"], b["alphas"])))
+    return sysm, opt, params, dev_batch, loss_fn
+
+
+def test_training_steps_see_updated_weights_eager_and_graphed():
+    """The optimiser step must reach the kernels' packed bf16 weight images on the NEXT step, both when
+    the step is launched eagerly and when it is replayed from a CUDA graph (fused/capturable Adam does not
+    bump Tensor._version, and a replay runs no Python): the loss sequence must move, fall, and agree
+    between the two launch modes."""
+    from anim_nerf_b200.graph_step import GraphedTrainStep
+    n_steps, n_warm = 6, 2
+    sysm, opt, params, batch, loss_fn = _train_setup()
+    eager = []
+    for _ in range(n_steps + n_warm):
+        opt.zero_grad(set_to_none=True)
+        loss = loss_fn(batch)
+        loss.backward()
+        opt.step()
+        eager.append(float(loss))
+    assert len(set(round(v, 7) for v in eager)) == n_steps + n_warm, eager       # every step saw new weights
+    assert eager[-1] < eager[0], eager
+    sysm, opt, params, batch, loss_fn = _train_setup()
+    g = GraphedTrainStep(loss_fn, opt, params, batch, world=1, warmup=n_warm)    # warm-up = real eager steps
+    graphed = [float(g()) for _ in range(n_steps)]
+    assert len(set(round(v, 7) for v in graphed)) == n_steps, graphed
+    np.testing.assert_allclose(graphed, eager[n_warm:], rtol=2e-2)

@@ -25,27 +25,43 @@ def _worker(rank, world, port, q):
     for i, p in enumerate(net.parameters()):
         p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
     du.allreduce_grads(list(net.parameters()))
-    ok_grad = all(torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1))) for i, p in enumerate(net.parameters()))
+    ok_grad = all(torch.allclose(p.grad, torch.full_like(p, (world + 1) / 2.0 * (i + 1))) for i, p in enumerate(net.parameters()))
     a, b = du.shard_range(17, rank, world)
     local = torch.arange(a, b, dtype=torch.float32)[:, None].repeat(1, 3)
     full = du.gather_slabs(local, 17)
     ok_gather = torch.equal(full[:, 0], torch.arange(17, dtype=torch.float32))
+    # unequal slabs with the remainder on the first ranks (16 rows over 3 would be 6,5,5; here 2 ranks: 5 -> 3,2)
+    for n in (5, 16):
+        a5, b5 = du.shard_range(n, rank, world)
+        img = torch.arange(n * 4, dtype=torch.float32).view(n, 4)
+        ok_gather = ok_gather and torch.equal(du.gather_slabs(img[a5:b5].clone(), n), img)
     q.put((rank, ok_grad, (a, b), ok_gather))
     dist.destroy_process_group()
 
 
-def test_two_rank_allreduce_and_sharding():
+def _spawn(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=120) for _ in procs)
     for p in procs:
         p.join(60)
+    return res
+
+
+def test_two_rank_allreduce_and_sharding():
+    res = _spawn(2)
     assert all(r[1] for r in res), res
     assert [r[2] for r in res] == [(0, 9), (9, 17)]
+    assert all(r[3] for r in res), res
+
+
+def test_three_rank_unequal_slabs_gather():
+    res = _spawn(3)          # 16 rows -> 6,5,5: the padded slab is not the last one
+    assert [r[2] for r in res] == [(0, 6), (6, 12), (12, 17)]
     assert all(r[3] for r in res), res
 
 
