@@ -97,6 +97,45 @@ class AnimNeRF(nn.Module):
             if self.use_fine:
                 self.nerf_fine.mark_dirty()
 
+    # ------------------------------------------------------------------ fused per-frame setup
+    def setup_frame(self, body_model_params, body_model_params_template, rays=None):
+        """`set_body_model` -> `convert_to_body_model_space(rays)` -> `clac_ober2cano_transform` in one
+        call (the sequence of train.py:201-203 / novel_view.py:79-85).  When no SMPL parameter needs a
+        gradient the tables come from the fused kernels (`an_body_tables_fwd`: two launches instead of
+        ~250) and only the state the rendering path reads is set (`verts`, `ober2cano_transform`,
+        `verts_template`, `global_transform`); otherwise the differentiable torch builder runs.
+        Returns (rays in body space or None, ginv (B,4,4))."""
+        tensors = [v for d in (body_model_params, body_model_params_template) for v in d.values() if torch.is_tensor(v)]
+        if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+            self.set_body_model(body_model_params, body_model_params_template)
+            ginv = affine_inverse(self.global_transform)
+            rays = self.convert_to_body_model_space(rays)
+            self.clac_ober2cano_transform()
+            return rays, ginv
+        verts, o2c, ginv, vt = ops.body_tables(self.body_model, body_model_params, body_model_params_template)
+        self.verts, self.ober2cano_transform, self.verts_template = verts, o2c, vt
+        self.global_transform = torch.eye(4, device=verts.device).expand(verts.shape[0], 4, 4)
+        self.joints = self.verts_transform = self.joints_transform = None      # not built on the fused path
+        self._grid = None
+        if torch.is_grad_enabled():
+            self.nerf.mark_dirty()
+            if self.use_fine:
+                self.nerf_fine.mark_dirty()
+        if rays is not None:
+            rays = self.rays_to_body_space(rays, ginv)
+        return rays, ginv
+
+    @staticmethod
+    def rays_to_body_space(rays, ginv):
+        """Ray part of `convert_to_body_model_space` (models/anim_nerf.py:128-137)."""
+        g = ginv.unsqueeze(1)
+        rays_o = batch_transform(g, rays[:, :, 0:3], True)
+        rays_d = batch_transform(g, rays[:, :, 3:6], False)
+        cam_dist = torch.norm(rays_o, dim=-1, keepdim=True)
+        near = torch.max(rays[:, :, 6:7], cam_dist - 1.0)
+        far = torch.min(rays[:, :, 7:8], cam_dist + 1.0)
+        return torch.cat((rays_o, rays_d, near, far), dim=-1)
+
     def convert_to_body_model_space(self, rays):
         """rays=None re-expresses only the per-frame tables (the rays then come from `an_raygen_fwd`,
         which applies the same root-frame transform and near/far clamp while generating them)."""
@@ -129,7 +168,8 @@ class AnimNeRF(nn.Module):
             self._grid = (ops.vertex_grid(verts, self.dis_threshold) if self.knn_mode == 1 else None, self.dis_threshold)
         net = self.nerf_fine if use_fine else self.nerf
         return dict(verts=verts, lbs=self.body_model.lbs_weights, grid=self._grid[0], thr=float(self.dis_threshold),
-                    net=net, knn_mode=self.knn_mode, mlp_impl=self.mlp_impl, unpose=self.use_unpose)
+                    net=net, knn_mode=self.knn_mode, mlp_impl=self.mlp_impl, unpose=self.use_unpose,
+                    grad=torch.is_grad_enabled())
 
     def render_pass(self, rays, z, use_fine=False, sigma_noise=None, white_bkgd=True):
         """Fused composite pass used by VolumeRenderer: -> (weights, rgb, depth, acc)."""

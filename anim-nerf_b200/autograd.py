@@ -23,7 +23,9 @@ class RenderPass(torch.autograd.Function):
         net = cfg["net"]
         B, R, K = z.shape
         dev = z.device
-        need_grad = any(ctx.needs_input_grad)
+        # Function.forward always runs with grad mode off and needs_input_grad ignores torch.no_grad():
+        # the caller records the ambient grad mode in cfg["grad"] (inference must not write the stash)
+        need_grad = cfg.get("grad", True) and any(ctx.needs_input_grad)
         rays_c, z_c, o2c_c = rays.contiguous(), z.contiguous(), ober2cano.contiguous()
         sigma = torch.empty(B, R, K, device=dev)
         rgb = torch.empty(B, R, K, 3, device=dev)
@@ -81,7 +83,7 @@ class PointQuery(torch.autograd.Function):
         net = cfg["net"]
         B, N = xyz.shape[:2]
         dev = xyz.device
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = cfg.get("grad", True) and any(ctx.needs_input_grad)
         xyz_c = xyz.contiguous()
         sigma = torch.empty(B, N, device=dev)
         rgb = torch.empty(B, N, 3, device=dev)
@@ -125,7 +127,7 @@ class PointQuery(torch.autograd.Function):
 
 def mlp_query(net, xyz):
     """Canonical-space NeRF query (no unposing): xyz (B,N,3) -> rgb (B,N,3), sigma (B,N,1)."""
-    cfg = dict(net=net, unpose=False)
+    cfg = dict(net=net, unpose=False, grad=torch.is_grad_enabled())
     return PointQuery.apply(xyz, None, cfg, *net.param_list())
 
 

@@ -1,9 +1,10 @@
 """Per-frame table builder: SMPL linear blend skinning in plain torch (host side).
 
 SURVEY §8 row A16: the per-frame inputs of the hot path (posed vertices, per-vertex
-4x4 transforms, shape/pose offsets) are microseconds of work on 6890 vertices and
-stay in torch so autograd reaches the SMPL parameters; the CUDA kernels consume the
-tables this module produces.  The arithmetic follows the reference's *modified*
+4x4 transforms, shape/pose offsets).  This torch formulation is the differentiable
+builder, used when SMPL parameters are being optimised (autograd reaches them); every
+other step / frame goes through the fused kernels (`an_body_tables_fwd`,
+csrc/body_tables.cu), which read the constant buffers registered here.  The arithmetic follows the reference's *modified*
 smplx (`smplx/lbs.py:152-251` `lbs`, `:298-330` `batch_rodrigues`, `:348-420`
 `batch_rigid_transform`; `smplx/body_models.py:289-387` `SMPL.forward`, which adds
 `transl` into `A` and `T` and returns the shape/pose offsets) so that the tables
@@ -71,7 +72,7 @@ class BodyModel(nn.Module):
         self.register_buffer("v_template", t(data["v_template"]))
         self.register_buffer("shapedirs", t(np.asarray(data["shapedirs"])[:, :, :10]))
         nposes = np.asarray(data["posedirs"]).shape[-1]
-        self.register_buffer("posedirs", t(np.reshape(data["posedirs"], [-1, nposes]).T))
+        self.register_buffer("posedirs", t(np.reshape(data["posedirs"], [-1, nposes]).T).contiguous())
         self.register_buffer("J_regressor", t(data["J_regressor"]))
         parents = torch.as_tensor(np.asarray(data["kintree_table"])[0]).long().clone()
         parents[0] = -1
@@ -79,6 +80,11 @@ class BodyModel(nn.Module):
         self.parents_host = [int(p) for p in parents]   # the kinematic tree is static: keep it on the host
         self.register_buffer("parent_idx", parents[1:].clone())
         self.register_buffer("lbs_weights", t(data["weights"]))
+        # constants of the fused table builder (an_body_tables_fwd): the joint regressor applied to the
+        # linear shape model once, and the kinematic tree as int32
+        self.register_buffer("J_template", torch.matmul(self.J_regressor, self.v_template).contiguous())
+        self.register_buffer("J_shapedirs", torch.einsum("ji,ikl->jkl", self.J_regressor, self.shapedirs).contiguous())
+        self.register_buffer("parents_i32", parents.to(torch.int32))
 
     def forward(self, betas, body_pose, global_orient, transl=None, **_):
         B = max(betas.shape[0], body_pose.shape[0], global_orient.shape[0])

@@ -413,16 +413,37 @@ knn_classify_kernel(const float* __restrict__ xyz, const float* __restrict__ ray
     }
 }
 
-__global__ void __launch_bounds__(KNN_THREADS)
+// Insert a candidate known to beat the current 4th entry: overwrite it, then three predicated
+// compare-exchanges restore the (d2, index) order -- no data-dependent branches inside.
+__device__ __forceinline__ void best_insert_sorted(Best4& b, float d2, int idx) {
+    b.d[3] = d2; b.i[3] = idx;
+#pragma unroll
+    for (int k = 3; k > 0; --k) {
+        const bool sw = key_less(b.d[k], b.i[k], b.d[k - 1], b.i[k - 1]);
+        const float td = sw ? b.d[k - 1] : b.d[k]; const int ti = sw ? b.i[k - 1] : b.i[k];
+        b.d[k - 1] = sw ? b.d[k] : b.d[k - 1]; b.i[k - 1] = sw ? b.i[k] : b.i[k - 1];
+        b.d[k] = td; b.i[k] = ti;
+    }
+}
+
+#define SEARCH_THREADS 128
+#define SEARCH_MAX_ENT 50                 // 49 rows, row 0 may split around the own cell
+#define SEARCH_SMEM (SEARCH_MAX_ENT * SEARCH_THREADS * 8)
+
+__global__ void __launch_bounds__(SEARCH_THREADS)
 knn_search_kernel(int64_t N, const float* __restrict__ verts, int V, const char* __restrict__ ws,
                   int64_t frame_bytes, QueryWs* __restrict__ qws, const float* __restrict__ ober2cano,
                   const float* __restrict__ lbsw, int J, float thr, UnposeOut o)
 {
+    // per-thread list of candidate ranges, layout [entry][thread] (bank = thread: conflict-free for any
+    // per-lane entry index): .x = start | end << 16 (positions in the cell-sorted table), .y = row slab gap^2
+    extern __shared__ uint2 s_ent[];
     const float4* __restrict__ work = (const float4*)(qws + 1);
     const int lane = threadIdx.x & 31;
     const unsigned n_work = qws->n_work;
     const unsigned n_chunks = (n_work + 31) / 32;
     const float thr2 = thr * thr * (1.0f + 1e-5f);   // prune only what is invalid beyond rounding doubt
+    uint2* __restrict__ my_ent = s_ent + threadIdx.x;
     for (;;) {
         unsigned chunk = 0;
         if (lane == 0) chunk = atomicAdd(&qws->next_chunk, 1u);
@@ -448,13 +469,14 @@ knn_search_kernel(int64_t N, const float* __restrict__ verts, int V, const char*
                   cz = (int)floorf((qz - h.oz) * inv_cell);
         const bool own = active && cx >= 0 && cx < h.nx && cy >= 0 && cy < h.ny && cz >= 0 && cz < h.nz;
         Best4 mine; best_init(mine);
-        if (own) {                                // own cell first: usually yields four candidates and a tight bound
-            const int c = (cz * h.ny + cy) * h.nx + cx;
-            const int s = __ldg(cell_start + c), e1 = __ldg(cell_start + c + 1);
-            for (int p = s; p < e1; ++p) {
+        {   // phase 0 -- own cell: usually yields four candidates and a tight bound.  One flat loop: all lanes
+            // that still have a vertex left evaluate it together.
+            int p = 0, pe = 0;
+            if (own) { const int c = (cz * h.ny + cy) * h.nx + cx; p = __ldg(cell_start + c); pe = __ldg(cell_start + c + 1); }
+            for (; p < pe; ++p) {
                 const float4 v = __ldg(sorted + p);
                 const float d2 = dist2_rn(qx, qy, qz, v.x, v.y, v.z);
-                if (key_less(d2, __float_as_int(v.w), mine.d[3], mine.i[3])) best_push_any(mine, d2, __float_as_int(v.w));
+                if (key_less(d2, __float_as_int(v.w), mine.d[3], mine.i[3])) best_insert_sorted(mine, d2, __float_as_int(v.w));
             }
         }
         {   // neighbouring lanes are neighbouring samples of a ray: d4(q) <= d4(q') + |q - q'| tightens the
@@ -477,42 +499,58 @@ knn_search_kernel(int64_t N, const float* __restrict__ verts, int V, const char*
             }
             B = fminf(B, u * u * (1.0f + 1e-4f));
         }
-        if (active) {
-            float Bm = fminf(fminf(B, mine.d[3]) * 1.001f, box_r2 * 1.01f);
-            // position of the query inside its cell -> exact slab gaps per row
+        float Bm = fminf(fminf(B, mine.d[3]) * 1.001f, box_r2 * 1.01f);
+        // phase 1 -- every lane walks the 49 rows of its 7x7 cell box in lockstep and lists the candidate
+        // ranges that intersect the ball of radius sqrt(Bm) (row slab gap <= Bm, x range trimmed to the ball)
+        int n_ent = 0;
+        {
             const float fy = qy - (h.oy + cy * h.cell), fz = qz - (h.oz + cz * h.cell);
+#pragma unroll 7
             for (int r = 0; r < (2 * GRID_R + 1) * (2 * GRID_R + 1); ++r) {
-                const int ring = c_row_ring[r];
-                if (ring >= 2) {                  // nearest row of ring k is at least (k-1) cells away
-                    const float rg = (float)(ring - 1) * h.cell;
-                    if (rg * rg > Bm) break;
-                }
                 const int dy = c_row_dy[r], dz = c_row_dz[r];
                 const int gy = cy + dy, gz = cz + dz;
-                if (gz < 0 || gz >= h.nz || gy < 0 || gy >= h.ny) continue;
                 const float gapy = dy == 0 ? 0.f : (dy > 0 ? (float)dy * h.cell - fy : fy - (float)(dy + 1) * h.cell);
                 const float gapz = dz == 0 ? 0.f : (dz > 0 ? (float)dz * h.cell - fz : fz - (float)(dz + 1) * h.cell);
                 const float g2 = (gapy > 0.f ? gapy * gapy : 0.f) + (gapz > 0.f ? gapz * gapz : 0.f);
-                if (g2 > Bm) continue;
-                const float w = sqrtf(Bm - g2) + 1e-3f * h.cell;
+                bool ok = active && gz >= 0 && gz < h.nz && gy >= 0 && gy < h.ny && g2 <= Bm;
+                const float w = sqrtf(fmaxf(Bm - g2, 0.f)) + 1e-3f * h.cell;
                 int x0 = max(cx - GRID_R, (int)floorf((qx - w - h.ox) * inv_cell));
                 int x1 = min(cx + GRID_R, (int)floorf((qx + w - h.ox) * inv_cell));
                 x0 = max(x0, 0); x1 = min(x1, h.nx - 1);
-                if (x0 > x1) continue;
-                const int row = (gz * h.ny + gy) * h.nx;
-                // candidate ranges of the row; the own cell (row 0) was scanned above: skip it
-                int s0 = __ldg(cell_start + row + x0), e0r = 0, s1 = 0, e1 = __ldg(cell_start + row + x1 + 1);
-                if (r == 0 && own && cx >= x0 && cx <= x1) { e0r = __ldg(cell_start + row + cx); s1 = __ldg(cell_start + row + cx + 1); }
-                else { e0r = e1; s1 = e1; }
-                for (int part = 0; part < 2; ++part) {
-                    const int ps = part ? s1 : s0, pe = part ? e1 : e0r;
-                    for (int p = ps; p < pe; ++p) {
-                        const float4 v = __ldg(sorted + p);
-                        const float d2 = dist2_rn(qx, qy, qz, v.x, v.y, v.z);
-                        if (key_less(d2, __float_as_int(v.w), mine.d[3], mine.i[3])) {
-                            best_push_any(mine, d2, __float_as_int(v.w));
-                            Bm = fminf(Bm, mine.d[3] * 1.001f);
-                        }
+                ok = ok && x0 <= x1;
+                if (ok) {
+                    const int row = (gz * h.ny + gy) * h.nx;
+                    const int s0 = __ldg(cell_start + row + x0), e1 = __ldg(cell_start + row + x1 + 1);
+                    if (r == 0 && own && cx >= x0 && cx <= x1) {     // the own cell was scanned in phase 0: split around it
+                        const int e0 = __ldg(cell_start + row + cx), s1 = __ldg(cell_start + row + cx + 1);
+                        if (e0 > s0) { my_ent[n_ent * SEARCH_THREADS] = make_uint2((unsigned)s0 | ((unsigned)e0 << 16), __float_as_uint(g2)); ++n_ent; }
+                        if (e1 > s1) { my_ent[n_ent * SEARCH_THREADS] = make_uint2((unsigned)s1 | ((unsigned)e1 << 16), __float_as_uint(g2)); ++n_ent; }
+                    } else if (e1 > s0) {
+                        my_ent[n_ent * SEARCH_THREADS] = make_uint2((unsigned)s0 | ((unsigned)e1 << 16), __float_as_uint(g2)); ++n_ent;
+                    }
+                }
+            }
+        }
+        {   // phase 2 -- one flat loop over the listed candidates: a lane whose range is used up pops its next
+            // entry (rows that fell outside the shrunken ball are skipped whole), then every lane that still has
+            // a candidate evaluates it -- the distance / insert code runs convergent across the warp.
+            int k = 0, p = 0, pe = 0;
+            bool live = n_ent > 0;
+            for (;;) {
+                if (live && p >= pe) {
+                    live = false;
+                    while (k < n_ent) {
+                        const uint2 en = my_ent[k * SEARCH_THREADS]; ++k;
+                        if (__uint_as_float(en.y) <= Bm) { p = (int)(en.x & 0xffffu); pe = (int)(en.x >> 16); live = true; break; }
+                    }
+                }
+                if (!__any_sync(0xffffffffu, live)) break;
+                if (live) {
+                    const float4 v = __ldg(sorted + p); ++p;
+                    const float d2 = dist2_rn(qx, qy, qz, v.x, v.y, v.z);
+                    if (key_less(d2, __float_as_int(v.w), mine.d[3], mine.i[3])) {
+                        best_insert_sorted(mine, d2, __float_as_int(v.w));
+                        Bm = fminf(Bm, mine.d[3] * 1.001f);
                     }
                 }
             }
@@ -639,9 +677,12 @@ extern "C" int an_knn_unpose_fwd(const float* xyz, const float* rays, const floa
             xyz, rays, z, K, N, total, (const char*)grid_ws, grid_frame_bytes(V), qws, o);
         AN_CHECK_LAUNCH();
         // persistent search CTAs pull 32-query chunks from the work list (its length is device-side)
-        int64_t sb = (total + KNN_THREADS - 1) / KNN_THREADS;
-        if (sb > (int64_t)sms * 8) sb = (int64_t)sms * 8;
-        knn_search_kernel<<<(unsigned)sb, KNN_THREADS, 0, (cudaStream_t)stream>>>(
+        if (V > 65535) return AN_ERR_UNSUPPORTED;                          // candidate ranges are packed 16+16 bits
+        e = cudaFuncSetAttribute(knn_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEARCH_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        int64_t sb = (total + SEARCH_THREADS - 1) / SEARCH_THREADS;
+        if (sb > (int64_t)sms * 4) sb = (int64_t)sms * 4;
+        knn_search_kernel<<<(unsigned)sb, SEARCH_THREADS, SEARCH_SMEM, (cudaStream_t)stream>>>(
             N, verts, V, (const char*)grid_ws, grid_frame_bytes(V), qws, ober2cano, lbs_weights, J, dis_threshold, o);
     } else return AN_ERR_ARG;
     AN_CHECK_LAUNCH();

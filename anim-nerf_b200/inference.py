@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .anim_nerf import affine_inverse, batch_transform
+from .anim_nerf import batch_transform
 from .dist_utils import gather_slabs, shard_range
 
 
@@ -39,9 +39,7 @@ def batched_inference(volume_renderer, anim_nerf, rays, body_model_params, body_
     """reference novel_view.py:75-116.  rays (B,R,8) world space -> dict of (B,R,.) outputs.
     `P` (B,1|R,4,4): extra rigid transform of the rays in body space (the novel-view turntable)."""
     bs, n_rays = rays.shape[:2]
-    anim_nerf.set_body_model(body_model_params, body_model_params_template)
-    rays = anim_nerf.convert_to_body_model_space(rays)
-    anim_nerf.clac_ober2cano_transform()
+    rays, _ = anim_nerf.setup_frame(body_model_params, body_model_params_template, rays)
     if latent_code is not None:
         anim_nerf.set_latent_code(latent_code)
     return _render_body_space(volume_renderer, anim_nerf, rays, P, chunk)
@@ -70,10 +68,7 @@ def render_frame(volume_renderer, anim_nerf, c2w, focal, center, H, W, body_mode
     (`models/anim_nerf.py:128-137`) run fused in `an_raygen_fwd`, then the render path.
     c2w (B,3,4), focal (B,2), center (B,2).  rows=(r0,r1) renders only that slab of image rows.
     Returns dict of (B, rows, W, .)."""
-    anim_nerf.set_body_model(body_model_params, body_model_params_template)
-    ginv = affine_inverse(anim_nerf.global_transform)
-    anim_nerf.convert_to_body_model_space(None)
-    anim_nerf.clac_ober2cano_transform()
+    _, ginv = anim_nerf.setup_frame(body_model_params, body_model_params_template, None)
     r0, r1 = rows if rows is not None else (0, H)
     B = c2w.shape[0]
     if r0 == 0 and r1 == H:

@@ -46,6 +46,36 @@ def sample_coarse(rays, n_coarse, perturb=0.0, noise_u=None, seed=0):
     return z
 
 
+# ------------------------------------------------------------------------ per-frame tables
+def body_tables(model, posed, template, want_template_verts=True):
+    """A16 + A2 (vertex part) + clac_ober2cano_transform in two kernels.  `model`: BodyModel (constant
+    buffers); posed / template: dicts betas (B|1,10), global_orient (B,3), body_pose (B,69), transl (B,3).
+    Returns verts (B,V,3) root frame, ober2cano (B,V,4,4), ginv (B,4,4), verts_template (B,V,3)."""
+    def prep(d):
+        go, bp = _f32c(d["global_orient"]), _f32c(d["body_pose"])
+        B = max(go.shape[0], d["betas"].shape[0])
+        pose = torch.cat([go.reshape(go.shape[0], -1), bp.reshape(bp.shape[0], -1)], 1).contiguous()
+        betas = _f32c(d["betas"])
+        if betas.shape[0] != B:
+            betas = betas.expand(B, -1).contiguous()
+        tr = d.get("transl")
+        return B, betas, pose, (_f32c(tr) if tr is not None else None)
+    B, betas, pose, transl = prep(posed)
+    Bt, betas_t, pose_t, transl_t = prep(template)
+    V = model.v_template.shape[0]
+    dev = pose.device
+    ws = torch.empty(_lib.load().an_body_tables_ws_bytes(B), device=dev, dtype=torch.uint8)
+    verts = torch.empty(B, V, 3, device=dev)
+    o2c = torch.empty(B, V, 4, 4, device=dev)
+    ginv = torch.empty(B, 4, 4, device=dev)
+    vt = torch.empty(B, V, 3, device=dev) if want_template_verts else None
+    call("an_body_tables_fwd", ptr(betas), ptr(pose), ptr(transl), ptr(betas_t), ptr(pose_t), ptr(transl_t), B, Bt,
+         ptr(model.v_template), ptr(model.shapedirs), ptr(model.posedirs), ptr(model.J_template), ptr(model.J_shapedirs),
+         ptr(model.lbs_weights), ptr(model.parents_i32), V, model.J_regressor.shape[0], model.shapedirs.shape[-1], ptr(ws),
+         ptr(verts), ptr(o2c), ptr(ginv), ptr(vt), stream())
+    return verts, o2c, ginv, vt
+
+
 # ------------------------------------------------------------------------ KNN + unpose
 def vertex_grid(verts, dis_threshold):
     """Per-frame vertex grid for the pruned search.  cell = 1.25*threshold/3 (+0.1 %): the kernel's

@@ -57,9 +57,7 @@ class AnimNeRFSystem(nn.Module):
         bs, h, w = rays.shape[:3]
         n_rays = h * w
         rays = rays.view(bs, n_rays, -1)
-        self.anim_nerf.set_body_model(body_model_params, body_model_params_template)
-        rays = self.anim_nerf.convert_to_body_model_space(rays)
-        self.anim_nerf.clac_ober2cano_transform()
+        rays, _ = self.anim_nerf.setup_frame(body_model_params, body_model_params_template, rays)
         chunk = getattr(self.hparams, "chunk", None) or n_rays
         results = defaultdict(list)
         for i in range(0, n_rays, chunk):

@@ -165,6 +165,26 @@ int an_sample_fine_merge_fwd(const float* weights, const float* z_coarse, const 
                              int64_t n_rays, int Kc, int Kf, int det, uint64_t seed,
                              float* z_fine, float* z_all, uint8_t* src, void* stream);
 
+/* ---- A16 (+ vertex part of A2): per-frame tables ------------------------------------------
+ * replaces, for frames whose SMPL parameters are not being optimised, the torch chain
+ * set_body_model -> SMPL.forward/lbs (smplx/body_models.py:289-387, smplx/lbs.py:152-251),
+ * the vertex part of convert_to_body_model_space (models/anim_nerf.py:139-143) and
+ * clac_ober2cano_transform (:147-151).  Inputs: betas (B,10), pose (B,24,3) = [global_orient,
+ * body_pose] axis-angle, transl (B,3) or NULL -- posed body -- and the same three for the
+ * template body with batch Bt (1 = shared by all frames, or B).  Model constants: v_template
+ * (V,3), shapedirs (V,3,10), posedirs (207, V*3), J_template (24,3) = J_regressor . v_template,
+ * J_shapedirs (24,3,10) = J_regressor . shapedirs, lbs_weights (V,24), parents int32[24].
+ * ws: an_body_tables_ws_bytes(B) scratch.  Outputs: verts (B,V,3) in the root frame, ober2cano
+ * (B,V,4,4; 16-byte aligned), ginv (B,4,4) = inverse root transform (feeds an_raygen_fwd),
+ * verts_template (B,V,3) or NULL.  Forward only.                                             */
+int64_t an_body_tables_ws_bytes(int B);
+int an_body_tables_fwd(const float* betas, const float* pose, const float* transl,
+                       const float* betas_t, const float* pose_t, const float* transl_t, int B, int Bt,
+                       const float* v_template, const float* shapedirs, const float* posedirs,
+                       const float* J_template, const float* J_shapedirs, const float* lbs_weights,
+                       const int32_t* parents, int V, int J, int n_betas, void* ws,
+                       float* verts, float* ober2cano, float* ginv, float* verts_template, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -407,3 +407,43 @@ def test_mlp_backward(n, with_gx, emu):
     print({k: round(v, 4) for k, v in errs.items()})
     bad = {k: v for k, v in errs.items() if not v < tol}
     assert not bad, bad
+
+
+# ------------------------------------------------------------------ per-frame tables (A16, 8(f)#1)
+@pytest.mark.parametrize("shared_template", [False, True])
+def test_body_tables_match_torch_builder(shared_template):
+    """an_body_tables_fwd vs the differentiable torch builder (BodyModel + AnimNeRF.set_body_model /
+    convert_to_body_model_space / clac_ober2cano_transform, themselves pinned to the reference's tables by
+    the golden fixtures): posed vertices in the root frame, observation->canonical transforms, inverse root
+    transform, template vertices.  fp32, different summation order: tolerance 2e-5 absolute."""
+    from anim_nerf_b200.anim_nerf import AnimNeRF, affine_inverse
+    B = 5
+    net = AnimNeRF(use_unpose=True, use_knn=True, use_fine=False, freqs_dir=0, body_model_data=synthetic.make_smpl_dict(0)).to(DEV)
+    posed_np, tmpl_np = synthetic.make_body_params(B, seed=7)
+    rs = np.random.RandomState(3)
+    posed_np["betas"] = rs.normal(0, 0.5, size=posed_np["betas"].shape).astype(np.float32)
+    posed = {k: torch.from_numpy(v).to(DEV) for k, v in posed_np.items()}
+    tmpl = {k: torch.from_numpy(v[:1] if shared_template else v).to(DEV) for k, v in tmpl_np.items()}
+    with torch.no_grad():
+        net.set_body_model(posed, {k: v.expand(B, *v.shape[1:]) for k, v in tmpl.items()} if shared_template else tmpl)
+        ginv_ref = affine_inverse(net.global_transform)
+        net.convert_to_body_model_space(None)
+        net.clac_ober2cano_transform()
+        verts_ref, o2c_ref, vt_ref = net.verts.clone(), net.ober2cano_transform.clone(), net.verts_template.clone()
+    verts, o2c, ginv, vt = ops().body_tables(net.body_model, posed, tmpl)
+    assert float((verts - verts_ref).abs().max()) < 2e-5
+    assert float((ginv - ginv_ref).abs().max()) < 2e-5
+    assert float((vt - vt_ref).abs().max()) < 2e-5
+    assert float((o2c - o2c_ref).abs().max()) < 1e-4
+    assert torch.equal(o2c[..., 3, :], torch.tensor([0.0, 0.0, 0.0, 1.0], device=DEV).expand(B, o2c.shape[1], 4))
+    # the path picks the fused builder when nothing needs a gradient, the torch builder otherwise
+    with torch.no_grad():
+        rays_w = torch.from_numpy(synthetic.rays_at_bbox(posed_np["transl"][:, None] + np.zeros((B, 4, 3), np.float32), 8)).to(DEV)
+        rays_b, ginv2 = net.setup_frame(posed, tmpl, rays_w)
+    assert net.verts_transform is None and torch.equal(ginv2, ginv) and torch.equal(net.verts, verts)
+    posed_g = dict(posed, body_pose=posed["body_pose"].clone().requires_grad_(True))
+    rays_b2, _ = net.setup_frame(posed_g, tmpl if not shared_template else {k: v.expand(B, *v.shape[1:]) for k, v in tmpl.items()}, rays_w)
+    assert net.verts_transform is not None and net.ober2cano_transform.requires_grad
+    assert float((rays_b2 - rays_b).abs().max()) < 2e-5
+    net.ober2cano_transform.sum().backward()
+    assert posed_g["body_pose"].grad is not None and float(posed_g["body_pose"].grad.abs().sum()) > 0
