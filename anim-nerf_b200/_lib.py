@@ -24,7 +24,9 @@ SIGNATURES = {
     "an_vertex_grid_build": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp]),
     "an_knn_query_ws_bytes": (_i64, [_i32, _i64]),
     "an_knn_unpose_fwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _i32,
+                                 _vp, _vp, _vp, _i32,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "an_debug_knn_variant": (_i32, [_i32]),
     "an_knn_unpose_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "an_mlp_packed_bytes": (_i64, []),
     "an_mlp_pack": (_i32, [_vp, _vp, _vp, _vp]),
@@ -40,7 +42,7 @@ SIGNATURES = {
     "an_searchsorted_right": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "an_body_tables_ws_bytes": (_i64, [_i32]),
     "an_body_tables_fwd": (_i32, [_vp] * 6 + [_i32, _i32] + [_vp] * 7 + [_i32, _i32, _i32] + [_vp] * 6),
-    "an_sample_fine_merge_fwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _u64, _vp, _vp, _vp, _vp]),
+    "an_sample_fine_merge_fwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _u64, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

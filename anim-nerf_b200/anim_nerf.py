@@ -171,13 +171,18 @@ class AnimNeRF(nn.Module):
                     net=net, knn_mode=self.knn_mode, mlp_impl=self.mlp_impl, unpose=self.use_unpose,
                     grad=torch.is_grad_enabled())
 
-    def render_pass(self, rays, z, use_fine=False, sigma_noise=None, white_bkgd=True):
-        """Fused composite pass used by VolumeRenderer: -> (weights, rgb, depth, acc)."""
+    def render_pass(self, rays, z, use_fine=False, sigma_noise=None, white_bkgd=True, want_seed=False, seed=None):
+        """Fused composite pass used by VolumeRenderer: -> (weights, rgb, depth, acc).
+        want_seed: keep this pass's neighbour table in `self.last_knn_idx`; seed: dict(src, nn, idx) from
+        `sample_fine_merge` + an earlier pass over the same rays (see `ops.knn_unpose`)."""
         if not self.use_unpose:
             raise NotImplementedError("render_pass is built for use_unpose=True (every shipped config)")
         cfg = self._cfg(use_fine)
         cfg["white"] = bool(white_bkgd)
+        if self.knn_mode == 1:
+            cfg["want_seed"], cfg["seed"] = bool(want_seed), seed
         rgb, depth, acc, w = RenderPass.apply(rays, z, self.ober2cano_transform, sigma_noise, cfg, *cfg["net"].param_list())
+        self.last_knn_idx = cfg.get("knn_idx") if (want_seed and self.knn_mode == 1) else None
         return w, rgb, depth, acc
 
     # ------------------------------------------------------------------ point queries (B2)

@@ -29,9 +29,13 @@ class RenderPass(torch.autograd.Function):
         rays_c, z_c, o2c_c = rays.contiguous(), z.contiguous(), ober2cano.contiguous()
         sigma = torch.empty(B, R, K, device=dev)
         rgb = torch.empty(B, R, K, 3, device=dev)
+        # cfg["seed"]: (src, nn, idx) of the coarse pass over the same rays -- the fine pass reuses / starts
+        # from those neighbours; cfg["want_seed"]: this pass's idx table is handed back in cfg["knn_idx"]
+        want_idx = need_grad or cfg.get("want_seed", False)
         out = ops.knn_unpose(cfg["verts"], o2c_c, cfg["lbs"], cfg["thr"], rays=rays_c, z=z_c, grid=cfg["grid"],
-                             mode=cfg.get("knn_mode", 1), want_idx=need_grad, want_qw=need_grad,
-                             sigma=sigma, rgb=rgb, compact=True)
+                             mode=cfg.get("knn_mode", 1), want_idx=want_idx, want_qw=need_grad,
+                             sigma=sigma, rgb=rgb, compact=True, seed=cfg.get("seed"))
+        cfg["knn_idx"] = out["idx"]
         if COUNT_LOG is not None:
             COUNT_LOG.append((K, out["count"]))
         packed = net.packed()
@@ -157,14 +161,14 @@ class SampleFineMerge(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, weights, z_coarse, n_fine, det, u, seed):
-        z_fine, z_all, src = ops.sample_fine_merge(weights, z_coarse, n_fine, det, u, seed)
+        z_fine, z_all, src, nn = ops.sample_fine_merge(weights, z_coarse, n_fine, det, u, seed)
         ctx.save_for_backward(src)
         ctx.kc = z_coarse.shape[-1]
-        ctx.mark_non_differentiable(z_fine)
-        return z_all, z_fine
+        ctx.mark_non_differentiable(z_fine, src, nn)
+        return z_all, z_fine, src, nn
 
     @staticmethod
-    def backward(ctx, g_all, _g_fine):
+    def backward(ctx, g_all, _g_fine, _g_src, _g_nn):
         (src,) = ctx.saved_tensors
         g_cat = torch.zeros_like(g_all).scatter_(-1, src.long(), g_all)
         return None, g_cat[..., :ctx.kc].contiguous(), None, None, None, None

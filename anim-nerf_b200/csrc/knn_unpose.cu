@@ -104,8 +104,9 @@ struct UnposeOut {
     float* sigma; float* rgb; int32_t* cidx; int32_t* count;
 };
 
-// Epilogue shared by both search kernels.  `found`: best holds the exact 4-NN.
-__device__ __forceinline__ void unpose_epilogue(const Best4& best, bool found, float qx, float qy, float qz,
+// Epilogue shared by the search kernels.  `have4`: best holds the exact 4-NN (idx/dist are emitted);
+// `found`: ... and the nearest one is within the threshold, so the point may be valid (blend evaluated).
+__device__ __forceinline__ void unpose_epilogue(const Best4& best, bool have4, bool found, float qx, float qy, float qz,
                                                 int64_t gid, int b, int V, int J,
                                                 const float* __restrict__ ober2cano,
                                                 const float* __restrict__ lbsw, float thr,
@@ -114,9 +115,11 @@ __device__ __forceinline__ void unpose_epilogue(const Best4& best, bool found, f
     bool valid = false;
     float xc0 = 0.f, xc1 = 0.f, xc2 = 0.f;
     float dd[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-    if (active && found) {
+    if (active && have4) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) dd[j] = __fsqrt_rn(best.d[j]);
+    }
+    if (active && found) {
         // confidence: skinning rows of neighbour j vs neighbour 0
         const float* w0 = lbsw + (int64_t)best.i[0] * J;
         float l1[4] = {0.f, 0.f, 0.f, 0.f};
@@ -166,7 +169,7 @@ __device__ __forceinline__ void unpose_epilogue(const Best4& best, bool found, f
         o.xyz_cano[gid * 3] = xc0; o.xyz_cano[gid * 3 + 1] = xc1; o.xyz_cano[gid * 3 + 2] = xc2;
         o.valid[gid] = valid ? 1 : 0;
         if (o.idx) {
-            int4 v = found ? make_int4(best.i[0], best.i[1], best.i[2], best.i[3]) : make_int4(-1, -1, -1, -1);
+            int4 v = have4 ? make_int4(best.i[0], best.i[1], best.i[2], best.i[3]) : make_int4(-1, -1, -1, -1);
             ((int4*)o.idx)[gid] = v;
         }
         if (o.dist) ((float4*)o.dist)[gid] = make_float4(dd[0], dd[1], dd[2], dd[3]);
@@ -218,7 +221,7 @@ knn_unpose_brute_kernel(const float* __restrict__ xyz, const float* __restrict__
                 best_push_ordered(best, dist2_rn(qx, qy, qz, p.x, p.y, p.z), v);
             }
         }
-        unpose_epilogue(best, true, qx, qy, qz, gid, b, V, J, ober2cano, lbsw, thr, o, active);
+        unpose_epilogue(best, true, true, qx, qy, qz, gid, b, V, J, ober2cano, lbsw, thr, o, active);
     }
 }
 
@@ -333,19 +336,31 @@ vertex_grid_build_kernel(const float* __restrict__ verts, int V, float cell_in, 
 //      App. A): it gets its final outputs here.  Every other query is appended (x,y,z,id) to a
 //      compact work list, 32 consecutive queries per warp-aggregated append, so consecutive list
 //      entries are (almost always) consecutive samples of one ray.
-//  knn_search_kernel    one thread per listed query, a warp pulling 32 consecutive entries at a time,
-//      so every lane has work and neighbouring lanes walk nearly the same cells (L1 hits).  The
-//      search is a shrinking-ball walk of the cell box: own cell first; the bound is then tightened
-//      from the neighbouring lanes by the triangle inequality (d4(q) <= d4(q') + |q - q'|:
-//      consecutive ray samples are centimetres apart); then the rows (dy,dz) nearest ring first; a
-//      row is skipped when its slab is farther than the bound B, its x-range is trimmed to the
-//      ball of radius sqrt(B), and B drops to the current 4th-best distance as soon as four
-//      candidates are in hand.
+//      Seeded pass (fine pass of VolumeRenderer.forward, models/volume_rendering.py:199-207): half of
+//      the sorted samples ARE coarse samples (same ray, same depth bits => the same point), so their
+//      4-NN are read back from the coarse pass's idx table, the four distances re-evaluated (same
+//      arithmetic => same bits) and the epilogue runs right here, without any search.
+//  knn_search_kernel    one thread per listed query, a warp pulling 32 consecutive entries at a time.
+//      Every lane first gets an upper bound on its 4th-neighbour distance:
+//        warm   (seeded pass) the 4-NN of the nearest coarse sample of the same ray are four real
+//               vertices: the largest of their distances to this query bounds d4 -- typically within
+//               half a coarse step (1.5 cm) of the truth;
+//        cold   the query's own cell, scanned first, usually yields four candidates;
+//        then the bounds travel along the warp by the triangle inequality
+//               d4(q) <= d4(q') + |q - q'| in doubling strides (a min-plus scan in both directions).
+//      The exact search is then a ball-pruned walk of the 7x7 rows of the cell box, nearest ring first:
+//      a row is skipped when its slab is farther than the bound, its x range is trimmed to the ball,
+//      and the bound drops to the current 4th-best distance as candidates arrive.
 // Exactness: everything skipped is provably farther than the final 4th neighbour whenever that
 // neighbour lies within the query's initial bound and the box (margins absorb fp32 rounding);
 // otherwise the warp rescans the whole table cooperatively.  The (d2,index) order key makes the
 // result independent of the scan order: both modes return identical bits.
-struct QueryWs { unsigned int n_work; unsigned int next_chunk; unsigned int pad[2]; };   // then float4 work[B*N]
+struct QueryWs { unsigned int n_work; unsigned int next_chunk; unsigned int pad[2]; unsigned long long stats[4]; };   // then float4 work[B*N]
+
+// Seeds from an earlier pass over the same rays (all NULL/0 when absent): src[g] < Kc says query g is
+// coarse sample src[g] of its ray, nn[g] is the coarse sample nearest in depth, idx is the earlier
+// pass's (B*R*Kc, 4) neighbour table.
+struct SeedIn { const uint8_t* src; const uint8_t* nn; const int32_t* idx; int Kc; };
 
 __device__ __forceinline__ void warp_merge4(Best4& lb, Best4& g)
 {
@@ -368,40 +383,74 @@ __constant__ int8_t c_row_dy[49] = {0, -1, 0, 1, -1, 1, -1, 0, 1, -2, -1, 0, 1, 
 __constant__ int8_t c_row_dz[49] = {0, -1, -1, -1, 0, 0, 1, 1, 1, -2, -2, -2, -2, -2, -1, -1, 0, 0, 1, 1, 2, 2, 2, 2, 2, -3, -3, -3, -3, -3, -3, -3, -2, -2, -1, -1, 0, 0, 1, 1, 2, 2, 3, 3, 3, 3, 3, 3, 3};
 __constant__ int8_t c_row_ring[49] = {0, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3};
 static_assert(GRID_R == 3, "row tables are generated for a 7x7 box");
+#define N_ROWS ((2 * GRID_R + 1) * (2 * GRID_R + 1))
+
+// the four seed vertices of a query: distances re-evaluated with the contract's arithmetic
+__device__ __forceinline__ void seed_distances(const float* __restrict__ vb, const int4 si, float qx, float qy, float qz,
+                                               float d[4])
+{
+    const int ids[4] = {si.x, si.y, si.z, si.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float* v = vb + (int64_t)ids[j] * 3;
+        d[j] = dist2_rn(qx, qy, qz, __ldg(v), __ldg(v + 1), __ldg(v + 2));
+    }
+}
 
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_classify_kernel(const float* __restrict__ xyz, const float* __restrict__ rays, const float* __restrict__ z,
-                    int K, int64_t N, int64_t total, const char* __restrict__ ws, int64_t frame_bytes,
-                    QueryWs* __restrict__ qws, UnposeOut o)
+                    int K, int64_t N, int64_t total, const float* __restrict__ verts, int V,
+                    const char* __restrict__ ws, int64_t frame_bytes, QueryWs* __restrict__ qws,
+                    const float* __restrict__ ober2cano, const float* __restrict__ lbsw, int J, float thr,
+                    SeedIn sd, UnposeOut o)
 {
     float4* __restrict__ work = (float4*)(qws + 1);
     const int lane = threadIdx.x & 31;
+    const float thr2 = thr * thr * (1.0f + 1e-5f);
     for (int64_t g0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) & ~31ll; g0 < total; g0 += (int64_t)gridDim.x * blockDim.x) {
         const int64_t gid = g0 + lane;
         const bool active = gid < total;
-        bool maybe = false;
+        bool maybe = false, same = false, have4 = false, found = false;
         float qx = 0.f, qy = 0.f, qz = 0.f;
+        Best4 sb; best_init(sb);
+        const int b = active ? (int)(gid / N) : 0;
         if (active) {
-            const int b = (int)(gid / N);
-            const GridHeader h = *(const GridHeader*)(ws + (int64_t)b * frame_bytes);
-            const uint8_t* __restrict__ flags = (const uint8_t*)(ws + (int64_t)b * frame_bytes + GRID_OFF_FLAGS);
             load_query(xyz, rays, z, gid, K, qx, qy, qz);
-            const float inv_cell = 1.0f / h.cell;
-            const int ex = (int)floorf((qx - h.ox) * inv_cell) + GRID_R, ey = (int)floorf((qy - h.oy) * inv_cell) + GRID_R,
-                      ez = (int)floorf((qz - h.oz) * inv_cell) + GRID_R;
-            const int ex_n = h.nx + 2 * GRID_R, ey_n = h.ny + 2 * GRID_R, ez_n = h.nz + 2 * GRID_R;
-            maybe = ex >= 0 && ex < ex_n && ey >= 0 && ey < ey_n && ez >= 0 && ez < ez_n;
-            if (maybe) maybe = __ldg(flags + ((int64_t)ez * ey_n + ey) * ex_n + ex) != 0;
-            if (!maybe) {            // no vertex within the box radius (>= threshold): final outputs of an invalid point
-                o.xyz_cano[gid * 3] = 0.f; o.xyz_cano[gid * 3 + 1] = 0.f; o.xyz_cano[gid * 3 + 2] = 0.f;
-                o.valid[gid] = 0;
-                if (o.idx) ((int4*)o.idx)[gid] = make_int4(-1, -1, -1, -1);
-                if (o.dist) ((float4*)o.dist)[gid] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (o.qw) ((float4*)o.qw)[gid] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (o.sigma) o.sigma[gid] = -1e5f;
-                if (o.rgb) { o.rgb[gid * 3] = 0.f; o.rgb[gid * 3 + 1] = 0.f; o.rgb[gid * 3 + 2] = 0.f; }
+            if (sd.idx) {
+                const int s = sd.src[gid];
+                if (s < sd.Kc) {          // this sample IS coarse sample s of its ray: reuse that pass's neighbours
+                    same = true;
+                    const int4 si = __ldg((const int4*)sd.idx + (gid / K) * sd.Kc + s);
+                    if (si.x >= 0) {
+                        have4 = true;
+                        seed_distances(verts + (int64_t)b * V * 3, si, qx, qy, qz, sb.d);
+                        sb.i[0] = si.x; sb.i[1] = si.y; sb.i[2] = si.z; sb.i[3] = si.w;
+                        found = sb.d[0] < thr2;
+                    }
+                }
+            }
+            if (!same) {
+                const GridHeader h = *(const GridHeader*)(ws + (int64_t)b * frame_bytes);
+                const uint8_t* __restrict__ flags = (const uint8_t*)(ws + (int64_t)b * frame_bytes + GRID_OFF_FLAGS);
+                const float inv_cell = 1.0f / h.cell;
+                const int ex = (int)floorf((qx - h.ox) * inv_cell) + GRID_R, ey = (int)floorf((qy - h.oy) * inv_cell) + GRID_R,
+                          ez = (int)floorf((qz - h.oz) * inv_cell) + GRID_R;
+                const int ex_n = h.nx + 2 * GRID_R, ey_n = h.ny + 2 * GRID_R, ez_n = h.nz + 2 * GRID_R;
+                maybe = ex >= 0 && ex < ex_n && ey >= 0 && ey < ey_n && ez >= 0 && ez < ez_n;
+                if (maybe) maybe = __ldg(flags + ((int64_t)ez * ey_n + ey) * ex_n + ex) != 0;
+                if (!maybe) {            // no vertex within the box radius (>= threshold): final outputs of an invalid point
+                    o.xyz_cano[gid * 3] = 0.f; o.xyz_cano[gid * 3 + 1] = 0.f; o.xyz_cano[gid * 3 + 2] = 0.f;
+                    o.valid[gid] = 0;
+                    if (o.idx) ((int4*)o.idx)[gid] = make_int4(-1, -1, -1, -1);
+                    if (o.dist) ((float4*)o.dist)[gid] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (o.qw) ((float4*)o.qw)[gid] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (o.sigma) o.sigma[gid] = -1e5f;
+                    if (o.rgb) { o.rgb[gid * 3] = 0.f; o.rgb[gid * 3 + 1] = 0.f; o.rgb[gid * 3 + 2] = 0.f; }
+                }
             }
         }
+        if (sd.idx)      // (warp-uniform) samples shared with the seeding pass finish here
+            unpose_epilogue(sb, have4, found, qx, qy, qz, gid, b, V, J, ober2cano, lbsw, thr, o, active && same);
         const unsigned mask = __ballot_sync(0xffffffffu, maybe);
         if (mask) {
             const int leader = __ffs(mask) - 1;
@@ -425,17 +474,45 @@ __device__ __forceinline__ void best_insert_sorted(Best4& b, float d2, int idx) 
         b.d[k] = td; b.i[k] = ti;
     }
 }
+// A vertex may be met twice (a seed, then again in its cell): equal keys never pass the strict
+// comparison against slot 3, slots 0-2 are checked by index.
+__device__ __forceinline__ bool best_accepts(const Best4& b, float d2, int idx) {
+    return key_less(d2, idx, b.d[3], b.i[3]) && idx != b.i[0] && idx != b.i[1] && idx != b.i[2];
+}
 
 #define SEARCH_THREADS 128
-#define SEARCH_MAX_ENT 50                 // 49 rows, row 0 may split around the own cell
-#define SEARCH_SMEM (SEARCH_MAX_ENT * SEARCH_THREADS * 8)
 
-__global__ void __launch_bounds__(SEARCH_THREADS)
-knn_search_kernel(int64_t N, const float* __restrict__ verts, int V, const char* __restrict__ ws,
-                  int64_t frame_bytes, QueryWs* __restrict__ qws, const float* __restrict__ ober2cano,
-                  const float* __restrict__ lbsw, int J, float thr, UnposeOut o)
+// One row of the cell box for one query: slab gap^2 and the candidate range [s0, e1) of the cell-sorted
+// table after trimming the x extent to the ball of radius sqrt(Bm).  Returns false when nothing is left.
+struct RowCtx { float qx, fy, fz, ox, cell, inv_cell, Bm; int cx, cy, cz, nx, ny, nz; };
+__device__ __forceinline__ bool row_range(const RowCtx& c, int r, const int* __restrict__ cell_start,
+                                          float& g2, int& row, int& x0, int& x1)
 {
-    // per-thread list of candidate ranges, layout [entry][thread] (bank = thread: conflict-free for any
+    const int dy = c_row_dy[r], dz = c_row_dz[r];
+    const int gy = c.cy + dy, gz = c.cz + dz;
+    const float gapy = dy == 0 ? 0.f : (dy > 0 ? (float)dy * c.cell - c.fy : c.fy - (float)(dy + 1) * c.cell);
+    const float gapz = dz == 0 ? 0.f : (dz > 0 ? (float)dz * c.cell - c.fz : c.fz - (float)(dz + 1) * c.cell);
+    g2 = (gapy > 0.f ? gapy * gapy : 0.f) + (gapz > 0.f ? gapz * gapz : 0.f);
+    if (!(gz >= 0 && gz < c.nz && gy >= 0 && gy < c.ny && g2 <= c.Bm)) return false;
+    const float w = sqrtf(fmaxf(c.Bm - g2, 0.f)) + 1e-3f * c.cell;
+    x0 = max(c.cx - GRID_R, (int)floorf((c.qx - w - c.ox) * c.inv_cell));
+    x1 = min(c.cx + GRID_R, (int)floorf((c.qx + w - c.ox) * c.inv_cell));
+    x0 = max(x0, 0); x1 = min(x1, c.nx - 1);
+    row = (gz * c.ny + gy) * c.nx;
+    return x0 <= x1;
+}
+
+// VAR 1: nested loops, no shared memory (each lane walks its rows and candidates on its own).
+// VAR 3: rows listed in lockstep into a CAP-entry shared-memory list per thread, then one flat loop in
+//        which every lane that still has a candidate evaluates it; the list is refilled (with the
+//        tightened bound) until the rows run out.
+template <int VAR, int CAP>
+__global__ void __launch_bounds__(SEARCH_THREADS)
+knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, const char* __restrict__ ws,
+                  int64_t frame_bytes, QueryWs* __restrict__ qws, const float* __restrict__ ober2cano,
+                  const float* __restrict__ lbsw, int J, float thr, SeedIn sd, UnposeOut o, int want_stats, int drain_t)
+{
+    // VAR 3: per-thread list of candidate ranges, layout [entry][thread] (bank = thread: conflict-free for any
     // per-lane entry index): .x = start | end << 16 (positions in the cell-sorted table), .y = row slab gap^2
     extern __shared__ uint2 s_ent[];
     const float4* __restrict__ work = (const float4*)(qws + 1);
@@ -444,6 +521,7 @@ knn_search_kernel(int64_t N, const float* __restrict__ verts, int V, const char*
     const unsigned n_chunks = (n_work + 31) / 32;
     const float thr2 = thr * thr * (1.0f + 1e-5f);   // prune only what is invalid beyond rounding doubt
     uint2* __restrict__ my_ent = s_ent + threadIdx.x;
+    unsigned n_cand = 0, n_iter = 0, n_redo = 0;   // statistics (tools/bench_knn.py)
     for (;;) {
         unsigned chunk = 0;
         if (lane == 0) chunk = atomicAdd(&qws->next_chunk, 1u);
@@ -469,29 +547,41 @@ knn_search_kernel(int64_t N, const float* __restrict__ verts, int V, const char*
                   cz = (int)floorf((qz - h.oz) * inv_cell);
         const bool own = active && cx >= 0 && cx < h.nx && cy >= 0 && cy < h.ny && cz >= 0 && cz < h.nz;
         Best4 mine; best_init(mine);
-        {   // phase 0 -- own cell: usually yields four candidates and a tight bound.  One flat loop: all lanes
-            // that still have a vertex left evaluate it together.
+        bool warm = false;
+        if (active && sd.idx) {       // seeds: the 4-NN of the nearest coarse sample of this ray
+            const int4 si = __ldg((const int4*)sd.idx + (gid / K) * sd.Kc + sd.nn[gid]);
+            if (si.x >= 0) {
+                warm = true;
+                float d[4];
+                seed_distances(verts + (int64_t)b * V * 3, si, qx, qy, qz, d);
+                best_insert_sorted(mine, d[0], si.x); best_insert_sorted(mine, d[1], si.y);
+                best_insert_sorted(mine, d[2], si.z); best_insert_sorted(mine, d[3], si.w);
+            }
+        }
+        const bool did_own = own && !warm;
+        {   // cold lanes -- own cell: usually yields four candidates and a tight bound
             int p = 0, pe = 0;
-            if (own) { const int c = (cz * h.ny + cy) * h.nx + cx; p = __ldg(cell_start + c); pe = __ldg(cell_start + c + 1); }
+            if (did_own) { const int c = (cz * h.ny + cy) * h.nx + cx; p = __ldg(cell_start + c); pe = __ldg(cell_start + c + 1); }
+            n_cand += (unsigned)(pe - p);
             for (; p < pe; ++p) {
                 const float4 v = __ldg(sorted + p);
                 const float d2 = dist2_rn(qx, qy, qz, v.x, v.y, v.z);
                 if (key_less(d2, __float_as_int(v.w), mine.d[3], mine.i[3])) best_insert_sorted(mine, d2, __float_as_int(v.w));
             }
         }
-        {   // neighbouring lanes are neighbouring samples of a ray: d4(q) <= d4(q') + |q - q'| tightens the
-            // bound of the lanes whose own cell held fewer than four vertices
+        {   // bounds travel along the warp (neighbouring lanes are neighbouring samples of a ray):
+            // d4(q) <= d4(q') + |q - q'|, doubling strides in both directions
             float u = active ? sqrtf(fminf(mine.d[3], B)) : CUDART_INF_F;
 #pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
+            for (int s = 1; s < 32; s <<= 1) {
 #pragma unroll
-                for (int dl = -1; dl <= 1; dl += 2) {
-                    const int src = min(31, max(0, lane + dl));
-                    const float ou = __shfl_sync(0xffffffffu, u, src);
-                    const float ox = __shfl_sync(0xffffffffu, qx, src), oy = __shfl_sync(0xffffffffu, qy, src), oz = __shfl_sync(0xffffffffu, qz, src);
-                    const int ob = __shfl_sync(0xffffffffu, b, src);
-                    const bool oact = __shfl_sync(0xffffffffu, (int)active, src) != 0;
-                    if (oact && ob == b) {
+                for (int dir = -1; dir <= 1; dir += 2) {
+                    const int src = lane + dir * s;
+                    const int srcc = min(31, max(0, src));
+                    const float ou = __shfl_sync(0xffffffffu, u, srcc);
+                    const float ox = __shfl_sync(0xffffffffu, qx, srcc), oy = __shfl_sync(0xffffffffu, qy, srcc), oz = __shfl_sync(0xffffffffu, qz, srcc);
+                    const int ob = __shfl_sync(0xffffffffu, b, srcc);
+                    if (src == srcc && ob == b) {           // inactive lanes carry u = inf
                         const float sx = qx - ox, sy = qy - oy, sz = qz - oz;
                         u = fminf(u, (ou + sqrtf(sx * sx + sy * sy + sz * sz)) * (1.0f + 1e-4f));
                     }
@@ -500,67 +590,146 @@ knn_search_kernel(int64_t N, const float* __restrict__ verts, int V, const char*
             B = fminf(B, u * u * (1.0f + 1e-4f));
         }
         float Bm = fminf(fminf(B, mine.d[3]) * 1.001f, box_r2 * 1.01f);
-        // phase 1 -- every lane walks the 49 rows of its 7x7 cell box in lockstep and lists the candidate
-        // ranges that intersect the ball of radius sqrt(Bm) (row slab gap <= Bm, x range trimmed to the ball)
-        int n_ent = 0;
-        {
-            const float fy = qy - (h.oy + cy * h.cell), fz = qz - (h.oz + cz * h.cell);
-#pragma unroll 7
-            for (int r = 0; r < (2 * GRID_R + 1) * (2 * GRID_R + 1); ++r) {
-                const int dy = c_row_dy[r], dz = c_row_dz[r];
-                const int gy = cy + dy, gz = cz + dz;
-                const float gapy = dy == 0 ? 0.f : (dy > 0 ? (float)dy * h.cell - fy : fy - (float)(dy + 1) * h.cell);
-                const float gapz = dz == 0 ? 0.f : (dz > 0 ? (float)dz * h.cell - fz : fz - (float)(dz + 1) * h.cell);
-                const float g2 = (gapy > 0.f ? gapy * gapy : 0.f) + (gapz > 0.f ? gapz * gapz : 0.f);
-                bool ok = active && gz >= 0 && gz < h.nz && gy >= 0 && gy < h.ny && g2 <= Bm;
-                const float w = sqrtf(fmaxf(Bm - g2, 0.f)) + 1e-3f * h.cell;
-                int x0 = max(cx - GRID_R, (int)floorf((qx - w - h.ox) * inv_cell));
-                int x1 = min(cx + GRID_R, (int)floorf((qx + w - h.ox) * inv_cell));
-                x0 = max(x0, 0); x1 = min(x1, h.nx - 1);
-                ok = ok && x0 <= x1;
-                if (ok) {
-                    const int row = (gz * h.ny + gy) * h.nx;
-                    const int s0 = __ldg(cell_start + row + x0), e1 = __ldg(cell_start + row + x1 + 1);
-                    if (r == 0 && own && cx >= x0 && cx <= x1) {     // the own cell was scanned in phase 0: split around it
-                        const int e0 = __ldg(cell_start + row + cx), s1 = __ldg(cell_start + row + cx + 1);
-                        if (e0 > s0) { my_ent[n_ent * SEARCH_THREADS] = make_uint2((unsigned)s0 | ((unsigned)e0 << 16), __float_as_uint(g2)); ++n_ent; }
-                        if (e1 > s1) { my_ent[n_ent * SEARCH_THREADS] = make_uint2((unsigned)s1 | ((unsigned)e1 << 16), __float_as_uint(g2)); ++n_ent; }
-                    } else if (e1 > s0) {
-                        my_ent[n_ent * SEARCH_THREADS] = make_uint2((unsigned)s0 | ((unsigned)e1 << 16), __float_as_uint(g2)); ++n_ent;
+        RowCtx rc;
+        rc.qx = qx; rc.fy = qy - (h.oy + cy * h.cell); rc.fz = qz - (h.oz + cz * h.cell);
+        rc.ox = h.ox; rc.cell = h.cell; rc.inv_cell = inv_cell; rc.cx = cx; rc.cy = cy; rc.cz = cz;
+        rc.nx = h.nx; rc.ny = h.ny; rc.nz = h.nz;
+        if (VAR == 1) {
+            if (active) {
+                for (int r = 0; r < N_ROWS; ++r) {
+                    const int ring = c_row_ring[r];
+                    if (ring >= 2) {                  // nearest row of ring k is at least (k-1) cells away
+                        const float rg = (float)(ring - 1) * h.cell;
+                        if (rg * rg > Bm) break;
+                    }
+                    float g2; int row, x0, x1;
+                    rc.Bm = Bm;
+                    if (!row_range(rc, r, cell_start, g2, row, x0, x1)) continue;
+                    // candidate ranges of the row; an own cell scanned above (row 0) is skipped
+                    int s0 = __ldg(cell_start + row + x0), e0r, s1, e1 = __ldg(cell_start + row + x1 + 1);
+                    if (r == 0 && did_own && cx >= x0 && cx <= x1) { e0r = __ldg(cell_start + row + cx); s1 = __ldg(cell_start + row + cx + 1); }
+                    else { e0r = e1; s1 = e1; }
+                    for (int part = 0; part < 2; ++part) {
+                        const int ps = part ? s1 : s0, pe = part ? e1 : e0r;
+                        n_cand += (unsigned)max(pe - ps, 0);
+                        for (int p = ps; p < pe; ++p) {
+                            const float4 v = __ldg(sorted + p);
+                            const float d2 = dist2_rn(qx, qy, qz, v.x, v.y, v.z);
+                            if (best_accepts(mine, d2, __float_as_int(v.w))) {
+                                best_insert_sorted(mine, d2, __float_as_int(v.w));
+                                Bm = fminf(Bm, mine.d[3] * 1.001f);
+                            }
+                        }
                     }
                 }
             }
-        }
-        {   // phase 2 -- one flat loop over the listed candidates: a lane whose range is used up pops its next
-            // entry (rows that fell outside the shrunken ball are skipped whole), then every lane that still has
-            // a candidate evaluates it -- the distance / insert code runs convergent across the warp.
-            int k = 0, p = 0, pe = 0;
-            bool live = n_ent > 0;
+        } else {
+            int r = 0;                                // warp-uniform row cursor
+            bool done = !active;                      // this lane's ball ends before the current ring
             for (;;) {
-                if (live && p >= pe) {
-                    live = false;
-                    while (k < n_ent) {
-                        const uint2 en = my_ent[k * SEARCH_THREADS]; ++k;
-                        if (__uint_as_float(en.y) <= Bm) { p = (int)(en.x & 0xffffu); pe = (int)(en.x >> 16); live = true; break; }
+                // list the next rows that intersect the ball (at most CAP entries per lane per round)
+                int n_ent = 0;
+                for (; r < N_ROWS; ++r) {
+                    if (__any_sync(0xffffffffu, n_ent > CAP - 2)) break;
+                    const int ring = c_row_ring[r];
+                    if (ring >= 2) { const float rg = (float)(ring - 1) * h.cell; if (rg * rg > Bm) done = true; }
+                    if (!__any_sync(0xffffffffu, !done)) { r = N_ROWS; break; }
+                    float g2; int row, x0, x1;
+                    rc.Bm = Bm;
+                    if (!done && row_range(rc, r, cell_start, g2, row, x0, x1)) {
+                        const int s0 = __ldg(cell_start + row + x0), e1 = __ldg(cell_start + row + x1 + 1);
+                        if (r == 0 && did_own && cx >= x0 && cx <= x1) {     // the own cell was scanned above: split around it
+                            const int e0 = __ldg(cell_start + row + cx), s1 = __ldg(cell_start + row + cx + 1);
+                            if (e0 > s0) { my_ent[n_ent * SEARCH_THREADS] = make_uint2((unsigned)s0 | ((unsigned)e0 << 16), __float_as_uint(g2)); ++n_ent; }
+                            if (e1 > s1) { my_ent[n_ent * SEARCH_THREADS] = make_uint2((unsigned)s1 | ((unsigned)e1 << 16), __float_as_uint(g2)); ++n_ent; }
+                        } else if (e1 > s0) {
+                            my_ent[n_ent * SEARCH_THREADS] = make_uint2((unsigned)s0 | ((unsigned)e1 << 16), __float_as_uint(g2)); ++n_ent;
+                        }
                     }
                 }
-                if (!__any_sync(0xffffffffu, live)) break;
-                if (live) {
-                    const float4 v = __ldg(sorted + p); ++p;
-                    const float d2 = dist2_rn(qx, qy, qz, v.x, v.y, v.z);
-                    if (key_less(d2, __float_as_int(v.w), mine.d[3], mine.i[3])) {
-                        best_insert_sorted(mine, d2, __float_as_int(v.w));
-                        Bm = fminf(Bm, mine.d[3] * 1.001f);
+                // one flat loop over the listed candidates: a lane whose range is used up pops its next entry
+                // (rows that fell outside the shrunken ball are skipped whole), then every lane that still has
+                // a candidate evaluates it -- the distance / insert code runs convergent across the warp.
+                int k = 0, p = 0, pe = 0;
+                bool live = n_ent > 0;
+                for (;;) {
+                    if (live && p >= pe) {
+                        live = false;
+                        while (k < n_ent) {
+                            const uint2 en = my_ent[k * SEARCH_THREADS]; ++k;
+                            if (__uint_as_float(en.y) <= Bm) { p = (int)(en.x & 0xffffu); pe = (int)(en.x >> 16); live = true; break; }
+                        }
+                    }
+                    const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+                    if (__popc(live_mask) <= drain_t) break;      // few lanes left: drain them cooperatively below
+                    ++n_iter;
+                    if (live) {               // two candidates per trip: both loads in flight before the first use
+                        const bool two = p + 1 < pe;
+                        const float4 v0 = __ldg(sorted + p), v1 = __ldg(sorted + (two ? p + 1 : p));
+                        p += 2;
+                        n_cand += two ? 2u : 1u;
+                        const float d0 = dist2_rn(qx, qy, qz, v0.x, v0.y, v0.z);
+                        const float d1 = two ? dist2_rn(qx, qy, qz, v1.x, v1.y, v1.z) : CUDART_INF_F;
+                        if (fminf(d0, d1) <= mine.d[3]) {          // cheap reject first: almost every candidate fails it
+                            if (best_accepts(mine, d0, __float_as_int(v0.w))) best_insert_sorted(mine, d0, __float_as_int(v0.w));
+                            if (two && best_accepts(mine, d1, __float_as_int(v1.w))) best_insert_sorted(mine, d1, __float_as_int(v1.w));
+                            Bm = fminf(Bm, mine.d[3] * 1.001f);
+                        }
                     }
                 }
+                // The lanes still holding candidates (long lists: far queries with a wide ball) are drained one
+                // at a time by the whole warp: 32 consecutive table entries per step (coalesced), the step's
+                // minimum found by REDUX and handed to the owning lane while it beats that lane's 4th best.
+                unsigned heavy = __ballot_sync(0xffffffffu, live);
+                while (heavy) {
+                    const int L = __ffs(heavy) - 1;
+                    heavy &= heavy - 1;
+                    const float ux = __shfl_sync(0xffffffffu, qx, L), uy = __shfl_sync(0xffffffffu, qy, L), uz = __shfl_sync(0xffffffffu, qz, L);
+                    int up = __shfl_sync(0xffffffffu, p, L), upe = __shfl_sync(0xffffffffu, pe, L), uk = __shfl_sync(0xffffffffu, k, L);
+                    const int un = __shfl_sync(0xffffffffu, n_ent, L);
+                    float uBm = __shfl_sync(0xffffffffu, Bm, L), bd3 = __shfl_sync(0xffffffffu, mine.d[3], L);
+                    const int ub = __shfl_sync(0xffffffffu, b, L);
+                    const float4* __restrict__ usorted = (const float4*)(ws + (int64_t)ub * frame_bytes + GRID_OFF_SORTED);
+                    const uint2* __restrict__ uent = s_ent + (threadIdx.x & ~31) + L;
+                    for (;;) {
+                        if (up >= upe) {                          // (warp-uniform) next listed range still inside the ball
+                            bool got = false;
+                            while (uk < un) {
+                                const uint2 en = uent[uk * SEARCH_THREADS]; ++uk;
+                                if (__uint_as_float(en.y) <= uBm) { up = (int)(en.x & 0xffffu); upe = (int)(en.x >> 16); got = true; break; }
+                            }
+                            if (!got) break;
+                        }
+                        const int pos = up + lane;
+                        const bool in = pos < upe;
+                        up += 32;
+                        ++n_iter; n_cand += in ? 1u : 0u;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (in) v = __ldg(usorted + pos);
+                        unsigned key = in ? __float_as_uint(dist2_rn(ux, uy, uz, v.x, v.y, v.z)) : 0x7f800000u;   // d2 >= 0: uint order == float order
+                        for (;;) {
+                            const unsigned mn = __reduce_min_sync(0xffffffffu, key);
+                            if (mn >= 0x7f800000u || __uint_as_float(mn) > bd3) break;    // ties with the 4th best go to the exact test
+                            const int w = __ffs(__ballot_sync(0xffffffffu, key == mn)) - 1;
+                            const int vi = __shfl_sync(0xffffffffu, __float_as_int(v.w), w);
+                            if (lane == L && best_accepts(mine, __uint_as_float(mn), vi)) best_insert_sorted(mine, __uint_as_float(mn), vi);
+                            if (lane == w) key = 0x7f800000u;
+                            bd3 = __shfl_sync(0xffffffffu, mine.d[3], L);
+                        }
+                        uBm = fminf(uBm, bd3 * 1.001f);
+                    }
+                    if (lane == L) Bm = fminf(Bm, mine.d[3] * 1.001f);
+                }
+                if (r >= N_ROWS) break;
             }
         }
         // the walk saw every vertex within sqrt(min(B, box_r2)): four of them => the 4-NN are exact
         const bool exact4 = active && mine.d[3] <= B && mine.d[3] <= box_r2;
         const bool near_ = active && mine.d[0] < thr2;          // may be valid: needs the exact 4-NN
-        bool found = near_ && exact4;
+        bool have4 = exact4;
         const bool redo = near_ && !exact4;            // rare: 4th neighbour not provably inside the scanned ball
         unsigned redo_mask = __ballot_sync(0xffffffffu, redo);
+        n_redo += redo ? 1 : 0;
         while (redo_mask) {                            // exhaustive rescan, warp-cooperative
             const int qi = __ffs(redo_mask) - 1;
             redo_mask &= redo_mask - 1;
@@ -574,9 +743,13 @@ knn_search_kernel(int64_t N, const float* __restrict__ verts, int V, const char*
             }
             Best4 g;
             warp_merge4(lb, g);
-            if (lane == qi) { mine = g; found = true; }
+            if (lane == qi) { mine = g; have4 = true; }
         }
-        unpose_epilogue(mine, found, qx, qy, qz, gid, b, V, J, ober2cano, lbsw, thr, o, active);
+        unpose_epilogue(mine, have4, have4 && near_, qx, qy, qz, gid, b, V, J, ober2cano, lbsw, thr, o, active);
+    }
+    if (want_stats) {
+        atomicAdd(&qws->stats[0], (unsigned long long)n_cand); atomicAdd(&qws->stats[1], (unsigned long long)n_iter);
+        atomicAdd(&qws->stats[2], (unsigned long long)n_redo);
     }
 }
 
@@ -639,10 +812,34 @@ extern "C" int64_t an_knn_query_ws_bytes(int B, int64_t N)
     return (B > 0 && N > 0) ? (int64_t)sizeof(QueryWs) + (int64_t)B * N * (int64_t)sizeof(float4) : 0;
 }
 
+// Search-kernel variant (tools/bench_knn.py A/B switch; the default is the shipped one).
+static int g_knn_variant = 3 | (8 << 12);     // bits 0-7 kernel, 8 statistics, 12-17 drain threshold (lanes)
+extern "C" int an_debug_knn_variant(int v) { const int old = g_knn_variant; if (v > 0) g_knn_variant = v; return old; }
+
+template <int VAR, int CAP>
+static int launch_search(int sms, int64_t total, cudaStream_t st, int K, int64_t N, const float* verts, int V,
+                         const char* grid_ws, int64_t frame_bytes, QueryWs* qws, const float* ober2cano,
+                         const float* lbsw, int J, float thr, SeedIn sd, UnposeOut o, int want_stats, int drain_t)
+{
+    const int smem = VAR == 3 ? CAP * SEARCH_THREADS * 8 : 0;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(knn_search_kernel<VAR, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    // persistent search CTAs pull 32-query chunks from the work list (its length is device-side)
+    int64_t sb = (total + SEARCH_THREADS - 1) / SEARCH_THREADS;
+    if (sb > (int64_t)sms * 8) sb = (int64_t)sms * 8;
+    knn_search_kernel<VAR, CAP><<<(unsigned)sb, SEARCH_THREADS, smem, st>>>(
+        K, N, verts, V, grid_ws, frame_bytes, qws, ober2cano, lbsw, J, thr, sd, o, want_stats, drain_t);
+    AN_CHECK_LAUNCH();
+    return AN_OK;
+}
+
 extern "C" int an_knn_unpose_fwd(const float* xyz, const float* rays, const float* z, int B, int R, int K,
                                  int64_t N, const float* verts, int V, const void* grid_ws, void* query_ws,
                                  const float* ober2cano, const float* lbs_weights, int J,
                                  float dis_threshold, int mode,
+                                 const uint8_t* seed_src, const uint8_t* seed_nn, const int32_t* seed_idx, int seed_Kc,
                                  float* xyz_cano, uint8_t* valid, int32_t* idx, float* dist, float* qw,
                                  float* sigma, float* rgb, int32_t* cidx, int32_t* count, void* stream)
 {
@@ -651,6 +848,10 @@ extern "C" int an_knn_unpose_fwd(const float* xyz, const float* rays, const floa
     if (cidx && !count) return AN_ERR_ARG;
     if ((int64_t)B * N > 0x7fffffffLL) return AN_ERR_UNSUPPORTED;        // compact ids are int32
     if ((((uintptr_t)ober2cano) | ((uintptr_t)rays) | ((uintptr_t)idx) | ((uintptr_t)dist) | ((uintptr_t)qw)) & 15) return AN_ERR_ALIGN;
+    if (seed_idx) {                                                       // seeds refer to samples of the same rays
+        if (xyz || !seed_src || !seed_nn || seed_Kc <= 0 || seed_Kc > 255 || mode != 1) return AN_ERR_ARG;
+        if (((uintptr_t)seed_idx) & 15) return AN_ERR_ALIGN;
+    }
     UnposeOut o{xyz_cano, valid, idx, dist, qw, sigma, rgb, cidx, count};
     const int sms = an_num_sms();
     int64_t bx = (N + KNN_THREADS - 1) / KNN_THREADS;
@@ -667,23 +868,28 @@ extern "C" int an_knn_unpose_fwd(const float* xyz, const float* rays, const floa
     } else if (mode == 1) {
         if (!grid_ws || !query_ws) return AN_ERR_ARG;
         if (((uintptr_t)query_ws) & 15) return AN_ERR_ALIGN;
+        if (V > 65535) return AN_ERR_UNSUPPORTED;                          // candidate ranges are packed 16+16 bits
         QueryWs* qws = (QueryWs*)query_ws;
-        cudaError_t e = cudaMemsetAsync(qws, 0, sizeof(QueryWs), (cudaStream_t)stream);
+        cudaStream_t st = (cudaStream_t)stream;
+        cudaError_t e = cudaMemsetAsync(qws, 0, sizeof(QueryWs), st);
         if (e != cudaSuccess) return (int)e;
+        const SeedIn sd{seed_idx ? seed_src : nullptr, seed_idx ? seed_nn : nullptr, seed_idx, seed_Kc};
         const int64_t total = (int64_t)B * N;
         int64_t cb = (total + KNN_THREADS - 1) / KNN_THREADS;
         if (cb > (int64_t)sms * 32) cb = (int64_t)sms * 32;
-        knn_classify_kernel<<<(unsigned)cb, KNN_THREADS, 0, (cudaStream_t)stream>>>(
-            xyz, rays, z, K, N, total, (const char*)grid_ws, grid_frame_bytes(V), qws, o);
+        knn_classify_kernel<<<(unsigned)cb, KNN_THREADS, 0, st>>>(
+            xyz, rays, z, K, N, total, verts, V, (const char*)grid_ws, grid_frame_bytes(V), qws, ober2cano, lbs_weights, J,
+            dis_threshold, sd, o);
         AN_CHECK_LAUNCH();
-        // persistent search CTAs pull 32-query chunks from the work list (its length is device-side)
-        if (V > 65535) return AN_ERR_UNSUPPORTED;                          // candidate ranges are packed 16+16 bits
-        e = cudaFuncSetAttribute(knn_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEARCH_SMEM);
-        if (e != cudaSuccess) return (int)e;
-        int64_t sb = (total + SEARCH_THREADS - 1) / SEARCH_THREADS;
-        if (sb > (int64_t)sms * 4) sb = (int64_t)sms * 4;
-        knn_search_kernel<<<(unsigned)sb, SEARCH_THREADS, SEARCH_SMEM, (cudaStream_t)stream>>>(
-            N, verts, V, (const char*)grid_ws, grid_frame_bytes(V), qws, ober2cano, lbs_weights, J, dis_threshold, o);
+        const int var = g_knn_variant & 0xff, stats = (g_knn_variant >> 8) & 1, drain = (g_knn_variant >> 12) & 0x3f;
+        const char* gw = (const char*)grid_ws;
+        const int64_t fb = grid_frame_bytes(V);
+        int rc;
+        if (var == 1) rc = launch_search<1, 1>(sms, total, st, K, N, verts, V, gw, fb, qws, ober2cano, lbs_weights, J, dis_threshold, sd, o, stats, drain);
+        else if (var == 2) rc = launch_search<3, 50>(sms, total, st, K, N, verts, V, gw, fb, qws, ober2cano, lbs_weights, J, dis_threshold, sd, o, stats, drain);
+        else if (var == 4) rc = launch_search<3, 8>(sms, total, st, K, N, verts, V, gw, fb, qws, ober2cano, lbs_weights, J, dis_threshold, sd, o, stats, drain);
+        else rc = launch_search<3, 16>(sms, total, st, K, N, verts, V, gw, fb, qws, ober2cano, lbs_weights, J, dis_threshold, sd, o, stats, drain);
+        return rc;
     } else return AN_ERR_ARG;
     AN_CHECK_LAUNCH();
     return AN_OK;

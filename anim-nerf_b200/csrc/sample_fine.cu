@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(SF_WARPS * 32)
 sample_fine_merge_kernel(const float* __restrict__ weights, const float* __restrict__ z_coarse,
                          const float* __restrict__ u_in, int64_t n_rays, int Kc, int Kf, int det,
                          uint64_t seed, float* __restrict__ z_fine, float* __restrict__ z_all,
-                         uint8_t* __restrict__ src)
+                         uint8_t* __restrict__ src, uint8_t* __restrict__ nn_coarse)
 {
     __shared__ float s_zc[SF_WARPS][SF_MAXK];
     __shared__ float s_bins[SF_WARPS][SF_MAXK];
@@ -109,13 +109,19 @@ sample_fine_merge_kernel(const float* __restrict__ weights, const float* __restr
             const int pos = i + cnt;
             z_all[ray * Ka + pos] = a;
             if (src) src[ray * Ka + pos] = (uint8_t)i;
+            if (nn_coarse) nn_coarse[ray * Ka + pos] = (uint8_t)i;
         }
         for (int j = lane; j < Kf; j += 32) {
             const float b = zf[j];
-            int cnt = upper_bound_smem(zc, Kc, b);
+            const int nc = upper_bound_smem(zc, Kc, b);     // coarse depths <= b: samples nc-1 and nc bracket b
+            int cnt = nc;
             for (int f = 0; f < Kf; ++f) cnt += (zf[f] < b) || (zf[f] == b && f < j);
             z_all[ray * Ka + cnt] = b;
             if (src) src[ray * Ka + cnt] = (uint8_t)(Kc + j);
+            if (nn_coarse) {
+                int nn = nc == 0 ? 0 : (nc >= Kc ? Kc - 1 : ((b - zc[nc - 1] <= zc[nc] - b) ? nc - 1 : nc));
+                nn_coarse[ray * Ka + cnt] = (uint8_t)nn;
+            }
         }
         __syncwarp();
     }
@@ -135,7 +141,7 @@ extern "C" int an_searchsorted_right(const float* cdf, const float* u, int64_t n
 
 extern "C" int an_sample_fine_merge_fwd(const float* weights, const float* z_coarse, const float* u,
                                         int64_t n_rays, int Kc, int Kf, int det, uint64_t seed,
-                                        float* z_fine, float* z_all, uint8_t* src, void* stream)
+                                        float* z_fine, float* z_all, uint8_t* src, uint8_t* nn_coarse, void* stream)
 {
     if (!weights || !z_coarse || !z_all || n_rays <= 0 || Kc < 3 || Kf <= 0) return AN_ERR_ARG;
     if (Kc > SF_MAXK || Kf > SF_MAXK || Kc + Kf > 256) return AN_ERR_UNSUPPORTED;
@@ -143,7 +149,7 @@ extern "C" int an_sample_fine_merge_fwd(const float* weights, const float* z_coa
     const int64_t cap = (int64_t)an_num_sms() * 16;
     const int blocks = (int)(want < cap ? want : cap);
     sample_fine_merge_kernel<<<blocks, SF_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        weights, z_coarse, u, n_rays, Kc, Kf, det, seed, z_fine, z_all, src);
+        weights, z_coarse, u, n_rays, Kc, Kf, det, seed, z_fine, z_all, src, nn_coarse);
     AN_CHECK_LAUNCH();
     return AN_OK;
 }

@@ -90,9 +90,12 @@ def vertex_grid(verts, dis_threshold):
 
 
 def knn_unpose(verts, ober2cano, lbs_weights, dis_threshold, xyz=None, rays=None, z=None, grid=None,
-               mode=1, want_idx=False, want_dist=False, want_qw=False, sigma=None, rgb=None, compact=False):
+               mode=1, want_idx=False, want_dist=False, want_qw=False, sigma=None, rgb=None, compact=False,
+               seed=None, qws=None):
     """A5-A8.  Query points: xyz (B,N,3) or rays (B,R,8) + z (B,R,K).  Returns a dict with
-    xyz_cano (B,N,3), valid (B,N) uint8 and the optional idx/dist/qw/cidx/count."""
+    xyz_cano (B,N,3), valid (B,N) uint8 and the optional idx/dist/qw/cidx/count.
+    seed (mode 1, rays+z): dict(src, nn (B,R,K) uint8 from `sample_fine_merge`, idx (B,R*Kc,4) int32 = the
+    `idx` output of the coarse pass over the same rays): same results, far less search."""
     verts, ober2cano, lbs_weights = _f32c(verts), _f32c(ober2cano), _f32c(lbs_weights)
     B, V = verts.shape[:2]
     dev = verts.device
@@ -111,11 +114,18 @@ def knn_unpose(verts, ober2cano, lbs_weights, dis_threshold, xyz=None, rays=None
     out["count"] = torch.zeros(1, device=dev, dtype=torch.int32) if compact else None
     if mode == 1 and grid is None:
         grid = vertex_grid(verts, dis_threshold)
-    qws = None
-    if mode == 1:       # work list of the queries that survive the occupancy test (scratch, freed on return)
+    if mode == 1 and qws is None:   # work list of the queries that survive the occupancy test (scratch, freed on return)
         qws = torch.empty(_lib.load().an_knn_query_ws_bytes(B, N), device=dev, dtype=torch.uint8)
+    s_src = s_nn = s_idx = None
+    s_kc = 0
+    if seed is not None and mode == 1 and xyz is None:
+        s_src, s_nn, s_idx = seed["src"], seed["nn"], seed["idx"]
+        s_kc = s_idx.numel() // (4 * B * R)
+        assert s_src.dtype == torch.uint8 and s_nn.dtype == torch.uint8 and s_idx.dtype == torch.int32
+        assert s_src.numel() == B * N and s_nn.numel() == B * N and s_idx.numel() == B * R * s_kc * 4
     call("an_knn_unpose_fwd", ptr(xyz), ptr(rays), ptr(z), B, R, K, N, ptr(verts), V, ptr(grid), ptr(qws),
          ptr(ober2cano), ptr(lbs_weights), lbs_weights.shape[1], float(dis_threshold), int(mode),
+         ptr(s_src), ptr(s_nn), ptr(s_idx), int(s_kc),
          ptr(out["xyz_cano"]), ptr(out["valid"]), ptr(out["idx"]), ptr(out["dist"]), ptr(out["qw"]),
          ptr(sigma), ptr(rgb), ptr(out["cidx"]), ptr(out["count"]), stream())
     return out
@@ -238,7 +248,8 @@ def searchsorted_right(cdf, u):
 
 
 def sample_fine_merge(weights, z_coarse, n_fine, det, u=None, seed=0, want_src=True):
-    """A13/A14.  weights, z_coarse (...,Kc) -> z_fine (...,Kf), z_all (...,Kc+Kf) ascending, src uint8."""
+    """A13/A14.  weights, z_coarse (...,Kc) -> z_fine (...,Kf), z_all (...,Kc+Kf) ascending, src uint8 (index
+    into cat(z_coarse, z_fine) of every sorted entry), nn uint8 (nearest coarse sample of every sorted entry)."""
     lead = z_coarse.shape[:-1]
     Kc = z_coarse.shape[-1]
     n = z_coarse.numel() // Kc
@@ -246,8 +257,9 @@ def sample_fine_merge(weights, z_coarse, n_fine, det, u=None, seed=0, want_src=T
     z_fine = torch.empty(*lead, n_fine, device=dev)
     z_all = torch.empty(*lead, Kc + n_fine, device=dev)
     src = torch.empty(*lead, Kc + n_fine, device=dev, dtype=torch.uint8) if want_src else None
+    nn = torch.empty(*lead, Kc + n_fine, device=dev, dtype=torch.uint8) if want_src else None
     if u is not None:
         u = _f32c(u)
     call("an_sample_fine_merge_fwd", ptr(_f32c(weights)), ptr(_f32c(z_coarse)), ptr(u), n, Kc, n_fine, int(det), int(seed),
-         ptr(z_fine), ptr(z_all), ptr(src), stream())
-    return z_fine, z_all, src
+         ptr(z_fine), ptr(z_all), ptr(src), ptr(nn), stream())
+    return z_fine, z_all, src, nn

@@ -62,7 +62,8 @@ class VolumeRenderer(nn.Module):
             sigma_noise = torch.randn(bs, n_rays, K, device=z_samp.device) * self.noise_std
         if hasattr(model, "render_pass"):
             return model.render_pass(rays[..., :8].contiguous(), z_samp, use_fine=not coarse,
-                                     sigma_noise=sigma_noise, white_bkgd=self.white_bkgd)
+                                     sigma_noise=sigma_noise, white_bkgd=self.white_bkgd,
+                                     want_seed=kwargs.get("want_seed", False), seed=kwargs.get("seed"))
         # generic callable: reference semantics, compositing on the kernel (forward only)
         xyz = (rays[..., None, :3] + z_samp.unsqueeze(-1) * rays[..., None, 3:6]).reshape(bs, -1, 3)
         viewdir = rays[..., None, 3:6].expand(-1, -1, K, -1).reshape(bs, -1, 3)
@@ -77,14 +78,24 @@ class VolumeRenderer(nn.Module):
         rays = rays[..., :8].contiguous()
         z_coarse = self.sample_coarse(rays, perturb=perturb, noise_u=noise.get("coarse_u"))
         no_grad_coarse = self.n_fine > 0 and self.share_fine
+        # the fine pass re-queries the coarse samples of the same rays plus n_fine new depths: a fused model
+        # hands its coarse-pass neighbour table over as seeds for the fine pass's search (bit-identical results)
+        fused = hasattr(model, "render_pass") and self.n_fine > 0
+        if fused:
+            kwargs = dict(kwargs, want_seed=True)
         with torch.set_grad_enabled(torch.is_grad_enabled() and not no_grad_coarse):
             weights, rgbs, depths, alphas = self.composite(model, rays, z_coarse, coarse=True, far=True, perturb=perturb,
                                                            sigma_noise=noise.get("sigma_c"), **kwargs)
         output = {"rgbs": rgbs, "alphas": alphas, "depths": depths}
         if self.n_fine > 0:
-            z_combine, _ = self.sample_fine_merge(z_coarse, weights, det=(perturb == 0), u=noise.get("fine_u"))
+            z_combine, _, src, nn = self.sample_fine_merge(z_coarse, weights, det=(perturb == 0), u=noise.get("fine_u"))
+            if fused:
+                idx_c = getattr(model, "last_knn_idx", None)
+                kwargs = dict(kwargs, want_seed=False, seed=dict(src=src, nn=nn, idx=idx_c) if idx_c is not None else None)
             _, rgbs_f, depths_f, alphas_f = self.composite(model, rays, z_combine, coarse=False, far=True, perturb=perturb,
                                                            sigma_noise=noise.get("sigma_f"), **kwargs)
+            if fused:
+                model.last_knn_idx = None
             if self.share_fine:
                 output = {"rgbs": rgbs_f, "alphas": alphas_f, "depths": depths_f}
             else:

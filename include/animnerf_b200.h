@@ -78,14 +78,29 @@ int an_vertex_grid_build(const float* verts, int B, int V, float cell, void* ws,
  *   ids (global id b*N+n), *count incremented atomically (caller zeroes it).
  * ober2cano (B,V,4,4) row-major (rows 0-2 used), lbs_weights (V,J).
  * query_ws (mode 1 only, else NULL): scratch of an_knn_query_ws_bytes(B,N) bytes, 16-byte
- * aligned, holding the work list of the queries that survive the occupancy test.           */
+ * aligned, holding the work list of the queries that survive the occupancy test.
+ * idx/dist hold the exact 4-NN of every query for which the search established them (always in mode
+ * 0; in mode 1 every query that may be valid, plus the pruned ones the walk happened to resolve) and
+ * -1 / 0 otherwise -- a query with idx -1 is provably farther than dis_threshold from every vertex.
+ * Seeds (mode 1, rays+z queries; all NULL/0 when absent): the fine pass of VolumeRenderer.forward
+ * (models/volume_rendering.py:199-207) re-queries the coarse samples of the same rays plus Kf new
+ * depths.  seed_idx = the idx table (B*R*seed_Kc,4) a previous call wrote for the same rays with
+ * K = seed_Kc; seed_src/seed_nn (B*N) u8 come from an_sample_fine_merge_fwd: seed_src[g] < seed_Kc
+ * means query g IS that coarse sample (its neighbours are reused, distances re-evaluated: same bits),
+ * seed_nn[g] = the coarse sample nearest in depth, whose four neighbours bound the search ball.
+ * Results are bit-identical with and without seeds.                                          */
 int64_t an_knn_query_ws_bytes(int B, int64_t N);
 int an_knn_unpose_fwd(const float* xyz, const float* rays, const float* z, int B, int R, int K,
                       int64_t N, const float* verts, int V, const void* grid_ws, void* query_ws,
                       const float* ober2cano, const float* lbs_weights, int J,
                       float dis_threshold, int mode,
+                      const uint8_t* seed_src, const uint8_t* seed_nn, const int32_t* seed_idx, int seed_Kc,
                       float* xyz_cano, uint8_t* valid, int32_t* idx, float* dist, float* qw,
                       float* sigma, float* rgb, int32_t* cidx, int32_t* count, void* stream);
+
+/* tools/bench_knn.py only: selects the search-kernel variant (bit 8: collect candidate statistics in the
+ * query workspace); returns the previous value, v <= 0 only queries.                                   */
+int an_debug_knn_variant(int v);
 
 /* backward of the blend + affine apply (autograd of models/anim_nerf.py:173-174,188; no
  * gradient through dist/idx/valid, as under the reference's no_grad KNN).
@@ -158,12 +173,14 @@ int an_composite_bwd(const float* sigma, const float* rgb, const float* z, const
  * an_sample_fine_merge_fwd: weights (n_rays,Kc) coarse weights, z_coarse (n_rays,Kc);
  * u (n_rays,Kf) explicit draws or NULL (det ? linspace(0,1,Kf) : Philox(seed));
  * outputs z_fine (n_rays,Kf) (may be NULL), z_all (n_rays,Kc+Kf) ascending, src (n_rays,Kc+Kf)
- * u8 = index into cat(z_coarse,z_fine) of each sorted entry (may be NULL).                   */
+ * u8 = index into cat(z_coarse,z_fine) of each sorted entry (may be NULL), nn_coarse (n_rays,Kc+Kf)
+ * u8 = the coarse sample nearest in depth to each sorted entry (itself for a coarse entry; may be
+ * NULL) -- the seed tables of an_knn_unpose_fwd.                                               */
 int an_searchsorted_right(const float* cdf, const float* u, int64_t n_rows, int M, int F,
                           int32_t* inds, void* stream);
 int an_sample_fine_merge_fwd(const float* weights, const float* z_coarse, const float* u,
                              int64_t n_rays, int Kc, int Kf, int det, uint64_t seed,
-                             float* z_fine, float* z_all, uint8_t* src, void* stream);
+                             float* z_fine, float* z_all, uint8_t* src, uint8_t* nn_coarse, void* stream);
 
 /* ---- A16 (+ vertex part of A2): per-frame tables ------------------------------------------
  * replaces, for frames whose SMPL parameters are not being optimised, the torch chain

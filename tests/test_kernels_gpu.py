@@ -129,6 +129,46 @@ def test_knn_million_queries_bit_exact():
     assert torch.equal(outs[0]["xyz_cano"][v], outs[1]["xyz_cano"][v])
 
 
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+def test_knn_seeded_fine_pass_bit_identical(det, variant):
+    """Fine pass of VolumeRenderer.forward: seeds from the coarse pass (neighbour reuse for the shared
+    samples, search-ball bound for the new ones) change nothing -- every output bit for bit equal to the
+    unseeded search and to the exhaustive one, for every search-kernel variant."""
+    from anim_nerf_b200 import _lib
+    old = _lib.load().an_debug_knn_variant(variant)
+    try:
+        verts, o2c, lbs = (t.to(DEV) for t in golden_tables(det))
+        rays = torch.from_numpy(det["rays_body"]).to(DEV)
+        zc = torch.from_numpy(det["z_coarse"]).to(DEV)
+        w = torch.from_numpy(det["weights_coarse"]).to(DEV)
+        kw = dict(want_idx=True, want_dist=True, want_qw=True, compact=True)
+        coarse = ops().knn_unpose(verts, o2c, lbs, 0.2, rays=rays, z=zc, mode=1, **kw)
+        brute_c = ops().knn_unpose(verts, o2c, lbs, 0.2, rays=rays, z=zc, mode=0, **kw)
+        fc = coarse["idx"][..., 0] >= 0
+        assert torch.equal(coarse["idx"][fc], brute_c["idx"][fc]) and torch.equal(coarse["dist"][fc], brute_c["dist"][fc])
+        assert torch.equal(coarse["valid"], brute_c["valid"])
+        for u, nf in ((None, 64), (torch.rand(*zc.shape[:-1], 48, device=DEV, generator=torch.Generator(DEV).manual_seed(3)), 48)):
+            _, z_all, src, nn = ops().sample_fine_merge(w, zc, nf, det=u is None, u=u)
+            seed = dict(src=src, nn=nn, idx=coarse["idx"])
+            a = ops().knn_unpose(verts, o2c, lbs, 0.2, rays=rays, z=z_all, mode=1, seed=seed, **kw)
+            b = ops().knn_unpose(verts, o2c, lbs, 0.2, rays=rays, z=z_all, mode=1, **kw)
+            c = ops().knn_unpose(verts, o2c, lbs, 0.2, rays=rays, z=z_all, mode=0, **kw)
+            assert torch.equal(a["valid"], b["valid"]) and torch.equal(a["valid"], c["valid"])
+            assert int(a["valid"].sum()) > 1000
+            v = a["valid"].bool()
+            for k in ("idx", "dist", "qw"):
+                assert torch.equal(a[k][v], b[k][v]) and torch.equal(a[k][v], c[k][v]), k
+            assert torch.equal(a["xyz_cano"][v], b["xyz_cano"][v]) and torch.equal(a["xyz_cano"][v], c["xyz_cano"][v])
+            # every emitted neighbour set is the exact one
+            f = a["idx"][..., 0] >= 0
+            assert torch.equal(a["idx"][f], c["idx"][f]) and torch.equal(a["dist"][f], c["dist"][f])
+            na, nb = int(a["count"]), int(b["count"])
+            assert na == nb == int(v.sum())
+            assert torch.equal(torch.sort(a["cidx"][:na])[0], torch.sort(b["cidx"][:nb])[0])
+    finally:
+        _lib.load().an_debug_knn_variant(old)
+
+
 # ------------------------------------------------------------------------------ MLP
 def _packed(seed):
     w = synthetic.make_nerf_weights(seed)
@@ -297,7 +337,7 @@ def test_sample_fine_merge(det, pert):
     # deterministic u (in-kernel linspace) on the reference's captured coarse weights
     w = torch.from_numpy(det["weights_coarse"]).to(DEV)
     zc = torch.from_numpy(det["z_coarse"]).to(DEV)
-    z_fine, z_all, src = ops().sample_fine_merge(w, zc, 64, det=True)
+    z_fine, z_all, src, nn = ops().sample_fine_merge(w, zc, 64, det=True)
     ref_all = det["z_combine"]
     za = z_all.cpu().numpy()
     assert (np.diff(za, axis=-1) >= 0).all()
@@ -306,10 +346,14 @@ def test_sample_fine_merge(det, pert):
     cat = torch.cat([zc, z_fine], -1)
     assert torch.equal(torch.gather(cat, -1, src.long()), z_all)        # src is the sort permutation
     assert (torch.sort(src.long(), -1)[0] == torch.arange(128, device=DEV)).all()
+    # nn = the coarse sample nearest in depth (itself for a coarse entry)
+    gap = (z_all[..., :, None] - zc[..., None, :]).abs()
+    assert torch.equal(torch.gather(gap, -1, nn.long()[..., None])[..., 0], gap.min(-1)[0])
+    assert torch.equal(nn[src < 64], src[src < 64])
     # explicit random u
     w = torch.from_numpy(pert["weights_coarse"]).to(DEV)
     zc = torch.from_numpy(pert["z_coarse"]).to(DEV)
-    _, z_all, _ = ops().sample_fine_merge(w, zc, 32, det=False, u=torch.from_numpy(pert["noise_fine_u"]).to(DEV))
+    _, z_all, _, _ = ops().sample_fine_merge(w, zc, 32, det=False, u=torch.from_numpy(pert["noise_fine_u"]).to(DEV))
     np.testing.assert_allclose(z_all.cpu().numpy(), pert["z_combine"], atol=2e-4)
 
 

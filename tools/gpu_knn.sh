@@ -1,11 +1,5 @@
 #!/bin/bash
+# KNN variants: parity (seeded / unseeded / exhaustive) + microbenchmark on the cfg2 batch
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_kernels_gpu.py -x -q -k "knn" 2>&1 | tail -8
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench3.json 2> gpurun_out/bench3.err; tail -3 gpurun_out/bench3.err
-python - <<'PY'
-import json
-d = json.load(open("gpurun_out/bench3.json"))
-print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["config"]["launch"])
-print(d["kernel_ms_per_step"])
-print(d["roofline"]["frac"], d["roofline"]["achieved"])
-PY
+timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q -k "knn or sample_fine" 2>&1 | tail -8
+timeout 600 python tools/bench_knn.py --variants ${1:-1,3:0,3:4,3:8,3:12,3:16,2:8,4:8} 2>&1 | tee gpurun_out/bench_knn.txt | tail -30
