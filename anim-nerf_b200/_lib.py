@@ -37,6 +37,7 @@ SIGNATURES = {
     "an_mlp_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "an_mlp_bwd_dgrad": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "an_mlp_bwd_wgrad": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "an_mlp_fwd_tangent": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "an_composite_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "an_composite_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "an_searchsorted_right": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),

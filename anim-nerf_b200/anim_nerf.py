@@ -195,7 +195,7 @@ class AnimNeRF(nn.Module):
     def query_canonical_space(self, xyz, viewdir=None, use_fine=False, only_sigma=False, only_normal=False):
         net = self.nerf_fine if use_fine else self.nerf
         if only_sigma:
-            return net.get_sigma(xyz, only_sigma=True)         # torch path: regularisers
+            return net.get_sigma(xyz, only_sigma=True)         # regulariser queries, on the kernels
         if only_normal:
             return net.get_normal(xyz)
         return net(xyz)

@@ -129,6 +129,62 @@ class PointQuery(torch.autograd.Function):
         return (g_xyz, g_o2c, None) + tuple(cfg["net"].split_flat_grad(g_flat))
 
 
+class SigmaWithGradient(torch.autograd.Function):
+    """Canonical-space density and its spatial gradient: xyz (...,3) -> sigma (...,1), s = d sigma/d xyz (...,3),
+    both differentiable with respect to the MLP parameters.  This is the second-order path behind the
+    reference's `NeRF.get_normal` (models/nerf.py:177-190: `autograd.grad(alpha, xyz, create_graph=True)`),
+    used by the normal-smoothness regulariser (train.py:286-309), without torch double backward:
+
+      forward   an_mlp_fwd (stash) -> sigma;  an_mlp_bwd_dgrad with g_sigma = 1, g_rgb = 0 -> s and the
+                delta_l = d sigma/d a_l images (kept)
+      backward  through s:      tau = an_mlp_fwd_tangent(v = dL/ds)  (forward-mode tangent on the tensor cores),
+                                dL/dW_l = delta_l tau_{l-1}^T = an_mlp_bwd_wgrad(tau images, delta images); no
+                                bias terms (biases do not enter s)
+                through sigma:  the ordinary an_mlp_bwd_dgrad + an_mlp_bwd_wgrad with g_sigma = dL/dsigma.
+    There is no gradient to xyz (the regulariser's sample points are detached in the reference)."""
+
+    @staticmethod
+    def forward(ctx, xyz, net, *params):
+        lead = xyz.shape[:-1]
+        x = xyz.detach().reshape(-1, 3).contiguous().float()
+        n, dev = x.shape[0], x.device
+        sigma = torch.empty(n, device=dev)
+        rgb = torch.empty(n, 3, device=dev)
+        packed = net.packed()
+        stash = ops.mlp_stash(n, dev)
+        ops.mlp_fwd(packed, x, sigma, rgb, n_max=n, stash=stash)
+        scratch = ops.mlp_bwd_scratch(n, dev)
+        s = ops.mlp_bwd_dgrad(packed, stash, x, rgb, torch.ones(n, device=dev), torch.zeros(n, 3, device=dev), scratch,
+                              n_max=n, want_g_xyz=True)
+        ctx.net, ctx.packed, ctx.stash, ctx.scratch, ctx.n = net, packed, stash, scratch, n
+        ctx.save_for_backward(x, rgb)
+        return sigma.view(*lead, 1), s.view(*lead, 3)
+
+    @staticmethod
+    def backward(ctx, g_sigma, g_s):
+        x, rgb = ctx.saved_tensors
+        net, packed, stash, scratch, n = ctx.net, ctx.packed, ctx.stash, ctx.scratch, ctx.n
+        dev = x.device
+        # through s = d sigma/d xyz: weight gradients only
+        tstash, _ = ops.mlp_fwd_tangent(packed, x, g_s.reshape(n, 3).contiguous(), stash, n_max=n)
+        flat = ops.mlp_bwd_wgrad(packed, tstash, scratch, n_max=n)
+        del tstash
+        grads = net.split_flat_grad(flat)
+        for gb in grads[12:]:
+            gb.zero_()                      # the wgrad kernel's bias sums are not gradients on this path
+        # through sigma (the delta images are no longer needed: reuse their buffer)
+        ops.mlp_bwd_dgrad(packed, stash, x, rgb, g_sigma.reshape(n).contiguous(), torch.zeros(n, 3, device=dev), scratch,
+                          n_max=n, want_g_xyz=False)
+        flat1 = ops.mlp_bwd_wgrad(packed, stash, scratch, n_max=n)
+        flat += flat1
+        ctx.stash = ctx.scratch = None
+        return (None, None) + tuple(net.split_flat_grad(flat))
+
+
+def sigma_with_gradient(net, xyz):
+    return SigmaWithGradient.apply(xyz, net, *net.param_list())
+
+
 def mlp_query(net, xyz):
     """Canonical-space NeRF query (no unposing): xyz (B,N,3) -> rgb (B,N,3), sigma (B,N,1)."""
     cfg = dict(net=net, unpose=False, grad=torch.is_grad_enabled())

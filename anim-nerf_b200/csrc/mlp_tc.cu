@@ -60,14 +60,23 @@ __device__ unsigned long long* g_trace = nullptr;
 
 }  // namespace
 
-template <bool TRAIN>
+// MODE 0 = inference, 1 = training (activation stash), 2 = tangent (forward-mode derivative of the
+// trunk: tau_l = m_l * (W_l tau_{l-1}), no biases, ReLU masks m_l read from the primal stash `pstash`,
+// input tau_0 = d enc(x) . tvec; writes the tau images to `stash` in the activation layout -- the weight
+// gradient of a loss on d sigma/d xyz is then the ordinary wgrad kernel on (tau images, dY images),
+// see an_mlp_fwd_tangent).  The tangent runs the 8 trunk layers + the fused head layer (for tau_sigma).
+template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ xyz_cano,
                   const int32_t* __restrict__ cidx, const int32_t* __restrict__ count, int64_t n_max,
-                  float* __restrict__ sigma_out, float* __restrict__ rgb_out, uint8_t* __restrict__ stash)
+                  float* __restrict__ sigma_out, float* __restrict__ rgb_out, uint8_t* __restrict__ stash,
+                  const float* __restrict__ tvec, const uint8_t* __restrict__ pstash)
 {
     using namespace mlp;
     using namespace tc;
+    constexpr bool TRAIN = MODE >= 1;          // writes the image stash
+    constexpr bool TAN = MODE == 2;
+    constexpr int NGT = TAN ? 9 : NG;          // layer steps per iteration
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;
@@ -103,7 +112,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             TRACE_DECL;
             uint32_t it = 0;
             for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x)
-                for (int g = 0; g < NG; ++g) {
+                for (int g = 0; g < NGT; ++g) {
                     const uint32_t bytes = g_chunk_bytes(g);
                     for (int t = 0; t < 2; ++t)
                         for (int kc = 0; kc < g_chunks(g); ++kc, ++it) {
@@ -121,7 +130,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             TRACE_DECL;
             uint32_t it = 0, act_phase = 0;
             for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x)
-                for (int g = 0; g < NG; ++g) {
+                for (int g = 0; g < NGT; ++g) {
                     const uint32_t idesc = make_idesc_bf16(128, g_N(g), 0, 0);
                     for (int t = 0; t < 2; ++t) {
                         TRACE(1, 0, g, t);
@@ -174,7 +183,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             for (int blk = 0; blk < 8; ++blk) {
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
-                    const uint4 b4 = __ldg((const uint4*)(small + SM_BIAS + blk * 32) + c4);
+                    const uint4 b4 = TAN ? make_uint4(0u, 0u, 0u, 0u) : __ldg((const uint4*)(small + SM_BIAS + blk * 32) + c4);
                     b0[4 * c4] = b4.x; b0[4 * c4 + 1] = b4.y; b0[4 * c4 + 2] = b4.z; b0[4 * c4 + 3] = b4.w;
                 }
                 tmem_st32(tm + blk * 32, b0);
@@ -188,21 +197,30 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             const bool in = p < n;
             const int64_t id = in ? (cidx ? (int64_t)cidx[p] : p) : 0;
             uint8_t* st_tile = TRAIN ? stash + (iter * 2 + t) * ST_TILE : nullptr;
+            const uint8_t* pst_tile = TAN ? pstash + (iter * 2 + t) * ST_TILE : nullptr;
             float x[3] = {0.f, 0.f, 0.f};
+            float tv[3] = {0.f, 0.f, 0.f};
             if (in) { x[0] = xyz_cano[id * 3]; x[1] = xyz_cano[id * 3 + 1]; x[2] = xyz_cano[id * 3 + 2]; }
+            if (TAN && in) { tv[0] = tvec[id * 3]; tv[1] = tvec[id * 3 + 1]; tv[2] = tvec[id * 3 + 2]; }
             {   // positional encoding -> bf16 K-major image (64 columns, last one zero)
                 float ev[64];
                 float s[3], c[3];
 #pragma unroll
-                for (int a = 0; a < 3; ++a) { ev[a] = x[a]; sincosf(x[a], &s[a], &c[a]); }
+                for (int a = 0; a < 3; ++a) { ev[a] = TAN ? tv[a] : x[a]; sincosf(x[a], &s[a], &c[a]); }
+                float fk = 1.f;
 #pragma unroll
                 for (int k = 0; k < 10; ++k) {
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
-                        ev[3 + 6 * k + a] = s[a]; ev[6 + 6 * k + a] = c[a];
+                        if (TAN) {     // d/dx [sin(2^k x), cos(2^k x)] . tv
+                            ev[3 + 6 * k + a] = fk * c[a] * tv[a]; ev[6 + 6 * k + a] = -fk * s[a] * tv[a];
+                        } else {
+                            ev[3 + 6 * k + a] = s[a]; ev[6 + 6 * k + a] = c[a];
+                        }
                         const float s2 = 2.f * s[a] * c[a], c2 = 1.f - 2.f * s[a] * s[a];
                         s[a] = s2; c[a] = c2;
                     }
+                    fk *= 2.f;
                 }
                 ev[63] = 0.f;
                 if (TRAIN) {      // previous iteration's TMA stores must have drained this tile's smem
@@ -224,7 +242,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             }
             mbar_arrive(my_act);
 
-            for (int g = 0; g < NG; ++g) {
+            for (int g = 0; g < NGT; ++g) {
                 // accumulator blocks (32 columns) to drain, and blocks whose bias is re-initialised: the
                 // accumulators start from the bias -- while draining layer g, every block of TMEM columns is
                 // rewritten (tcgen05.st) with the bias of the layer that writes it next: layer g+1, or layer 0
@@ -236,7 +254,13 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 // wait); they are staged in shared memory and read back as broadcast 128-bit loads per block
                 const int c2 = 2 * (e & 127);
                 const int bl = g < 8 ? g + 1 : (g == 8 ? (c2 < 32 ? 9 : 0) : 0);
-                const float2 bmine = __ldg((const float2*)(small + SM_BIAS + bl * 256 + c2));
+                const float2 bmine = TAN ? make_float2(0.f, 0.f) : __ldg((const float2*)(small + SM_BIAS + bl * 256 + c2));
+                uint32_t pmw[8];               // tangent: the primal's ReLU masks of this layer ([block][row] words)
+                if (TAN) {
+#pragma unroll
+                    for (int cb = 0; cb < 8; ++cb)
+                        pmw[cb] = g <= 7 ? __ldg((const uint32_t*)(pst_tile + ST_MASK + g * 4096 + cb * 512 + row * 4)) : 0xffffffffu;
+                }
                 if (leader) TRACE(2 + t, 0, g, 0);
                 mbar_wait(my_acc, acc_phase); acc_phase ^= 1u;
                 if (leader) TRACE(2 + t, 1, g, 0);
@@ -268,7 +292,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                             tmem_st32(tm + blk * 32, bq);
                         }
                         if (blk >= nld) continue;
-                        if (g == 9) {                 // rgb head: columns 0..2 (bias already in the accumulator)
+                        if (!TAN && g == 9) {         // rgb head: columns 0..2 (bias already in the accumulator)
                             if (in) {
                                 rgb_out[id * 3] = 1.f / (1.f + __expf(-__uint_as_float(v[0])));
                                 rgb_out[id * 3 + 1] = 1.f / (1.f + __expf(-__uint_as_float(v[1])));
@@ -277,10 +301,15 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                             continue;
                         }
                         if (g == 8 && blk == 4) {     // density head: column 128 of the head layer, raw
-                            if (in) sigma_out[id] = __uint_as_float(v[0]);
+                            if (in && (!TAN || sigma_out)) sigma_out[id] = __uint_as_float(v[0]);
                             continue;
                         }
-                        if (TRAIN) {
+                        if (TAN) {                    // tau = mask * (W tau_prev): the primal's ReLU pattern, no clamp
+                            const uint32_t m = pmw[blk];
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) v[c] = ((m >> mask_bit_of_col(c)) & 1u) ? v[c] : 0u;
+                        }
+                        if (TRAIN && !TAN) {
                             // 1-bit ReLU mask from the sign bits: one funnel shift per column; bit (31-c) of the
                             // word <-> column c of the block (tc::mask_bit_of_col)
                             // (four independent 8-column chains, then merged, so the shifts are not one serial chain)
@@ -296,7 +325,9 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                         }
                         uint32_t w[16];
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) w[k] = pack_relu_bf16(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
+                        for (int k = 0; k < 16; ++k)
+                            w[k] = TAN ? pack_bf16(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]))
+                                       : pack_relu_bf16(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
                         uint8_t* dst = act_row + (blk >> 1) * 16384;
 #pragma unroll
                         for (uint32_t u = 0; u < 4; ++u)
@@ -308,7 +339,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 tmem_st_wait();
                 if (leader) TRACE(2 + t, 5, g, 0);
                 tc_fence_before();                // TMEM reads/writes done before the MMAs that follow the arrive
-                if (g < 9) {
+                if (g < 9) {      // (tangent mode ends at g = 8: its c image is stored too, so every image of the stash is defined)
                     fence_proxy_async();
                     if (TRAIN) {
                         named_bar_sync(1 + t, 128);
@@ -318,7 +349,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                             bulk_commit();
                         }
                     }
-                    mbar_arrive(my_act);
+                    if (g < NGT - 1) mbar_arrive(my_act);
                 }
                 if (leader) TRACE(2 + t, 3, g, 0);
             }
@@ -354,19 +385,48 @@ extern "C" int an_mlp_fwd(const void* packed, const float* xyz_cano, const int32
     if (stash && (((uintptr_t)stash) & 127)) return AN_ERR_ALIGN;
     if (impl == 1) return mlp_fwd_ref_launch(packed, xyz_cano, cidx, count, n_max, sigma, rgb, (cudaStream_t)stream);
     if (impl != 0) return AN_ERR_ARG;
-    cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);
+    cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);
+    e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
     const int64_t iters = (n_max + 255) / 256;
     const int sms = an_num_sms();
     const int grid = (int)(iters < sms ? iters : sms);
     if (stash)
-        mlp_fwd_tc_kernel<true><<<grid, THREADS, SM_ALLOC, (cudaStream_t)stream>>>(
-            (const uint8_t*)packed, xyz_cano, cidx, count, n_max, sigma, rgb, (uint8_t*)stash);
+        mlp_fwd_tc_kernel<1><<<grid, THREADS, SM_ALLOC, (cudaStream_t)stream>>>(
+            (const uint8_t*)packed, xyz_cano, cidx, count, n_max, sigma, rgb, (uint8_t*)stash, nullptr, nullptr);
     else
-        mlp_fwd_tc_kernel<false><<<grid, THREADS, SM_ALLOC, (cudaStream_t)stream>>>(
-            (const uint8_t*)packed, xyz_cano, cidx, count, n_max, sigma, rgb, nullptr);
+        mlp_fwd_tc_kernel<0><<<grid, THREADS, SM_ALLOC, (cudaStream_t)stream>>>(
+            (const uint8_t*)packed, xyz_cano, cidx, count, n_max, sigma, rgb, nullptr, nullptr, nullptr);
+    AN_CHECK_LAUNCH();
+    return AN_OK;
+}
+
+// Forward-mode tangent of the trunk (the normal-smoothness regulariser differentiates
+// d sigma/d xyz with respect to the weights -- torch double backward in the reference, nerf.py:177-190).
+// For a loss L(s), s = d sigma/d xyz, with v = dL/ds per point:  dL/dW_l = (m_l * delta_l) tau_{l-1}^T where
+// delta_l = d sigma/d h_l are the dY images of an an_mlp_bwd_dgrad run with g_sigma = 1, g_rgb = 0 over the
+// same points, and tau_l = m_l * (W_l tau_{l-1}), tau_0 = (d enc/d xyz) v is what this kernel writes to
+// `tstash` (activation-stash layout): an_mlp_bwd_wgrad(packed, tstash, dY scratch) then yields the weight
+// gradients (its bias outputs are not gradients of L -- biases do not enter d sigma/d xyz -- the caller
+// zeroes them).  pstash = the primal forward's stash over the same compacted points (ReLU masks).
+// tsigma (ids) receives w_sigma . tau_8 when non-NULL.
+extern "C" int an_mlp_fwd_tangent(const void* packed, const float* xyz_cano, const float* tvec, const void* pstash,
+                                  const int32_t* cidx, const int32_t* count, int64_t n_max, float* tsigma,
+                                  void* tstash, void* stream)
+{
+    if (!packed || !xyz_cano || !tvec || !pstash || !tstash || n_max <= 0) return AN_ERR_ARG;
+    if (cidx && !count) return AN_ERR_ARG;
+    if (((uintptr_t)packed) & 1023) return AN_ERR_ALIGN;
+    if ((((uintptr_t)pstash) & 127) || (((uintptr_t)tstash) & 127)) return AN_ERR_ALIGN;
+    cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);
+    if (e != cudaSuccess) return (int)e;
+    const int64_t iters = (n_max + 255) / 256;
+    const int sms = an_num_sms();
+    const int grid = (int)(iters < sms ? iters : sms);
+    mlp_fwd_tc_kernel<2><<<grid, THREADS, SM_ALLOC, (cudaStream_t)stream>>>(
+        (const uint8_t*)packed, xyz_cano, cidx, count, n_max, tsigma, nullptr, (uint8_t*)tstash, tvec,
+        (const uint8_t*)pstash);
     AN_CHECK_LAUNCH();
     return AN_OK;
 }

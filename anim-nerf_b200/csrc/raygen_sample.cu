@@ -5,6 +5,8 @@
 // thread per ray (32 B out, written as two float4) / per sample.
 #include "common.cuh"
 
+#include "raygen.cuh"
+
 __global__ void raygen_kernel(const float* __restrict__ c2w, const float* __restrict__ focal,
                               const float* __restrict__ center, const int32_t* __restrict__ pix,
                               const float* __restrict__ ginv, int B, int R, int H, int W,
@@ -18,32 +20,8 @@ __global__ void raygen_kernel(const float* __restrict__ c2w, const float* __rest
         int row, col;
         if (pix) { row = pix[2 * i]; col = pix[2 * i + 1]; }
         else     { row = r / W;      col = r - row * W; }
-        const float* C = c2w + b * 12;
-        const float fx = focal[2 * b], fy = focal[2 * b + 1];
-        const float cx = center[2 * b], cy = center[2 * b + 1];
-        float dx = ((float)col - cx) / fx, dy = -((float)row - cy) / fy, dz = -1.0f;
-        const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
-        dx /= nrm; dy /= nrm; dz /= nrm;
-        float d0 = dx * C[0] + dy * C[1] + dz * C[2];
-        float d1 = dx * C[4] + dy * C[5] + dz * C[6];
-        float d2 = dx * C[8] + dy * C[9] + dz * C[10];
-        float o0 = C[3], o1 = C[7], o2 = C[11];
-        float nr = near_, fr = far_;
-        if (ginv) {
-            const float* G = ginv + b * 16;
-            const float p0 = G[0] * o0 + G[1] * o1 + G[2] * o2 + G[3];
-            const float p1 = G[4] * o0 + G[5] * o1 + G[6] * o2 + G[7];
-            const float p2 = G[8] * o0 + G[9] * o1 + G[10] * o2 + G[11];
-            const float e0 = G[0] * d0 + G[1] * d1 + G[2] * d2;
-            const float e1 = G[4] * d0 + G[5] * d1 + G[6] * d2;
-            const float e2 = G[8] * d0 + G[9] * d1 + G[10] * d2;
-            o0 = p0; o1 = p1; o2 = p2; d0 = e0; d1 = e1; d2 = e2;
-            const float cam = sqrtf(o0 * o0 + o1 * o1 + o2 * o2);
-            nr = fmaxf(near_, cam - 1.0f);
-            fr = fminf(far_, cam + 1.0f);
-        }
-        rays[2 * i]     = make_float4(o0, o1, o2, d0);
-        rays[2 * i + 1] = make_float4(d1, d2, nr, fr);
+        an_make_ray(c2w + b * 12, focal + 2 * b, center + 2 * b, ginv ? ginv + b * 16 : nullptr, row, col,
+                    near_, far_, rays + 2 * i);
     }
 }
 

@@ -5,8 +5,9 @@ checkpoints stay interchangeable (state-dict keys `xyz_encoding_{1..8}.0.*`,
 `xyz_encoding_final.*`, `dir_encoding.0.*`, `sigma.*`, `rgb.0.*`).  The rendering
 path never runs these modules: it consumes `packed()` -- the bf16 UMMA-ready repack made by
 the `an_mlp_pack` kernel, refreshed whenever a parameter's version counter moved (i.e. after
-each optimiser step).  `get_sigma` / `get_normal` are the reference's torch formulations used
-only by the training regularisers, sharing the same parameters.
+each optimiser step).  `get_sigma` / `get_normal` -- the queries of the training regularisers
+(train.py:264-309) -- run on the same kernels; their torch formulations live in
+the oracle (`oracle.nerf_sigma` / `oracle.nerf_normal`, pinned to the reference by a golden fixture).
 """
 import torch
 import torch.nn as nn
@@ -99,26 +100,23 @@ class NeRF(nn.Module):
             bs.append(flat[o:o + nb].view_as(l.bias)); o += nb
         return ws + bs
 
-    # ---- torch formulations (regularisers only; reference nerf.py:155-190)
+    # ---- regulariser queries (reference nerf.py:155-190) on the kernels
     def get_sigma(self, xyz, deformation_code=None, only_sigma=False):
-        e = self.encoding_xyz(xyz)
-        h = e
-        for i in range(self.D):
-            if i in self.skips:
-                h = torch.cat([e, h], -1)
-            h = torch.relu(getattr(self, "xyz_encoding_%d" % (i + 1))[0](h))
-        sigma = self.sigma(h)
-        if only_sigma:
-            return sigma
-        return sigma, self.xyz_encoding_final(h)
+        """Raw density of canonical-space points (nerf.py:155-175) through the CUDA MLP."""
+        if not only_sigma:
+            raise NotImplementedError("get_sigma(only_sigma=False) has no caller on the rendering/training path")
+        from .autograd import mlp_query
+        lead = xyz.shape[:-1]
+        return mlp_query(self, xyz.reshape(1, -1, 3))[1].view(*lead, 1)
 
     def get_normal(self, xyz, deformation_code=None, delta=0.02):
-        with torch.set_grad_enabled(True):
-            xyz.requires_grad_(True)
-            sigma = self.get_sigma(xyz, only_sigma=True)
-            alpha = 1 - torch.exp(-delta * torch.relu(sigma))
-            return torch.autograd.grad(alpha, xyz, torch.ones_like(alpha), create_graph=True,
-                                       retain_graph=True, only_inputs=True)[0]
+        """d alpha/d xyz with alpha = 1 - exp(-delta * relu(sigma)) (nerf.py:177-190), differentiable w.r.t. the
+        weights: d alpha/d xyz = delta * exp(-delta * relu(sigma)) * [sigma > 0] * d sigma/d xyz, with
+        (sigma, d sigma/d xyz) from `SigmaWithGradient` (forward + dgrad kernels; its backward is the
+        tangent + wgrad kernels instead of torch double backward)."""
+        from .autograd import sigma_with_gradient
+        sigma, s = sigma_with_gradient(self, xyz)
+        return delta * torch.exp(-delta * torch.relu(sigma)) * (sigma > 0).to(sigma.dtype) * s
 
     def forward(self, xyz, viewdir=None, deformation_code=None, apperance_code=None):
         """Canonical-space query through the CUDA MLP (no unposing)."""

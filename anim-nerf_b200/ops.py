@@ -207,6 +207,43 @@ def mlp_bwd(packed, stash, xyz_cano, rgb, g_sigma, g_rgb, cidx=None, count=None,
 _last_bwd_scratch = None
 
 
+def mlp_bwd_scratch(n_max, device):
+    nscr = _lib.load().an_mlp_bwd_scratch_bytes(int(n_max))
+    buf = torch.empty(nscr + 128, device=device, dtype=torch.uint8)
+    off = (-buf.data_ptr()) % 128
+    return buf[off:off + nscr]
+
+
+def mlp_bwd_dgrad(packed, stash, xyz_cano, rgb, g_sigma, g_rgb, scratch, cidx=None, count=None, n_max=None,
+                  want_g_xyz=True):
+    """Activation-gradient chain only: fills `scratch` with the dY images, returns g_xyz_cano (or None)."""
+    if n_max is None:
+        n_max = xyz_cano.numel() // 3
+    g_xyz = torch.zeros_like(xyz_cano) if want_g_xyz else None
+    call("an_mlp_bwd_dgrad", ptr(packed), ptr(stash), ptr(xyz_cano), ptr(rgb), ptr(cidx), ptr(count), int(n_max),
+         ptr(g_sigma), ptr(g_rgb), ptr(g_xyz), ptr(scratch), stream())
+    return g_xyz
+
+
+def mlp_bwd_wgrad(packed, stash, scratch, cidx=None, count=None, n_max=None, g_params=None):
+    """dW/db of every layer from the images in `stash` (X) and `scratch` (dY); accumulates into g_params."""
+    if g_params is None:
+        g_params = torch.zeros(mlp_grad_floats(), device=stash.device)
+    call("an_mlp_bwd_wgrad", ptr(packed), ptr(stash), ptr(scratch), ptr(cidx), ptr(count), int(n_max), ptr(g_params), stream())
+    return g_params
+
+
+def mlp_fwd_tangent(packed, xyz_cano, tvec, pstash, cidx=None, count=None, n_max=None, want_tsigma=False):
+    """Forward-mode tangent of the trunk (an_mlp_fwd_tangent): returns (tstash, tsigma or None)."""
+    if n_max is None:
+        n_max = xyz_cano.numel() // 3
+    tstash = mlp_stash(n_max, xyz_cano.device)
+    tsig = torch.zeros(xyz_cano.numel() // 3, device=xyz_cano.device) if want_tsigma else None
+    call("an_mlp_fwd_tangent", ptr(packed), ptr(xyz_cano), ptr(_f32c(tvec)), ptr(pstash), ptr(cidx), ptr(count),
+         int(n_max), ptr(tsig), ptr(tstash), stream())
+    return tstash, tsig
+
+
 # ------------------------------------------------------------------------ compositing
 def composite(sigma, rgb, z, rays, white_bkgd=True, sigma_noise=None, want_weights=True):
     """A12.  sigma (...,K), rgb (...,K,3), z (...,K), rays (...,8) -> weights, rgb (...,3), depth (...,1), acc (...,1)."""

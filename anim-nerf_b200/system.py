@@ -10,8 +10,9 @@ gathers; the fused kernels need no chunking, so `chunk` only caps the rays per l
 
 Losses (train.py:228-322): rgb MSE + 0.1 * alpha L1 on coarse and fine run on the render outputs;
 the foreground/background density and the normal-smoothness regularisers query the MLP through
-the reference's torch formulation (`NeRF.get_sigma/get_normal`, double backward) -- SURVEY §8(f)#2
-marks moving them onto the kernels as the next step.  They share the same nn.Parameters.
+`NeRF.get_sigma/get_normal`, which run on the same kernels: the density queries
+through `PointQuery`, the normals through `SigmaWithGradient` (forward + dgrad; its backward is the
+tensor-core tangent pass + the wgrad kernel instead of the reference's torch double backward).
 """
 from collections import defaultdict
 from types import SimpleNamespace
@@ -92,29 +93,30 @@ class AnimNeRFSystem(nn.Module):
             return loss, det
         k = -2.0 / hp.n_samples
         q = self.anim_nerf.query_canonical_space
-        if hp.use_unpose and fg_points is not None:
-            add("loss_foreground", torch.mean(torch.exp(k * torch.relu(q(fg_points, use_fine=False, only_sigma=True)))),
-                hp.train.lambda_foreground)
-            if fine:
-                add("loss_foreground_fine", torch.mean(torch.exp(k * torch.relu(q(fg_points, use_fine=True, only_sigma=True)))),
-                    hp.train.lambda_foreground)
-        if hp.use_unpose and bg_points is not None:
-            add("loss_background", torch.mean(1 - torch.exp(k * torch.relu(q(bg_points, use_fine=False, only_sigma=True)))),
-                hp.train.lambda_background)
-            if fine:
-                add("loss_background_fine", torch.mean(1 - torch.exp(k * torch.relu(q(bg_points, use_fine=True, only_sigma=True)))),
-                    hp.train.lambda_background)
+        if hp.use_unpose and (fg_points is not None or bg_points is not None):
+            # train.py:264-284; foreground and background points of a net go through one MLP launch
+            n_fg = fg_points.shape[1] if fg_points is not None else 0
+            pts = torch.cat([p for p in (fg_points, bg_points) if p is not None], 1)
+            for use_fine, sfx in (((False, ""), (True, "_fine")) if fine else ((False, ""),)):
+                e = torch.exp(k * torch.relu(q(pts, use_fine=use_fine, only_sigma=True)))
+                if fg_points is not None:
+                    add("loss_foreground" + sfx, torch.mean(e[:, :n_fg]), hp.train.lambda_foreground)
+                if bg_points is not None:
+                    add("loss_background" + sfx, torch.mean(1 - e[:, n_fg:]), hp.train.lambda_background)
         points = self.anim_nerf.verts_template.detach().clone()
         points = points + torch.randn_like(points) * hp.dis_threshold * 0.5
         neighbs = points + torch.randn_like(points) * hp.train.epsilon
 
         def unit(v):
             return v / (torch.norm(v, p=2, dim=-1, keepdim=True) + 1e-5)
-        add("loss_normals", F.mse_loss(unit(q(points, use_fine=False, only_normal=True)),
-                                       unit(q(neighbs, use_fine=False, only_normal=True))), hp.train.lambda_normals)
+
+        def normals_loss(use_fine):
+            # both point sets in one query (one forward/dgrad launch pair per net instead of two)
+            n = q(torch.cat([points, neighbs], 0), use_fine=use_fine, only_normal=True)
+            return F.mse_loss(unit(n[:points.shape[0]]), unit(n[points.shape[0]:]))
+        add("loss_normals", normals_loss(False), hp.train.lambda_normals)
         if fine:
-            add("loss_normals_fine", F.mse_loss(unit(q(points, use_fine=True, only_normal=True)),
-                                                unit(q(neighbs, use_fine=True, only_normal=True))), hp.train.lambda_normals)
+            add("loss_normals_fine", normals_loss(True), hp.train.lambda_normals)
         return loss, det
 
     def decode_batch(self, batch):

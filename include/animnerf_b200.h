@@ -153,6 +153,22 @@ int an_mlp_bwd_dgrad(const void* packed, const void* stash, const float* xyz_can
 int an_mlp_bwd_wgrad(const void* packed, const void* stash, const void* scratch, const int32_t* cidx,
                      const int32_t* count, int64_t n_max, float* g_params, void* stream);
 
+/* ---- A18 (normal-smoothness regulariser): second-order path of NeRF.get_normal --------------
+ * replaces the torch double backward of models/nerf.py:177-190 (get_normal: autograd.grad of
+ * alpha = 1 - exp(-delta*relu(sigma)) w.r.t. xyz with create_graph=True) as used by
+ * train.py:286-309.  With s = d sigma / d xyz (an_mlp_bwd_dgrad run with g_sigma = 1, g_rgb = 0;
+ * its g_xyz_cano output is s and its scratch holds delta_l = d sigma / d a_l) and v = dL/ds per
+ * point, the weight gradient of L through s is  dL/dW_l = delta_l tau_{l-1}^T  where
+ * tau_l = relu'(a_l) * (W_l tau_{l-1}),  tau_0 = (d enc / d xyz) v  is the forward-mode tangent this
+ * entry point computes on the tensor cores (same kernel skeleton as an_mlp_fwd; ReLU pattern from
+ * the primal stash `pstash`, no biases) and writes to `tstash` in the activation-stash layout, so
+ * that an_mlp_bwd_wgrad(packed, tstash, that scratch, ...) accumulates dL/dW (its bias outputs are
+ * then meaningless -- biases do not enter s -- and must be discarded by the caller).
+ * tvec (ids,3) = v; tsigma (ids) receives w_sigma . tau_8 when non-NULL.                      */
+int an_mlp_fwd_tangent(const void* packed, const float* xyz_cano, const float* tvec, const void* pstash,
+                       const int32_t* cidx, const int32_t* count, int64_t n_max, float* tsigma,
+                       void* tstash, void* stream);
+
 /* ---- A12: alpha compositing ------------------------------------------------------------
  * replaces models/volume_rendering.py:128-160 (composite tail), far=True, white_bkgd flag.
  * sigma (n_rays,K), rgb (n_rays,K,3), z (n_rays,K), rays (n_rays,8) (far = rays[:,7]);

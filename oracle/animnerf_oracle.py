@@ -262,6 +262,30 @@ def nerf_forward(p, xc):
     return rgb, sigma
 
 
+def nerf_sigma(p, xc):
+    """NeRF.get_sigma(only_sigma=True) (models/nerf.py:155-175): raw density of canonical points (...,3) -> (...,1)."""
+    e = embed(xc)
+    h = e
+    for i in range(8):
+        if i == 4:
+            h = torch.cat([e, h], -1)
+        w, b = p["xyz_encoding_%d.0" % (i + 1)]
+        h = torch.relu(h @ w.T + b)
+    return h @ p["sigma"][0].T + p["sigma"][1]
+
+
+def nerf_normal(p, xc, delta=0.02):
+    """NeRF.get_normal (models/nerf.py:177-190): d alpha/d xyz with alpha = 1 - exp(-delta * relu(sigma)),
+    taken by autograd with create_graph=True so that a loss on it can be differentiated w.r.t. the weights
+    (double backward) -- the formulation the normal-smoothness regulariser uses (train.py:286-309)."""
+    with torch.set_grad_enabled(True):
+        xc = xc.detach().requires_grad_(True)
+        sigma = nerf_sigma(p, xc)
+        alpha = 1 - torch.exp(-delta * torch.relu(sigma))
+        return torch.autograd.grad(alpha, xc, torch.ones_like(alpha), create_graph=True, retain_graph=True,
+                                   only_inputs=True)[0]
+
+
 def field(p, xyz, tables, dis_threshold=0.2):
     """AnimNeRF.forward: unpose -> MLP -> sigma := -1e5 where invalid."""
     verts, ober2cano, lbs_weights = tables

@@ -218,8 +218,52 @@ def gen_rays_case():
     print("wrote gen_rays.npz")
 
 
+def regularizers_case():
+    """The MLP queries of the training regularisers through the reference's own `NeRF` (models/nerf.py:155-190):
+    `get_sigma(only_sigma=True)` on foreground/background points and `get_normal` (autograd.grad with
+    create_graph=True) on points / neighbours, combined exactly as train.py:264-297 does, then backward
+    (torch double backward) -> per-parameter gradients."""
+    from models.nerf import NeRF
+    import torch.nn.functional as F
+    net = NeRF(freqs_xyz=10, freqs_dir=0, use_view=False)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in synthetic.make_nerf_weights(10).items()}, strict=True)
+    rs = np.random.RandomState(31)
+    B, n, n_samples, dis_threshold, epsilon = 2, 192, 64, 0.2, 0.02
+    base = rs.uniform(-0.8, 0.8, size=(B, n, 3)).astype(np.float32)
+    points = base + rs.normal(size=base.shape).astype(np.float32) * dis_threshold * 0.5
+    neighbs = points + rs.normal(size=base.shape).astype(np.float32) * epsilon
+    fg = rs.normal(0, 0.1, size=(B, 128, 3)).astype(np.float32)
+    bg = rs.normal(0, 1.0, size=(B, 128, 3)).astype(np.float32)
+    t = torch.from_numpy
+    sig_fg = net.get_sigma(t(fg), only_sigma=True)
+    sig_bg = net.get_sigma(t(bg), only_sigma=True)
+    loss_fg = torch.mean(torch.exp(-2.0 / n_samples * torch.relu(sig_fg)))
+    loss_bg = torch.mean(1 - torch.exp(-2.0 / n_samples * torch.relu(sig_bg)))
+    n_p = net.get_normal(t(points.copy()))
+    n_q = net.get_normal(t(neighbs.copy()))
+    u_p = n_p / (torch.norm(n_p, p=2, dim=-1, keepdim=True) + 1e-5)
+    u_q = n_q / (torch.norm(n_q, p=2, dim=-1, keepdim=True) + 1e-5)
+    loss_n = F.mse_loss(u_p, u_q)
+    loss = 0.01 * loss_fg + 0.01 * loss_bg + 0.01 * loss_n
+    loss.backward()
+    fx = dict(points=points, neighbs=neighbs, fg=fg, bg=bg, sigma_fg=sig_fg.detach().numpy(), sigma_bg=sig_bg.detach().numpy(),
+              normal_points=n_p.detach().numpy(), normal_neighbs=n_q.detach().numpy(),
+              loss_fg=np.float32(loss_fg.item()), loss_bg=np.float32(loss_bg.item()), loss_normals=np.float32(loss_n.item()))
+    for name, prm in net.named_parameters():
+        g = prm.grad.numpy() if prm.grad is not None else np.zeros(tuple(prm.shape), np.float32)
+        fx["gnorm_" + name] = np.float32(np.linalg.norm(g))
+        fx["grad_" + name + ("" if g.size <= 1024 else "_blk")] = g if g.size <= 1024 else g[:32, :32].copy()
+    path = os.path.join(OUT, "regularizers.npz")
+    np.savez_compressed(path, **fx)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024), "loss_normals=%.5f" % fx["loss_normals"])
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if "--regularizers-only" in sys.argv:
+        regularizers_case()
+        sys.exit(0)
+    regularizers_case()
     with tempfile.TemporaryDirectory() as tmp:
         net, VR = build_reference(tmp)
         run_case(net, VR, B=2, R=96, Kc=64, Kf=64, perturb=0.0, tag="det")

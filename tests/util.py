@@ -53,3 +53,14 @@ def golden_tables(fx):
     B, V = o2c3.shape[:2]
     last = torch.tensor([0, 0, 0, 1.0]).expand(B, V, 1, 4)
     return verts, torch.cat([o2c3, last], 2), body_model().lbs_weights
+
+
+def regulariser_losses(fx, get_sigma, get_normal, dev="cpu"):
+    """train.py:264-297 on the fixture's points; returns (loss_fg, loss_bg, loss_normals, normals)."""
+    t = lambda a: torch.from_numpy(a).to(dev)                                   # noqa: E731
+    k = -2.0 / 64
+    l_fg = torch.mean(torch.exp(k * torch.relu(get_sigma(t(fx["fg"])))))
+    l_bg = torch.mean(1 - torch.exp(k * torch.relu(get_sigma(t(fx["bg"])))))
+    n_p, n_q = get_normal(t(fx["points"])), get_normal(t(fx["neighbs"]))
+    unit = lambda v: v / (torch.norm(v, p=2, dim=-1, keepdim=True) + 1e-5)      # noqa: E731
+    return l_fg, l_bg, torch.nn.functional.mse_loss(unit(n_p), unit(n_q)), (n_p, n_q)
