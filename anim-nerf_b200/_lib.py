@@ -19,6 +19,7 @@ SIGNATURES = {
     "an_version": (_i32, []),
     "an_error_string": (_c.c_char_p, [_i32]),
     "an_raygen_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp]),
+    "an_sample_training_rays_fwd": (_i32, [_vp] * 11 + [_i32] * 5 + [_f32, _f32, _i32, _i32, _vp, _u64] + [_vp] * 5),
     "an_sample_coarse_fwd": (_i32, [_vp, _i64, _i32, _f32, _vp, _u64, _vp, _vp]),
     "an_vertex_grid_bytes": (_i64, [_i32, _i32]),
     "an_vertex_grid_build": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp]),

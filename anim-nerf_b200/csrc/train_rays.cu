@@ -43,8 +43,9 @@ __global__ void sample_training_rays_kernel(
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             float v = (float)images[px * 3 + a] / 255.0f;      // img / 255.   (:200)
-            if (!with_background) v = v * m;                    // (:203-204)
-            if (white_bkgd) v = v * m + (1.0f - m);            // (:244-245)
+            // separate roundings, as torch evaluates img * mask + (1 - mask): no FMA contraction (bit-exact colours)
+            if (!with_background) v = __fmul_rn(v, m);                                   // (:203-204)
+            if (white_bkgd) v = __fadd_rn(__fmul_rn(v, m), __fsub_rn(1.0f, m));          // (:244-245)
             c[a] = v;
         }
         rgbs[i * 3] = c[0]; rgbs[i * 3 + 1] = c[1]; rgbs[i * 3 + 2] = c[2];

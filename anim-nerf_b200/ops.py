@@ -34,6 +34,28 @@ def raygen(c2w, focal, center, H, W, near, far, pix=None, ginv=None):
     return rays
 
 
+def sample_training_rays(store, frame_ids, c2w, focal, center, ginv, n, n_fg, near=0.1, far=10.0, sel=None, seed=0):
+    """SURVEY 8(f)#3 (an_sample_training_rays_fwd).  store: DeviceFrameStore.  -> rays (B,n,8), rgbs (B,n,3),
+    alphas (B,n), pix (B,n,2) int32."""
+    dev = store.images.device
+    frame_ids = torch.as_tensor(frame_ids, dtype=torch.int32, device=dev).contiguous()
+    B = frame_ids.shape[0]
+    c2w, focal, center = _f32c(c2w), _f32c(focal), _f32c(center)
+    if ginv is not None:
+        ginv = _f32c(ginv)
+    if sel is not None:
+        sel = sel.to(torch.int32).contiguous()
+    rays = torch.empty(B, n, 8, device=dev)
+    rgbs = torch.empty(B, n, 3, device=dev)
+    alphas = torch.empty(B, n, device=dev)
+    pix = torch.empty(B, n, 2, device=dev, dtype=torch.int32)
+    call("an_sample_training_rays_fwd", ptr(store.images), ptr(store.masks), ptr(store.fg_list), ptr(store.fg_off),
+         ptr(store.bg_list), ptr(store.bg_off), ptr(frame_ids), ptr(c2w), ptr(focal), ptr(center), ptr(ginv),
+         B, n, n_fg, store.H, store.W, float(near), float(far), int(store.white_bkgd), int(store.with_background),
+         ptr(sel), int(seed), ptr(rays), ptr(rgbs), ptr(alphas), ptr(pix), stream())
+    return rays, rgbs, alphas, pix
+
+
 def sample_coarse(rays, n_coarse, perturb=0.0, noise_u=None, seed=0):
     """A3.  rays (...,8) -> z (...,Kc)."""
     rays = _f32c(rays)

@@ -47,6 +47,26 @@ int an_raygen_fwd(const float* c2w, const float* focal, const float* center, con
                   const float* ginv, int B, int R, int H, int W, float near_, float far_,
                   float* rays, void* stream);
 
+/* ---- A1 for training batches: pixel sampling + gathers + ray generation ----------
+ * replaces, per training step, datasets/anim_nerf_dataset.py:235-262 (__getitem__): get_pixelcoords'
+ * 'foreground_pixel' draws (:10-54; the first n_fg samples from the eroded-silhouette list, the rest from the
+ * outside-band list, with replacement), the rgb/alpha gathers at those pixels (:259-261) with the
+ * mask / white-background composite (:200-204, :244-245), and gen_rays (:56-85) at the drawn pixels only,
+ * fused with the body-space ray transform (ginv as in an_raygen_fwd).
+ * images (F,H,W,3) uint8 RGB and masks (F,H,W) uint8 stay resident in device memory; fg/bg lists are CSR per
+ * stored frame: *_off (F+1) int32, *_list linear pixel ids row*W+col of mask_inside>0 / mask_outside>0.
+ * frame_ids (B) int32 selects the stored frame of each batch entry.  sel (B,n) int32 explicit positions in
+ * the lists (parity with the reference's np.random.choice draws) or NULL for the in-kernel Philox stream.
+ * Outputs rays (B,n,8), rgbs (B,n,3), alphas (B,n), pix (B,n,2) int32 (row,col; may be NULL).            */
+int an_sample_training_rays_fwd(const uint8_t* images, const uint8_t* masks,
+                                const int32_t* fg_list, const int32_t* fg_off,
+                                const int32_t* bg_list, const int32_t* bg_off,
+                                const int32_t* frame_ids, const float* c2w, const float* focal,
+                                const float* center, const float* ginv, int B, int n, int n_fg, int H, int W,
+                                float near_, float far_, int white_bkgd, int with_background,
+                                const int32_t* sel, uint64_t seed,
+                                float* rays, float* rgbs, float* alphas, int32_t* pix, void* stream);
+
 /* ---- A3: stratified sampling ------------------------------------------------------------
  * replaces models/volume_rendering.py:29-56 VolumeRenderer.sample_coarse (lindisp=True,
  * i.e. linear in depth).  rays (n_rays,8), z (n_rays,Kc).  perturb>0: noise_u (n_rays,Kc)

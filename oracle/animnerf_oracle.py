@@ -61,6 +61,71 @@ def gen_rays(c2w, H, W, focal, near, far, c=None):
     return torch.cat([o, d, near * one, far * one], dim=-1)
 
 
+# --------------------------------------------------------------------- training-ray sampling (8(f)#3)
+def _morph(mask, k, op):
+    """cv2.erode / cv2.dilate with a k x k all-ones kernel, default anchor (k//2, k//2) and default border
+    (out-of-image pixels are ignored), as called at datasets/anim_nerf_dataset.py:32-37:
+    dst(r,c) = op over src(r+i-k//2, c+j-k//2), 0 <= i,j < k."""
+    H, W = mask.shape
+    a = k // 2
+    fill = np.inf if op == "erode" else -np.inf
+    pad = np.full((H + k - 1, W + k - 1), fill, np.float64)
+    pad[a:a + H, a:a + W] = mask
+    red = np.minimum if op == "erode" else np.maximum
+    # separable: rows then columns
+    tmp = pad[:, 0:W].copy()
+    for j in range(1, k):
+        tmp = red(tmp, pad[:, j:j + W])
+    out = tmp[0:H].copy()
+    for i in range(1, k):
+        out = red(out, tmp[i:i + H])
+    return out.astype(mask.dtype)
+
+
+def pixel_candidate_masks(mask, fore_erode=3):
+    """get_pixelcoords('foreground_pixel'), datasets/anim_nerf_dataset.py:30-37: mask (H,W) float ->
+    (mask_inside > 0, mask_outside > 0) boolean maps: the silhouette eroded by fore_erode, and the band between
+    its 64-px and fore_erode-px dilations."""
+    inside = _morph(mask, fore_erode, "erode")
+    d1 = _morph(mask, fore_erode, "dilate")
+    d2 = _morph(mask, 64, "dilate")
+    return inside > 0, (d2 - d1) > 0
+
+
+def get_pixelcoords(mask, subsamplesize=32, fore_rate=0.9, fore_erode=3, rng=np.random):
+    """datasets/anim_nerf_dataset.py:10-54, subsampletype='foreground_pixel'.  mask (H,W,1) or (H,W) float.
+    Draws come from `rng.choice` in the reference's order (foreground, then background) -> coords (n,2)
+    (row, col) int, plus the draw positions (for the kernel's parity mode)."""
+    m = np.asarray(mask, np.float32).reshape(mask.shape[0], mask.shape[1])
+    inside, outside = pixel_candidate_masks(m, fore_erode)
+    n = subsamplesize * subsamplesize
+    n_fg = int(n * fore_rate)
+    fx, fy = np.where(inside)
+    sf = rng.choice(fx.shape[0], n_fg, replace=True)
+    bx, by = np.where(outside)
+    sb = rng.choice(bx.shape[0], n - n_fg, replace=True)
+    px = np.concatenate((fx[sf], bx[sb]), 0)
+    py = np.concatenate((fy[sf], by[sb]), 0)
+    return np.stack((px, py), -1).reshape(-1, 2), np.concatenate((sf, sb), 0)
+
+
+def training_sample(img_u8, mask_u8, coords, c2w, focal, c, near=0.1, far=10.0, white_bkgd=True, with_background=False):
+    """datasets/anim_nerf_dataset.py:200-204 (img/255, mask/255, img*mask), :244-245 (white background),
+    :246-261 (full-frame gen_rays then the gathers at coords).  img_u8 (H,W,3), mask_u8 (H,W) ->
+    rays (n,8), rgbs (n,3), alphas (n,1) torch fp32."""
+    img = torch.from_numpy(img_u8 / 255.).float().permute(2, 0, 1)
+    mask = torch.from_numpy(mask_u8 / 255.).float().unsqueeze(0)
+    if not with_background:
+        img = img * mask
+    if white_bkgd:
+        img = img * mask + (1 - mask)
+    rgbs, alphas = img.permute(1, 2, 0), mask.permute(1, 2, 0)
+    H, W = mask_u8.shape
+    rays = gen_rays(c2w, H, W, focal, near, far, c)
+    r, cc = coords[:, 0], coords[:, 1]
+    return rays[r, cc], rgbs[r, cc], alphas[r, cc]
+
+
 def _affine(M, v, w):
     """(M @ [v; w])[:3] for batched 4x4 M broadcast against points v (...,3)."""
     out = torch.matmul(M[..., :3, :3], v[..., None])[..., 0]

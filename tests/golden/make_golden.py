@@ -218,6 +218,45 @@ def gen_rays_case():
     print("wrote gen_rays.npz")
 
 
+def pixel_sampling_case():
+    """Training-ray sampling: the reference's own `get_pixelcoords` ('foreground_pixel', seeded numpy global RNG)
+    and `gen_rays` (datasets/anim_nerf_dataset.py:10-85) on a synthetic soft-edged silhouette, combined by the
+    lines of `__getitem__` (:242-261; the dataset class itself needs People-Snapshot files, so those ten lines
+    are restated here around the reference's functions)."""
+    from datasets.anim_nerf_dataset import get_pixelcoords, gen_rays
+    import cv2
+    rs = np.random.RandomState(41)
+    H, W, n_side = 120, 96, 8
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    body = (((xx - 50) / 14.0) ** 2 + ((yy - 58) / 36.0) ** 2 < 1) | (((xx - 30) / 5.0) ** 2 + ((yy - 40) / 22.0) ** 2 < 1)
+    mask_u8 = cv2.GaussianBlur((body * 255).astype(np.uint8), (5, 5), 1.2)        # soft edge: values strictly between 0 and 255
+    img_u8 = rs.randint(0, 256, size=(H, W, 3)).astype(np.uint8)
+    R = np.linalg.qr(rs.normal(size=(3, 3)))[0]
+    c2w = np.concatenate([R, rs.normal(size=(3, 1))], 1).astype(np.float32)
+    focal = np.array([105.5, 99.25], np.float32)
+    c = np.array([47.3, 61.1], np.float32)
+    fx = dict(img_u8=img_u8, mask_u8=mask_u8, c2w=c2w, focal=focal, c=c, n_side=n_side)
+    # :200-204, :244-245
+    img = torch.from_numpy(img_u8 / 255.).float().permute(2, 0, 1)
+    mask = torch.from_numpy(mask_u8 / 255.).float().unsqueeze(0)
+    img = img * mask                       # with_background = False
+    img = img * mask + (1 - mask)          # white_bkgd = True
+    rgbs, alphas = img.permute(1, 2, 0), mask.permute(1, 2, 0)
+    rays = gen_rays(torch.from_numpy(c2w), H, W, focal, 0.1, 10.0, c)
+    for fore_erode in (3, 5):
+        np.random.seed(5)
+        coords = get_pixelcoords(H, W, alphas.numpy(), subsampletype="foreground_pixel", subsamplesize=n_side,
+                                 fore_rate=0.9, fore_erode=fore_erode)
+        fx["coords_e%d" % fore_erode] = coords.astype(np.int32)
+    coords = fx["coords_e3"]
+    fx["rays"] = rays[coords[:, 0], coords[:, 1]].numpy()
+    fx["rgbs"] = rgbs[coords[:, 0], coords[:, 1]].numpy()
+    fx["alphas"] = alphas[coords[:, 0], coords[:, 1]].numpy()
+    path = os.path.join(OUT, "pixel_sampling.npz")
+    np.savez_compressed(path, **fx)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024), "soft pixels:", int(((mask_u8 > 0) & (mask_u8 < 255)).sum()))
+
+
 def regularizers_case():
     """The MLP queries of the training regularisers through the reference's own `NeRF` (models/nerf.py:155-190):
     `get_sigma(only_sigma=True)` on foreground/background points and `get_normal` (autograd.grad with
@@ -263,7 +302,11 @@ if __name__ == "__main__":
     if "--regularizers-only" in sys.argv:
         regularizers_case()
         sys.exit(0)
+    if "--pixel-sampling-only" in sys.argv:
+        pixel_sampling_case()
+        sys.exit(0)
     regularizers_case()
+    pixel_sampling_case()
     with tempfile.TemporaryDirectory() as tmp:
         net, VR = build_reference(tmp)
         run_case(net, VR, B=2, R=96, Kc=64, Kf=64, perturb=0.0, tag="det")
