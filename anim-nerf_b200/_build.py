@@ -7,9 +7,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libanimnerf_b200.so")
+LIB = os.environ.get("AN_LIB_PATH") or os.path.join(HERE, "libanimnerf_b200.so")   # AN_LIB_PATH: A/B kernel variants (dev only)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+NVCC_FLAGS += os.environ.get("AN_NVCC_EXTRA", "").split()      # e.g. -DAN_FWD_SPLIT=0 (variant builds, dev only)
 if os.environ.get("AN_MLP_TRACE"):      # debug timeline build (tools/trace_mlp.py); never the shipped library
     NVCC_FLAGS.append("-DAN_MLP_TRACE")
 
@@ -26,7 +27,7 @@ def build_lib(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     hdrs = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(ROOT, "include", "animnerf_b200.h")]
-    objdir = os.path.join(ROOT, "build", "obj")
+    objdir = os.path.join(ROOT, "build", "obj" + ("_" + os.path.basename(LIB) if os.environ.get("AN_LIB_PATH") else ""))
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []

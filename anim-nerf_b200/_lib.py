@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libanimnerf_b200.so")
+LIB_PATH = os.environ.get("AN_LIB_PATH") or os.path.join(_HERE, "libanimnerf_b200.so")   # AN_LIB_PATH: A/B variant builds (dev only)
 
 _c = ctypes
 _vp, _i32, _i64, _f32, _u64 = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float, _c.c_uint64

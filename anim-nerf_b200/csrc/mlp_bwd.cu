@@ -165,6 +165,32 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
             for (int i = 0; i < 11; ++i) {
                 const int s = step_of(i);
                 if (!want_gx && (s == 6 || s == 10)) continue;
+                // which ReLU mask applies to this step's output, and where the dY image goes; the mask words are
+                // fetched now, so that their (HBM) latency hides behind the accumulator wait
+                int mask_layer = -1;            // index into the stash's h masks (0..7 = h1..h8); step 0 uses the c mask
+                int64_t dy_off = 0;
+                if (s == 0) { dy_off = DY_HEAD; }
+                else if (s >= 1 && s <= 4) { mask_layer = 8 - s; dy_off = DY_H + (int64_t)(8 - s) * 65536; }
+                else if (s == 5) { mask_layer = 3; dy_off = DY_H + 3 * 65536; }
+                else { mask_layer = 9 - s; dy_off = DY_H + (int64_t)(9 - s) * 65536; }     // s = 7,8,9 -> h3,h2,h1
+                uint32_t mw[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+                if (s != 6 && s != 10) {
+                    if (mask_layer >= 0) {
+                        const uint8_t* mp = st_tile + ST_MASK + mask_layer * 4096 + row * 4;     // [block][row] words
+#pragma unroll
+                        for (int cb = 0; cb < 8; ++cb) mw[cb] = __ldg((const uint32_t*)(mp + cb * 512));
+                    } else {                        // step 0: d c (128 columns) masked by [c > 0]
+#pragma unroll
+                        for (int cb = 0; cb < 4; ++cb) mw[cb] = __ldg((const uint32_t*)(st_tile + ST_CMASK + cb * 512 + row * 4));
+                    }
+                }
+                if (s != 6 && s != 10) {
+                    // the previous image's bulk store must have drained before this step overwrites the image; waited
+                    // for here (the overwrite itself happens after the accumulator wait, i.e. after the MMAs that
+                    // read the image as their A operand), off the critical path
+                    if (leader) bulk_wait_read0();
+                    named_bar_sync(1 + t, 128);
+                }
                 mbar_wait(my_acc, acc_phase); acc_phase ^= 1u;
                 tc_fence_after();
                 if (s == 6 || s == 10) {
@@ -200,25 +226,6 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                         mbar_arrive(my_act);           // A image unchanged; accumulator region is free again
                     }
                     continue;
-                }
-                // wait until the previous image's bulk store has drained before overwriting it
-                if (leader) bulk_wait_read0();
-                named_bar_sync(1 + t, 128);
-                // which ReLU mask applies to this step's output, and where the dY image goes
-                int mask_layer = -1;            // index into the stash's h masks (0..7 = h1..h8); step 0 uses the c mask
-                int64_t dy_off = 0;
-                if (s == 0) { dy_off = DY_HEAD; }
-                else if (s >= 1 && s <= 4) { mask_layer = 8 - s; dy_off = DY_H + (int64_t)(8 - s) * 65536; }
-                else if (s == 5) { mask_layer = 3; dy_off = DY_H + 3 * 65536; }
-                else { mask_layer = 9 - s; dy_off = DY_H + (int64_t)(9 - s) * 65536; }     // s = 7,8,9 -> h3,h2,h1
-                uint32_t mw[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-                if (mask_layer >= 0) {
-                    const uint8_t* mp = st_tile + ST_MASK + mask_layer * 4096 + row * 4;     // [block][row] words
-#pragma unroll
-                    for (int cb = 0; cb < 8; ++cb) mw[cb] = *(const uint32_t*)(mp + cb * 512);
-                } else {                        // step 0: d c (128 columns) masked by [c > 0]
-#pragma unroll
-                    for (int cb = 0; cb < 4; ++cb) mw[cb] = *(const uint32_t*)(st_tile + ST_CMASK + cb * 512 + row * 4);
                 }
                 const int ncb = s == 0 ? 4 : 8;
                 uint32_t va[32], vb[32];

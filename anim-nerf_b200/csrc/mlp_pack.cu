@@ -138,15 +138,25 @@ mlp_unfuse_grad_kernel(const uint8_t* __restrict__ packed, float* __restrict__ g
 #pragma unroll 8
         for (int i = 0; i < 128; ++i) acc += s_v[i] * dWp[i * 256 + j];
         g[flat_w_off(8) + k * 256 + j] += acc;
-    } else if (blk < 384) {              // dW_dir[i][k = j] = sum_jj dW'[i][jj] Wf[k][jj] + db'[i] bf[k]
+    } else if (blk < 384) {              // dW_dir[i][k] = sum_jj dW'[i][jj] Wf[k][jj] + db'[i] bf[k]
+        // warp per output k, lanes over jj: every W_final row is read as coalesced 128-byte segments
         const int i = blk - 256;
         s_v[j] = dWp[i * 256 + j];
         __syncthreads();
-        float acc = dbp[i] * bf[j];
-        const float* wrow = Wf + (int64_t)j * 256;
-#pragma unroll 8
-        for (int jj = 0; jj < 256; ++jj) acc += s_v[jj] * wrow[jj];
-        g[flat_w_off(9) + i * 256 + j] += acc;
+        const int warp = j >> 5, lane = j & 31;
+        float sv[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) sv[m] = s_v[lane + 32 * m];
+        const float dbi = dbp[i];
+        for (int k = warp; k < 256; k += 8) {
+            const float* wrow = Wf + (int64_t)k * 256;
+            float acc = 0.f;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) acc += sv[m] * wrow[lane + 32 * m];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) g[flat_w_off(9) + i * 256 + k] += acc + dbi * bf[k];
+        }
     } else {                             // db_final[k = j] = sum_i Wd[i][k] db'[i];  db_dir = db'
         float acc = 0.f;
         for (int i = 0; i < 128; ++i) acc += Wd[i * 256 + j] * dbp[i];

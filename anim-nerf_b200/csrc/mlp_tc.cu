@@ -262,10 +262,13 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                         pmw[cb] = g <= 7 ? __ldg((const uint32_t*)(pst_tile + ST_MASK + g * 4096 + cb * 512 + row * 4)) : 0xffffffffu;
                 }
                 if (leader) TRACE(2 + t, 0, g, 0);
+                // act image of layer g-1 is being stored: its bulk store must have drained before the image is
+                // overwritten below (after the accumulator wait); waited for here, off the critical path -- the
+                // named barrier after the accumulator wait publishes it to the tile's other threads
+                if (TRAIN && g > 0 && leader) bulk_wait_read0();
                 mbar_wait(my_acc, acc_phase); acc_phase ^= 1u;
                 if (leader) TRACE(2 + t, 1, g, 0);
                 tc_fence_after();
-                if (TRAIN && g > 0 && leader) bulk_wait_read0();   // act image of layer g-1 is being stored: wait before overwriting it
                 ((float2*)bias_s)[e & 127] = bmine;
                 named_bar_sync(1 + t, 128);
                 if (leader) TRACE(2 + t, 2, g, 0);

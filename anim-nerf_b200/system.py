@@ -22,6 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .anim_nerf import AnimNeRF
+from .body_model_params import BodyModelParams
 from .volume_rendering import VolumeRenderer
 
 
@@ -33,7 +34,8 @@ def default_hparams(**over):
               query_inside=False, n_samples=64, n_importance=32, n_depth=0, chunk=None, white_bkgd=True,
               optim_body_params=False, num_frames=1,
               train=SimpleNamespace(lr=5e-4, lambda_alphas=0.1, lambda_foreground=0.01, lambda_background=0.01,
-                                    lambda_normals=0.01, epsilon=0.02, optimizer="adam", weight_decay=0.0))
+                                    lambda_normals=0.01, epsilon=0.02, optimizer="adam", weight_decay=0.0,
+                                    max_epochs=20, scheduler="poly", poly_exp=0.9))
     hp.update(over)
     return SimpleNamespace(**hp)
 
@@ -51,8 +53,49 @@ class AnimNeRFSystem(nn.Module):
                                   use_fine=hp.n_importance > 0 or hp.n_depth > 0, share_fine=hp.share_fine,
                                   dis_threshold=hp.dis_threshold, query_inside=hp.query_inside,
                                   body_model_data=body_model_data)
+        # train.py:139-146: per-frame SMPL parameter table (filled by `init_body_model_params`; the reference reads
+        # <root_dir>/smpls/*.pkl here -- file IO is outside the path, the tensors are handed in instead)
+        self.body_model_params = BodyModelParams(hp.num_frames, model_type=hp.model_type)
+        if hp.optim_body_params:
+            for name in self.body_model_params.param_names:
+                self.body_model_params.set_requires_grad(name, True)
         self.volume_renderer = VolumeRenderer(n_coarse=hp.n_samples, n_fine=hp.n_importance, n_fine_depth=hp.n_depth,
                                               share_fine=hp.share_fine, white_bkgd=hp.white_bkgd)
+
+    def init_body_model_params(self, params):
+        """train.py:155-165 (`load_body_model_params`) from tensors: params[name] (num_frames, dim) per SMPL parameter."""
+        for name in self.body_model_params.param_names:
+            self.body_model_params.init_parameters(name, params[name].float(), requires_grad=self.hparams.optim_body_params)
+
+    def load_reference_state_dict(self, state_dict, strict=True):
+        """Load the `state_dict` of a reference checkpoint (pytorch-lightning `.ckpt['state_dict']` of
+        train.py:AnimNeRFSystem, README.md:110).  Parameter names and shapes are the reference's own
+        (`anim_nerf.nerf[_fine].*`, `anim_nerf.body_model.*`, `body_model_params.*.weight`); the smplx module's
+        unused default-pose parameters / bookkeeping buffers (`body_model.betas`, `.global_orient`, `.body_pose`,
+        `.transl`, `.faces_tensor`, `.vertex_joint_selector.*`) have no counterpart here and are dropped; buffers
+        this package derives from the model file (joint template, parents) are kept.  Returns (missing, dropped)."""
+        drop = ("anim_nerf.body_model.betas", "anim_nerf.body_model.global_orient", "anim_nerf.body_model.body_pose",
+                "anim_nerf.body_model.transl", "anim_nerf.body_model.faces_tensor", "anim_nerf.body_model.vertex_joint_selector.")
+        own = self.state_dict()
+        sd, dropped = {}, []
+        for k, v in state_dict.items():
+            if k.startswith(drop) or k.startswith("evaluator."):
+                dropped.append(k)
+            elif k in own and own[k].shape != v.shape and k.startswith("body_model_params."):
+                emb = self.body_model_params
+                emb.init_parameters(k.split(".")[1], v.clone(), requires_grad=self.hparams.optim_body_params)   # other frame count
+            else:
+                sd[k] = v
+        res = self.load_state_dict(sd, strict=False)
+        derived = ("anim_nerf.body_model.parent_idx", "anim_nerf.body_model.J_template", "anim_nerf.body_model.J_shapedirs",
+                   "anim_nerf.body_model.parents_i32")
+        missing = [k for k in res.missing_keys if not k.startswith(derived) and not k.startswith("body_model_params.")]
+        if strict and (missing or res.unexpected_keys):
+            raise RuntimeError("reference checkpoint does not match: missing %s unexpected %s" % (missing, res.unexpected_keys))
+        for net in (self.anim_nerf.nerf, getattr(self.anim_nerf, "nerf_fine", None)):
+            if net is not None:
+                net.mark_dirty()
+        return missing, dropped
 
     def forward(self, rays, body_model_params, body_model_params_template, latent_code=None, perturb=1.0, noise=None):
         bs, h, w = rays.shape[:3]
@@ -68,10 +111,21 @@ class AnimNeRFSystem(nn.Module):
         return {k: torch.cat(v, 1).view(bs, h, w, -1) for k, v in results.items()}
 
     def configure_optimizers(self):
+        """train.py:217-226 + utils/__init__.py:33-58: Adam(eps 1e-8) on the MLPs at lr, on the SMPL table at lr/2 when
+        it is optimised; per-epoch poly decay (1 - epoch/max_epochs)**poly_exp."""
         hp = self.hparams
         groups = [{"params": self.anim_nerf.parameters(), "lr": hp.train.lr}]
+        if hp.optim_body_params:
+            groups.append({"params": self.body_model_params.parameters(), "lr": hp.train.lr * 0.5})
+        if hp.train.optimizer != "adam":
+            raise NotImplementedError("train.optimizer = 'adam' (every shipped config)")
         self.optimizer = torch.optim.Adam(groups, lr=hp.train.lr, eps=1e-8, weight_decay=hp.train.weight_decay)
-        return [self.optimizer], []
+        sched = []
+        if getattr(hp.train, "scheduler", None) == "poly":
+            self.scheduler = torch.optim.lr_scheduler.LambdaLR(
+                self.optimizer, lambda epoch: (1 - epoch / hp.train.max_epochs) ** hp.train.poly_exp)
+            sched = [self.scheduler]
+        return [self.optimizer], sched
 
     def compute_loss(self, rgbs, alphas, results, frame_idx=None, latent_code=None, fg_points=None, bg_points=None,
                      with_regularizers=True):
@@ -120,12 +174,20 @@ class AnimNeRFSystem(nn.Module):
         return loss, det
 
     def decode_batch(self, batch):
+        """train.py:167-187.  Accepts the reference dataset's flat keys (`betas`, ..., `betas_template`, ...) or the two
+        dicts already assembled (`body_model_params`, `body_model_params_template`)."""
         g = batch.get
+        names = ("betas", "global_orient", "body_pose", "transl")
+        params = batch["body_model_params"] if "body_model_params" in batch else {k: batch[k] for k in names}
+        params_t = batch["body_model_params_template"] if "body_model_params_template" in batch \
+            else {k: batch[k + "_template"] for k in names}
         return (g("frame_id"), g("cam_id"), g("frame_idx"), batch["rays"], batch["rgbs"], batch["alphas"],
-                batch["body_model_params"], batch["body_model_params_template"], g("fg_points"), g("bg_points"))
+                params, params_t, g("fg_points"), g("bg_points"))
 
     def training_step(self, batch, batch_idx=0, with_regularizers=True):
         (_, _, frame_idx, rays, rgbs, alphas, params, params_t, fg, bg) = self.decode_batch(batch)
+        if self.hparams.optim_body_params:                       # train.py:330-331: the table's rows, not the batch's copies
+            params = self.body_model_params(frame_idx)
         results = self(rays, params, params_t)
         loss, details = self.compute_loss(rgbs, alphas, results, frame_idx=frame_idx, fg_points=fg, bg_points=bg,
                                           with_regularizers=with_regularizers)

@@ -257,6 +257,19 @@ def pixel_sampling_case():
     print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024), "soft pixels:", int(((mask_u8 > 0) & (mask_u8 < 255)).sum()))
 
 
+def state_dict_case(tmp):
+    """Names and shapes of the parameters/buffers a reference checkpoint carries for the hot path's modules:
+    `AnimNeRF` (under `anim_nerf.`) and `BodyModelParams` (under `body_model_params.`), as train.py:110-146 nests them."""
+    import json
+    from models.body_model_params import BodyModelParams
+    net, _ = build_reference(tmp)
+    keys = {"anim_nerf." + k: list(v.shape) for k, v in net.state_dict().items()}
+    keys.update({"body_model_params." + k: list(v.shape) for k, v in BodyModelParams(7, model_type="smpl").state_dict().items()})
+    with open(os.path.join(OUT, "state_dict_keys.json"), "w") as f:
+        json.dump(keys, f, indent=0, sort_keys=True)
+    print("wrote state_dict_keys.json", len(keys), "entries")
+
+
 def regularizers_case():
     """The MLP queries of the training regularisers through the reference's own `NeRF` (models/nerf.py:155-190):
     `get_sigma(only_sigma=True)` on foreground/background points and `get_normal` (autograd.grad with
@@ -302,11 +315,17 @@ if __name__ == "__main__":
     if "--regularizers-only" in sys.argv:
         regularizers_case()
         sys.exit(0)
+    if "--state-dict-only" in sys.argv:
+        with tempfile.TemporaryDirectory() as tmp:
+            state_dict_case(tmp)
+        sys.exit(0)
     if "--pixel-sampling-only" in sys.argv:
         pixel_sampling_case()
         sys.exit(0)
     regularizers_case()
     pixel_sampling_case()
+    with tempfile.TemporaryDirectory() as tmp:
+        state_dict_case(tmp)
     with tempfile.TemporaryDirectory() as tmp:
         net, VR = build_reference(tmp)
         run_case(net, VR, B=2, R=96, Kc=64, Kf=64, perturb=0.0, tag="det")

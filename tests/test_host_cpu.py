@@ -90,3 +90,69 @@ def test_body_model_gradients_reach_smpl_params():
     out = bm(**t)
     (out["vertices"].sum() + out["vertices_transform"].sum()).backward()
     assert all(v.grad is not None and torch.isfinite(v.grad).all() for v in t.values())
+
+
+# ------------------------------------------------------------------ B4: system state, checkpoints, optimiser groups
+def _system(**over):
+    from anim_nerf_b200.system import AnimNeRFSystem
+    return AnimNeRFSystem(body_model_data=synthetic.make_smpl_dict(0), n_samples=64, n_importance=64, **over)
+
+
+def test_reference_checkpoint_state_dict_loads():
+    """A state dict with exactly the names/shapes a reference checkpoint carries (captured from the reference's
+    modules, tests/golden/state_dict_keys.json) loads strictly; the MLP weights and the SMPL table arrive intact."""
+    import json
+    keys = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_keys.json")))
+    g = torch.Generator().manual_seed(0)
+    sd = {k: torch.randn(*shape, generator=g) if shape else torch.zeros(()) for k, shape in keys.items()}
+    for k in list(sd):
+        if k.endswith("parents") or k.endswith("extra_joints_idxs") or k.endswith("faces_tensor"):
+            sd[k] = torch.zeros(keys[k], dtype=torch.long)
+    sysm = _system(num_frames=3, optim_body_params=True)          # table of another length: rows come from the checkpoint
+    parents_before = sysm.anim_nerf.body_model.parents.clone()
+    sd["anim_nerf.body_model.parents"] = parents_before.clone()
+    missing, dropped = sysm.load_reference_state_dict(sd, strict=True)
+    assert not missing and len(dropped) == 6
+    assert torch.equal(sysm.anim_nerf.nerf.xyz_encoding_5[0].weight, sd["anim_nerf.nerf.xyz_encoding_5.0.weight"])
+    assert torch.equal(sysm.anim_nerf.nerf_fine.rgb[0].bias, sd["anim_nerf.nerf_fine.rgb.0.bias"])
+    assert torch.equal(sysm.body_model_params.body_pose.weight, sd["body_model_params.body_pose.weight"])
+    assert sysm.body_model_params.body_pose.weight.shape == (7, 69) and sysm.body_model_params.body_pose.weight.requires_grad
+    # every reference key is either consumed or one of the six smplx leftovers
+    own = set(sysm.state_dict())
+    assert all(k in own or k in dropped for k in keys)
+    with pytest.raises(RuntimeError):
+        sysm.load_reference_state_dict({k: v for k, v in sd.items() if "xyz_encoding_3" not in k}, strict=True)
+
+
+def test_body_model_params_table_and_optimiser_groups():
+    """models/body_model_params.py:5-66 semantics + train.py:217-226 optimiser groups and the poly schedule."""
+    F = 5
+    sysm = _system(num_frames=F, optim_body_params=True)
+    posed, _ = synthetic.make_body_params(F, seed=4)
+    sysm.init_body_model_params({k: torch.from_numpy(v) for k, v in posed.items()})
+    tab = sysm.body_model_params
+    assert tab.betas.weight.shape == (1, 10) and tab.body_pose.weight.shape == (F, 69)
+    np.testing.assert_allclose(tab.betas.weight.detach().numpy()[0], posed["betas"].mean(0), atol=1e-7)   # betas: mean over frames
+    out = tab(torch.tensor([3, 1]))
+    assert torch.equal(out["body_pose"], torch.from_numpy(posed["body_pose"][[3, 1]]))
+    assert torch.equal(out["betas"][0], out["betas"][1]) and out["betas"].shape == (2, 10)
+    assert all(p.requires_grad for p in tab.parameters())
+    (opt,), (sched,) = sysm.configure_optimizers()
+    assert [g["lr"] for g in opt.param_groups] == [5e-4, 2.5e-4]
+    assert len(opt.param_groups[0]["params"]) == 48 and len(opt.param_groups[1]["params"]) == 4
+    opt.step(); sched.step()
+    assert abs(opt.param_groups[0]["lr"] - 5e-4 * (1 - 1 / 20) ** 0.9) < 1e-12
+    frozen = _system(num_frames=F)                               # optim_body_params=False: table frozen, one group
+    assert not any(p.requires_grad for p in frozen.body_model_params.parameters())
+    assert len(frozen.configure_optimizers()[0][0].param_groups) == 1
+
+
+def test_decode_batch_accepts_the_reference_datasets_flat_keys():
+    sysm = _system()
+    posed, tmpl = synthetic.make_body_params(2, seed=4)
+    flat = {k: torch.from_numpy(v) for k, v in posed.items()}
+    flat.update({k + "_template": torch.from_numpy(v) for k, v in tmpl.items()})
+    flat.update(rays=torch.zeros(2, 4, 4, 8), rgbs=torch.zeros(2, 4, 4, 3), alphas=torch.zeros(2, 4, 4, 1), frame_idx=torch.tensor([0, 1]))
+    out = sysm.decode_batch(flat)
+    assert set(out[6]) == set(out[7]) == {"betas", "global_orient", "body_pose", "transl"}
+    assert torch.equal(out[7]["body_pose"], flat["body_pose_template"]) and out[8] is None
