@@ -145,16 +145,16 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                 const float a0 = rgb[id * 3], a1 = rgb[id * 3 + 1], a2 = rgb[id * 3 + 2];
                 dp0 = g_rgb[id * 3] * a0 * (1.f - a0); dp1 = g_rgb[id * 3 + 1] * a1 * (1.f - a1); dp2 = g_rgb[id * 3 + 2] * a2 * (1.f - a2);
             }
-            // previous iteration's bulk stores must have finished reading this tile's image
-            if (leader) bulk_wait_read0();
-            named_bar_sync(1 + t, 128);
+            // this warp's bulk stores of the previous iteration must have finished reading its rows of the image
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
             {   // d rgb_pre -> A image of step 0 (K = 16: units 0,1 of chunk 0; columns 0..2 carry data)
                 *(uint4*)(act_row + ((0u ^ sw) << 4)) = make_uint4(pack_bf16(dp0, dp1), pack_bf16(dp2, 0.f), 0u, 0u);
                 *(uint4*)(act_row + ((1u ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
             }
             fence_proxy_async();
-            named_bar_sync(1 + t, 128);
-            if (leader) { bulk_s2g(dy_tile + DY_RGB, act_s, 16384); bulk_commit(); }
+            __syncwarp();         // every warp streams its own 32 rows (4 KB, contiguous in the image) to the scratch
+            if (lane == 0) { bulk_s2g(dy_tile + DY_RGB + q * 4096, act_s + q * 4096u, 4096); bulk_commit(); }
             mbar_arrive(my_act);
 
             // encoding derivative factors (same double-angle recurrence as the forward)
@@ -185,11 +185,11 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                     }
                 }
                 if (s != 6 && s != 10) {
-                    // the previous image's bulk store must have drained before this step overwrites the image; waited
-                    // for here (the overwrite itself happens after the accumulator wait, i.e. after the MMAs that
-                    // read the image as their A operand), off the critical path
-                    if (leader) bulk_wait_read0();
-                    named_bar_sync(1 + t, 128);
+                    // this warp's bulk stores of the previous image must have drained before this step overwrites its
+                    // rows; waited for here (the overwrite itself happens after the accumulator wait, i.e. after the
+                    // MMAs that read the image as their A operand), off the critical path
+                    if (lane == 0) bulk_wait_read0();
+                    __syncwarp();
                 }
                 mbar_wait(my_acc, acc_phase); acc_phase ^= 1u;
                 tc_fence_after();
@@ -250,6 +250,17 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                         o.z = pack_bf16(f[8 * u + 4], f[8 * u + 5]); o.w = pack_bf16(f[8 * u + 6], f[8 * u + 7]);
                         *(uint4*)(dst + ((((uint32_t)(cb & 1) * 4 + u) ^ sw) << 4)) = o;
                     }
+                    if (cb & 1) {
+                        // a 64-column chunk of the dY image is complete for this warp's 32 rows: stream those 4 KB to
+                        // the scratch now -- small stores spread over the epilogue, no 128-thread barrier
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            const uint32_t off = (uint32_t)(cb >> 1) * 16384u + (uint32_t)q * 4096u;
+                            bulk_s2g(dy_tile + dy_off + off, act_s + off, 4096);
+                            bulk_commit();
+                        }
+                    }
                 }
                 if (s == 0) {   // third chunk of the head layer's dY: column 0 = d sigma (K-step 0 = units 0,1)
                     *(uint4*)(act_row + 2 * 16384 + ((0u ^ sw) << 4)) = make_uint4(pack_bf16(gs, 0.f), 0u, 0u, 0u);
@@ -257,12 +268,18 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                 }
                 tc_fence_before();
                 fence_proxy_async();
-                named_bar_sync(1 + t, 128);
-                if (leader) { bulk_s2g(dy_tile + dy_off, act_s, s == 0 ? 49152u : 65536u); bulk_commit(); }
+                if (s == 0) {   // the d sigma chunk of the head layer's dY
+                    __syncwarp();
+                    if (lane == 0) {
+                        const uint32_t off = 2u * 16384u + (uint32_t)q * 4096u;
+                        bulk_s2g(dy_tile + dy_off + off, act_s + off, 4096);
+                        bulk_commit();
+                    }
+                }
                 if (!(s == 9 && !want_gx)) mbar_arrive(my_act);      // last step has no consumer MMA
             }
         }
-        if (leader) bulk_wait0();
+        if (lane == 0) bulk_wait0();
     }
     tc_fence_before();
     __syncthreads();

@@ -223,9 +223,9 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                     fk *= 2.f;
                 }
                 ev[63] = 0.f;
-                if (TRAIN) {      // previous iteration's TMA stores must have drained this tile's smem
-                    if (leader) bulk_wait_read0();
-                    named_bar_sync(1 + t, 128);
+                if (TRAIN) {      // this warp's TMA stores of the previous iteration must have drained its rows
+                    if (lane == 0) bulk_wait_read0();
+                    __syncwarp();
                 }
 #pragma unroll
                 for (uint32_t u = 0; u < 8; ++u) {
@@ -236,9 +236,9 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 }
             }
             fence_proxy_async();
-            if (TRAIN) {
-                named_bar_sync(1 + t, 128);
-                if (leader) { bulk_s2g(st_tile + ST_ENC, enc_s, 16384); bulk_commit(); }
+            if (TRAIN) {          // every warp streams its own 32 rows (4 KB, contiguous in the image) to the stash
+                __syncwarp();
+                if (lane == 0) { bulk_s2g(st_tile + ST_ENC + q * 4096, enc_s + q * 4096u, 4096); bulk_commit(); }
             }
             mbar_arrive(my_act);
 
@@ -262,10 +262,10 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                         pmw[cb] = g <= 7 ? __ldg((const uint32_t*)(pst_tile + ST_MASK + g * 4096 + cb * 512 + row * 4)) : 0xffffffffu;
                 }
                 if (leader) TRACE(2 + t, 0, g, 0);
-                // act image of layer g-1 is being stored: its bulk store must have drained before the image is
-                // overwritten below (after the accumulator wait); waited for here, off the critical path -- the
-                // named barrier after the accumulator wait publishes it to the tile's other threads
-                if (TRAIN && g > 0 && leader) bulk_wait_read0();
+                // this warp's rows of the layer g-1 image are being stored: those bulk stores must have drained before
+                // the rows are overwritten below (after the accumulator wait); waited for here, off the critical
+                // path -- the named barrier after the accumulator wait also orders the warp's lanes behind lane 0
+                if (TRAIN && g > 0 && lane == 0) bulk_wait_read0();
                 mbar_wait(my_acc, acc_phase); acc_phase ^= 1u;
                 if (leader) TRACE(2 + t, 1, g, 0);
                 tc_fence_after();
@@ -336,6 +336,18 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                         for (uint32_t u = 0; u < 4; ++u)
                             *(uint4*)(dst + ((((uint32_t)(blk & 1) * 4 + u) ^ sw) << 4)) =
                                 make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+                        if (TRAIN && (blk & 1)) {
+                            // a 64-column chunk of the image is complete for this warp's 32 rows: stream those 4 KB to
+                            // the stash now (h_{g+1}, or c after the head layer) -- small stores spread over the epilogue
+                            // instead of one 64 KB burst behind a 128-thread barrier at its end
+                            fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) {
+                                const uint32_t off = (uint32_t)(blk >> 1) * 16384u + (uint32_t)q * 4096u;
+                                bulk_s2g(st_tile + (g == 8 ? ST_C : ST_H + (int64_t)g * 65536) + off, act_s + off, 4096);
+                                bulk_commit();
+                            }
+                        }
                     }
                 }
                 if (leader) TRACE(2 + t, 4, g, 0);
@@ -344,20 +356,12 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 tc_fence_before();                // TMEM reads/writes done before the MMAs that follow the arrive
                 if (g < 9) {      // (tangent mode ends at g = 8: its c image is stored too, so every image of the stash is defined)
                     fence_proxy_async();
-                    if (TRAIN) {
-                        named_bar_sync(1 + t, 128);
-                        if (leader) TRACE(2 + t, 6, g, 0);
-                        if (leader) {             // h_{g+1} (64 KB), or c (32 KB) after the head layer
-                            bulk_s2g(st_tile + (g == 8 ? ST_C : ST_H + (int64_t)g * 65536), act_s, g == 8 ? 32768u : 65536u);
-                            bulk_commit();
-                        }
-                    }
                     if (g < NGT - 1) mbar_arrive(my_act);
                 }
                 if (leader) TRACE(2 + t, 3, g, 0);
             }
         }
-        if (TRAIN && leader) bulk_wait0();
+        if (TRAIN && lane == 0) bulk_wait0();
     }
     tc_fence_before();
     __syncthreads();
