@@ -34,6 +34,7 @@ if ROOT not in sys.path:
 
 METRIC = "rays/sec render_rays fwd+bwd (64+64 samples)"
 FLOP_PER_POINT_FWD = 1179904
+WGRAD_BYTES_PER_POINT = 4480 + 4608   # bf16 images the weight-gradient kernel reads once: X (enc 128 + 8 x 512 + c 256) + dY (128 + 384 + 8 x 512)
 N_FRAMES, N_SIDE, KC, KF = 16, 32, 64, 64
 
 
@@ -308,25 +309,38 @@ def run_ours(args):
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    peak_hbm = float(peaks.get("hbm_gbs", 6500.0))
     dom = max(share, key=share.get) if share else None
-    roofline = None
+    roofline, rooflines = None, {}
     if dom is not None:
-        # algorithmic FLOP per launch of each MLP kernel = valid points of that pass x 1 179 904 (fwd, dgrad, wgrad alike)
-        n_calls = calls_per_step.get(dom, 1)
-        mlp_kernels = ("an_mlp_fwd", "an_mlp_bwd_dgrad", "an_mlp_bwd_wgrad")
-        k = dom if dom in mlp_kernels else "an_mlp_fwd"
+        try:        # DRAM bytes per launch from the committed ncu --set full capture (tools/ncu_traffic.py)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except Exception:
+            tj = {}
         # mean valid points per launch over the coarse (64/ray) and fine (128/ray) pass
         pts_per_launch = (pts_coarse + pts_fine) / 2.0
-        flops = pts_per_launch * FLOP_PER_POINT_FWD
-        achieved = flops / (per_kernel[k] * 1e-3) / 1e12
-        roofline = {"kernel": k, "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
-                    "avg_launch_ms": per_kernel[k], "share_of_step": share[k] / step_ms,
-                    "valid_points_per_step": pts_coarse + pts_fine,
-                    "dense_equivalent_tflops": (n_rays * (2 * KC + KF) / 2.0) * FLOP_PER_POINT_FWD / (per_kernel[k] * 1e-3) / 1e12,
-                    "note": "achieved = useful FLOP (valid, non-culled points x 1 179 904) / mean launch time over the coarse "
-                            "(64/ray) and fine (128/ray) launches; valid fraction coarse %.3f, fine %.3f; culling is exact "
-                            "(invalid samples have alpha = 0)" % (valid_frac_coarse, valid_frac_fine)}
+        note = ("per launch = mean over the coarse (64/ray) and fine (128/ray) launch; valid (non-culled) points only: "
+                "fraction coarse %.3f, fine %.3f; culling is exact (invalid samples have alpha = 0)" % (valid_frac_coarse, valid_frac_fine))
+        for k in ("an_mlp_fwd", "an_mlp_bwd_dgrad", "an_mlp_bwd_wgrad"):
+            if k not in per_kernel:
+                continue
+            t_s = per_kernel[k] * 1e-3
+            common = {"kernel": k, "avg_launch_ms": per_kernel[k], "share_of_step": share[k] / step_ms,
+                      "traffic": tj.get(k, {}).get("bytes_per_launch"), "traffic_unit": "B/launch, dram read+write (ncu)",
+                      "traffic_source": tj.get("_source"), "valid_points_per_launch": pts_per_launch, "note": note}
+            if k == "an_mlp_bwd_wgrad":
+                # HBM-bound by construction: every X image (4480 B/point) and dY image (4608 B/point) is read once
+                ach = pts_per_launch * WGRAD_BYTES_PER_POINT / t_s / 1e9
+                rooflines[k] = dict(common, bound="hbm", achieved=ach, peak=peak_hbm, unit="GB/s", frac=ach / peak_hbm,
+                                    algorithmic_bytes_per_point=WGRAD_BYTES_PER_POINT,
+                                    peak_source="measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6500 GB/s",
+                                    tensor_tflops=pts_per_launch * FLOP_PER_POINT_FWD / t_s / 1e12)
+            else:
+                ach = pts_per_launch * FLOP_PER_POINT_FWD / t_s / 1e12
+                rooflines[k] = dict(common, bound="tensor", achieved=ach, peak=peak_tf, unit="TFLOP/s", frac=ach / peak_tf,
+                                    algorithmic_flop_per_point=FLOP_PER_POINT_FWD, peak_source=peak_src,
+                                    dense_equivalent_tflops=(n_rays * (2 * KC + KF) / 2.0) * FLOP_PER_POINT_FWD / t_s / 1e12)
+        roofline = rooflines.get(dom if dom in rooflines else "an_mlp_fwd")
 
     line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
@@ -349,7 +363,9 @@ def run_ours(args):
             "full_training_step": full,
             "gpu_launches": int(launches),
             "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
-            "clocks": clk, "roofline": roofline}
+            "clocks": clk, "roofline": roofline,
+            "rooflines_mlp": {k: {kk: v[kk] for kk in ("bound", "achieved", "peak", "unit", "frac", "avg_launch_ms", "traffic")}
+                              for k, v in rooflines.items()}}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(sample_rays=args.cpu_rays)

@@ -1,7 +1,7 @@
 """Summarise an ncu launch list (`--metrics gpu__time_duration.sum --csv`) of bench.py: isolate one
 training step (the launches between two consecutive body_joints_kernel launches, i.e. from the
 per-frame table builder of one step to the next) and print per-kernel totals and shares.
-    python tools/launch_summary.py gpurun_out/launches.csv [step_index_from_end] > profiles/rNN_launches_step.txt"""
+    python tools/launch_summary.py gpurun_out/launches.csv [step_index_from_end] [launches_per_step] > profiles/rNN_launches_step.txt"""
 import collections, csv, sys
 path = sys.argv[1]
 back = int(sys.argv[2]) if len(sys.argv) > 2 else 3
@@ -17,6 +17,8 @@ marks = [i for i, (k, _) in enumerate(rows) if k.startswith("body_joints_kernel"
 seg = [(a, b) for a, b in zip(marks[:-1], marks[1:])]
 lens = collections.Counter(b - a for a, b in seg)
 L = max(lens, key=lambda n: (lens[n] > 1, n))
+if len(sys.argv) > 3:          # explicit segment length: pick the render-only step / the step with regularisers
+    L = min(lens, key=lambda n: abs(n - int(sys.argv[3])))
 steps = [s for s in seg if s[1] - s[0] == L]
 a, b = steps[-min(back, len(steps))]
 agg = collections.OrderedDict()
