@@ -76,6 +76,13 @@ class VolumeRenderer(nn.Module):
     def forward(self, model, rays, perturb=0., noise=None, **kwargs):
         noise = noise or {}
         rays = rays[..., :8].contiguous()
+        if rays.shape[0] * rays.shape[1] == 0:
+            # no rays: the reference's torch chain returns empty tensors of the right shapes; the kernels are not launched
+            bs, n = rays.shape[:2]
+            keys = ["rgbs", "alphas", "depths"]
+            if self.n_fine > 0 and not self.share_fine:
+                keys += ["rgbs_fine", "alphas_fine", "depths_fine"]
+            return {k: rays.new_zeros(bs, n, 3 if k.startswith("rgbs") else 1) for k in keys}
         z_coarse = self.sample_coarse(rays, perturb=perturb, noise_u=noise.get("coarse_u"))
         no_grad_coarse = self.n_fine > 0 and self.share_fine
         # the fine pass re-queries the coarse samples of the same rays plus n_fine new depths: a fused model

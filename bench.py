@@ -461,7 +461,9 @@ def run_reference(args):
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg2: training step, 16 frames x 1024 rays, 64+64 samples (bounded sample per step)"},
+            "config": {"workload": "cfg2: training step, 16 frames x 1024 rays, 64+64 samples, fwd+bwd+Adam, per GPU",
+                       "reference_arm": "bounded sample of that workload per step (%d rays of the cfg2 batch, fwd+bwd, no Adam) "
+                                        "through the oracle port of the reference algorithm on %d host threads" % (per_step, threads)},
             "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

@@ -196,3 +196,44 @@ def test_training_steps_see_updated_weights_eager_and_graphed():
     graphed = [float(g()) for _ in range(n_steps)]
     assert len(set(round(v, 7) for v in graphed)) == n_steps, graphed
     np.testing.assert_allclose(graphed, eager[n_warm:], rtol=2e-2)
+
+
+def test_edge_shapes_empty_single_ray_and_all_background():
+    """Edge cases of the public call (B3): no rays -> empty outputs of the right shapes;
+    one single ray and a ragged batch (3 frames x 37 rays) match the oracle; rays that miss the body entirely
+    (no valid sample: the compacted MLP launch processes zero points) give exactly the white background."""
+    from anim_nerf_b200.system import AnimNeRFSystem
+    sysm = AnimNeRFSystem(body_model_data=synthetic.make_smpl_dict(0), n_samples=64, n_importance=64).to(DEV)
+    for name, seed in (("nerf", 10), ("nerf_fine", 11)):
+        getattr(sysm.anim_nerf, name).load_state_dict(
+            {k: torch.from_numpy(v) for k, v in synthetic.make_nerf_weights(seed).items()}, strict=True)
+    B = 3
+    posed_np, tmpl_np = synthetic.make_body_params(B, seed=1)
+    posed = {k: torch.from_numpy(v) for k, v in posed_np.items()}
+    tmpl = {k: torch.from_numpy(v) for k, v in tmpl_np.items()}
+    bm = body_model()
+    with torch.no_grad():
+        po, to = bm(**posed), bm(**tmpl)
+    verts_w = po["vertices"].numpy()
+    d = lambda t: {k: v.to(DEV) for k, v in t.items()}                                     # noqa: E731
+    # -- empty
+    out = sysm(torch.zeros(B, 0, 1, 8, device=DEV), d(posed), d(tmpl), perturb=0.0)
+    assert out["rgbs_fine"].shape == (B, 0, 1, 3) and out["alphas"].shape == (B, 0, 1, 1)
+    # -- single ray and a ragged batch vs the oracle
+    verts_b, o2c = oracle.ober2cano_tables(po, to)
+    for R in (1, 37):
+        rays_w = torch.from_numpy(synthetic.rays_at_bbox(verts_w, R, seed=4 + R))
+        with torch.no_grad():
+            got = sysm(rays_w.view(B, R, 1, 8).to(DEV), d(posed), d(tmpl), perturb=0.0)
+        rays_b = oracle.rays_to_body_space(rays_w, po["joints_transform"][:, 0])
+        ref = oracle.render_rays(nerf_params(10), nerf_params(11), rays_b, (verts_b, o2c, bm.lbs_weights), n_coarse=64, n_fine=64)
+        for k in ("rgbs", "alphas", "rgbs_fine", "alphas_fine"):
+            err = float((got[k].view(B, R, -1).cpu() - ref[k]).abs().max())
+            assert err < 1e-2, (R, k, err)
+    # -- rays that miss the body: all samples invalid
+    rays_w = torch.from_numpy(synthetic.rays_at_bbox(verts_w, 16, seed=9)).clone()
+    rays_w[..., 3:6] = -rays_w[..., 3:6]                    # look away from the body
+    with torch.no_grad():
+        got = sysm(rays_w.view(B, 16, 1, 8).to(DEV), d(posed), d(tmpl), perturb=0.0)
+    assert float(got["alphas_fine"].abs().max()) == 0.0 and float(got["alphas"].abs().max()) == 0.0
+    assert torch.equal(got["rgbs_fine"], torch.ones_like(got["rgbs_fine"]))
