@@ -369,7 +369,7 @@ def run_ours(args):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(sample_rays=args.cpu_rays)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -466,10 +466,28 @@ def run_reference(args):
                                         "through the oracle port of the reference algorithm on %d host threads" % (per_step, threads)},
             "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_OUT_FD = None
+
+
+def emit(line):
+    """The one JSON line, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _OUT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_OUT_FD, data)
 
 
 def main():
+    # stdout carries exactly one JSON line: anything else written to fd 1 by libraries (NCCL prints its version
+    # banner there) is sent to stderr instead
+    global _OUT_FD
+    sys.stdout.flush()
+    _OUT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
