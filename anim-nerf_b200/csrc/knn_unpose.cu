@@ -506,8 +506,11 @@ __device__ __forceinline__ bool row_range(const RowCtx& c, int r, const int* __r
 // VAR 3: rows listed in lockstep into a CAP-entry shared-memory list per thread, then one flat loop in
 //        which every lane that still has a candidate evaluates it; the list is refilled (with the
 //        tightened bound) until the rows run out.
+#ifndef AN_KNN_MINB
+#define AN_KNN_MINB 1
+#endif
 template <int VAR, int CAP>
-__global__ void __launch_bounds__(SEARCH_THREADS)
+__global__ void __launch_bounds__(SEARCH_THREADS, AN_KNN_MINB)
 knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, const char* __restrict__ ws,
                   int64_t frame_bytes, QueryWs* __restrict__ qws, const float* __restrict__ ober2cano,
                   const float* __restrict__ lbsw, int J, float thr, SeedIn sd, UnposeOut o, int want_stats, int drain_t)
