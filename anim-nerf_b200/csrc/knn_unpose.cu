@@ -397,7 +397,10 @@ __device__ __forceinline__ void seed_distances(const float* __restrict__ vb, con
     }
 }
 
-__global__ void __launch_bounds__(KNN_THREADS)
+#ifndef AN_KNN_CLS_MINB
+#define AN_KNN_CLS_MINB 4
+#endif
+__global__ void __launch_bounds__(KNN_THREADS, AN_KNN_CLS_MINB)
 knn_classify_kernel(const float* __restrict__ xyz, const float* __restrict__ rays, const float* __restrict__ z,
                     int K, int64_t N, int64_t total, const float* __restrict__ verts, int V,
                     const char* __restrict__ ws, int64_t frame_bytes, QueryWs* __restrict__ qws,
@@ -506,8 +509,10 @@ __device__ __forceinline__ bool row_range(const RowCtx& c, int r, const int* __r
 // VAR 3: rows listed in lockstep into a CAP-entry shared-memory list per thread, then one flat loop in
 //        which every lane that still has a candidate evaluates it; the list is refilled (with the
 //        tightened bound) until the rows run out.
+// 8 CTAs of 128 threads per SM (64 registers): the search is bound by L2 gather latency (69 % long-scoreboard
+// stalls at 24 resident warps), 32 resident warps hide more of it: 0.71 -> 0.60 ms coarse, 0.82 -> 0.69 ms fine pass
 #ifndef AN_KNN_MINB
-#define AN_KNN_MINB 1
+#define AN_KNN_MINB 8
 #endif
 template <int VAR, int CAP>
 __global__ void __launch_bounds__(SEARCH_THREADS, AN_KNN_MINB)

@@ -100,15 +100,15 @@ class AnimNeRFSystem(nn.Module):
     def forward(self, rays, body_model_params, body_model_params_template, latent_code=None, perturb=1.0, noise=None):
         bs, h, w = rays.shape[:3]
         n_rays = h * w
-        rays = rays.view(bs, n_rays, -1)
+        rays = rays.view(bs, n_rays, rays.shape[-1])
         rays, _ = self.anim_nerf.setup_frame(body_model_params, body_model_params_template, rays)
         chunk = getattr(self.hparams, "chunk", None) or n_rays
         results = defaultdict(list)
-        for i in range(0, n_rays, chunk):
+        for i in range(0, max(n_rays, 1), max(chunk, 1)):
             out = self.volume_renderer(self.anim_nerf, rays[:, i:i + chunk, :], perturb=perturb, noise=noise)
             for k, v in out.items():
                 results[k].append(v)
-        return {k: torch.cat(v, 1).view(bs, h, w, -1) for k, v in results.items()}
+        return {k: torch.cat(v, 1).view(bs, h, w, v[0].shape[-1]) for k, v in results.items()}
 
     def configure_optimizers(self):
         """train.py:217-226 + utils/__init__.py:33-58: Adam(eps 1e-8) on the MLPs at lr, on the SMPL table at lr/2 when

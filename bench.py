@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -75,15 +75,22 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Median SM clock / throttle reasons over the samples taken inside [t0, t1] (the timed region); when the
+        region is shorter than the sampling period, over every sample since start() (all taken under the same load:
+        the warm-up replays, the timed region and the end-to-end loop that follows it)."""
         if self.proc is None:
             return None
         time.sleep(0.15)
         self.proc.terminate()
+        rows = [r for ts, r in self.rows if t0 is not None and t0 <= ts <= t1]
+        window = "timed region"
+        if len(rows) < 2:
+            rows, window = [r for _, r in self.rows], "warm-up + timed region + e2e loop (same load)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
@@ -93,7 +100,8 @@ class ClockSampler:
                 pass
         if not sm:
             return None
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 # ----------------------------------------------------------------------------- ours
@@ -181,19 +189,20 @@ def run_ours(args):
     # ---- headline: the same step replayed from CUDA graphs (inputs resident in HBM)
     from anim_nerf_b200.graph_step import GraphedTrainStep
     gstep = GraphedTrainStep(loss_fn, opt, mlp_params, resident, world=world, warmup=args.warmup)
+    clocks = ClockSampler(local)
+    clocks.start()
     for _ in range(args.warmup):
         gstep()
     barrier()
-    clocks = ClockSampler(local)
-    clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_region0 = time.time()
     ev0.record()
     for _ in range(args.steps):
         gstep()
     ev1.record()
     barrier()
-    clk = clocks.stop()
+    t_region1 = time.time()
     ms = ev0.elapsed_time(ev1)
     launches = launches_per_step * args.steps
     step_ms = ms / args.steps
@@ -212,6 +221,7 @@ def run_ours(args):
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    clk = clocks.stop(t_region0, t_region1)
 
     # ---- the reference's whole training_step (train.py:324-348): the same step plus the regularisers of
     # compute_loss (fg/bg density on 2 x 16 x 128 points, normal smoothness on 2 x 16 x 6890 points, both nets;
