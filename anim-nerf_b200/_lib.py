@@ -38,7 +38,8 @@ SIGNATURES = {
     "an_mlp_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "an_mlp_bwd_dgrad": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "an_mlp_bwd_wgrad": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
-    "an_mlp_fwd_tangent": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "an_mlp_fwd_tangent": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "an_mlp_bwd_wgrad_scaled": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "an_composite_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "an_composite_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "an_searchsorted_right": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
@@ -90,7 +91,7 @@ def check(code, what):
 
 
 # kernels launched per entry point (for bench.py's gpu_launches claim)
-KERNELS_PER_CALL = {"an_mlp_bwd": 3, "an_mlp_bwd_wgrad": 2, "an_mlp_pack": 2, "an_knn_unpose_fwd": 2,
+KERNELS_PER_CALL = {"an_mlp_bwd": 3, "an_mlp_bwd_wgrad": 2, "an_mlp_bwd_wgrad_scaled": 2, "an_mlp_pack": 2, "an_knn_unpose_fwd": 2,
                     "an_body_tables_fwd": 2}
 launch_count = 0
 _timing = None          # bench.py: dict name -> list of (start_event, stop_event) on the launching stream

@@ -137,10 +137,9 @@ class SigmaWithGradient(torch.autograd.Function):
 
       forward   an_mlp_fwd (stash) -> sigma;  an_mlp_bwd_dgrad with g_sigma = 1, g_rgb = 0 -> s and the
                 delta_l = d sigma/d a_l images (kept)
-      backward  through s:      tau = an_mlp_fwd_tangent(v = dL/ds)  (forward-mode tangent on the tensor cores),
-                                dL/dW_l = delta_l tau_{l-1}^T = an_mlp_bwd_wgrad(tau images, delta images); no
-                                bias terms (biases do not enter s)
-                through sigma:  the ordinary an_mlp_bwd_dgrad + an_mlp_bwd_wgrad with g_sigma = dL/dsigma.
+      backward  T = an_mlp_fwd_tangent(v = dL/ds, c = dL/dsigma): forward-mode tangent on the tensor cores plus c times
+                the primal activations, then ONE an_mlp_bwd_wgrad_scaled(T images, delta images, c): weights
+                delta T^T (second-order term delta tau^T + first-order term (c delta) X^T), biases sum c delta.
     There is no gradient to xyz (the regulariser's sample points are detached in the reference)."""
 
     @staticmethod
@@ -165,18 +164,14 @@ class SigmaWithGradient(torch.autograd.Function):
         x, rgb = ctx.saved_tensors
         net, packed, stash, scratch, n = ctx.net, ctx.packed, ctx.stash, ctx.scratch, ctx.n
         dev = x.device
-        # through s = d sigma/d xyz: weight gradients only
-        tstash, _ = ops.mlp_fwd_tangent(packed, x, g_s.reshape(n, 3).contiguous(), stash, n_max=n)
-        flat = ops.mlp_bwd_wgrad(packed, tstash, scratch, n_max=n)
-        del tstash
-        grads = net.split_flat_grad(flat)
-        for gb in grads[12:]:
-            gb.zero_()                      # the wgrad kernel's bias sums are not gradients on this path
-        # through sigma (the delta images are no longer needed: reuse their buffer)
-        ops.mlp_bwd_dgrad(packed, stash, x, rgb, g_sigma.reshape(n).contiguous(), torch.zeros(n, 3, device=dev), scratch,
-                          n_max=n, want_g_xyz=False)
-        flat1 = ops.mlp_bwd_wgrad(packed, stash, scratch, n_max=n)
-        flat += flat1
+        # One tangent pass + one weight-gradient pass give the whole gradient.  With v = dL/ds and c = dL/dsigma:
+        #   through s:      dW_l = sum_p delta_l tau_{l-1}^T,            no bias term
+        #   through sigma:  dW_l = sum_p (c delta_l) X_{l-1}^T,          db_l = sum_p c delta_l
+        # (the sigma-only activation-gradient chain is linear in its per-point seed, so its images are c * delta).
+        # The tangent kernel writes T = tau + c X; the wgrad kernel forms delta T^T and the c-weighted bias sums.
+        c = g_sigma.reshape(n).contiguous().float()
+        tstash, _ = ops.mlp_fwd_tangent(packed, x, g_s.reshape(n, 3).contiguous(), stash, n_max=n, tscale=c)
+        flat = ops.mlp_bwd_wgrad(packed, tstash, scratch, n_max=n, bias_scale=c)
         ctx.stash = ctx.scratch = None
         return (None, None) + tuple(net.split_flat_grad(flat))
 

@@ -329,7 +329,7 @@ constexpr uint32_t WG_ALLOC = WG_BAR + 128 + 1024;
 __global__ void __launch_bounds__(WG_THREADS, 1)
 mlp_bwd_wgrad_kernel(const uint8_t* __restrict__ stash, const uint8_t* __restrict__ dy,
                      const int32_t* __restrict__ count, int has_count, int64_t n_max,
-                     float* __restrict__ g_params)
+                     float* __restrict__ g_params, const float* __restrict__ bias_scale)
 {
     using namespace mlp;
     using namespace tc;
@@ -420,10 +420,20 @@ mlp_bwd_wgrad_kernel(const uint8_t* __restrict__ stash, const uint8_t* __restric
                 if (do_bias) {
                     const uint8_t* img = sgen + st * WG_STAGE_BYTES + dy_img + (e >> 6) * 8192;
                     const int c = e & 63;
+                    if (bias_scale) {      // db = sum_p c_p dY_p: per-point weights in compact order (an_mlp_bwd_wgrad_scaled)
+                        const int64_t p0 = tile * 128 + half * 64;
 #pragma unroll 8
-                    for (int r = 0; r < 64; ++r) {
-                        const uint16_t raw16 = *(const uint16_t*)(img + r * 128 + ((((c >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1)));
-                        bsum += __uint_as_float((uint32_t)raw16 << 16);
+                        for (int r = 0; r < 64; ++r) {
+                            const uint16_t raw16 = *(const uint16_t*)(img + r * 128 + ((((c >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1)));
+                            const float sc = (p0 + r < n) ? __ldg(bias_scale + p0 + r) : 0.f;
+                            bsum += sc * __uint_as_float((uint32_t)raw16 << 16);
+                        }
+                    } else {
+#pragma unroll 8
+                        for (int r = 0; r < 64; ++r) {
+                            const uint16_t raw16 = *(const uint16_t*)(img + r * 128 + ((((c >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1)));
+                            bsum += __uint_as_float((uint32_t)raw16 << 16);
+                        }
                     }
                 }
                 mbar_arrive(bar_cs + 8 * st);
@@ -508,8 +518,8 @@ extern "C" int an_mlp_bwd_dgrad(const void* packed, const void* stash, const flo
     return AN_OK;
 }
 
-extern "C" int an_mlp_bwd_wgrad(const void* packed, const void* stash, const void* scratch, const int32_t* cidx,
-                                const int32_t* count, int64_t n_max, float* g_params, void* stream)
+static int wgrad_launch(const void* packed, const void* stash, const void* scratch, const int32_t* cidx,
+                        const int32_t* count, int64_t n_max, float* g_params, const float* bias_scale, void* stream)
 {
     if (!g_params || !packed) return AN_ERR_ARG;
     int rc = bwd_check(packed, stash, scratch, n_max, cidx, count);
@@ -523,10 +533,26 @@ extern "C" int an_mlp_bwd_wgrad(const void* packed, const void* stash, const voi
     if (splits < 1) splits = 1;
     dim3 wgrid((unsigned)splits, NJOBS);
     mlp_bwd_wgrad_kernel<<<wgrid, WG_THREADS, WG_ALLOC, (cudaStream_t)stream>>>(
-        (const uint8_t*)stash, (const uint8_t*)scratch, count, cidx ? 1 : 0, n_max, g_params);
+        (const uint8_t*)stash, (const uint8_t*)scratch, count, cidx ? 1 : 0, n_max, g_params, bias_scale);
     AN_CHECK_LAUNCH();
     // chain rule through the fused head layer: dW', db' -> xyz_encoding_final / dir_encoding gradients
     return mlp_unfuse_grad_launch(packed, g_params, (cudaStream_t)stream);
+}
+
+extern "C" int an_mlp_bwd_wgrad(const void* packed, const void* stash, const void* scratch, const int32_t* cidx,
+                                const int32_t* count, int64_t n_max, float* g_params, void* stream)
+{
+    return wgrad_launch(packed, stash, scratch, cidx, count, n_max, g_params, nullptr, stream);
+}
+
+// same, with the bias gradients weighted per point: db = sum_p bias_scale[p] dY_p (p in compact order, n_max entries);
+// the weight gradients are unchanged (dY^T X).  Pairs with an_mlp_fwd_tangent(tscale) -- see there.
+extern "C" int an_mlp_bwd_wgrad_scaled(const void* packed, const void* stash, const void* scratch, const int32_t* cidx,
+                                       const int32_t* count, int64_t n_max, const float* bias_scale, float* g_params,
+                                       void* stream)
+{
+    if (!bias_scale) return AN_ERR_ARG;
+    return wgrad_launch(packed, stash, scratch, cidx, count, n_max, g_params, bias_scale, stream);
 }
 
 extern "C" int an_mlp_bwd(const void* packed, const void* stash, const float* xyz_cano, const float* rgb,

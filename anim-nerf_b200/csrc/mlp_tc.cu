@@ -65,12 +65,14 @@ __device__ unsigned long long* g_trace = nullptr;
 // input tau_0 = d enc(x) . tvec; writes the tau images to `stash` in the activation layout -- the weight
 // gradient of a loss on d sigma/d xyz is then the ordinary wgrad kernel on (tau images, dY images),
 // see an_mlp_fwd_tangent).  The tangent runs the 8 trunk layers + the fused head layer (for tau_sigma).
+// With tscale (a per-point scalar c) the same pass produces T_l = tau_l + c * X_l (X = the primal activations):
+// T_l = m_l * (W_l T_{l-1} + c b_l), T_0 = tau_0 + c enc(x) -- the accumulators start from c * bias instead of 0.
 template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ xyz_cano,
                   const int32_t* __restrict__ cidx, const int32_t* __restrict__ count, int64_t n_max,
                   float* __restrict__ sigma_out, float* __restrict__ rgb_out, uint8_t* __restrict__ stash,
-                  const float* __restrict__ tvec, const uint8_t* __restrict__ pstash)
+                  const float* __restrict__ tvec, const uint8_t* __restrict__ pstash, const float* __restrict__ tscale)
 {
     using namespace mlp;
     using namespace tc;
@@ -201,19 +203,40 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             float x[3] = {0.f, 0.f, 0.f};
             float tv[3] = {0.f, 0.f, 0.f};
             if (in) { x[0] = xyz_cano[id * 3]; x[1] = xyz_cano[id * 3 + 1]; x[2] = xyz_cano[id * 3 + 2]; }
-            if (TAN && in) { tv[0] = tvec[id * 3]; tv[1] = tvec[id * 3 + 1]; tv[2] = tvec[id * 3 + 2]; }
+            float tsc = 0.f;           // tangent mode: weight of the primal activations in the images (0: pure tangent)
+            if (TAN && in) {
+                tv[0] = tvec[id * 3]; tv[1] = tvec[id * 3 + 1]; tv[2] = tvec[id * 3 + 2];
+                if (tscale) tsc = tscale[id];
+            }
+            if (TAN && tscale) {
+                // layer 0's accumulators start from c * b_0 of THIS iteration's point (the region is free: this
+                // thread finished draining the previous iteration's last layer)
+                uint32_t b0[32];
+#pragma unroll 1
+                for (int blk = 0; blk < 8; ++blk) {
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        const float4 b4 = __ldg((const float4*)(small + SM_BIAS + blk * 32) + c4);
+                        b0[4 * c4] = __float_as_uint(tsc * b4.x); b0[4 * c4 + 1] = __float_as_uint(tsc * b4.y);
+                        b0[4 * c4 + 2] = __float_as_uint(tsc * b4.z); b0[4 * c4 + 3] = __float_as_uint(tsc * b4.w);
+                    }
+                    tmem_st32(tm + blk * 32, b0);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+            }
             {   // positional encoding -> bf16 K-major image (64 columns, last one zero)
                 float ev[64];
                 float s[3], c[3];
 #pragma unroll
-                for (int a = 0; a < 3; ++a) { ev[a] = TAN ? tv[a] : x[a]; sincosf(x[a], &s[a], &c[a]); }
+                for (int a = 0; a < 3; ++a) { ev[a] = TAN ? tv[a] + tsc * x[a] : x[a]; sincosf(x[a], &s[a], &c[a]); }
                 float fk = 1.f;
 #pragma unroll
                 for (int k = 0; k < 10; ++k) {
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
                         if (TAN) {     // d/dx [sin(2^k x), cos(2^k x)] . tv
-                            ev[3 + 6 * k + a] = fk * c[a] * tv[a]; ev[6 + 6 * k + a] = -fk * s[a] * tv[a];
+                            ev[3 + 6 * k + a] = fk * c[a] * tv[a] + tsc * s[a]; ev[6 + 6 * k + a] = -fk * s[a] * tv[a] + tsc * c[a];
                         } else {
                             ev[3 + 6 * k + a] = s[a]; ev[6 + 6 * k + a] = c[a];
                         }
@@ -253,8 +276,8 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 // each thread fetches two of the (up to) 256 values now (latency hidden behind the accumulator
                 // wait); they are staged in shared memory and read back as broadcast 128-bit loads per block
                 const int c2 = 2 * (e & 127);
-                const int bl = g < 8 ? g + 1 : (g == 8 ? (c2 < 32 ? 9 : 0) : 0);
-                const float2 bmine = TAN ? make_float2(0.f, 0.f) : __ldg((const float2*)(small + SM_BIAS + bl * 256 + c2));
+                const int bl = g < 8 ? g + 1 : (g == 8 ? (c2 < 32 && !TAN ? 9 : 0) : 0);
+                const float2 bmine = (TAN && !tscale) ? make_float2(0.f, 0.f) : __ldg((const float2*)(small + SM_BIAS + bl * 256 + c2));
                 uint32_t pmw[8];               // tangent: the primal's ReLU masks of this layer ([block][row] words)
                 if (TAN) {
 #pragma unroll
@@ -291,6 +314,10 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                             for (int c4 = 0; c4 < 8; ++c4) {
                                 const uint4 b4 = *((const uint4*)(bias_s + blk * 128) + c4);
                                 bq[4 * c4] = b4.x; bq[4 * c4 + 1] = b4.y; bq[4 * c4 + 2] = b4.z; bq[4 * c4 + 3] = b4.w;
+                            }
+                            if (TAN) {        // tangent: the row's own weight of the bias (c * b, or 0)
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) bq[i] = __float_as_uint(tsc * __uint_as_float(bq[i]));
                             }
                             tmem_st32(tm + blk * 32, bq);
                         }
@@ -401,10 +428,10 @@ extern "C" int an_mlp_fwd(const void* packed, const float* xyz_cano, const int32
     const int grid = (int)(iters < sms ? iters : sms);
     if (stash)
         mlp_fwd_tc_kernel<1><<<grid, THREADS, SM_ALLOC, (cudaStream_t)stream>>>(
-            (const uint8_t*)packed, xyz_cano, cidx, count, n_max, sigma, rgb, (uint8_t*)stash, nullptr, nullptr);
+            (const uint8_t*)packed, xyz_cano, cidx, count, n_max, sigma, rgb, (uint8_t*)stash, nullptr, nullptr, nullptr);
     else
         mlp_fwd_tc_kernel<0><<<grid, THREADS, SM_ALLOC, (cudaStream_t)stream>>>(
-            (const uint8_t*)packed, xyz_cano, cidx, count, n_max, sigma, rgb, nullptr, nullptr, nullptr);
+            (const uint8_t*)packed, xyz_cano, cidx, count, n_max, sigma, rgb, nullptr, nullptr, nullptr, nullptr);
     AN_CHECK_LAUNCH();
     return AN_OK;
 }
@@ -418,9 +445,14 @@ extern "C" int an_mlp_fwd(const void* packed, const float* xyz_cano, const int32
 // gradients (its bias outputs are not gradients of L -- biases do not enter d sigma/d xyz -- the caller
 // zeroes them).  pstash = the primal forward's stash over the same compacted points (ReLU masks).
 // tsigma (ids) receives w_sigma . tau_8 when non-NULL.
-extern "C" int an_mlp_fwd_tangent(const void* packed, const float* xyz_cano, const float* tvec, const void* pstash,
-                                  const int32_t* cidx, const int32_t* count, int64_t n_max, float* tsigma,
-                                  void* tstash, void* stream)
+// tscale (ids) non-NULL: c = dL/d sigma per point.  Because the sigma-only activation-gradient chain is linear in its
+// per-point scalar seed (delta' = c * delta), the first-order term  sum_p c_p delta_p X_p^T  folds into the same
+// product: the kernel writes T_l = tau_l + c X_l (T_l = m_l * (W_l T_{l-1} + c b_l), T_0 = tau_0 + c enc(x)), and
+// an_mlp_bwd_wgrad_scaled(packed, tstash, delta scratch, bias_scale = c) yields the whole gradient of L(sigma, s) --
+// weights from delta T^T, biases from sum_p c_p delta_p -- in one pass instead of tangent + wgrad + dgrad + wgrad.
+extern "C" int an_mlp_fwd_tangent(const void* packed, const float* xyz_cano, const float* tvec, const float* tscale,
+                                  const void* pstash, const int32_t* cidx, const int32_t* count, int64_t n_max,
+                                  float* tsigma, void* tstash, void* stream)
 {
     if (!packed || !xyz_cano || !tvec || !pstash || !tstash || n_max <= 0) return AN_ERR_ARG;
     if (cidx && !count) return AN_ERR_ARG;
@@ -433,7 +465,7 @@ extern "C" int an_mlp_fwd_tangent(const void* packed, const float* xyz_cano, con
     const int grid = (int)(iters < sms ? iters : sms);
     mlp_fwd_tc_kernel<2><<<grid, THREADS, SM_ALLOC, (cudaStream_t)stream>>>(
         (const uint8_t*)packed, xyz_cano, cidx, count, n_max, tsigma, nullptr, (uint8_t*)tstash, tvec,
-        (const uint8_t*)pstash);
+        (const uint8_t*)pstash, tscale);
     AN_CHECK_LAUNCH();
     return AN_OK;
 }

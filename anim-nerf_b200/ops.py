@@ -247,22 +247,28 @@ def mlp_bwd_dgrad(packed, stash, xyz_cano, rgb, g_sigma, g_rgb, scratch, cidx=No
     return g_xyz
 
 
-def mlp_bwd_wgrad(packed, stash, scratch, cidx=None, count=None, n_max=None, g_params=None):
-    """dW/db of every layer from the images in `stash` (X) and `scratch` (dY); accumulates into g_params."""
+def mlp_bwd_wgrad(packed, stash, scratch, cidx=None, count=None, n_max=None, g_params=None, bias_scale=None):
+    """dW/db of every layer from the images in `stash` (X) and `scratch` (dY); accumulates into g_params.
+    bias_scale (n_max, compact order): db = sum_p bias_scale[p] dY_p instead of the plain column sums."""
     if g_params is None:
         g_params = torch.zeros(mlp_grad_floats(), device=stash.device)
-    call("an_mlp_bwd_wgrad", ptr(packed), ptr(stash), ptr(scratch), ptr(cidx), ptr(count), int(n_max), ptr(g_params), stream())
+    if bias_scale is None:
+        call("an_mlp_bwd_wgrad", ptr(packed), ptr(stash), ptr(scratch), ptr(cidx), ptr(count), int(n_max), ptr(g_params), stream())
+    else:
+        call("an_mlp_bwd_wgrad_scaled", ptr(packed), ptr(stash), ptr(scratch), ptr(cidx), ptr(count), int(n_max),
+             ptr(_f32c(bias_scale)), ptr(g_params), stream())
     return g_params
 
 
-def mlp_fwd_tangent(packed, xyz_cano, tvec, pstash, cidx=None, count=None, n_max=None, want_tsigma=False):
-    """Forward-mode tangent of the trunk (an_mlp_fwd_tangent): returns (tstash, tsigma or None)."""
+def mlp_fwd_tangent(packed, xyz_cano, tvec, pstash, cidx=None, count=None, n_max=None, want_tsigma=False, tscale=None):
+    """Forward-mode tangent of the trunk (an_mlp_fwd_tangent): returns (tstash, tsigma or None).
+    tscale (ids): the images become tau + tscale * X (see the header)."""
     if n_max is None:
         n_max = xyz_cano.numel() // 3
     tstash = mlp_stash(n_max, xyz_cano.device)
     tsig = torch.zeros(xyz_cano.numel() // 3, device=xyz_cano.device) if want_tsigma else None
-    call("an_mlp_fwd_tangent", ptr(packed), ptr(xyz_cano), ptr(_f32c(tvec)), ptr(pstash), ptr(cidx), ptr(count),
-         int(n_max), ptr(tsig), ptr(tstash), stream())
+    call("an_mlp_fwd_tangent", ptr(packed), ptr(xyz_cano), ptr(_f32c(tvec)), ptr(None if tscale is None else _f32c(tscale)),
+         ptr(pstash), ptr(cidx), ptr(count), int(n_max), ptr(tsig), ptr(tstash), stream())
     return tstash, tsig
 
 

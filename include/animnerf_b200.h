@@ -184,10 +184,18 @@ int an_mlp_bwd_wgrad(const void* packed, const void* stash, const void* scratch,
  * the primal stash `pstash`, no biases) and writes to `tstash` in the activation-stash layout, so
  * that an_mlp_bwd_wgrad(packed, tstash, that scratch, ...) accumulates dL/dW (its bias outputs are
  * then meaningless -- biases do not enter s -- and must be discarded by the caller).
- * tvec (ids,3) = v; tsigma (ids) receives w_sigma . tau_8 when non-NULL.                      */
-int an_mlp_fwd_tangent(const void* packed, const float* xyz_cano, const float* tvec, const void* pstash,
-                       const int32_t* cidx, const int32_t* count, int64_t n_max, float* tsigma,
-                       void* tstash, void* stream);
+ * tvec (ids,3) = v; tsigma (ids) receives w_sigma . tau_8 when non-NULL.
+ * tscale (ids) or NULL: c = dL/d sigma per point.  The sigma-only gradient chain is linear in its per-point seed
+ * (delta' = c delta), so the first-order term folds into the same product: with tscale the kernel writes
+ * T_l = tau_l + c X_l (accumulators start from c * bias, T_0 = tau_0 + c enc(x)), and
+ * an_mlp_bwd_wgrad_scaled(packed, tstash, that scratch, bias_scale = c) returns the complete gradient of a loss
+ * L(sigma, s): weights = delta T^T, biases = sum_p c_p delta_p (tsigma then holds w_sigma.T_8 + c b_sigma). */
+int an_mlp_fwd_tangent(const void* packed, const float* xyz_cano, const float* tvec, const float* tscale,
+                       const void* pstash, const int32_t* cidx, const int32_t* count, int64_t n_max,
+                       float* tsigma, void* tstash, void* stream);
+int an_mlp_bwd_wgrad_scaled(const void* packed, const void* stash, const void* scratch, const int32_t* cidx,
+                            const int32_t* count, int64_t n_max, const float* bias_scale, float* g_params,
+                            void* stream);
 
 /* ---- A12: alpha compositing ------------------------------------------------------------
  * replaces models/volume_rendering.py:128-160 (composite tail), far=True, white_bkgd flag.
