@@ -11,10 +11,6 @@ from . import _lib
 from ._lib import ptr, stream, call
 
 K_NEIGH = 4
-# forward-kernel organisation used when a caller asks for the default (impl 0): 0 = two-tile ping-pong (mlp_tc.cu),
-# 2 = single tile, alternating accumulators, chunk-level hand-over (mlp_tc2.cu); AN_MLP_FWD_IMPL overrides (A/B runs)
-import os as _os
-MLP_FWD_IMPL = int(_os.environ.get("AN_MLP_FWD_IMPL", "0"))
 
 
 def _f32c(t):
@@ -201,8 +197,6 @@ def mlp_fwd(packed, xyz_cano, sigma, rgb, cidx=None, count=None, n_max=None, sta
     """A9-A11 over compacted ids (or all n_max points when cidx is None); writes sigma/rgb in place."""
     if n_max is None:
         n_max = xyz_cano.numel() // 3
-    if impl == 0:
-        impl = MLP_FWD_IMPL
     call("an_mlp_fwd", ptr(packed), ptr(xyz_cano), ptr(cidx), ptr(count), int(n_max), ptr(sigma), ptr(rgb),
          ptr(stash), int(impl), stream())
 

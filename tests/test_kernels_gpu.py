@@ -202,7 +202,7 @@ def test_mlp_pack_images():
     assert torch.equal(img, W5[:, 63:127].bfloat16().float())
 
 
-@pytest.mark.parametrize("impl,n", [(1, 3000), (0, 3000), (0, 70001), (2, 3000), (2, 70001)])
+@pytest.mark.parametrize("impl,n", [(1, 3000), (0, 3000), (0, 70001)])
 def test_mlp_forward(impl, n):
     """impl 1 (fp32 SIMT reference kernel): 2e-4.  impl 0 (tcgen05, bf16 operands, fp32 accumulate):
     sigma within 3e-2 abs + 1e-2 rel, rgb within 1e-2 of the fp32 oracle."""
