@@ -688,6 +688,7 @@ knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, cons
                 // The lanes still holding candidates (long lists: far queries with a wide ball) are drained one
                 // at a time by the whole warp: 32 consecutive table entries per step (coalesced), the step's
                 // minimum found by REDUX and handed to the owning lane while it beats that lane's 4th best.
+                __syncwarp();     // the drain reads OTHER lanes' row lists from shared memory: order it after their writes
                 unsigned heavy = __ballot_sync(0xffffffffu, live);
                 while (heavy) {
                     const int L = __ffs(heavy) - 1;
@@ -729,6 +730,7 @@ knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, cons
                     if (lane == L) Bm = fminf(Bm, mine.d[3] * 1.001f);
                 }
                 if (r >= N_ROWS) break;
+                __syncwarp();     // ... and the next round's list writes after those reads
             }
         }
         // the walk saw every vertex within sqrt(min(B, box_r2)): four of them => the 4-NN are exact
