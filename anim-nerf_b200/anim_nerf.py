@@ -4,8 +4,9 @@ Same constructor keywords, same per-frame state setters (`set_body_model`,
 `convert_to_body_model_space`, `clac_ober2cano_transform`, `set_latent_code`) and the same
 `forward(xyz, viewdir, use_fine) -> (rgb, sigma)` / `query_canonical_space` contract; the work
 between the query points and (rgb, sigma) runs on the sm_100a kernels (KNN + unpose, MLP) --
-there is no torch fallback for it.  The per-frame table builder (SMPL LBS, 6890 4x4 inverses) is
-SURVEY §8 row A16 and stays in torch so autograd reaches the SMPL parameters.
+there is no torch fallback for it.  The per-frame table builder (SMPL LBS, 6890 4x4 inverses; SURVEY §8
+row A16) runs on the fused kernels (`an_body_tables_fwd`, see `setup_frame`) whenever no SMPL parameter needs
+a gradient, and through the differentiable torch builder (`body_model.py`) when one does.
 
 Only the shipped configuration is built (every reference yaml): use_unpose=True with k_neigh=4,
 use_view=False, use_deformation=False, no latent codes, query_inside=False.
