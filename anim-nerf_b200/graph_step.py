@@ -74,6 +74,8 @@ class GraphedTrainStep:
         if batch is not None:
             for k, v in batch.items():
                 self.static[k].copy_(v, non_blocking=True)
+        if hasattr(self.opt, "sync_lr"):
+            self.opt.sync_lr()              # FusedAdam: the schedule's current lr reaches the captured kernel through a device scalar
         self.g_a.replay()
         if self.world > 1:
             dist.all_reduce(self.bucket)

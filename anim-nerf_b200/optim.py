@@ -1,0 +1,85 @@
+"""Adam on the kernels: `FusedAdam` is `torch.optim.Adam` as the reference configures it (train.py:217-226,
+utils/__init__.py:33-45: eps 1e-8, betas (0.9, 0.999), L2 weight decay, no amsgrad) with the update of a whole
+parameter group done by one `an_adam_step` launch (<= 64 tensors per launch) instead of torch's multi-tensor chain.
+
+Same constructor arguments, `param_groups` (so LR schedulers work unchanged), `zero_grad`, `state_dict` layout of the
+moments (`state[p]["exp_avg"]`, `["exp_avg_sq"]`).  Graph-capturable: the step count lives in device memory and is
+advanced by the kernel; the learning rate is read from a device scalar that `sync_lr()` refreshes from
+`group["lr"]` (called by `step()` outside capture, and by `GraphedTrainStep` before every replay)."""
+import ctypes
+
+import torch
+
+from ._lib import call, ptr, stream
+
+_MAX = 64
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
+            raise ValueError("invalid Adam hyper-parameter")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._g = {}        # group index -> dict(lr_t, lr_host, chunks: list of dict(step, done))
+
+    def _gstate(self, gi, device, n_chunks):
+        st = self._g.get(gi)
+        if st is None or st["lr_t"].device != device or len(st["chunks"]) < n_chunks:
+            old = st["chunks"] if st is not None and st["lr_t"].device == device else []
+            st = dict(lr_t=torch.zeros(1, device=device), lr_host=None,
+                      chunks=old + [dict(step=torch.zeros(1, device=device), done=torch.zeros(1, device=device, dtype=torch.int32))
+                                    for _ in range(n_chunks - len(old))])
+            self._g[gi] = st
+        return st
+
+    def sync_lr(self):
+        """Copy every group's `lr` to its device scalar when it changed (a host-side write: not inside graph capture)."""
+        for gi, group in enumerate(self.param_groups):
+            st = self._g.get(gi)
+            if st is not None and st["lr_host"] != group["lr"]:
+                st["lr_t"].fill_(float(group["lr"]))
+                st["lr_host"] = group["lr"]
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        capturing = torch.cuda.is_current_stream_capturing()
+        for gi, group in enumerate(self.param_groups):
+            ps = [p for p in group["params"] if p.grad is not None]
+            if not ps:
+                continue
+            dev = ps[0].device
+            if dev.type != "cuda":
+                raise RuntimeError("FusedAdam runs on the CUDA library only; use torch.optim.Adam for CPU tensors")
+            n_chunks = (len(ps) + _MAX - 1) // _MAX
+            st = self._gstate(gi, dev, n_chunks)
+            if not capturing:
+                self.sync_lr()
+            elif st["lr_host"] is None:
+                raise RuntimeError("FusedAdam: call sync_lr() (or take one eager step) before capturing a CUDA graph")
+            b1, b2 = group["betas"]
+            for ci in range(n_chunks):
+                chunk = ps[ci * _MAX:(ci + 1) * _MAX]
+                P, G, M, V = [], [], [], []
+                for p in chunk:
+                    if p.dtype != torch.float32 or not p.is_contiguous():
+                        raise RuntimeError("FusedAdam expects contiguous fp32 parameters")
+                    s = self.state[p]
+                    if "exp_avg" not in s:
+                        s["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                        s["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    g = p.grad
+                    if g.dtype != torch.float32 or not g.is_contiguous():
+                        g = g.float().contiguous()
+                    P.append(p); G.append(g); M.append(s["exp_avg"]); V.append(s["exp_avg_sq"])
+                n = len(chunk)
+                arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])            # noqa: E731
+                sizes = (ctypes.c_int64 * n)(*[p.numel() for p in P])
+                cs = st["chunks"][ci]
+                call("an_adam_step", arr(P), arr(G), arr(M), arr(V), sizes, n, ptr(cs["step"]), ptr(st["lr_t"]),
+                     float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                     ptr(cs["done"]), stream())
+        return loss

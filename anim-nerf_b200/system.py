@@ -119,7 +119,13 @@ class AnimNeRFSystem(nn.Module):
             groups.append({"params": self.body_model_params.parameters(), "lr": hp.train.lr * 0.5})
         if hp.train.optimizer != "adam":
             raise NotImplementedError("train.optimizer = 'adam' (every shipped config)")
-        self.optimizer = torch.optim.Adam(groups, lr=hp.train.lr, eps=1e-8, weight_decay=hp.train.weight_decay)
+        groups = [dict(g, params=list(g["params"])) for g in groups]
+        on_gpu = all(p.is_cuda for g in groups for p in g["params"])
+        if on_gpu and getattr(hp.train, "fused_adam", False):          # same update, one an_adam_step launch per group
+            from .optim import FusedAdam
+            self.optimizer = FusedAdam(groups, lr=hp.train.lr, eps=1e-8, weight_decay=hp.train.weight_decay)
+        else:               # host-logic tests on CPU tensors
+            self.optimizer = torch.optim.Adam(groups, lr=hp.train.lr, eps=1e-8, weight_decay=hp.train.weight_decay)
         sched = []
         if getattr(hp.train, "scheduler", None) == "poly":
             self.scheduler = torch.optim.lr_scheduler.LambdaLR(
