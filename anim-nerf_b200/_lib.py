@@ -40,7 +40,7 @@ SIGNATURES = {
     "an_mlp_bwd_wgrad": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "an_mlp_fwd_tangent": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "an_mlp_bwd_wgrad_scaled": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
-    "an_adam_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _vp, _vp]),
+    "an_adam_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp]),
     "an_composite_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "an_composite_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "an_searchsorted_right": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),

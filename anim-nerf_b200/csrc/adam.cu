@@ -20,7 +20,8 @@ struct AdamList {
 
 __global__ void __launch_bounds__(256)
 adam_step_kernel(AdamList L, float* __restrict__ step, const float* __restrict__ lr_dev, float lr_host,
-                 float beta1, float beta2, float eps, float weight_decay, unsigned int* __restrict__ done)
+                 float beta1, float beta2, float omb1, float omb2, float eps, float weight_decay,
+                 unsigned int* __restrict__ done)
 {
     // every block reads the step count before any block can publish the incremented one (the last block to finish does)
     const float t = step[0] + 1.0f;
@@ -36,8 +37,9 @@ adam_step_kernel(AdamList L, float* __restrict__ step, const float* __restrict__
         float p = L.p[k][j];
         float g = L.g[k][j];
         if (weight_decay != 0.0f) g = g + weight_decay * p;
-        const float m = L.m[k][j] + (g - L.m[k][j]) * (1.0f - beta1);          // lerp_(grad, 1 - beta1)
-        const float v = L.v[k][j] * beta2 + (1.0f - beta2) * g * g;            // mul_(beta2).addcmul_(g, g, 1 - beta2)
+        // omb1 / omb2 = 1 - beta rounded from double on the host, as torch passes them (1.0f - 0.999f is off by 1.3e-5)
+        const float m = L.m[k][j] + (g - L.m[k][j]) * omb1;                    // lerp_(grad, 1 - beta1)
+        const float v = L.v[k][j] * beta2 + omb2 * g * g;                      // mul_(beta2).addcmul_(g, g, 1 - beta2)
         const float denom = sqrtf(v) / bc2_sqrt + eps;
         p = p - step_size * (m / denom);                                       // addcdiv_(m, denom, -step_size)
         L.p[k][j] = p; L.m[k][j] = m; L.v[k][j] = v;
@@ -51,7 +53,8 @@ adam_step_kernel(AdamList L, float* __restrict__ step, const float* __restrict__
 
 extern "C" int an_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
                             const int64_t* sizes, int n_tensors, float* step, const float* lr_dev, float lr,
-                            float beta1, float beta2, float eps, float weight_decay, unsigned int* done_counter, void* stream)
+                            float beta1, float beta2, float one_minus_beta1, float one_minus_beta2, float eps,
+                            float weight_decay, unsigned int* done_counter, void* stream)
 {
     if (!params || !grads || !exp_avg || !exp_avg_sq || !sizes || !step || !done_counter) return AN_ERR_ARG;
     if (n_tensors <= 0 || n_tensors > ADAM_MAX_TENSORS) return AN_ERR_UNSUPPORTED;
@@ -67,7 +70,8 @@ extern "C" int an_adam_step(float* const* params, const float* const* grads, flo
     const int threads = 256;
     const int64_t want = (total + threads - 1) / threads;
     const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
-    adam_step_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(L, step, lr_dev, lr, beta1, beta2, eps, weight_decay, done_counter);
+    adam_step_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(L, step, lr_dev, lr, beta1, beta2, one_minus_beta1,
+                                                                     one_minus_beta2, eps, weight_decay, done_counter);
     AN_CHECK_LAUNCH();
     return AN_OK;
 }

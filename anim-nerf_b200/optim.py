@@ -80,6 +80,7 @@ class FusedAdam(torch.optim.Optimizer):
                 sizes = (ctypes.c_int64 * n)(*[p.numel() for p in P])
                 cs = st["chunks"][ci]
                 call("an_adam_step", arr(P), arr(G), arr(M), arr(V), sizes, n, ptr(cs["step"]), ptr(st["lr_t"]),
-                     float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                     float(group["lr"]), float(b1), float(b2), float(1.0 - b1), float(1.0 - b2), float(group["eps"]),
+                     float(group["weight_decay"]),
                      ptr(cs["done"]), stream())
         return loss

@@ -121,7 +121,7 @@ class AnimNeRFSystem(nn.Module):
             raise NotImplementedError("train.optimizer = 'adam' (every shipped config)")
         groups = [dict(g, params=list(g["params"])) for g in groups]
         on_gpu = all(p.is_cuda for g in groups for p in g["params"])
-        if on_gpu and getattr(hp.train, "fused_adam", False):          # same update, one an_adam_step launch per group
+        if on_gpu and getattr(hp.train, "fused_adam", True):           # same update, one an_adam_step launch per group
             from .optim import FusedAdam
             self.optimizer = FusedAdam(groups, lr=hp.train.lr, eps=1e-8, weight_decay=hp.train.weight_decay)
         else:               # host-logic tests on CPU tensors

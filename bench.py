@@ -129,7 +129,7 @@ def run_ours(args):
         sd = {k: torch.from_numpy(v) for k, v in synthetic.make_nerf_weights(seed).items()}
         getattr(sysm.anim_nerf, name).load_state_dict(sd, strict=True)
     mlp_params = [p for n in ("nerf", "nerf_fine") for p in getattr(sysm.anim_nerf, n).parameters()]
-    if os.environ.get("AN_FUSED_ADAM", "0") == "1":
+    if os.environ.get("AN_FUSED_ADAM", "1") == "1":
         from anim_nerf_b200.optim import FusedAdam
         opt = FusedAdam(mlp_params, lr=5e-4, eps=1e-8)       # torch.optim.Adam's update in one an_adam_step launch
     else:

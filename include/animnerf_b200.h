@@ -202,10 +202,12 @@ int an_mlp_bwd_wgrad_scaled(const void* packed, const void* stash, const void* s
  * (0.9, 0.999), L2 weight decay, no amsgrad) for the step's 48 MLP tensors.  params/grads/exp_avg/exp_avg_sq: HOST
  * arrays of n_tensors (<= 64) DEVICE pointers to fp32 tensors of sizes[i] elements.  step: device float, the
  * number of steps taken so far (incremented by the kernel); lr_dev: device float or NULL (then `lr` is used);
- * done_counter: device uint32, zero before the first call (kernel-internal).  Graph-capturable.             */
+ * done_counter: device uint32, zero before the first call (kernel-internal); one_minus_beta*: 1 - beta evaluated
+ * in double by the caller (torch does the same; 1.0f - 0.999f differs by 1.3e-5).  Graph-capturable.       */
 int an_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
                  const int64_t* sizes, int n_tensors, float* step, const float* lr_dev, float lr,
-                 float beta1, float beta2, float eps, float weight_decay, unsigned int* done_counter, void* stream);
+                 float beta1, float beta2, float one_minus_beta1, float one_minus_beta2, float eps,
+                 float weight_decay, unsigned int* done_counter, void* stream);
 
 /* ---- A12: alpha compositing ------------------------------------------------------------
  * replaces models/volume_rendering.py:128-160 (composite tail), far=True, white_bkgd flag.
