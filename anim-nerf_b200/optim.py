@@ -46,7 +46,7 @@ class FusedAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        capturing = torch.cuda.is_current_stream_capturing()
+        capturing = None
         for gi, group in enumerate(self.param_groups):
             ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
@@ -54,6 +54,8 @@ class FusedAdam(torch.optim.Optimizer):
             dev = ps[0].device
             if dev.type != "cuda":
                 raise RuntimeError("FusedAdam runs on the CUDA library only; use torch.optim.Adam for CPU tensors")
+            if capturing is None:
+                capturing = torch.cuda.is_current_stream_capturing()
             n_chunks = (len(ps) + _MAX - 1) // _MAX
             st = self._gstate(gi, dev, n_chunks)
             if not capturing:

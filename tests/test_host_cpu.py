@@ -156,3 +156,23 @@ def test_decode_batch_accepts_the_reference_datasets_flat_keys():
     out = sysm.decode_batch(flat)
     assert set(out[6]) == set(out[7]) == {"betas", "global_orient", "body_pose", "transl"}
     assert torch.equal(out[7]["body_pose"], flat["body_pose_template"]) and out[8] is None
+
+
+def test_fused_adam_has_no_cpu_path_and_validates_arguments():
+    """FusedAdam is the CUDA library's optimiser: on CPU tensors it refuses to step (no silent fallback); bad
+    hyper-parameters are rejected like torch.optim.Adam rejects them; param_groups / schedulers work on the host side."""
+    from anim_nerf_b200.optim import FusedAdam
+    p = torch.zeros(4, 3, requires_grad=True)
+    opt = FusedAdam([p], lr=5e-4, eps=1e-8)
+    assert opt.param_groups[0]["lr"] == 5e-4 and opt.param_groups[0]["betas"] == (0.9, 0.999)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda e: 0.5 ** e)
+    p.grad = torch.ones_like(p)
+    with pytest.raises(RuntimeError):
+        opt.step()
+    opt.zero_grad(set_to_none=True)
+    opt.step()                                      # nothing to do without gradients: no launch, no error
+    sched.step()
+    assert abs(opt.param_groups[0]["lr"] - 2.5e-4) < 1e-12
+    for bad in (dict(lr=-1.0), dict(eps=-1e-8), dict(betas=(1.0, 0.999)), dict(weight_decay=-0.1)):
+        with pytest.raises(ValueError):
+            FusedAdam([p], **bad)
