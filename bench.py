@@ -129,7 +129,10 @@ def run_ours(args):
         sd = {k: torch.from_numpy(v) for k, v in synthetic.make_nerf_weights(seed).items()}
         getattr(sysm.anim_nerf, name).load_state_dict(sd, strict=True)
     mlp_params = [p for n in ("nerf", "nerf_fine") for p in getattr(sysm.anim_nerf, n).parameters()]
-    if os.environ.get("AN_FUSED_ADAM", "1") == "1":
+    # FusedAdam was validated on one GPU (tests/test_optim_gpu.py, single-graph replay); the two-graph N>1 step keeps
+    # torch's fused capturable Adam until it has had its own multi-GPU run (AN_FUSED_ADAM=1 forces it)
+    fused_adam = os.environ.get("AN_FUSED_ADAM", "1" if world == 1 else "0") == "1"
+    if fused_adam:
         from anim_nerf_b200.optim import FusedAdam
         opt = FusedAdam(mlp_params, lr=5e-4, eps=1e-8)       # torch.optim.Adam's update in one an_adam_step launch
     else:
@@ -361,6 +364,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "cfg2: training step, 16 frames x 1024 rays, 64+64 samples, fwd+bwd+Adam, per GPU",
                        "launch": "whole step replayed from CUDA graphs (GraphedTrainStep); eager launch: %.3f ms/step" % eager_ms,
+                       "optimizer": "Adam lr 5e-4 eps 1e-8: " + ("an_adam_step (FusedAdam), one launch" if fused_adam
+                                                                  else "torch.optim.Adam(fused, capturable)"),
                        "rays_per_step_per_gpu": n_rays, "points_per_ray": KC + KC + KF, "perturb": 1.0,
                        "regularizers": "not in the headline step (the metric names render_rays fwd+bwd); the whole training_step with them is timed separately in full_training_step",
                        "parallelism": "dp%d (rays sharded by frame, NCCL all-reduce of MLP grads)" % world,
