@@ -33,8 +33,8 @@ class Embedding(nn.Module):
 
 
 class NeRF(nn.Module):
-    def __init__(self, D=8, W=256, freqs_xyz=10, freqs_dir=4, use_view=False, use_normal=False,
-                 deformation_dim=0, apperance_dim=0, skips=(4,), actvn_type="relu"):
+    def __init__(self, D=8, W=256, freqs_xyz=10, freqs_dir=4, use_view=True, use_normal=False,
+                 deformation_dim=0, apperance_dim=0, skips=[4], actvn_type="relu"):    # noqa: B006  (the reference's defaults)
         super().__init__()
         if (D, W, freqs_xyz, tuple(skips)) != (8, 256, 10, (4,)) or use_view or use_normal \
                 or deformation_dim or apperance_dim or actvn_type != "relu":

@@ -270,6 +270,35 @@ def state_dict_case(tmp):
     print("wrote state_dict_keys.json", len(keys), "entries")
 
 
+def api_signatures_case():
+    """Constructor / method parameter names of the reference classes on the path's boundary (B2, B3, and the
+    modules B4 is built from), taken with `inspect.signature` from the imported reference."""
+    import inspect
+    import json
+    install_shim()
+    from models.anim_nerf import AnimNeRF
+    from models.volume_rendering import VolumeRenderer
+    from models.nerf import NeRF
+    from models.body_model_params import BodyModelParams
+    want = {
+        "AnimNeRF": (AnimNeRF, ["__init__", "set_latent_code", "set_body_model", "convert_to_body_model_space",
+                                "clac_ober2cano_transform", "unpose", "query_canonical_space", "forward"]),
+        "VolumeRenderer": (VolumeRenderer, ["__init__", "sample_coarse", "sample_fine", "composite", "forward"]),
+        "NeRF": (NeRF, ["__init__", "get_sigma", "get_normal", "forward"]),
+        "BodyModelParams": (BodyModelParams, ["__init__", "init_parameters", "set_requires_grad", "forward"]),
+    }
+    out = {}
+    for cname, (cls, methods) in want.items():
+        out[cname] = {}
+        for m in methods:
+            sig = inspect.signature(getattr(cls, m))
+            out[cname][m] = [[n, (None if p.default is inspect._empty else repr(p.default)), p.kind.name]
+                             for n, p in sig.parameters.items() if n != "self"]
+    with open(os.path.join(OUT, "api_signatures.json"), "w") as f:
+        json.dump(out, f, indent=0, sort_keys=True)
+    print("wrote api_signatures.json", {k: len(v) for k, v in out.items()})
+
+
 def regularizers_case():
     """The MLP queries of the training regularisers through the reference's own `NeRF` (models/nerf.py:155-190):
     `get_sigma(only_sigma=True)` on foreground/background points and `get_normal` (autograd.grad with
@@ -315,6 +344,9 @@ if __name__ == "__main__":
     if "--regularizers-only" in sys.argv:
         regularizers_case()
         sys.exit(0)
+    if "--api-only" in sys.argv:
+        api_signatures_case()
+        sys.exit(0)
     if "--state-dict-only" in sys.argv:
         with tempfile.TemporaryDirectory() as tmp:
             state_dict_case(tmp)
@@ -324,6 +356,7 @@ if __name__ == "__main__":
         sys.exit(0)
     regularizers_case()
     pixel_sampling_case()
+    api_signatures_case()
     with tempfile.TemporaryDirectory() as tmp:
         state_dict_case(tmp)
     with tempfile.TemporaryDirectory() as tmp:

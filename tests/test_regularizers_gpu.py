@@ -32,7 +32,7 @@ def _sigma_oracle(p, x, emulate_bf16):
 
 def _net(seed):
     from anim_nerf_b200.nerf import NeRF
-    net = NeRF(freqs_dir=0).to(DEV)
+    net = NeRF(freqs_dir=0, use_view=False).to(DEV)
     net.load_state_dict({k: torch.from_numpy(v) for k, v in synthetic.make_nerf_weights(seed).items()}, strict=True)
     return net
 

@@ -21,7 +21,7 @@ def _worker(rank, world, port, q):
     from anim_nerf_b200 import dist_utils as du
     from anim_nerf_b200.nerf import NeRF
     torch.manual_seed(0)
-    net = NeRF(freqs_dir=0)                      # same init on both ranks
+    net = NeRF(freqs_dir=0, use_view=False)      # same init on both ranks
     for i, p in enumerate(net.parameters()):
         p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
     du.allreduce_grads(list(net.parameters()))
