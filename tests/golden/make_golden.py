@@ -294,6 +294,18 @@ def api_signatures_case():
             sig = inspect.signature(getattr(cls, m))
             out[cname][m] = [[n, (None if p.default is inspect._empty else repr(p.default)), p.kind.name]
                              for n, p in sig.parameters.items() if n != "self"]
+    # train.py cannot be imported here (pytorch-lightning, yacs, ... are absent): its class is read with `ast`
+    import ast
+    tree = ast.parse(open(os.path.join(REF, "train.py")).read())
+    out["AnimNeRFSystem"] = {}
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == "AnimNeRFSystem":
+            for fn in node.body:
+                if isinstance(fn, ast.FunctionDef) and fn.name in ("__init__", "forward", "compute_loss", "decode_batch",
+                                                                   "training_step", "configure_optimizers"):
+                    args = [a.arg for a in fn.args.args if a.arg != "self"]
+                    defaults = [None] * (len(args) - len(fn.args.defaults)) + [ast.unparse(d) for d in fn.args.defaults]
+                    out["AnimNeRFSystem"][fn.name] = [[a, d, "POSITIONAL_OR_KEYWORD"] for a, d in zip(args, defaults)]
     with open(os.path.join(OUT, "api_signatures.json"), "w") as f:
         json.dump(out, f, indent=0, sort_keys=True)
     print("wrote api_signatures.json", {k: len(v) for k, v in out.items()})
