@@ -1,8 +1,9 @@
 // A17 (MLP part): backward of the positional encoding + 8x256 MLP on tcgen05/TMEM.
 // Autograd of models/nerf.py:129-175 + models/embedding.py:22-39.  Three kernels:
 //
-//  1. mlp_bwd_dgrad_kernel -- same skeleton as the forward (persistent CTA, 2 x 128-row tiles,
-//     TMA-streamed W^T chunk images, accumulators in TMEM).  The activation-gradient image dY
+//  1. mlp_bwd_dgrad_kernel -- same skeleton as the forward (persistent CTA pairs, cta_group::2 MMAs of
+//     M = 256 over tile t of both CTAs, 2 x 128-row tiles per CTA ping-ponging, each CTA streaming its
+//     half of every W^T chunk image by TMA, accumulators in TMEM).  The activation-gradient image dY
 //     stays in shared memory as the next layer's A operand; ReLU masks come from the forward's
 //     1-bit stash.  Both heads run on the tensor cores (mlp_layout.cuh): step 0 is the rgb head
 //     (K = 16: d rgb_pre -> d c), step 1 the fused head layer (K = 144: [d c_pre | d sigma] -> d h8).
@@ -24,12 +25,14 @@
 
 namespace {
 constexpr int THREADS = 320;
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 6;
+constexpr uint32_t STAGE_BYTES = 16384;                          // this CTA's half of a W^T chunk image
 constexpr uint32_t SM_ACT = 0;                                   // [2][4][16 KB]
-constexpr uint32_t SM_WST = 131072;                              // [NSTAGE][32 KB]
-constexpr uint32_t SM_BAR = SM_WST + NSTAGE * 32768;
-constexpr uint32_t SM_BYTES = SM_BAR + 128;
+constexpr uint32_t SM_WST = 131072;                              // [NSTAGE][16 KB]
+constexpr uint32_t SM_BAR = SM_WST + NSTAGE * STAGE_BYTES;
+constexpr uint32_t SM_BYTES = SM_BAR + 192;
 constexpr uint32_t SM_ALLOC = SM_BYTES + 1024;
+static_assert(SM_ALLOC <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
 
 // order in which the backward consumes the W^T steps of mlp_layout.cuh (s6 = layer-5 encoding
 // part runs before s5 so both read the same dY image and share one accumulator region)
@@ -39,7 +42,7 @@ __device__ __forceinline__ int step_of(int i) {
 }
 }  // namespace
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ stash,
                      const float* __restrict__ xyz_cano, const float* __restrict__ rgb,
                      const int32_t* __restrict__ cidx, const int32_t* __restrict__ count, int64_t n_max,
@@ -53,51 +56,68 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
     const uint32_t sbase = (raw + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sbase - raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bar_full = sbase + SM_BAR, bar_empty = sbase + SM_BAR + 32;
-    const uint32_t bar_act = sbase + SM_BAR + 64, bar_acc = sbase + SM_BAR + 80, tmem_slot = sbase + SM_BAR + 96;
+    const uint32_t bar_full = sbase + SM_BAR, bar_empty = sbase + SM_BAR + 64;
+    const uint32_t bar_act = sbase + SM_BAR + 128, bar_acc = sbase + SM_BAR + 144, tmem_slot = sbase + SM_BAR + 160;
     const bool want_gx = g_xyz != nullptr;
+    const uint32_t rank = cluster_ctarank();             // 0 = leader (issues the MMAs), 1 = peer
+    const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
     int64_t n = n_max;
     if (cidx) { const int64_t c = *count; n = c < n_max ? c : n_max; }
-    const int64_t num_iters = (n + 255) / 256;
+    const int64_t num_iters = (n + PAIR_POINTS - 1) / PAIR_POINTS;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int t = 0; t < 2; ++t) { mbar_init(bar_act + 8 * t, 128); mbar_init(bar_acc + 8 * t, 1); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, rank == 0 ? 2 : 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int t = 0; t < 2; ++t) { mbar_init(bar_act + 8 * t, 256); mbar_init(bar_acc + 8 * t, 1); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();          // barriers of both CTAs initialised and TMEM allocated before any remote arrive / MMA
     tc_fence_after();
-    const uint32_t tmem_base = *(volatile uint32_t*)(sgen + SM_BAR + 96);
+    const uint32_t tmem_base = *(volatile uint32_t*)(sgen + SM_BAR + 160);
 
-    // tiles ping-pong exactly as in the forward: MMAs of one tile overlap the other tile's epilogue
+    // roles as in the forward (mlp_tc.cu): producer in both CTAs, MMA issuer in the leader / stage relay in the
+    // peer, epilogue warps; the tiles of a CTA ping-pong: MMAs of one tile overlap the other tile's epilogue
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
-            for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x)
+            for (int64_t iter = pair; iter < num_iters; iter += npairs)
                 for (int i = 0; i < 11; ++i) {
                     const int s = step_of(i);
                     if (!want_gx && (s == 6 || s == 10)) continue;
-                    const uint32_t bytes = bs_chunk_bytes(s);
+                    const uint32_t bytes = bs_chunk_bytes(s) >> 1;       // this CTA's half of the rows
                     for (int t = 0; t < 2; ++t)
                         for (int kc = 0; kc < bs_chunks(s); ++kc, ++it) {
                             const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1u;
                             mbar_wait(bar_empty + 8 * st, ph ^ 1u);
                             mbar_expect_tx(bar_full + 8 * st, bytes);
-                            bulk_g2s(sbase + SM_WST + st * 32768u, packed + bwd_chunk_off(s, kc), bytes, bar_full + 8 * st);
+                            bulk_g2s(sbase + SM_WST + st * STAGE_BYTES, packed + bwd_chunk_off(s, kc) + rank * bytes, bytes, bar_full + 8 * st);
                         }
                 }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            uint32_t it = 0, act_phase = 0;
-            for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x)
+    } else if (warp == 1 && rank != 0) {
+        if (lane == 0) {          // peer: tell the leader when this CTA's half of a stage has landed
+            uint32_t it = 0;
+            for (int64_t iter = pair; iter < num_iters; iter += npairs)
                 for (int i = 0; i < 11; ++i) {
                     const int s = step_of(i);
                     if (!want_gx && (s == 6 || s == 10)) continue;
-                    const uint32_t idesc = make_idesc_bf16(128, bs_rows(s), 0, 0);
+                    for (int j = 0; j < 2 * bs_chunks(s); ++j, ++it) {
+                        const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+                        mbar_wait(bar_full + 8 * st, ph);
+                        mbar_arrive_remote(bar_full + 8 * st, 0);
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {          // leader: MMA issuer for both CTAs
+            uint32_t it = 0, act_phase = 0;
+            for (int64_t iter = pair; iter < num_iters; iter += npairs)
+                for (int i = 0; i < 11; ++i) {
+                    const int s = step_of(i);
+                    if (!want_gx && (s == 6 || s == 10)) continue;
+                    const uint32_t idesc = make_idesc_bf16(256, bs_rows(s), 0, 0);
                     for (int t = 0; t < 2; ++t) {
                         mbar_wait(bar_act + 8 * t, act_phase);
                         tc_fence_after();
@@ -105,15 +125,15 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                             const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1u;
                             mbar_wait(bar_full + 8 * st, ph);
                             tc_fence_after();
-                            const uint32_t wb = sbase + SM_WST + st * 32768u;
+                            const uint32_t wb = sbase + SM_WST + st * STAGE_BYTES;
                             const uint32_t ab = sbase + SM_ACT + t * 65536u + kc * 16384u;
                             const int nk = bs_ksteps(s, kc);
                             for (int k = 0; k < nk; ++k)
-                                umma(tmem_base + t * 256u, make_desc(ab + k * 32u, 16, 1024),
-                                     make_desc(wb + k * 32u, 16, 1024), idesc, (kc > 0 || k > 0) ? 1u : 0u);
-                            umma_commit(bar_empty + 8 * st);
+                                umma_pair(tmem_base + t * 256u, make_desc(ab + k * 32u, 16, 1024),
+                                          make_desc(wb + k * 32u, 16, 1024), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                            umma_commit_pair(bar_empty + 8 * st);
                         }
-                        umma_commit(bar_acc + 8 * t);
+                        umma_commit_pair(bar_acc + 8 * t);
                     }
                     act_phase ^= 1u;
                 }
@@ -132,9 +152,9 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
         const uint32_t my_act = bar_act + 8 * t, my_acc = bar_acc + 8 * t;
         uint32_t acc_phase = 0;
 
-        for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x) {
-            const int64_t tile = iter * 2 + t;
-            const int64_t p = iter * 256 + t * 128 + row;
+        for (int64_t iter = pair; iter < num_iters; iter += npairs) {
+            const int64_t tile = (iter * 2 + rank) * 2 + t;          // = compact point index / 128
+            const int64_t p = tile * 128 + row;
             const bool in = p < n;
             const int64_t id = in ? (cidx ? (int64_t)cidx[p] : p) : 0;
             const uint8_t* st_tile = stash + tile * ST_TILE;
@@ -155,7 +175,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
             fence_proxy_async();
             __syncwarp();         // every warp streams its own 32 rows (4 KB, contiguous in the image) to the scratch
             if (lane == 0) { bulk_s2g(dy_tile + DY_RGB + q * 4096, act_s + q * 4096u, 4096); bulk_commit(); }
-            mbar_arrive(my_act);
+            mbar_arrive_remote(my_act, 0);
 
             // encoding derivative factors (same double-angle recurrence as the forward)
             float gx[3] = {0.f, 0.f, 0.f};
@@ -223,7 +243,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                     if (s == 10) {
                         if (in) { g_xyz[id * 3] = gx[0]; g_xyz[id * 3 + 1] = gx[1]; g_xyz[id * 3 + 2] = gx[2]; }
                     } else {
-                        mbar_arrive(my_act);           // A image unchanged; accumulator region is free again
+                        mbar_arrive_remote(my_act, 0);  // A image unchanged; accumulator region is free again
                     }
                     continue;
                 }
@@ -276,14 +296,14 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                         bulk_commit();
                     }
                 }
-                if (!(s == 9 && !want_gx)) mbar_arrive(my_act);      // last step has no consumer MMA
+                if (!(s == 9 && !want_gx)) mbar_arrive_remote(my_act, 0);      // last step has no consumer MMA
             }
         }
         if (lane == 0) bulk_wait0();
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+    cluster_sync_all();          // the peer's shared memory / TMEM stay alive until the leader's last MMA has retired
+    if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------ wgrad
@@ -343,7 +363,7 @@ mlp_bwd_wgrad_kernel(const uint8_t* __restrict__ stash, const uint8_t* __restric
 
     int64_t n = n_max;
     if (has_count) { const int64_t c = *count; n = c < n_max ? c : n_max; }
-    const int64_t n_tiles = ((n + 255) / 256) * 2;       // tiles written by the forward (zero rows beyond n)
+    const int64_t n_tiles = n_tiles_for(n);              // tiles written by the forward / dgrad pairs (zero dY rows beyond n)
     const WJob job = wjob(blockIdx.y);
     const int M_halves = (job.a_chunks + 1) / 2;          // 128 accumulator lanes per half
     const int N = job.N;                                  // accumulator columns per half
@@ -486,7 +506,7 @@ int mlp_unfuse_grad_launch(const void* packed, float* g_params, cudaStream_t str
 extern "C" int64_t an_mlp_bwd_scratch_bytes(int64_t n_max)
 {
     if (n_max <= 0) return 0;
-    return ((n_max + 255) / 256) * 2 * mlp::DY_TILE;
+    return mlp::n_tiles_for(n_max) * mlp::DY_TILE;
 }
 
 static int bwd_check(const void* packed, const void* stash, const void* scratch, int64_t n_max,
@@ -508,9 +528,9 @@ extern "C" int an_mlp_bwd_dgrad(const void* packed, const void* stash, const flo
     if (rc) return rc;
     cudaError_t e = cudaFuncSetAttribute(mlp_bwd_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
-    const int sms = an_num_sms();
-    const int64_t iters = (n_max + 255) / 256;
-    const int grid = (int)(iters < sms ? iters : sms);
+    const int64_t iters = (n_max + mlp::PAIR_POINTS - 1) / mlp::PAIR_POINTS;
+    const int pairs = an_num_sms() / 2;
+    const int grid = 2 * (int)(iters < pairs ? iters : pairs);      // persistent CTA pairs, one per TPC
     mlp_bwd_dgrad_kernel<<<grid, THREADS, SM_ALLOC, (cudaStream_t)stream>>>(
         (const uint8_t*)packed, (const uint8_t*)stash, xyz_cano, rgb, cidx, count, n_max, g_sigma, g_rgb,
         g_xyz_cano, (uint8_t*)scratch);
@@ -527,9 +547,9 @@ static int wgrad_launch(const void* packed, const void* stash, const void* scrat
     cudaError_t e = cudaFuncSetAttribute(mlp_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_ALLOC);
     if (e != cudaSuccess) return (int)e;
     const int sms = an_num_sms();
-    const int64_t iters = (n_max + 255) / 256;
+    const int64_t tiles = mlp::n_tiles_for(n_max);
     int64_t splits = sms / NJOBS;                      // 13 on a 148-SM part -> 143 CTAs, one wave
-    if (splits > iters * 2) splits = iters * 2;
+    if (splits > tiles) splits = tiles;
     if (splits < 1) splits = 1;
     dim3 wgrid((unsigned)splits, NJOBS);
     mlp_bwd_wgrad_kernel<<<wgrid, WG_THREADS, WG_ALLOC, (cudaStream_t)stream>>>(

@@ -25,9 +25,17 @@
 //    stored exactly as the UMMA K-major SWIZZLE_128B canonical layout wants it in shared
 //    memory (16-byte unit u of row r lives at r*128 + ((u ^ (r&7))*16), 8-row groups 1024 B
 //    apart), so one cp.async.bulk (TMA bulk copy) moves a chunk with no tensor map.
-//  * fwd chunk order = streaming order of the forward kernel: for g, for kc.  Layer 0 has one
-//    chunk (63 inputs + zero pad); layer 4 has five: chunk 0 = encoding columns 0..62 of W5,
-//    chunks 1..4 = hidden columns 63..318.
+//  * fwd chunk order = streaming order of the forward kernel: for g, for kc, then the layer's
+//    bias slab.  Layer 0 has one chunk (63 inputs + zero pad); layer 4 has five: chunk 0 =
+//    encoding columns 0..62 of W5, chunks 1..4 = hidden columns 63..318.
+//  * bias slab (g 0..8): the bias enters through the tensor core as one more K = 16 step against
+//    the encoding image's K-step 3, whose last column (63, the pad) holds the constant 1 (or the
+//    row's scale in tangent mode).  B operand of that step: N rows x 16 k-values, bf16, all zero
+//    except k = 15 = bias[row]; K-major without swizzle: 8-row groups of 256 B = two 128-byte core
+//    matrices (k 0..7, k 8..15), element (row r, k) at (r/8)*256 + (k/8)*128 + (r%8)*16 + (k%8)*2.
+//    The density bias and the rgb bias are added in fp32 by the epilogue (slab rows 128.. are zero).
+//  * a CTA pair (cta_group::2) splits every B operand by rows: CTA rank r stages rows
+//    [r*N/2, (r+1)*N/2) = the r-th half of the bytes of a chunk image / slab.
 //  * dgrad images hold W^T (rows = input features, K = output features) in streaming order of
 //    the backward kernel (see mlp_bwd.cu).
 #pragma once
@@ -62,13 +70,20 @@ constexpr int64_t GRAD_FLOATS = GRAD_FUSED_B + 128;
 __host__ __device__ constexpr int g_N(int g) { return g < 8 ? 256 : g == 8 ? HEAD_N : RGB_N; }
 __host__ __device__ constexpr int g_chunks(int g) { return g == 0 ? 1 : g == 4 ? 5 : g == 9 ? 2 : 4; }
 __host__ __device__ constexpr uint32_t g_chunk_bytes(int g) { return (uint32_t)g_N(g) * 128u; }
-__host__ __device__ constexpr int64_t fwd_chunk_off(int g, int kc) {
+__host__ __device__ constexpr uint32_t g_bias_bytes(int g) { return g < 9 ? (uint32_t)g_N(g) * 32u : 0u; }
+__host__ __device__ constexpr int64_t fwd_chunk_off(int g, int kc) {     // kc == g_chunks(g): the bias slab
     int64_t o = 0;
-    for (int i = 0; i < g; ++i) o += (int64_t)g_chunks(i) * g_chunk_bytes(i);
+    for (int i = 0; i < g; ++i) o += (int64_t)g_chunks(i) * g_chunk_bytes(i) + g_bias_bytes(i);
     return o + (int64_t)kc * g_chunk_bytes(g);
 }
+__host__ __device__ constexpr int64_t fwd_bias_off(int g) { return fwd_chunk_off(g, g_chunks(g)); }
 constexpr int64_t FWD_BYTES = fwd_chunk_off(NG, 0);
 constexpr int FWD_CHUNKS = 1 + 4 * 3 + 5 + 4 * 3 + 4 + 2;         // 36
+constexpr int FWD_SLABS = 9;
+// byte offset of element (row r, k in [0,16)) inside a bias slab
+__host__ __device__ constexpr uint32_t slab_off(int r, int k) {
+    return (uint32_t)(r >> 3) * 256u + (uint32_t)(k >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(k & 7) * 2u;
+}
 
 // ---- dgrad images (W^T): step s of the backward kernel, see mlp_bwd.cu
 //  s 0: rgb^T   rows 128 (c features),  K = 16  (1 chunk, K-step 0 only: columns 0..2 = W_rgb[j][row])
@@ -110,6 +125,11 @@ __host__ __device__ constexpr uint32_t img_off(int r, int c) {
     return (uint32_t)r * 128u + (uint32_t)((((c >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1));
 }
 
+// ---- tiling: the forward / dgrad kernels run as CTA pairs; one pair iteration owns PAIR_POINTS compacted points
+//      (CTA rank r: points [r*256, r*256+256) of the iteration, two 128-row tiles each), so the point images are
+//      always written in whole groups of 4 tiles: tile index = compact point index / 128
+constexpr int PAIR_POINTS = 512;
+__host__ __device__ constexpr int64_t n_tiles_for(int64_t n) { return (n + PAIR_POINTS - 1) / PAIR_POINTS * 4; }
 // ---- forward stash per 128-row tile (training): bf16 images + 1-bit ReLU masks
 constexpr int64_t ST_ENC = 0;                      // 16 KB image
 constexpr int64_t ST_H = 16384;                    // h1..h8: 8 x 64 KB images

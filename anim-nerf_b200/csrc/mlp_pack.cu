@@ -44,7 +44,7 @@ __device__ __forceinline__ float fwd_weight(const PackPtrs& P, const float* fuse
     return r < 3 ? P.w[11][r * 128 + c] : 0.f;
 }
 
-// one CTA per chunk image (fwd: 36, bwd: 40), then CTAs for the fp32 blocks
+// one CTA per chunk image (fwd: 36, bwd: 40) and per bias slab (9), then CTAs for the fp32 blocks
 __global__ void __launch_bounds__(256)
 mlp_pack_kernel(PackPtrs P, uint8_t* __restrict__ packed)
 {
@@ -69,6 +69,18 @@ mlp_pack_kernel(PackPtrs P, uint8_t* __restrict__ packed)
         return;
     }
     job -= FWD_CHUNKS;
+    if (job < FWD_SLABS) {        // bias slab of GEMM layer g: k = 15 carries the bias, everything else is zero
+        const int g = job, N = g_N(g);
+        uint8_t* dst = packed + fwd_bias_off(g);
+        for (int e = threadIdx.x; e < N * 16; e += blockDim.x) {
+            const int r = e >> 4, k = e & 15;
+            float v = 0.f;
+            if (k == 15) v = g < 8 ? P.b[g][r] : (r < 128 ? fused[128 * 256 + r] : 0.f);
+            *(__nv_bfloat16*)(dst + slab_off(r, k)) = __float2bfloat16_rn(v);
+        }
+        return;
+    }
+    job -= FWD_SLABS;
     if (job < BWD_CHUNKS) {
         int s = 0, kc = job;
         while (kc >= bs_chunks(s)) { kc -= bs_chunks(s); ++s; }
@@ -104,7 +116,7 @@ mlp_pack_kernel(PackPtrs P, uint8_t* __restrict__ packed)
         return;
     }
     // flat fp32 copy: remaining CTAs stride over all linears
-    const int nflat = gridDim.x - FWD_CHUNKS - BWD_CHUNKS - 1;
+    const int nflat = gridDim.x - FWD_CHUNKS - FWD_SLABS - BWD_CHUNKS - 1;
     float* flat = (float*)(packed + FLAT_OFF);
     for (int id = 0; id < NLIN; ++id) {
         const int64_t nw = (int64_t)lin_out(id) * lin_in(id);
@@ -186,7 +198,7 @@ extern "C" int an_mlp_pack(const float* const* w_host, const float* const* b_hos
     }
     mlp_fuse_kernel<<<129, 256, 0, (cudaStream_t)stream>>>(P, (uint8_t*)packed);
     AN_CHECK_LAUNCH();
-    const int blocks = mlp::FWD_CHUNKS + mlp::BWD_CHUNKS + 1 + 64;
+    const int blocks = mlp::FWD_CHUNKS + mlp::FWD_SLABS + mlp::BWD_CHUNKS + 1 + 64;
     mlp_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(P, (uint8_t*)packed);
     AN_CHECK_LAUNCH();
     return AN_OK;

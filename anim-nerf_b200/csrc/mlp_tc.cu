@@ -1,29 +1,39 @@
 // A9-A11: positional encoding + 8x256 NeRF MLP forward on the 5th-gen tensor cores
-// (tcgen05.mma, accumulators in TMEM, weights streamed by TMA bulk copies, activations never
-// leave the SM).  Reference: models/embedding.py:22-39 + models/nerf.py:129-175.
+// (tcgen05.mma.cta_group::2, accumulators in TMEM, weights streamed by TMA bulk copies, activations
+// never leave the SM).  Reference: models/embedding.py:22-39 + models/nerf.py:129-175.
 //
-// One persistent CTA per SM; each loop iteration owns 256 compacted (valid) points = two
-// 128-row tiles that ping-pong: the tensor core runs layer g of one tile while the other tile's
-// epilogue runs on the CUDA cores (each tile streams its own copy of the weight chunks from L2).
-//   warp 0      weight producer: cp.async.bulk of pre-swizzled 64-wide K-chunk images into a
-//               2-stage ring (full/empty mbarriers); runs ahead across layers and tiles.
-//   warp 1      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=256|128, K=16),
-//               4 K-steps per chunk; tcgen05.commit releases the stage / publishes the tile's
-//               accumulators.  Also owns the TMEM allocation (512 columns = 2 x 128x256 fp32).
-//   warps 2-9   epilogue, one thread per row: tcgen05.ld 32 columns at a time, ReLU + bf16 pack
-//               in one cvt, st.shared into the K-major SWIZZLE_128B image that is the next
-//               layer's A operand (in place: the layer's MMAs have completed).  Biases are not
-//               added here: the accumulators start from them (tcgen05.st while draining).  Both
-//               heads run on the tensor cores too (mlp_layout.cuh): the density is one more
-//               output column of the fused final+colour layer, the rgb head a 16-wide GEMM.
-//               The encoding (sin/cos by double-angle recurrence from one sincosf per
-//               coordinate; inputs stay fp32 until after the encoding) is the prologue.
+// Persistent CTA PAIRS (cluster of 2 = the two SMs of a TPC), one pair per TPC.  A pair iteration owns
+// 512 compacted (valid) points: CTA rank r holds two 128-row tiles (points r*256 .. r*256+255).  Every
+// MMA is a cta_group::2 instruction with M = 256: tile t of both CTAs against one weight chunk, of which
+// each CTA stages only its half of the rows (N/2) -- per SM that halves the B-operand shared-memory
+// reads and the L2 -> shared-memory weight stream compared with one CTA per tile.  The two tiles of a
+// CTA ping-pong: the tensor cores run layer g of tile t (both CTAs) while the epilogue of tile 1-t runs
+// on the CUDA cores.
+//   warp 0      weight producer (both CTAs): cp.async.bulk of this CTA's half of every pre-swizzled
+//               64-wide K-chunk image / bias slab into a 4-stage ring of 16 KB (full/empty mbarriers);
+//               runs ahead across layers and tiles.
+//   warp 1      leader CTA: MMA issuer -- one elected thread issues tcgen05.mma (M=256, N=256|144|16,
+//               K=16), 4 K-steps per chunk; tcgen05.commit (multicast to both CTAs) releases the stage /
+//               publishes the tile's accumulators.  Peer CTA: relays "my half of the stage has landed"
+//               to the leader's full barrier (a bulk copy can only signal an mbarrier of its own CTA).
+//               Owns the TMEM allocation (512 columns = 2 x 128x256 fp32 per CTA).
+//   warps 2-9   epilogue, one thread per row: tcgen05.ld 32 columns at a time, ReLU + bf16 pack in one
+//               cvt, st.shared into the K-major SWIZZLE_128B image that is the next layer's A operand
+//               (in place: the layer's MMAs have completed); the peer's threads arrive on the leader's
+//               barrier through the cluster.  The bias is NOT added here: it enters as one more K = 16
+//               MMA per layer against the encoding image's K-step 3, whose pad column holds 1.0
+//               (mlp_layout.cuh: bias slab) -- no per-thread bias loads, no accumulator re-initialisation.
+//               Both heads run on the tensor cores too: the density is one more output column of the
+//               fused final+colour layer, the rgb head a 16-wide GEMM; their biases are added in fp32.
+//               The encoding (sin/cos by double-angle recurrence from one sincosf per coordinate;
+//               inputs stay fp32 until after the encoding) is the prologue.
 // Training mode (stash != NULL) additionally streams every activation image to HBM with TMA
 // bulk stores plus 1-bit ReLU masks; the backward kernels consume them (mlp_bwd.cu).
 //
 // Roofline: tensor-bound.  1 179 904 algorithmic FLOP per point (the reference's 12 linears; the
-// fused head layer executes 1 118 208 of them); per 256-point iteration the kernel issues
-// 36 chunks x 2 tiles x 4 MMAs.  Algorithmic HBM bytes per point: 16 B in (id + xyz), 16 B out.
+// fused head layer executes 1 118 208 of them, the bias steps add 9 x 8192); per 512-point iteration
+// the pair issues (36 chunks x 4 + 9) x 2 tiles MMAs of M = 256.  Algorithmic HBM bytes per point:
+// 16 B in (id + xyz), 16 B out.
 #include "common.cuh"
 #include "mlp_layout.cuh"
 #include "tc_common.cuh"
@@ -31,14 +41,14 @@
 namespace {
 
 constexpr int THREADS = 320;
-constexpr int NSTAGE = 2;
+constexpr int NSTAGE = 4;
+constexpr uint32_t STAGE_BYTES = 16384;            // this CTA's half of a 64-wide chunk of a 256-row weight image
 constexpr uint32_t SM_ACT = 0;                     // [2 tiles][4 chunks][128 rows x 128 B]
 constexpr uint32_t SM_ENC = 131072;                // [2 tiles][128 rows x 128 B]
-constexpr uint32_t SM_WST = 163840;                // [NSTAGE][32 KB]
-constexpr uint32_t SM_BAR = SM_WST + NSTAGE * 32768;   // 229376
-constexpr uint32_t SM_BIASBUF = SM_BAR + 128;      // [2 tiles][256 fp32]: bias of the layer that writes the accumulators next
-constexpr uint32_t SM_BYTES = SM_BIASBUF + 2048;
-constexpr uint32_t SM_ALLOC = SM_BYTES + 896;      // slack for manual 1024-B alignment (the base is at least 128-B aligned)
+constexpr uint32_t SM_WST = 163840;                // [NSTAGE][16 KB]
+constexpr uint32_t SM_BAR = SM_WST + NSTAGE * STAGE_BYTES;   // 229376
+constexpr uint32_t SM_BYTES = SM_BAR + 128;
+constexpr uint32_t SM_ALLOC = SM_BYTES + 1024;     // slack for manual 1024-B alignment
 static_assert(SM_ALLOC <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
 
 #ifdef AN_MLP_TRACE
@@ -58,6 +68,9 @@ __device__ unsigned long long* g_trace = nullptr;
 #define TRACE(role, ev, a, b)
 #endif
 
+// ring steps of GEMM layer g: its weight chunks, then (g < 9) the bias slab
+__device__ __forceinline__ int ring_steps(int g) { return mlp::g_chunks(g) + (g < 9 ? 1 : 0); }
+
 }  // namespace
 
 // MODE 0 = inference, 1 = training (activation stash), 2 = tangent (forward-mode derivative of the
@@ -66,9 +79,10 @@ __device__ unsigned long long* g_trace = nullptr;
 // gradient of a loss on d sigma/d xyz is then the ordinary wgrad kernel on (tau images, dY images),
 // see an_mlp_fwd_tangent).  The tangent runs the 8 trunk layers + the fused head layer (for tau_sigma).
 // With tscale (a per-point scalar c) the same pass produces T_l = tau_l + c * X_l (X = the primal activations):
-// T_l = m_l * (W_l T_{l-1} + c b_l), T_0 = tau_0 + c enc(x) -- the accumulators start from c * bias instead of 0.
+// T_l = m_l * (W_l T_{l-1} + c b_l), T_0 = tau_0 + c enc(x) -- the bias column of the encoding image holds c
+// instead of 1, so the bias step adds c * bias.
 template <int MODE>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ xyz_cano,
                   const int32_t* __restrict__ cidx, const int32_t* __restrict__ count, int64_t n_max,
                   float* __restrict__ sigma_out, float* __restrict__ rgb_out, uint8_t* __restrict__ stash,
@@ -84,78 +98,100 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     const uint32_t sbase = (raw + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sbase - raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();             // 0 = leader (issues the MMAs), 1 = peer
+    const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
-    const uint32_t bar_full = sbase + SM_BAR;            // [NSTAGE]  TMA -> MMA
-    const uint32_t bar_empty = sbase + SM_BAR + 16;      // [NSTAGE]  MMA -> TMA
-    const uint32_t bar_act = sbase + SM_BAR + 32;        // [2 tiles] epilogue -> MMA (128 arrivals)
-    const uint32_t bar_acc = sbase + SM_BAR + 48;        // [2 tiles] MMA -> epilogue (tcgen05.commit)
-    const uint32_t tmem_slot = sbase + SM_BAR + 64;
+    const uint32_t bar_full = sbase + SM_BAR;            // [NSTAGE]  TMA (+ peer relay) -> MMA
+    const uint32_t bar_empty = sbase + SM_BAR + 32;      // [NSTAGE]  MMA -> TMA (both CTAs)
+    const uint32_t bar_act = sbase + SM_BAR + 64;        // [2 tiles] epilogue of both CTAs -> MMA (leader's copy: 256 arrivals)
+    const uint32_t bar_acc = sbase + SM_BAR + 80;        // [2 tiles] MMA -> epilogue (tcgen05.commit, both CTAs)
+    const uint32_t tmem_slot = sbase + SM_BAR + 96;
 
     int64_t n = n_max;
     if (cidx) { const int64_t c = *count; n = c < n_max ? c : n_max; }
-    const int64_t num_iters = (n + 255) / 256;
+    const int64_t num_iters = (n + PAIR_POINTS - 1) / PAIR_POINTS;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int t = 0; t < 2; ++t) { mbar_init(bar_act + 8 * t, 128); mbar_init(bar_acc + 8 * t, 1); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, rank == 0 ? 2 : 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int t = 0; t < 2; ++t) { mbar_init(bar_act + 8 * t, 256); mbar_init(bar_acc + 8 * t, 1); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();          // barriers of both CTAs initialised and TMEM allocated before any remote arrive / MMA
     tc_fence_after();
-    const uint32_t tmem_base = *(volatile uint32_t*)(sgen + SM_BAR + 64);
+    const uint32_t tmem_base = *(volatile uint32_t*)(sgen + SM_BAR + 96);
 
-    // The two 128-row tiles ping-pong: while the tensor core runs layer g of one tile, the other
-    // tile's epilogue (TMEM -> bias/ReLU -> bf16 image) runs on the CUDA cores.  Each tile streams
-    // its own copy of the layer's weight chunks (L2 hits).
     if (warp == 0) {
-        // ------------------------------------------------------------ weight producer
+        // ------------------------------------------------------------ weight producer (this CTA's half of every B operand)
         if (lane == 0) {
             TRACE_DECL;
             uint32_t it = 0;
-            for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x)
+            for (int64_t iter = pair; iter < num_iters; iter += npairs)
                 for (int g = 0; g < NGT; ++g) {
-                    const uint32_t bytes = g_chunk_bytes(g);
+                    const int nc = g_chunks(g), ns = ring_steps(g);
                     for (int t = 0; t < 2; ++t)
-                        for (int kc = 0; kc < g_chunks(g); ++kc, ++it) {
+                        for (int kc = 0; kc < ns; ++kc, ++it) {
+                            const uint32_t bytes = (kc < nc ? g_chunk_bytes(g) : g_bias_bytes(g)) >> 1;
                             const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
                             mbar_wait(bar_empty + 8 * s, ph ^ 1u);
                             TRACE(0, 0, g, t * 8 + kc);
                             mbar_expect_tx(bar_full + 8 * s, bytes);
-                            bulk_g2s(sbase + SM_WST + s * 32768u, packed + fwd_chunk_off(g, kc), bytes, bar_full + 8 * s);
+                            bulk_g2s(sbase + SM_WST + s * STAGE_BYTES, packed + fwd_chunk_off(g, kc) + rank * bytes, bytes, bar_full + 8 * s);
                         }
                 }
         }
+    } else if (warp == 1 && rank != 0) {
+        // ------------------------------------------------------------ peer: tell the leader when this CTA's half of a stage has landed
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t iter = pair; iter < num_iters; iter += npairs)
+                for (int g = 0; g < NGT; ++g) {
+                    const int ns = 2 * ring_steps(g);
+                    for (int i = 0; i < ns; ++i, ++it) {
+                        const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+                        mbar_wait(bar_full + 8 * s, ph);
+                        mbar_arrive_remote(bar_full + 8 * s, 0);
+                    }
+                }
+        }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
+        // ------------------------------------------------------------ leader: MMA issuer for both CTAs
         if (lane == 0) {
             TRACE_DECL;
             uint32_t it = 0, act_phase = 0;
-            for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x)
+            for (int64_t iter = pair; iter < num_iters; iter += npairs)
                 for (int g = 0; g < NGT; ++g) {
-                    const uint32_t idesc = make_idesc_bf16(128, g_N(g), 0, 0);
+                    const uint32_t idesc = make_idesc_bf16(256, g_N(g), 0, 0);
+                    const int nc = g_chunks(g), ns = ring_steps(g);
                     for (int t = 0; t < 2; ++t) {
                         TRACE(1, 0, g, t);
                         mbar_wait(bar_act + 8 * t, act_phase);
                         TRACE(1, 1, g, t);
                         tc_fence_after();
-                        for (int kc = 0; kc < g_chunks(g); ++kc, ++it) {
+                        for (int kc = 0; kc < ns; ++kc, ++it) {
                             const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+                            TRACE(1, 3, g, t * 8 + kc);
                             mbar_wait(bar_full + 8 * s, ph);
                             TRACE(1, 2, g, t * 8 + kc);
                             tc_fence_after();
-                            const uint32_t wb = sbase + SM_WST + s * 32768u;
-                            const bool from_enc = (g == 0) || (g == 4 && kc == 0);
-                            const int ac = (g == 4) ? kc - 1 : kc;
-                            const uint32_t ab = from_enc ? (sbase + SM_ENC + t * 16384u)
-                                                         : (sbase + SM_ACT + t * 65536u + ac * 16384u);
+                            const uint32_t wb = sbase + SM_WST + s * STAGE_BYTES;
+                            if (kc < nc) {
+                                const bool from_enc = (g == 0) || (g == 4 && kc == 0);
+                                const int ac = (g == 4) ? kc - 1 : kc;
+                                const uint32_t ab = from_enc ? (sbase + SM_ENC + t * 16384u)
+                                                             : (sbase + SM_ACT + t * 65536u + ac * 16384u);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma(tmem_base + t * 256u, make_desc(ab + k * 32u, 16, 1024),
-                                     make_desc(wb + k * 32u, 16, 1024), idesc, 1u);   // accumulators start from the bias
-                            umma_commit(bar_empty + 8 * s);       // stage free once these MMAs retire
+                                for (int k = 0; k < 4; ++k)
+                                    umma_pair(tmem_base + t * 256u, make_desc(ab + k * 32u, 16, 1024),
+                                              make_desc(wb + k * 32u, 16, 1024), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                            } else {
+                                // bias step: A = K-step 3 of the encoding image (column 63 = 1), B = the slab (k = 15 = bias)
+                                umma_pair(tmem_base + t * 256u, make_desc(sbase + SM_ENC + t * 16384u + 96u, 16, 1024),
+                                          make_desc_noswz(wb, 128, 256), idesc, 1u);
+                            }
+                            umma_commit_pair(bar_empty + 8 * s);   // stage free (in both CTAs) once these MMAs retire
                         }
-                        umma_commit(bar_acc + 8 * t);              // accumulators of (layer g, tile t) complete
+                        umma_commit_pair(bar_acc + 8 * t);          // accumulators of (layer g, tile t) complete in both CTAs
                     }
                     act_phase ^= 1u;
                 }
@@ -174,32 +210,20 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
         const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
         const uint32_t my_act = bar_act + 8 * t, my_acc = bar_acc + 8 * t;
         const float* small = (const float*)(packed + SMALL_OFF);
-        uint8_t* bias_s = sgen + SM_BIASBUF + t * 1024;
-        const bool leader = (e & 127) == 0;          // issues the tile's TMA stores
+        const float b_sigma = __ldg(small + SM_BIAS + 8 * 256 + 128);
+        const float b_rgb0 = __ldg(small + SM_BIAS + 9 * 256), b_rgb1 = __ldg(small + SM_BIAS + 9 * 256 + 1),
+                    b_rgb2 = __ldg(small + SM_BIAS + 9 * 256 + 2);
+        const bool leader = (e & 127) == 0;          // trace only
         uint32_t acc_phase = 0;
         TRACE_DECL;
 
-        {   // layer 0's accumulators start from its bias (later layers: re-initialised while draining, see below)
-            uint32_t b0[32];
-#pragma unroll 1
-            for (int blk = 0; blk < 8; ++blk) {
-#pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const uint4 b4 = TAN ? make_uint4(0u, 0u, 0u, 0u) : __ldg((const uint4*)(small + SM_BIAS + blk * 32) + c4);
-                    b0[4 * c4] = b4.x; b0[4 * c4 + 1] = b4.y; b0[4 * c4 + 2] = b4.z; b0[4 * c4 + 3] = b4.w;
-                }
-                tmem_st32(tm + blk * 32, b0);
-            }
-            tmem_st_wait();
-            tc_fence_before();
-        }
-
-        for (int64_t iter = blockIdx.x; iter < num_iters; iter += gridDim.x) {
-            const int64_t p = iter * 256 + t * 128 + row;
+        for (int64_t iter = pair; iter < num_iters; iter += npairs) {
+            const int64_t tile = (iter * 2 + rank) * 2 + t;          // = compact point index / 128
+            const int64_t p = tile * 128 + row;
             const bool in = p < n;
             const int64_t id = in ? (cidx ? (int64_t)cidx[p] : p) : 0;
-            uint8_t* st_tile = TRAIN ? stash + (iter * 2 + t) * ST_TILE : nullptr;
-            const uint8_t* pst_tile = TAN ? pstash + (iter * 2 + t) * ST_TILE : nullptr;
+            uint8_t* st_tile = TRAIN ? stash + tile * ST_TILE : nullptr;
+            const uint8_t* pst_tile = TAN ? pstash + tile * ST_TILE : nullptr;
             float x[3] = {0.f, 0.f, 0.f};
             float tv[3] = {0.f, 0.f, 0.f};
             if (in) { x[0] = xyz_cano[id * 3]; x[1] = xyz_cano[id * 3 + 1]; x[2] = xyz_cano[id * 3 + 2]; }
@@ -208,24 +232,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 tv[0] = tvec[id * 3]; tv[1] = tvec[id * 3 + 1]; tv[2] = tvec[id * 3 + 2];
                 if (tscale) tsc = tscale[id];
             }
-            if (TAN && tscale) {
-                // layer 0's accumulators start from c * b_0 of THIS iteration's point (the region is free: this
-                // thread finished draining the previous iteration's last layer)
-                uint32_t b0[32];
-#pragma unroll 1
-                for (int blk = 0; blk < 8; ++blk) {
-#pragma unroll
-                    for (int c4 = 0; c4 < 8; ++c4) {
-                        const float4 b4 = __ldg((const float4*)(small + SM_BIAS + blk * 32) + c4);
-                        b0[4 * c4] = __float_as_uint(tsc * b4.x); b0[4 * c4 + 1] = __float_as_uint(tsc * b4.y);
-                        b0[4 * c4 + 2] = __float_as_uint(tsc * b4.z); b0[4 * c4 + 3] = __float_as_uint(tsc * b4.w);
-                    }
-                    tmem_st32(tm + blk * 32, b0);
-                }
-                tmem_st_wait();
-                tc_fence_before();
-            }
-            {   // positional encoding -> bf16 K-major image (64 columns, last one zero)
+            {   // positional encoding -> bf16 K-major image (64 columns; the last one multiplies the bias slabs)
                 float ev[64];
                 float s[3], c[3];
 #pragma unroll
@@ -245,7 +252,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                     }
                     fk *= 2.f;
                 }
-                ev[63] = 0.f;
+                ev[63] = TAN ? tsc : 1.f;
                 if (TRAIN) {      // this warp's TMA stores of the previous iteration must have drained its rows
                     if (lane == 0) bulk_wait_read0();
                     __syncwarp();
@@ -263,21 +270,10 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 __syncwarp();
                 if (lane == 0) { bulk_s2g(st_tile + ST_ENC + q * 4096, enc_s + q * 4096u, 4096); bulk_commit(); }
             }
-            mbar_arrive(my_act);
+            mbar_arrive_remote(my_act, 0);
 
             for (int g = 0; g < NGT; ++g) {
-                // accumulator blocks (32 columns) to drain, and blocks whose bias is re-initialised: the
-                // accumulators start from the bias -- while draining layer g, every block of TMEM columns is
-                // rewritten (tcgen05.st) with the bias of the layer that writes it next: layer g+1, or layer 0
-                // of the next iteration for the columns the narrow head layers leave alone.  The MMAs always
-                // accumulate; there is no bias add in the epilogue.
-                const int nld = g < 8 ? 8 : (g == 8 ? 5 : 1);
-                const int nst = g < 9 ? 8 : 1;
-                // each thread fetches two of the (up to) 256 values now (latency hidden behind the accumulator
-                // wait); they are staged in shared memory and read back as broadcast 128-bit loads per block
-                const int c2 = 2 * (e & 127);
-                const int bl = g < 8 ? g + 1 : (g == 8 ? (c2 < 32 && !TAN ? 9 : 0) : 0);
-                const float2 bmine = (TAN && !tscale) ? make_float2(0.f, 0.f) : __ldg((const float2*)(small + SM_BIAS + bl * 256 + c2));
+                const int nld = g < 8 ? 8 : (g == 8 ? 5 : 1);      // accumulator blocks (32 columns) to drain
                 uint32_t pmw[8];               // tangent: the primal's ReLU masks of this layer ([block][row] words)
                 if (TAN) {
 #pragma unroll
@@ -286,52 +282,36 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 }
                 if (leader) TRACE(2 + t, 0, g, 0);
                 // this warp's rows of the layer g-1 image are being stored: those bulk stores must have drained before
-                // the rows are overwritten below (after the accumulator wait); waited for here, off the critical
-                // path -- the named barrier after the accumulator wait also orders the warp's lanes behind lane 0
-                if (TRAIN && g > 0 && lane == 0) bulk_wait_read0();
+                // the rows are overwritten below (after the accumulator wait); waited for here, off the critical path
+                if (TRAIN && g > 0) {
+                    if (lane == 0) bulk_wait_read0();
+                    __syncwarp();
+                }
                 mbar_wait(my_acc, acc_phase); acc_phase ^= 1u;
                 if (leader) TRACE(2 + t, 1, g, 0);
                 tc_fence_after();
-                ((float2*)bias_s)[e & 127] = bmine;
-                named_bar_sync(1 + t, 128);
                 if (leader) TRACE(2 + t, 2, g, 0);
                 uint32_t va[32], vb[32];
                 tmem_ld32(tm, va);
 #pragma unroll 1
-                for (int cb = 0; cb < nst; cb += 2) {
+                for (int cb = 0; cb < nld; cb += 2) {
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         const int blk = cb + half;
-                        if (blk >= nst) break;
+                        if (blk >= nld) break;
                         uint32_t (&v)[32] = half ? vb : va;
-                        if (blk < nld) {
-                            tmem_ld_wait();
-                            if (blk + 1 < nld) tmem_ld32(tm + (blk + 1) * 32, half ? va : vb);   // prefetch the next block
-                        }
-                        {   // bias for the next writer of these columns
-                            uint32_t bq[32];
-#pragma unroll
-                            for (int c4 = 0; c4 < 8; ++c4) {
-                                const uint4 b4 = *((const uint4*)(bias_s + blk * 128) + c4);
-                                bq[4 * c4] = b4.x; bq[4 * c4 + 1] = b4.y; bq[4 * c4 + 2] = b4.z; bq[4 * c4 + 3] = b4.w;
-                            }
-                            if (TAN) {        // tangent: the row's own weight of the bias (c * b, or 0)
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) bq[i] = __float_as_uint(tsc * __uint_as_float(bq[i]));
-                            }
-                            tmem_st32(tm + blk * 32, bq);
-                        }
-                        if (blk >= nld) continue;
-                        if (!TAN && g == 9) {         // rgb head: columns 0..2 (bias already in the accumulator)
+                        tmem_ld_wait();
+                        if (blk + 1 < nld) tmem_ld32(tm + (blk + 1) * 32, half ? va : vb);   // prefetch the next block
+                        if (!TAN && g == 9) {         // rgb head: columns 0..2
                             if (in) {
-                                rgb_out[id * 3] = 1.f / (1.f + __expf(-__uint_as_float(v[0])));
-                                rgb_out[id * 3 + 1] = 1.f / (1.f + __expf(-__uint_as_float(v[1])));
-                                rgb_out[id * 3 + 2] = 1.f / (1.f + __expf(-__uint_as_float(v[2])));
+                                rgb_out[id * 3] = 1.f / (1.f + __expf(-(__uint_as_float(v[0]) + b_rgb0)));
+                                rgb_out[id * 3 + 1] = 1.f / (1.f + __expf(-(__uint_as_float(v[1]) + b_rgb1)));
+                                rgb_out[id * 3 + 2] = 1.f / (1.f + __expf(-(__uint_as_float(v[2]) + b_rgb2)));
                             }
                             continue;
                         }
                         if (g == 8 && blk == 4) {     // density head: column 128 of the head layer, raw
-                            if (in && (!TAN || sigma_out)) sigma_out[id] = __uint_as_float(v[0]);
+                            if (in && (!TAN || sigma_out)) sigma_out[id] = __uint_as_float(v[0]) + (TAN ? tsc * b_sigma : b_sigma);
                             continue;
                         }
                         if (TAN) {                    // tau = mask * (W tau_prev): the primal's ReLU pattern, no clamp
@@ -378,12 +358,10 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                     }
                 }
                 if (leader) TRACE(2 + t, 4, g, 0);
-                tmem_st_wait();
-                if (leader) TRACE(2 + t, 5, g, 0);
-                tc_fence_before();                // TMEM reads/writes done before the MMAs that follow the arrive
+                tc_fence_before();                // TMEM reads done before the MMAs that follow the arrive overwrite the accumulators
                 if (g < 9) {      // (tangent mode ends at g = 8: its c image is stored too, so every image of the stash is defined)
                     fence_proxy_async();
-                    if (g < NGT - 1) mbar_arrive(my_act);
+                    if (g < NGT - 1) mbar_arrive_remote(my_act, 0);
                 }
                 if (leader) TRACE(2 + t, 3, g, 0);
             }
@@ -391,8 +369,8 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
         if (TRAIN && lane == 0) bulk_wait0();
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
+    cluster_sync_all();          // the peer's shared memory / TMEM stay alive until the leader's last MMA has retired
+    if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
 }
 
 int mlp_fwd_ref_launch(const void* packed, const float* xyz_cano, const int32_t* cidx, const int32_t* count,
@@ -407,7 +385,15 @@ extern "C" int an_debug_trace_fwd(void* buf) {
 extern "C" int64_t an_mlp_stash_bytes(int64_t n_max)
 {
     if (n_max <= 0) return 0;
-    return ((n_max + 255) / 256) * 2 * mlp::ST_TILE;
+    return mlp::n_tiles_for(n_max) * mlp::ST_TILE;
+}
+
+// persistent CTA pairs: one pair per TPC, never more pairs than 512-point iterations
+static inline int pair_grid(int64_t n_max)
+{
+    const int64_t iters = (n_max + mlp::PAIR_POINTS - 1) / mlp::PAIR_POINTS;
+    const int pairs = an_num_sms() / 2;
+    return 2 * (int)(iters < pairs ? iters : pairs);
 }
 
 extern "C" int an_mlp_fwd(const void* packed, const float* xyz_cano, const int32_t* cidx, const int32_t* count,
@@ -423,9 +409,7 @@ extern "C" int an_mlp_fwd(const void* packed, const float* xyz_cano, const int32
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
-    const int64_t iters = (n_max + 255) / 256;
-    const int sms = an_num_sms();
-    const int grid = (int)(iters < sms ? iters : sms);
+    const int grid = pair_grid(n_max);
     if (stash)
         mlp_fwd_tc_kernel<1><<<grid, THREADS, SM_ALLOC, (cudaStream_t)stream>>>(
             (const uint8_t*)packed, xyz_cano, cidx, count, n_max, sigma, rgb, (uint8_t*)stash, nullptr, nullptr, nullptr);
@@ -460,9 +444,7 @@ extern "C" int an_mlp_fwd_tangent(const void* packed, const float* xyz_cano, con
     if ((((uintptr_t)pstash) & 127) || (((uintptr_t)tstash) & 127)) return AN_ERR_ALIGN;
     cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
-    const int64_t iters = (n_max + 255) / 256;
-    const int sms = an_num_sms();
-    const int grid = (int)(iters < sms ? iters : sms);
+    const int grid = pair_grid(n_max);
     mlp_fwd_tc_kernel<2><<<grid, THREADS, SM_ALLOC, (cudaStream_t)stream>>>(
         (const uint8_t*)packed, xyz_cano, cidx, count, n_max, tsigma, nullptr, (uint8_t*)tstash, tvec,
         (const uint8_t*)pstash, tscale);

@@ -31,16 +31,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster.  Default semantics
+// (release at CTA scope), as in CUTLASS's ClusterBarrier::arrive(cta_id): a cluster-scope release would cost a
+// MEMBAR.ALL.GPU + L1 invalidate per arrive (it waits for the thread's outstanding GLOBAL stores -- the stash
+// writes), which nothing here needs: the data handed over is this CTA's own shared memory (made visible to the
+// async proxy by fence.proxy.async before the arrive) and tensor memory (tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(bar), "r"(cta) : "memory");
+}
+
 // ---- TMA bulk copies (no tensor map: the global images are already in shared-memory layout)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-// multicast variant: the bytes land at the same CTA-relative offset in every CTA of `cta_mask`, and
-// each destination CTA's mbarrier (same offset) receives the complete_tx
-__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask) : "memory");
 }
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
@@ -64,6 +72,14 @@ __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {     // whole warp
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// CTA-pair variants (cta_group::2): issued by the same warp of BOTH CTAs of the pair
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t slot_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 // 32 lanes x 32 consecutive 32-bit columns: thread i of the warp gets lane (base_lane+i)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -105,6 +121,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)2 << 61;
     return d;
 }
+// K-major, no swizzle ("interleaved" core matrices of 8 rows x 16 B): the two K halves of a K=16 slab are
+// LBO apart, 8-row groups SBO apart (cute: ((8,n),2):((1,SBO),LBO) in 16-byte units)
+__device__ __forceinline__ uint64_t make_desc_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
 // instruction descriptor, kind::f16, bf16 x bf16 -> fp32, M=128
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
@@ -122,16 +147,24 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// commit that arrives on the mbarrier at the same offset in every CTA of `cta_mask`
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(cta_mask) : "memory");
+// CTA pair (cta_group::2): one thread of the leader CTA issues the MMA for both SMs -- M = 256 (128 rows per
+// CTA, each from its own shared memory at the descriptor's offset), each CTA stages N/2 rows of B; the commit
+// arrives on the mbarrier at the same offset in both CTAs.
+__device__ __forceinline__ void umma_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
 // ---- thread-block cluster
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t cluster_nctaid_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");

@@ -190,12 +190,18 @@ def test_mlp_pack_images():
     packed = _packed(10)
     w = synthetic.make_nerf_weights(10)
     W2 = torch.from_numpy(w["xyz_encoding_2.0.weight"]).to(DEV)
-    # fwd chunk (g=1, kc=2) starts after layer 0's single 32 KB chunk
-    off = 32768 + 2 * 32768
+    # fwd chunk (g=1, kc=2) starts after layer 0's single 32 KB chunk and its 8 KB bias slab
+    off = 32768 + 8192 + 2 * 32768
     img = _unswizzle(packed[off:off + 32768], 256)
     assert torch.equal(img, W2[:, 128:192].bfloat16().float())
+    # bias slab of layer 1 (after its 4 chunks): 8-row groups of 256 B = core matrices k 0..7 | k 8..15; k = 15 = bias
+    off = 32768 + 8192 + 4 * 32768
+    slab = packed[off:off + 8192].view(torch.bfloat16).reshape(32, 2, 8, 8)      # (group, k half, row in group, k in half)
+    b2 = torch.from_numpy(w["xyz_encoding_2.0.bias"]).to(DEV)
+    assert torch.equal(slab[:, 1, :, 7].reshape(256).float(), b2.bfloat16().float())
+    assert (slab[:, 0] == 0).all() and (slab[:, 1, :, :7] == 0).all()
     W5 = torch.from_numpy(w["xyz_encoding_5.0.weight"]).to(DEV)
-    off = (1 + 12) * 32768
+    off = (32768 + 8192) + 3 * (4 * 32768 + 8192)
     img = _unswizzle(packed[off:off + 32768], 256)
     assert torch.equal(img[:, :63], W5[:, :63].bfloat16().float()) and (img[:, 63] == 0).all()
     img = _unswizzle(packed[off + 32768:off + 65536], 256)
@@ -381,7 +387,7 @@ def _mlp_bwd_case(n, seed=10, with_gx=True, emulate_bf16=True):
         if i == 4:
             h = torch.cat([e, h], -1)
         w, b = p["xyz_encoding_%d.0" % (i + 1)]
-        a = h @ rd(w).T + b
+        a = h @ rd(w).T + rd(b)              # the bias enters through a bf16 tensor-core step (mlp_layout.cuh: bias slab)
         a.retain_grad(); pre.append(a)
         h32 = torch.relu(a)
         h = rd(h32)
@@ -390,7 +396,7 @@ def _mlp_bwd_case(n, seed=10, with_gx=True, emulate_bf16=True):
     Wf, bf = p["xyz_encoding_final"]
     Wd, bd = p["dir_encoding.0"]
     sig = (h @ rd(p["sigma"][0]).T + p["sigma"][1])[:, 0]
-    cpre = h @ rd(Wd @ Wf).T + (Wd @ bf + bd)
+    cpre = h @ rd(Wd @ Wf).T + rd(Wd @ bf + bd)
     cpre.retain_grad()
     rgbpre = rd(torch.relu(cpre)) @ rd(p["rgb.0"][0]).T + p["rgb.0"][1]
     rgbpre.retain_grad()

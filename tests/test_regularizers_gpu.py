@@ -26,7 +26,7 @@ def _sigma_oracle(p, x, emulate_bf16):
         if i == 4:
             h = torch.cat([e, h], -1)
         w, b = p["xyz_encoding_%d.0" % (i + 1)]
-        h = rd(torch.relu(h @ rd(w).T + b))
+        h = rd(torch.relu(h @ rd(w).T + rd(b)))       # trunk biases enter through a bf16 tensor-core step (bias slab)
     return (h @ rd(p["sigma"][0]).T + p["sigma"][1])[:, 0]
 
 

@@ -60,15 +60,17 @@ for t in (0, 1):
 m = role == 1
 c, ee, aa, bb = clk[m], e[m], a[m], b[m]
 o = np.argsort(c, kind="stable"); c, ee, aa, bb = c[o], ee[o], aa[o], bb[o]
-wact = {}; wfull = {}
+wact = {}; wfull = {}; issue = {}
 prev = None
 for ci, ei, gi, bi in zip(c, ee, aa, bb):
     if ei == 1: wact.setdefault((gi, bi), []).append(ci - prev)
-    if ei == 2: wfull.setdefault((gi, bi >> 3), []).append(ci - prev)
+    if ei == 2: wfull.setdefault((gi, bi >> 3), []).append(ci - prev)       # time inside the full-barrier wait
+    if ei == 3 and prev is not None: issue.setdefault((gi, bi >> 3), []).append(ci - prev)   # previous step's issue + commit
     prev = ci
-print("MMA issuer: median clk waiting for act[g,t]; per-chunk issue interval (full wait + issue) [g,t]")
+print("MMA issuer [median clk]: wait for act[g,t] | per ring step: wait for the weights (full barrier) | issue 4 MMAs + commit")
 for g in range(10):
-    print("   g=%d  act: %7.0f %7.0f   chunk: %7.0f %7.0f" % (g, np.median(wact[(g, 0)]), np.median(wact[(g, 1)]),
-                                                              np.median(wfull[(g, 0)]), np.median(wfull[(g, 1)])))
+    print("   g=%d  act: %7.0f %7.0f   full-wait: %7.0f %7.0f   issue: %7.0f %7.0f" % (
+        g, np.median(wact[(g, 0)]), np.median(wact[(g, 1)]), np.median(wfull[(g, 0)]), np.median(wfull[(g, 1)]),
+        np.median(issue.get((g, 0), [0])), np.median(issue.get((g, 1), [0]))))
 tot_iter = len(wact[(0, 0)])
 print("iterations traced:", tot_iter, " clk/iteration:", clk.max() / tot_iter)
