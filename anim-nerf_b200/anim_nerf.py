@@ -5,8 +5,9 @@ Same constructor keywords, same per-frame state setters (`set_body_model`,
 `forward(xyz, viewdir, use_fine) -> (rgb, sigma)` / `query_canonical_space` contract; the work
 between the query points and (rgb, sigma) runs on the sm_100a kernels (KNN + unpose, MLP) --
 there is no torch fallback for it.  The per-frame table builder (SMPL LBS, 6890 4x4 inverses; SURVEY §8
-row A16) runs on the fused kernels (`an_body_tables_fwd`, see `setup_frame`) whenever no SMPL parameter needs
-a gradient, and through the differentiable torch builder (`body_model.py`) when one does.
+row A16) runs on the fused kernels (`an_body_tables_fwd` / `an_body_tables_bwd`, see `setup_frame`), with gradients to
+the posed body's SMPL parameters when they are being optimised (`optim_body_params`, the reference's shipped default);
+the differentiable torch builder (`body_model.py`) remains for gradients to the template body's parameters.
 
 Only the shipped configuration is built (every reference yaml): use_unpose=True with k_neigh=4,
 use_view=False, use_deformation=False, no latent codes, query_inside=False.
@@ -15,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import ops, synthetic
-from .autograd import PointQuery, RenderPass
+from .autograd import BodyTables, PointQuery, RenderPass
 from .body_model import BodyModel
 from .nerf import NeRF
 
@@ -62,6 +63,7 @@ class AnimNeRF(nn.Module):
         self.weight_std = 0.1
         self.knn_mode = 1          # 1 = grid-pruned exact search (default), 0 = exhaustive
         self.mlp_impl = 0          # 0 = tcgen05 kernel; 1 = fp32 SIMT reference (tests only)
+        self.fused_tables = True   # per-frame tables on the kernels (forward and backward); False: differentiable torch builder
         if body_model_data is None:
             import os
             path = os.path.join(model_path, model_type, "%s_%s.pkl" % (model_type.upper(), gender.upper()))
@@ -101,19 +103,27 @@ class AnimNeRF(nn.Module):
     # ------------------------------------------------------------------ fused per-frame setup
     def setup_frame(self, body_model_params, body_model_params_template, rays=None):
         """`set_body_model` -> `convert_to_body_model_space(rays)` -> `clac_ober2cano_transform` in one
-        call (the sequence of train.py:201-203 / novel_view.py:79-85).  When no SMPL parameter needs a
-        gradient the tables come from the fused kernels (`an_body_tables_fwd`: two launches instead of
-        ~250) and only the state the rendering path reads is set (`verts`, `ober2cano_transform`,
-        `verts_template`, `global_transform`); otherwise the differentiable torch builder runs.
-        Returns (rays in body space or None, ginv (B,4,4))."""
-        tensors = [v for d in (body_model_params, body_model_params_template) for v in d.values() if torch.is_tensor(v)]
-        if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+        call (the sequence of train.py:201-203 / novel_view.py:79-85).  The tables come from the fused kernels
+        (`an_body_tables_fwd`: two launches instead of ~250; with gradients to the posed body's parameters through
+        `an_body_tables_bwd` when they require them) and only the state the rendering path reads is set (`verts`,
+        `ober2cano_transform`, `verts_template`, `global_transform`).  Returns (rays in body space or None, ginv (B,4,4))."""
+        posed_grad = torch.is_grad_enabled() and any(torch.is_tensor(v) and v.requires_grad for v in body_model_params.values())
+        tmpl_grad = torch.is_grad_enabled() and any(torch.is_tensor(v) and v.requires_grad
+                                                    for v in body_model_params_template.values())
+        if tmpl_grad or not self.fused_tables:
+            # gradients to the TEMPLATE body's parameters (never requested by the reference's training loop) or the
+            # torch builder asked for explicitly (tests): the differentiable torch chain
             self.set_body_model(body_model_params, body_model_params_template)
             ginv = affine_inverse(self.global_transform)
             rays = self.convert_to_body_model_space(rays)
             self.clac_ober2cano_transform()
             return rays, ginv
-        verts, o2c, ginv, vt = ops.body_tables(self.body_model, body_model_params, body_model_params_template)
+        if posed_grad:      # optim_body_params (the reference's shipped default): kernels forward and backward
+            p = body_model_params
+            verts, o2c, ginv, vt = BodyTables.apply(self.body_model, body_model_params_template, p["betas"], p["global_orient"],
+                                                    p["body_pose"], p.get("transl"))
+        else:
+            verts, o2c, ginv, vt = ops.body_tables(self.body_model, body_model_params, body_model_params_template)
         self.verts, self.ober2cano_transform, self.verts_template = verts, o2c, vt
         self.global_transform = torch.eye(4, device=verts.device).expand(verts.shape[0], 4, 4)
         self.joints = self.verts_transform = self.joints_transform = None      # not built on the fused path

@@ -79,6 +79,37 @@ class RenderPass(torch.autograd.Function):
         return (g_rays, g_zz, g_o2c, None, None) + tuple(g_params)
 
 
+class BodyTables(torch.autograd.Function):
+    """Per-frame tables (A16 + vertex part of A2 + clac_ober2cano_transform) as a differentiable function of the POSED
+    body's parameters: forward `an_body_tables_fwd`, backward `an_body_tables_bwd` (the reference's shipped
+    optim_body_params=True path, train.py:141-145,330-331).  Outputs: verts (root frame; no gradient -- the
+    neighbour search is not differentiated), ober2cano, ginv, verts_template (no gradient).  The template body's
+    parameters come from the batch and receive no gradient."""
+
+    @staticmethod
+    def forward(ctx, model, template, betas, global_orient, body_pose, transl):
+        posed = dict(betas=betas, global_orient=global_orient, body_pose=body_pose, transl=transl)
+        verts, o2c, ginv, vt, c = ops.body_tables(model, posed, template, want_ctx=True)
+        ctx.c = c
+        ctx.shapes = (betas.shape, global_orient.shape, body_pose.shape, None if transl is None else transl.shape)
+        ctx.mark_non_differentiable(verts, vt)
+        return verts, o2c, ginv, vt
+
+    @staticmethod
+    def backward(ctx, _gv, g_o2c, g_ginv, _gvt):
+        c = ctx.c
+        if g_o2c is None:
+            g_o2c = torch.zeros(c["B"], c["V"], 4, 4, device=c["pose"].device)
+        g_betas, g_pose, g_transl = ops.body_tables_bwd(c, g_o2c, g_ginv)
+        sb, sg, sp, st = ctx.shapes
+        if sb[0] != g_betas.shape[0]:                   # one shared shape row (BodyModelParams.betas): sum over the frames
+            g_betas = g_betas.sum(0, keepdim=True)
+        g_go = g_pose[:, :3].reshape(sg)
+        g_bp = g_pose[:, 3:].reshape(sp)
+        ctx.c = None
+        return None, None, g_betas.reshape(sb), g_go, g_bp, (None if st is None else g_transl.reshape(st))
+
+
 class PointQuery(torch.autograd.Function):
     """AnimNeRF.forward / NeRF.forward on explicit points: (optional unpose) -> MLP -> mask."""
 

@@ -69,21 +69,25 @@ def sample_coarse(rays, n_coarse, perturb=0.0, noise_u=None, seed=0):
 
 
 # ------------------------------------------------------------------------ per-frame tables
-def body_tables(model, posed, template, want_template_verts=True):
+def _body_params(d):
+    """dict(betas (B|1,10), global_orient (B,3), body_pose (B,69), transl (B,3)|None) -> B, betas (B,10), pose (B,72), transl."""
+    go, bp = _f32c(d["global_orient"].detach()), _f32c(d["body_pose"].detach())
+    B = max(go.shape[0], d["betas"].shape[0])
+    pose = torch.cat([go.reshape(go.shape[0], -1), bp.reshape(bp.shape[0], -1)], 1).contiguous()
+    betas = _f32c(d["betas"].detach())
+    if betas.shape[0] != B:
+        betas = betas.expand(B, -1).contiguous()
+    tr = d.get("transl")
+    return B, betas, pose, (_f32c(tr.detach()) if tr is not None else None)
+
+
+def body_tables(model, posed, template, want_template_verts=True, want_ctx=False):
     """A16 + A2 (vertex part) + clac_ober2cano_transform in two kernels.  `model`: BodyModel (constant
     buffers); posed / template: dicts betas (B|1,10), global_orient (B,3), body_pose (B,69), transl (B,3).
-    Returns verts (B,V,3) root frame, ober2cano (B,V,4,4), ginv (B,4,4), verts_template (B,V,3)."""
-    def prep(d):
-        go, bp = _f32c(d["global_orient"]), _f32c(d["body_pose"])
-        B = max(go.shape[0], d["betas"].shape[0])
-        pose = torch.cat([go.reshape(go.shape[0], -1), bp.reshape(bp.shape[0], -1)], 1).contiguous()
-        betas = _f32c(d["betas"])
-        if betas.shape[0] != B:
-            betas = betas.expand(B, -1).contiguous()
-        tr = d.get("transl")
-        return B, betas, pose, (_f32c(tr) if tr is not None else None)
-    B, betas, pose, transl = prep(posed)
-    Bt, betas_t, pose_t, transl_t = prep(template)
+    Returns verts (B,V,3) root frame, ober2cano (B,V,4,4), ginv (B,4,4), verts_template (B,V,3)
+    [, ctx: what `body_tables_bwd` needs]."""
+    B, betas, pose, transl = _body_params(posed)
+    Bt, betas_t, pose_t, transl_t = _body_params(template)
     V = model.v_template.shape[0]
     dev = pose.device
     ws = torch.empty(_lib.load().an_body_tables_ws_bytes(B), device=dev, dtype=torch.uint8)
@@ -95,7 +99,28 @@ def body_tables(model, posed, template, want_template_verts=True):
          ptr(model.v_template), ptr(model.shapedirs), ptr(model.posedirs), ptr(model.J_template), ptr(model.J_shapedirs),
          ptr(model.lbs_weights), ptr(model.parents_i32), V, model.J_regressor.shape[0], model.shapedirs.shape[-1], ptr(ws),
          ptr(verts), ptr(o2c), ptr(ginv), ptr(vt), stream())
+    if want_ctx:
+        return verts, o2c, ginv, vt, dict(model=model, betas=betas, pose=pose, transl=transl, ws=ws, ginv=ginv, B=B, V=V)
     return verts, o2c, ginv, vt
+
+
+def body_tables_bwd(ctx, g_o2c, g_ginv=None):
+    """Gradients of `body_tables` w.r.t. the posed body's parameters (an_body_tables_bwd): g_o2c (B,V,4,4),
+    g_ginv (B,4,4) or None -> g_betas (B,10), g_pose (B,72) = [global_orient, body_pose], g_transl (B,3)."""
+    model, B, V = ctx["model"], ctx["B"], ctx["V"]
+    dev = ctx["pose"].device
+    g_o2c = _f32c(g_o2c)
+    if g_ginv is not None:
+        g_ginv = _f32c(g_ginv)
+    bws = torch.empty(_lib.load().an_body_tables_bwd_ws_bytes(B), device=dev, dtype=torch.uint8)
+    g_betas = torch.empty(B, 10, device=dev)
+    g_pose = torch.empty(B, 72, device=dev)
+    g_transl = torch.empty(B, 3, device=dev) if ctx["transl"] is not None else None
+    call("an_body_tables_bwd", ptr(g_o2c), ptr(g_ginv), ptr(ctx["betas"]), ptr(ctx["pose"]), ptr(ctx["transl"]), B,
+         ptr(model.shapedirs), ptr(model.posedirs), ptr(model.J_template), ptr(model.J_shapedirs), ptr(model.lbs_weights),
+         ptr(model.parents_i32), V, model.J_regressor.shape[0], model.shapedirs.shape[-1], ptr(ctx["ws"]), ptr(ctx["ginv"]),
+         ptr(bws), ptr(g_betas), ptr(g_pose), ptr(g_transl), stream())
+    return g_betas, g_pose, g_transl
 
 
 # ------------------------------------------------------------------------ KNN + unpose

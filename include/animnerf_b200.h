@@ -249,8 +249,24 @@ int an_sample_fine_merge_fwd(const float* weights, const float* z_coarse, const 
  * J_shapedirs (24,3,10) = J_regressor . shapedirs, lbs_weights (V,24), parents int32[24].
  * ws: an_body_tables_ws_bytes(B) scratch.  Outputs: verts (B,V,3) in the root frame, ober2cano
  * (B,V,4,4; 16-byte aligned), ginv (B,4,4) = inverse root transform (feeds an_raygen_fwd),
- * verts_template (B,V,3) or NULL.  Forward only.                                             */
+ * verts_template (B,V,3) or NULL.
+ *
+ * an_body_tables_bwd: autograd of that chain with respect to the POSED body's parameters -- what the reference
+ * optimises under its shipped optim_body_params=True (config.py:34, train.py:141-145,330-331; gradients of
+ * smplx/lbs.py:152-251 batch_rodrigues / batch_rigid_transform / blend shapes / skinning blend, and of the two
+ * matrix inverses of models/anim_nerf.py:131,148).  Inputs: g_ober2cano (B,V,4,4; rows 0-2 read; 16-byte aligned;
+ * from an_knn_unpose_bwd), g_ginv (B,4,4; rows 0-2 read) or NULL (gradient of the body-space rays), the forward's
+ * inputs, its workspace `ws` (unchanged since the forward) and its ginv output; bwd_ws: an_body_tables_bwd_ws_bytes(B)
+ * scratch.  Outputs (written, not accumulated): g_betas (B,10), g_pose (B,24,3), g_transl (B,3) or NULL.  Posed
+ * vertices carry no gradient (the neighbour search is not differentiated) and neither do the template parameters. */
 int64_t an_body_tables_ws_bytes(int B);
+int64_t an_body_tables_bwd_ws_bytes(int B);
+int an_body_tables_bwd(const float* g_ober2cano, const float* g_ginv,
+                       const float* betas, const float* pose, const float* transl, int B,
+                       const float* shapedirs, const float* posedirs,
+                       const float* J_template, const float* J_shapedirs, const float* lbs_weights,
+                       const int32_t* parents, int V, int J, int n_betas, const void* ws, const float* ginv,
+                       void* bwd_ws, float* g_betas, float* g_pose, float* g_transl, void* stream);
 int an_body_tables_fwd(const float* betas, const float* pose, const float* transl,
                        const float* betas_t, const float* pose_t, const float* transl_t, int B, int Bt,
                        const float* v_template, const float* shapedirs, const float* posedirs,

@@ -486,14 +486,57 @@ def test_body_tables_match_torch_builder(shared_template):
     assert float((vt - vt_ref).abs().max()) < 2e-5
     assert float((o2c - o2c_ref).abs().max()) < 1e-4
     assert torch.equal(o2c[..., 3, :], torch.tensor([0.0, 0.0, 0.0, 1.0], device=DEV).expand(B, o2c.shape[1], 4))
-    # the path picks the fused builder when nothing needs a gradient, the torch builder otherwise
+    # the path uses the fused builder with or without gradients to the posed body's parameters
     with torch.no_grad():
         rays_w = torch.from_numpy(synthetic.rays_at_bbox(posed_np["transl"][:, None] + np.zeros((B, 4, 3), np.float32), 8)).to(DEV)
         rays_b, ginv2 = net.setup_frame(posed, tmpl, rays_w)
     assert net.verts_transform is None and torch.equal(ginv2, ginv) and torch.equal(net.verts, verts)
     posed_g = dict(posed, body_pose=posed["body_pose"].clone().requires_grad_(True))
-    rays_b2, _ = net.setup_frame(posed_g, tmpl if not shared_template else {k: v.expand(B, *v.shape[1:]) for k, v in tmpl.items()}, rays_w)
-    assert net.verts_transform is not None and net.ober2cano_transform.requires_grad
-    assert float((rays_b2 - rays_b).abs().max()) < 2e-5
+    rays_b2, _ = net.setup_frame(posed_g, tmpl, rays_w)
+    assert net.verts_transform is None and net.ober2cano_transform.requires_grad and not net.verts.requires_grad
+    assert float((rays_b2.detach() - rays_b).abs().max()) < 2e-5
     net.ober2cano_transform.sum().backward()
     assert posed_g["body_pose"].grad is not None and float(posed_g["body_pose"].grad.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("shared_template", [False, True])
+def test_body_tables_backward_matches_torch_builder(shared_template):
+    """an_body_tables_bwd vs torch autograd through the differentiable torch builder (BodyModel +
+    set_body_model / convert_to_body_model_space / clac_ober2cano_transform): gradients of a random linear
+    functional of (ober2cano, body-space rays) w.r.t. betas, global_orient, body_pose, transl of the posed body.
+    The shared shape row (BodyModelParams.betas: one embedding row for all frames) is covered by passing (1,10) betas.
+    fp32 both sides, different summation order: relative L2 error <= 2e-4 per parameter."""
+    from anim_nerf_b200.anim_nerf import AnimNeRF
+    B = 4
+    net = AnimNeRF(use_unpose=True, use_knn=True, use_fine=False, freqs_dir=0, body_model_data=synthetic.make_smpl_dict(0)).to(DEV)
+    posed_np, tmpl_np = synthetic.make_body_params(B, seed=9)
+    rs = np.random.RandomState(5)
+    posed_np["betas"] = rs.normal(0, 0.5, size=(1, 10)).astype(np.float32).repeat(B, 0)
+    tmpl = {k: torch.from_numpy(v[:1] if shared_template else v).to(DEV) for k, v in tmpl_np.items()}
+    tmpl_full = {k: v.expand(B, *v.shape[1:]) for k, v in tmpl.items()} if shared_template else tmpl
+    rays_w = torch.from_numpy(synthetic.rays_at_bbox(posed_np["transl"][:, None] + np.zeros((B, 4, 3), np.float32), 16)).to(DEV)
+    V = net.body_model.v_template.shape[0]
+    c_o2c = torch.from_numpy(rs.normal(size=(B, V, 4, 4)).astype(np.float32)).to(DEV)
+    c_o2c[:, :, 3] = 0          # the last row is the constant [0,0,0,1]
+    c_rays = torch.from_numpy(rs.normal(size=tuple(rays_w.shape)).astype(np.float32)).to(DEV)
+
+    def run(fused, shared_betas):
+        net.fused_tables = fused
+        leaf = {k: torch.from_numpy(v).to(DEV).requires_grad_(True) for k, v in posed_np.items()}
+        if shared_betas:
+            leaf["betas"] = torch.from_numpy(posed_np["betas"][:1]).to(DEV).requires_grad_(True)
+        posed = dict(leaf)
+        if shared_betas and not fused:
+            posed["betas"] = leaf["betas"].expand(B, -1)
+        rays_b, _ = net.setup_frame(posed, tmpl if fused else tmpl_full, rays_w)
+        ((net.ober2cano_transform * c_o2c).sum() + (rays_b * c_rays).sum()).backward()
+        return {k: v.grad.clone() for k, v in leaf.items()}
+
+    for shared_betas in (False, True):
+        g_ref = run(False, shared_betas)
+        g_ker = run(True, shared_betas)
+        for k in g_ref:
+            err = float((g_ker[k] - g_ref[k]).norm() / (g_ref[k].norm() + 1e-20))
+            print(shared_betas, k, "rel err %.3g" % err, "norm %.3g" % float(g_ref[k].norm()))
+            assert g_ker[k].shape == g_ref[k].shape and err < 2e-4, (k, err)
+    net.fused_tables = True
