@@ -15,7 +15,7 @@ use_view=False, use_deformation=False, no latent codes, query_inside=False.
 import torch
 import torch.nn as nn
 
-from . import ops, synthetic
+from . import ops
 from .autograd import BodyTables, PointQuery, RenderPass
 from .body_model import BodyModel
 from .nerf import NeRF
@@ -67,7 +67,10 @@ class AnimNeRF(nn.Module):
         if body_model_data is None:
             import os
             path = os.path.join(model_path, model_type, "%s_%s.pkl" % (model_type.upper(), gender.upper()))
-            body_model_data = path if os.path.exists(path) else synthetic.make_smpl_dict(0)
+            if not os.path.exists(path):      # as smplx.create does (smplx/body_models.py:126-136): no silent stand-in body
+                raise FileNotFoundError("SMPL model file %s not found (pass body_model_data=<dict or path> explicitly, "
+                                        "e.g. synthetic.make_smpl_dict(0) for tests)" % path)
+            body_model_data = path
         self.body_model = BodyModel(body_model_data)
         self.lbs_dim = self.body_model.lbs_weights.shape[1]
         self.nerf = NeRF(freqs_xyz=freqs_xyz, freqs_dir=freqs_dir, use_view=use_view)
@@ -135,6 +138,15 @@ class AnimNeRF(nn.Module):
         if rays is not None:
             rays = self.rays_to_body_space(rays, ginv)
         return rays, ginv
+
+    def clear_frame_state(self):
+        """Drop the per-frame tensors (and with them the autograd graph of the step that built them: `ober2cano_transform`
+        hangs on to the table builder's node when SMPL parameters are optimised).  Needed before a training step is
+        captured on another stream: a live graph keeps the parameters' AccumulateGrad nodes bound to the stream they
+        were created on."""
+        self.verts = self.ober2cano_transform = self.verts_template = self.global_transform = None
+        self.joints = self.verts_transform = self.joints_transform = None
+        self._grid = None
 
     @staticmethod
     def rays_to_body_space(rays, ginv):

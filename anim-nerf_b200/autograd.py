@@ -16,6 +16,14 @@ from . import ops
 COUNT_LOG = None      # bench.py sets this to a list to collect (K, device count tensor) per pass
 
 
+def _param_grads(net, g_flat, sink):
+    """What a backward returns to autograd for the 24 MLP parameters: per-tensor views of this call's gradient
+    vector, or nothing when the kernel accumulated straight into the net's attached flat buffer."""
+    if sink is not None:
+        return [None] * 24
+    return net.split_flat_grad(g_flat)
+
+
 class RenderPass(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rays, z, ober2cano, sigma_noise, cfg, *params):
@@ -59,8 +67,9 @@ class RenderPass(torch.autograd.Function):
         B, R, K = z.shape
         g_sigma, g_rgb, g_z, g_far = ops.composite_bwd(sigma, rgb, z, rays, g_rgb_o, g_depth, g_acc, cfg["white"], noise)
         need_geo = ctx.needs_input_grad[0] or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        sink = net.grad_sink()
         g_flat, g_xc = ops.mlp_bwd(ctx.packed, ctx.stash, aux["xyz_cano"], rgb, g_sigma, g_rgb, cidx=aux["cidx"],
-                                   count=aux["count"], n_max=B * R * K, want_g_xyz=need_geo)
+                                   count=aux["count"], n_max=B * R * K, want_g_xyz=need_geo, g_params=sink)
         g_rays = g_zz = g_o2c = None
         if need_geo:
             g_o2c, g_xyz = ops.knn_unpose_bwd(g_xc, aux["cidx"], aux["count"], aux["idx"], aux["qw"], o2c, rays=rays, z=z)
@@ -74,7 +83,7 @@ class RenderPass(torch.autograd.Function):
                 g_zz = g_z + (g_xyz * rays[:, :, None, 3:6]).sum(-1)
             if not ctx.needs_input_grad[2]:
                 g_o2c = None
-        g_params = net.split_flat_grad(g_flat)
+        g_params = _param_grads(net, g_flat, sink)
         ctx.stash = ctx.aux = None
         return (g_rays, g_zz, g_o2c, None, None) + tuple(g_params)
 
@@ -145,9 +154,10 @@ class PointQuery(torch.autograd.Function):
         cfg, aux = ctx.cfg, ctx.aux
         B, N = xyz.shape[:2]
         need_geo = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        sink = cfg["net"].grad_sink()
         g_flat, g_xc = ops.mlp_bwd(ctx.packed, ctx.stash, aux["xyz_cano"], rgb, g_sigma.contiguous().view(B, N),
                                    g_rgb.contiguous(), cidx=aux["cidx"], count=aux["count"], n_max=B * N,
-                                   want_g_xyz=need_geo)
+                                   want_g_xyz=need_geo, g_params=sink)
         g_xyz = g_o2c = None
         if need_geo:
             if cfg.get("unpose", True):
@@ -157,7 +167,7 @@ class PointQuery(torch.autograd.Function):
             else:
                 g_xyz = g_xc.view_as(xyz)
         ctx.stash = ctx.aux = None
-        return (g_xyz, g_o2c, None) + tuple(cfg["net"].split_flat_grad(g_flat))
+        return (g_xyz, g_o2c, None) + tuple(_param_grads(cfg["net"], g_flat, sink))
 
 
 class SigmaWithGradient(torch.autograd.Function):
@@ -202,9 +212,10 @@ class SigmaWithGradient(torch.autograd.Function):
         # The tangent kernel writes T = tau + c X; the wgrad kernel forms delta T^T and the c-weighted bias sums.
         c = g_sigma.reshape(n).contiguous().float()
         tstash, _ = ops.mlp_fwd_tangent(packed, x, g_s.reshape(n, 3).contiguous(), stash, n_max=n, tscale=c)
-        flat = ops.mlp_bwd_wgrad(packed, tstash, scratch, n_max=n, bias_scale=c)
+        sink = net.grad_sink()
+        flat = ops.mlp_bwd_wgrad(packed, tstash, scratch, n_max=n, bias_scale=c, g_params=sink)
         ctx.stash = ctx.scratch = None
-        return (None, None) + tuple(net.split_flat_grad(flat))
+        return (None, None) + tuple(_param_grads(net, flat, sink))
 
 
 def sigma_with_gradient(net, xyz):

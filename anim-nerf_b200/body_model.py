@@ -86,6 +86,18 @@ class BodyModel(nn.Module):
         self.register_buffer("J_shapedirs", torch.einsum("ji,ikl->jkl", self.J_regressor, self.shapedirs).contiguous())
         self.register_buffer("parents_i32", parents.to(torch.int32))
 
+    def refresh_derived(self):
+        """Recompute everything derived from v_template / shapedirs / J_regressor / parents (after `load_state_dict` of a
+        reference checkpoint replaced those buffers): the fused table builder's constants and the host-side tree."""
+        parents = self.parents.long().clone()
+        parents[0] = -1
+        self.parents.copy_(parents)
+        self.parents_host = [int(p) for p in parents]
+        self.parent_idx.copy_(parents[1:])
+        self.J_template.copy_(torch.matmul(self.J_regressor, self.v_template))
+        self.J_shapedirs.copy_(torch.einsum("ji,ikl->jkl", self.J_regressor, self.shapedirs))
+        self.parents_i32.copy_(parents.to(torch.int32))
+
     def forward(self, betas, body_pose, global_orient, transl=None, **_):
         B = max(betas.shape[0], body_pose.shape[0], global_orient.shape[0])
         if betas.shape[0] != B:

@@ -16,6 +16,13 @@ def shard_range(n_items, rank, world):
     return start, start + base + (1 if rank < rem else 0)
 
 
+def shard_rows(n_rows, rank, world):
+    """Interleaved partition of image rows: rank r owns rows r, r + world, r + 2 world, ...  The body covers a band
+    of rows in the middle of a frame, so contiguous slabs are load-imbalanced (foreground fraction 0.22-0.28 of a slab
+    at 8 ranks, some slabs nearly empty); interleaving gives every rank the same share of every region."""
+    return list(range(rank, n_rows, world))
+
+
 def allreduce_grads(params, world=None, average=True):
     """Sum (and average) the .grad of `params` across ranks through one flat bucket."""
     world = world or (dist.get_world_size() if dist.is_initialized() else 1)
@@ -31,6 +38,23 @@ def allreduce_grads(params, world=None, average=True):
         n = p.numel()
         p.grad.copy_(bucket[o:o + n].view_as(p))
         o += n
+
+
+def gather_rows(local, n_rows, dim=0):
+    """all_gather of the per-rank row sets of a `shard_rows` partition along `dim`, back in image order."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return local
+    per = (n_rows + world - 1) // world
+    pad = per - local.shape[dim]
+    if pad:
+        shape = list(local.shape); shape[dim] = pad
+        local = torch.cat([local, local.new_zeros(shape)], dim)
+    out = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(out, local.contiguous())
+    full = torch.stack(out, dim + 1)                       # (.., per, world, ..): row = i * world + r
+    shape = list(local.shape); shape[dim] = per * world
+    return full.reshape(shape).narrow(dim, 0, n_rows)
 
 
 def gather_slabs(local, n_total, dim=0):

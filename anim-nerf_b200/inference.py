@@ -9,8 +9,8 @@ memory of its materialised gathers; the fused kernels keep 45 B per point, so `c
 bounds the per-launch working set (default: a whole 512x512 frame / 16 Mi grid points at once).
 
 Multi-GPU: rays and grid points are independent given the per-frame tables, so a
-frame is split into contiguous row slabs and a grid into slabs along its first axis, one per
-rank; every rank rebuilds the (tiny) per-frame tables itself; there is no data-path collective --
+frame's rows are dealt out round-robin (rank r: rows r, r+world, ...: equal foreground share per rank)
+and a grid is cut into slabs along its first axis, one per rank; every rank rebuilds the (tiny) per-frame tables itself; there is no data-path collective --
 only an optional all_gather of the finished slabs.
 """
 from collections import defaultdict
@@ -20,7 +20,7 @@ import torch
 
 from . import ops
 from .anim_nerf import batch_transform
-from .dist_utils import gather_slabs, shard_range
+from .dist_utils import gather_rows, gather_slabs, shard_range, shard_rows
 
 
 def _rank_world(rank, world):
@@ -66,33 +66,37 @@ def render_frame(volume_renderer, anim_nerf, c2w, focal, center, H, W, body_mode
     """One full frame per batch entry from camera parameters: the ray generation of
     `datasets/anim_nerf_dataset.py:56-85` and the ray part of `convert_to_body_model_space`
     (`models/anim_nerf.py:128-137`) run fused in `an_raygen_fwd`, then the render path.
-    c2w (B,3,4), focal (B,2), center (B,2).  rows=(r0,r1) renders only that slab of image rows.
-    Returns dict of (B, rows, W, .)."""
+    c2w (B,3,4), focal (B,2), center (B,2).  rows: (r0,r1) renders only that slab of image rows, a list / 1-D tensor
+    of row indices only those rows (in that order).  Returns dict of (B, rows, W, .)."""
     _, ginv = anim_nerf.setup_frame(body_model_params, body_model_params_template, None)
-    r0, r1 = rows if rows is not None else (0, H)
     B = c2w.shape[0]
-    if r0 == 0 and r1 == H:
-        pix = None
-    else:       # explicit pixel list for the slab (row, col)
-        rr = torch.arange(r0, r1, device=c2w.device, dtype=torch.int32)
+    if rows is None or (isinstance(rows, tuple) and tuple(rows) == (0, H)):
+        pix, n_rows = None, H
+    else:       # explicit pixel list (row, col)
+        if isinstance(rows, tuple):
+            rr = torch.arange(rows[0], rows[1], device=c2w.device, dtype=torch.int32)
+        else:
+            rr = torch.as_tensor(rows, device=c2w.device, dtype=torch.int32)
+        n_rows = rr.numel()
         cc = torch.arange(W, device=c2w.device, dtype=torch.int32)
         pix = torch.stack(torch.meshgrid(rr, cc, indexing="ij"), -1).view(1, -1, 2).expand(B, -1, -1).contiguous()
     rays = ops.raygen(c2w, focal, center, H, W, near, far, pix=pix, ginv=ginv)
     out = _render_body_space(volume_renderer, anim_nerf, rays, P, chunk)
-    return {k: v.view(B, r1 - r0, W, -1) for k, v in out.items()}
+    return {k: v.view(B, n_rows, W, -1) for k, v in out.items()}
 
 
 @torch.no_grad()
 def render_frame_sharded(volume_renderer, anim_nerf, c2w, focal, center, H, W, body_model_params,
                          body_model_params_template, rank=None, world=None, gather=True, **kw):
-    """Row-slab sharded frame: rank r renders rows shard_range(H, r, world); no collective on the
-    data path.  gather=True all-gathers the finished slabs so every rank returns the full frame."""
+    """Row-sharded frame: rank r renders rows r, r + world, ... (`shard_rows`: interleaved, so every rank gets the same
+    share of the body's rows); no collective on the data path.  gather=True all-gathers the finished rows, back in
+    image order, so every rank returns the full frame; gather=False returns this rank's rows (B, len(rows), W, .)."""
     rank, world = _rank_world(rank, world)
-    rows = shard_range(H, rank, world)
+    rows = shard_rows(H, rank, world) if world > 1 else None
     out = render_frame(volume_renderer, anim_nerf, c2w, focal, center, H, W, body_model_params,
                        body_model_params_template, rows=rows, **kw)
     if gather and world > 1:
-        out = {k: gather_slabs(v.transpose(0, 1).contiguous(), H, dim=0).transpose(0, 1) for k, v in out.items()}
+        out = {k: gather_rows(v.transpose(0, 1).contiguous(), H, dim=0).transpose(0, 1) for k, v in out.items()}
     return out
 
 

@@ -59,6 +59,7 @@ class NeRF(nn.Module):
         self._packed_key = None
         self._packed_buf = None
         self._dirty = False
+        self._flat_grad = None
 
     # ---- kernel-side view of the parameters
     def linears(self):
@@ -89,6 +90,23 @@ class NeRF(nn.Module):
             self._packed_key = key
             self._dirty = False
         return self._packed
+
+    def attach_flat_grad(self, region):
+        """Training plumbing: `region` (an_mlp_grad_floats fp32, zeroed by the caller every step) becomes the
+        storage of every parameter's `.grad` -- views in kernel order, which is the order the weight-gradient
+        kernel writes -- and the backward of the render / query functions accumulates into it directly instead of
+        returning per-tensor copies to autograd.  One memset clears all gradients, one NCCL all-reduce of the
+        buffer exchanges them, and the optimiser reads the views.  `region=None` detaches."""
+        self._flat_grad = region
+        if region is None:
+            return
+        assert region.numel() == ops.mlp_grad_floats() and region.is_contiguous() and region.dtype == torch.float32
+        for p, g in zip(self.param_list(), self.split_flat_grad(region)):
+            p.grad = g
+
+    def grad_sink(self):
+        """The attached flat gradient buffer, or None (gradients then flow through autograd as usual)."""
+        return self._flat_grad
 
     def split_flat_grad(self, flat):
         """flat gradient (an_mlp_grad_floats) -> 24 tensors matching param_list()."""

@@ -233,11 +233,25 @@ def mlp_stash(n_max, device):
     return buf[off:off + nbytes]
 
 
-def mlp_bwd(packed, stash, xyz_cano, rgb, g_sigma, g_rgb, cidx=None, count=None, n_max=None, want_g_xyz=True):
+def _grad_target(g_params, dev):
+    """Gradient vector the wgrad kernel accumulates into: a fresh zeroed one, or the caller's persistent buffer
+    (`NeRF.attach_flat_grad`), whose head-layer scratch tail is cleared first -- the chain rule back to the two
+    nn.Linear of the fused head layer adds this call's dW', db' only."""
+    if g_params is None:
+        return torch.zeros(mlp_grad_floats(), device=dev)
+    assert g_params.numel() == mlp_grad_floats() and g_params.is_contiguous() and g_params.dtype == torch.float32
+    g_params[FLAT_FLOATS:].zero_()
+    return g_params
+
+
+FLAT_FLOATS = 592388          # mlp_layout.cuh: parameters of one NeRF (the gradient vector's head)
+
+
+def mlp_bwd(packed, stash, xyz_cano, rgb, g_sigma, g_rgb, cidx=None, count=None, n_max=None, want_g_xyz=True, g_params=None):
     if n_max is None:
         n_max = xyz_cano.numel() // 3
     dev = xyz_cano.device
-    g_params = torch.zeros(mlp_grad_floats(), device=dev)
+    g_params = _grad_target(g_params, dev)
     g_xyz = torch.zeros_like(xyz_cano) if want_g_xyz else None
     nscr = _lib.load().an_mlp_bwd_scratch_bytes(int(n_max))
     scratch = torch.empty(nscr + 128, device=dev, dtype=torch.uint8)
@@ -275,8 +289,7 @@ def mlp_bwd_dgrad(packed, stash, xyz_cano, rgb, g_sigma, g_rgb, scratch, cidx=No
 def mlp_bwd_wgrad(packed, stash, scratch, cidx=None, count=None, n_max=None, g_params=None, bias_scale=None):
     """dW/db of every layer from the images in `stash` (X) and `scratch` (dY); accumulates into g_params.
     bias_scale (n_max, compact order): db = sum_p bias_scale[p] dY_p instead of the plain column sums."""
-    if g_params is None:
-        g_params = torch.zeros(mlp_grad_floats(), device=stash.device)
+    g_params = _grad_target(g_params, stash.device)
     if bias_scale is None:
         call("an_mlp_bwd_wgrad", ptr(packed), ptr(stash), ptr(scratch), ptr(cidx), ptr(count), int(n_max), ptr(g_params), stream())
     else:

@@ -15,12 +15,60 @@ from ._lib import call, ptr, stream
 _MAX = 64
 
 
+class FlatGradBuffer:
+    """One contiguous fp32 buffer holding every gradient of a training step: per NeRF the gradient vector the
+    weight-gradient kernel writes (an_mlp_grad_floats: 592 388 parameters + the fused head layer's scratch), then
+    any further parameters (the per-frame SMPL table of `optim_body_params`: <= 114 x 75 + 10 floats).
+    `NeRF.attach_flat_grad` makes the MLP parameters' `.grad` views of it and routes the kernels' accumulation
+    there; `zero()` is the step's one memset, `all_reduce()` the step's one exchange (NCCL all-reduce of
+    the flat bucket, averaged; the body-parameter gradients ride in the same bucket)."""
+
+    def __init__(self, nets, extra_params=()):
+        from . import ops
+        nets = list(dict.fromkeys(nets))              # share_fine: nerf_fine is nerf
+        extra = [p for p in extra_params if p.requires_grad]
+        dev = next(nets[0].parameters()).device
+        gf = ops.mlp_grad_floats()
+        per_net = (gf + 3) // 4 * 4                   # 16-byte aligned regions
+        sizes = [(p.numel() + 3) // 4 * 4 for p in extra]
+        self.buf = torch.zeros(per_net * len(nets) + sum(sizes), device=dev)
+        self.nets, self.extra = nets, extra
+        o = 0
+        for net in nets:
+            net.attach_flat_grad(self.buf[o:o + gf])
+            o += per_net
+        for p, n in zip(extra, sizes):
+            p.grad = self.buf[o:o + p.numel()].view_as(p)
+            o += n
+
+    def zero(self):
+        self.buf.zero_()
+
+    def all_reduce(self, world=None):
+        import torch.distributed as dist
+        world = world or (dist.get_world_size() if dist.is_initialized() else 1)
+        if world > 1:
+            dist.all_reduce(self.buf, op=dist.ReduceOp.AVG)
+
+    def detach(self):
+        for net in self.nets:
+            net.attach_flat_grad(None)
+
+
 class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
             raise ValueError("invalid Adam hyper-parameter")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._g = {}        # group index -> dict(lr_t, lr_host, chunks: list of dict(step, done))
+        self.flat = None    # FlatGradBuffer when the gradients live in one buffer (zero_grad is then one memset)
+        self.on_step = []   # callbacks after every update (the NeRFs' packed-weight invalidation)
+
+    def zero_grad(self, set_to_none=True):
+        if self.flat is not None:
+            self.flat.zero()       # .grad tensors are views of the flat buffer: they must stay in place
+            return
+        super().zero_grad(set_to_none=set_to_none)
 
     def _gstate(self, gi, device, n_chunks):
         st = self._g.get(gi)
@@ -85,4 +133,6 @@ class FusedAdam(torch.optim.Optimizer):
                      float(group["lr"]), float(b1), float(b2), float(1.0 - b1), float(1.0 - b2), float(group["eps"]),
                      float(group["weight_decay"]),
                      ptr(cs["done"]), stream())
+        for fn in self.on_step:
+            fn()
         return loss

@@ -27,17 +27,33 @@ from .volume_rendering import VolumeRenderer
 
 
 def default_hparams(**over):
-    """The hot-path-relevant keys of reference config.py / male-3-casual.yaml."""
-    hp = dict(model_path="smplx/models", model_type="smpl", gender="male", freqs_xyz=10, freqs_dir=0,
+    """The hot-path-relevant keys with the values of reference config.py:7-78 merged with
+    configs/people_snapshot/male-3-casual.yaml (freqs_dir 0, n_importance 32), in the reference's own schema:
+    `train.optimizer` / `train.scheduler` are nested nodes (`.type`, `.weight_decay`, `.poly_exp`)."""
+    hp = dict(model_path="./smplx/models", model_type="smpl", gender="male", freqs_xyz=10, freqs_dir=0,
               use_view=False, k_neigh=4, use_knn=True, use_unpose=True, unpose_view=False, use_deformation=False,
               deformation_dim=0, apperance_dim=0, latent_dim=0, use_fine=True, share_fine=False, dis_threshold=0.2,
-              query_inside=False, n_samples=64, n_importance=32, n_depth=0, chunk=None, white_bkgd=True,
-              optim_body_params=False, num_frames=1,
+              query_inside=False, n_samples=64, n_importance=32, n_depth=0, chunk=2048, white_bkgd=True,
+              optim_body_params=True, num_frames=1,
               train=SimpleNamespace(lr=5e-4, lambda_alphas=0.1, lambda_foreground=0.01, lambda_background=0.01,
-                                    lambda_normals=0.01, epsilon=0.02, optimizer="adam", weight_decay=0.0,
-                                    max_epochs=20, scheduler="poly", poly_exp=0.9))
+                                    lambda_normals=0.01, epsilon=0.01, max_epochs=30,
+                                    optimizer=SimpleNamespace(type="adam", momentum=0.9, weight_decay=0),
+                                    scheduler=SimpleNamespace(type="poly", poly_exp=0.9)))
     hp.update(over)
     return SimpleNamespace(**hp)
+
+
+def _node(cfg, name, key, default=None):
+    """`cfg.<name>.<key>` of the reference's nested schema (config.py:67-68; yacs CfgNode, dict or namespace), also
+    accepting the flat spelling `cfg.<name>` = value / `cfg.<key>`."""
+    node = getattr(cfg, name, None)
+    if node is not None and not isinstance(node, (str, int, float)):
+        if isinstance(node, dict):
+            return node.get(key, default)
+        return getattr(node, key, default)
+    if key == "type" and node is not None:
+        return node
+    return getattr(cfg, key, default)
 
 
 class AnimNeRFSystem(nn.Module):
@@ -92,9 +108,8 @@ class AnimNeRFSystem(nn.Module):
         missing = [k for k in res.missing_keys if not k.startswith(derived) and not k.startswith("body_model_params.")]
         if strict and (missing or res.unexpected_keys):
             raise RuntimeError("reference checkpoint does not match: missing %s unexpected %s" % (missing, res.unexpected_keys))
-        for net in (self.anim_nerf.nerf, getattr(self.anim_nerf, "nerf_fine", None)):
-            if net is not None:
-                net.mark_dirty()
+        self.anim_nerf.body_model.refresh_derived()       # joint template / tree follow the loaded model buffers
+        self.mark_weights_dirty()
         return missing, dropped
 
     def forward(self, rays, body_model_params, body_model_params_template, latent_code=None, perturb=1.0, noise=None):
@@ -110,28 +125,54 @@ class AnimNeRFSystem(nn.Module):
                 results[k].append(v)
         return {k: torch.cat(v, 1).view(bs, h, w, v[0].shape[-1]) for k, v in results.items()}
 
-    def configure_optimizers(self):
+    def nets(self):
+        a = self.anim_nerf
+        return [a.nerf] + ([a.nerf_fine] if a.use_fine and not a.share_fine else [])
+
+    def configure_optimizers(self, flat_grads=None):
         """train.py:217-226 + utils/__init__.py:33-58: Adam(eps 1e-8) on the MLPs at lr, on the SMPL table at lr/2 when
-        it is optimised; per-epoch poly decay (1 - epoch/max_epochs)**poly_exp."""
+        it is optimised; per-epoch poly decay (1 - epoch/max_epochs)**poly_exp.  Reads the reference's own config
+        schema (train.optimizer.{type,weight_decay}, train.scheduler.{type,poly_exp}; config.py:67-68).
+        On CUDA the update is `FusedAdam` (one an_adam_step launch per group) and, unless flat_grads=False, the
+        gradients live in one `FlatGradBuffer` (`self.flat_grads`): the weight-gradient kernels accumulate into it,
+        `optimizer.zero_grad()` is one memset, a data-parallel step all-reduces it in one call."""
         hp = self.hparams
-        groups = [{"params": self.anim_nerf.parameters(), "lr": hp.train.lr}]
-        if hp.optim_body_params:
-            groups.append({"params": self.body_model_params.parameters(), "lr": hp.train.lr * 0.5})
-        if hp.train.optimizer != "adam":
-            raise NotImplementedError("train.optimizer = 'adam' (every shipped config)")
-        groups = [dict(g, params=list(g["params"])) for g in groups]
+        tr = hp.train
+        opt_type = _node(tr, "optimizer", "type", "adam")
+        wd = float(_node(tr, "optimizer", "weight_decay", 0.0) or 0.0)
+        if opt_type != "adam":
+            raise NotImplementedError("train.optimizer.type = 'adam' (every shipped config); got %r" % (opt_type,))
+        groups = [{"params": list(self.anim_nerf.parameters()), "lr": tr.lr}]
+        body = [p for p in self.body_model_params.parameters() if p.requires_grad] if hp.optim_body_params else []
+        if body:
+            groups.append({"params": body, "lr": tr.lr * 0.5})
         on_gpu = all(p.is_cuda for g in groups for p in g["params"])
-        if on_gpu and getattr(hp.train, "fused_adam", True):           # same update, one an_adam_step launch per group
-            from .optim import FusedAdam
-            self.optimizer = FusedAdam(groups, lr=hp.train.lr, eps=1e-8, weight_decay=hp.train.weight_decay)
+        nets = self.nets()
+        if on_gpu and getattr(tr, "fused_adam", True):
+            from .optim import FlatGradBuffer, FusedAdam
+            self.optimizer = FusedAdam(groups, lr=tr.lr, eps=1e-8, weight_decay=wd)
+            if flat_grads is None or flat_grads:
+                self.flat_grads = FlatGradBuffer(nets, body)
+                self.optimizer.flat = self.flat_grads
+            self.optimizer.on_step.append(self.mark_weights_dirty)
         else:               # host-logic tests on CPU tensors
-            self.optimizer = torch.optim.Adam(groups, lr=hp.train.lr, eps=1e-8, weight_decay=hp.train.weight_decay)
+            self.optimizer = torch.optim.Adam(groups, lr=tr.lr, eps=1e-8, weight_decay=wd)
+            self.optimizer.register_step_post_hook(lambda *_: self.mark_weights_dirty())
         sched = []
-        if getattr(hp.train, "scheduler", None) == "poly":
-            self.scheduler = torch.optim.lr_scheduler.LambdaLR(
-                self.optimizer, lambda epoch: (1 - epoch / hp.train.max_epochs) ** hp.train.poly_exp)
+        sched_type = _node(tr, "scheduler", "type", None)
+        if sched_type == "poly":
+            poly_exp, max_epochs = float(_node(tr, "scheduler", "poly_exp", 0.9)), tr.max_epochs
+            self.scheduler = torch.optim.lr_scheduler.LambdaLR(self.optimizer, lambda epoch: (1 - epoch / max_epochs) ** poly_exp)
             sched = [self.scheduler]
+        elif sched_type not in (None, "none"):
+            raise NotImplementedError("train.scheduler.type = 'poly' (every shipped config); got %r" % (sched_type,))
         return [self.optimizer], sched
+
+    def mark_weights_dirty(self):
+        """The optimiser moved the weights: the bf16 images the kernels read are repacked on their next use, in any
+        grad mode (FusedAdam / graph replays write the parameters through raw pointers, invisible to `Tensor._version`)."""
+        for net in self.nets():
+            net.mark_dirty()
 
     def compute_loss(self, rgbs, alphas, results, frame_idx=None, latent_code=None, fg_points=None, bg_points=None,
                      with_regularizers=True):

@@ -164,7 +164,7 @@ def sample_coarse(rays, n_coarse, perturb=0.0, noise=None):
     """Stratified depths (B,R,Kc), linear in depth between near and far*(1-1/Kc).
     `noise` = the U[0,1) tensor the reference draws with torch.rand (explicit for parity)."""
     near, far = rays[..., 6:7], rays[..., 7:8]
-    t = torch.linspace(0, 1 - 1.0 / n_coarse, n_coarse)
+    t = torch.linspace(0, 1 - 1.0 / n_coarse, n_coarse).to(rays.device)
     z = near * (1 - t) + far * t
     if perturb > 0:
         mid = 0.5 * (z[..., 1:] + z[..., :-1])
@@ -189,10 +189,13 @@ def sample_fine(bins, weights, n_fine, det, u=None, eps=1e-5, inds=None):
     pdf = w / torch.sum(w, -1, keepdim=True)
     cdf = torch.cat([torch.zeros_like(pdf[..., :1]), torch.cumsum(pdf, -1)], -1)
     if det:
-        u = torch.linspace(0.0, 1.0, n_fine).expand(*bins.shape[:-1], n_fine)
+        u = torch.linspace(0.0, 1.0, n_fine).to(bins.device).expand(*bins.shape[:-1], n_fine)
     u = u.contiguous()
     if inds is None:
-        inds = torch.from_numpy(searchsorted_right(cdf.numpy(), u.numpy()))
+        if cdf.is_cuda:      # CUDA tensors (bench.py's gpu_eager_baseline): the reference's own call, volume_rendering.py:85
+            inds = torch.searchsorted(cdf, u, right=True)
+        else:
+            inds = torch.from_numpy(searchsorted_right(cdf.numpy(), u.numpy()))
     below = torch.clamp(inds - 1, min=0)
     above = torch.clamp(inds, max=n_bins - 1)
     c0, c1 = torch.gather(cdf, -1, below), torch.gather(cdf, -1, above)
@@ -258,24 +261,43 @@ def knn(verts, xyz, k=4):
 
 
 # ------------------------------------------------------------------------- unpose
+def knn_cdist(verts, xyz, k=4, chunk=16384):
+    """The `knn_cuda` stand-in of the reference run on torch tensors of any device:
+    torch.cdist(query, ref, compute_mode='donot_use_mm_for_euclid_dist').topk(k, largest=False), chunked over the
+    queries.  verts (V,3), xyz (N,3) -> dist (N,k), idx (N,k) int64.  Used for CUDA tensors (bench.py's
+    gpu_eager_baseline); CPU tensors go through the C / numpy restatement of the contract (`knn`)."""
+    ds, is_ = [], []
+    with torch.no_grad():
+        for s in range(0, xyz.shape[0], chunk):
+            d = torch.cdist(xyz[s:s + chunk][None], verts[None], compute_mode="donot_use_mm_for_euclid_dist")[0]
+            dd, ii = d.topk(k, dim=-1, largest=False)
+            ds.append(dd); is_.append(ii)
+    return torch.cat(ds, 0), torch.cat(is_, 0)
+
+
 def unpose(xyz, verts, ober2cano, lbs_weights, dis_threshold=0.2, k=4, weight_std=0.1):
     """xyz (B,N,3) body space -> (xyz_cano (B,N,3), valid (B,N,1) float, dist (B,N,k), idx (B,N,k)).
     Distances/indices are constants (the reference runs KNN under no_grad)."""
     B, N = xyz.shape[:2]
-    dist = np.empty((B, N, k), np.float32)
-    idx = np.empty((B, N, k), np.int64)
-    for b in range(B):
-        d, i = knn(verts[b].detach().numpy(), xyz[b].detach().numpy(), k)
-        dist[b], idx[b] = d, i
-    dist_t = torch.from_numpy(dist)
-    idx_t = torch.from_numpy(idx)
+    if xyz.is_cuda:
+        res = [knn_cdist(verts[b].detach(), xyz[b].detach(), k) for b in range(B)]
+        dist_t = torch.stack([r[0] for r in res], 0)
+        idx_t = torch.stack([r[1] for r in res], 0)
+    else:
+        dist = np.empty((B, N, k), np.float32)
+        idx = np.empty((B, N, k), np.int64)
+        for b in range(B):
+            d, i = knn(verts[b].detach().numpy(), xyz[b].detach().numpy(), k)
+            dist[b], idx[b] = d, i
+        dist_t = torch.from_numpy(dist)
+        idx_t = torch.from_numpy(idx)
     W = lbs_weights[idx_t]                                            # (B,N,k,24)
     l1 = torch.sum(torch.abs(W - W[..., 0:1, :]), dim=-1)
     conf = (torch.exp(-l1 / (2.0 * weight_std ** 2)) > 0.9).float()
     q = torch.exp(-dist_t) * conf
     q = q / q.sum(-1, keepdim=True)
     flat = ober2cano.reshape(B * ober2cano.shape[1], 4, 4)
-    M = flat[idx_t + (torch.arange(B) * ober2cano.shape[1])[:, None, None]]   # (B,N,k,4,4)
+    M = flat[idx_t + (torch.arange(B, device=idx_t.device) * ober2cano.shape[1])[:, None, None]]   # (B,N,k,4,4)
     That = torch.sum(q[..., None, None] * M, dim=2)
     dbar = torch.sum(q * dist_t, dim=2, keepdim=True)
     valid = (dbar < dis_threshold).float()

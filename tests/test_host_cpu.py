@@ -141,10 +141,46 @@ def test_body_model_params_table_and_optimiser_groups():
     assert [g["lr"] for g in opt.param_groups] == [5e-4, 2.5e-4]
     assert len(opt.param_groups[0]["params"]) == 48 and len(opt.param_groups[1]["params"]) == 4
     opt.step(); sched.step()
-    assert abs(opt.param_groups[0]["lr"] - 5e-4 * (1 - 1 / 20) ** 0.9) < 1e-12
-    frozen = _system(num_frames=F)                               # optim_body_params=False: table frozen, one group
+    assert abs(opt.param_groups[0]["lr"] - 5e-4 * (1 - 1 / 30) ** 0.9) < 1e-12      # config.py:64 max_epochs = 30
+    frozen = _system(num_frames=F, optim_body_params=False)      # table frozen, one group
     assert not any(p.requires_grad for p in frozen.body_model_params.parameters())
     assert len(frozen.configure_optimizers()[0][0].param_groups) == 1
+
+
+def test_system_builds_and_configures_from_the_reference_config_schema():
+    """The drop-in claim of B4: the system is constructed from a namespace shaped like the reference's
+    `get_default_config()` merged with male-3-casual.yaml (config.py:7-78: nested train.optimizer / train.scheduler
+    nodes, optim_body_params True, chunk 2048, epsilon 0.01, max_epochs 30) and `configure_optimizers` honours it;
+    the package's own defaults agree with those values."""
+    from types import SimpleNamespace as NS
+    from anim_nerf_b200.system import AnimNeRFSystem, default_hparams
+    cfg = NS(num_gpus=-1, exp_name="male-3-casual", dataset_name="anim_nerf", root_dir="./data/people_snapshot/male-3-casual",
+             model_type="smpl", gender="male", model_path="./smplx/models", img_wh=(512, 512), freqs_xyz=10, freqs_dir=0,
+             use_view=False, use_knn=True, k_neigh=4, use_unpose=True, unpose_view=False, use_deformation=False,
+             deformation_dim=0, apperance_dim=0, latent_dim=0, pose_dim=69, optim_body_params=True, dis_threshold=0.2,
+             n_samples=64, n_importance=32, n_depth=0, share_fine=False, chunk=2048, query_inside=False, white_bkgd=True,
+             num_frames=4, frame_IDs=[1, 5, 9, 13],
+             train=NS(lambda_alphas=0.1, lambda_foreground=0.01, lambda_background=0.01, lambda_normals=0.01, lambda_cycle=0.1,
+                      epsilon=0.01, batch_size=16, max_epochs=30, max_steps=200000, lr=5e-4,
+                      optimizer={"type": "adam", "momentum": 0.9, "weight_decay": 0},          # a CfgNode is a dict subclass
+                      scheduler=NS(type="poly", poly_exp=0.9), num_workers=8))
+    sysm = AnimNeRFSystem(cfg, body_model_data=synthetic.make_smpl_dict(0))
+    (opt,), (sched,) = sysm.configure_optimizers()
+    assert [g["lr"] for g in opt.param_groups] == [5e-4, 2.5e-4] and opt.defaults["weight_decay"] == 0 and opt.defaults["eps"] == 1e-8
+    opt.step(); sched.step(); sched.step()
+    assert abs(opt.param_groups[1]["lr"] - 2.5e-4 * (1 - 2 / 30) ** 0.9) < 1e-12
+    cfg.train.optimizer = {"type": "sgd", "momentum": 0.9, "weight_decay": 0}
+    with pytest.raises(NotImplementedError):
+        sysm.configure_optimizers()
+    d = default_hparams()
+    for k in ("freqs_xyz", "freqs_dir", "k_neigh", "use_knn", "use_unpose", "optim_body_params", "dis_threshold", "n_samples",
+              "n_importance", "n_depth", "share_fine", "chunk", "query_inside", "white_bkgd"):
+        assert getattr(d, k) == getattr(cfg, k), k
+    for k in ("lambda_alphas", "lambda_foreground", "lambda_background", "lambda_normals", "epsilon", "max_epochs", "lr"):
+        assert getattr(d.train, k) == getattr(cfg.train, k), k
+    # a missing model file is an error, not a silently substituted synthetic body
+    with pytest.raises(FileNotFoundError):
+        AnimNeRFSystem(cfg)
 
 
 def test_decode_batch_accepts_the_reference_datasets_flat_keys():

@@ -35,7 +35,26 @@ def _worker(rank, world, port, q):
         a5, b5 = du.shard_range(n, rank, world)
         img = torch.arange(n * 4, dtype=torch.float32).view(n, 4)
         ok_gather = ok_gather and torch.equal(du.gather_slabs(img[a5:b5].clone(), n), img)
-    q.put((rank, ok_grad, (a, b), ok_gather))
+        # interleaved rows (rank r: r, r+world, ...): gathered back in image order, also when n % world != 0
+        rows = du.shard_rows(n, rank, world)
+        ok_gather = ok_gather and rows == list(range(rank, n, world)) and torch.equal(du.gather_rows(img[rows].clone(), n), img)
+    # the training exchange: ONE all-reduce (average) of the flat gradient buffer the kernels accumulate into --
+    # both MLPs' gradient vectors and the SMPL table's rows; afterwards every parameter's .grad (a view) is the mean
+    from anim_nerf_b200.optim import FlatGradBuffer
+    net2 = NeRF(freqs_dir=0, use_view=False)
+    table = torch.nn.Parameter(torch.zeros(7, 69))
+    frozen = torch.nn.Parameter(torch.zeros(3), requires_grad=False)
+    fb = FlatGradBuffer([net, net2], [table, frozen])
+    ok_flat = frozen.grad is None and table.grad.data_ptr() >= fb.buf.data_ptr()
+    for i, p in enumerate(list(net.parameters()) + list(net2.parameters()) + [table]):
+        ok_flat = ok_flat and p.grad.data_ptr() >= fb.buf.data_ptr() and p.grad.shape == p.shape
+        p.grad.fill_(float(rank + 1) * (i + 1))
+    fb.all_reduce(world)
+    for i, p in enumerate(list(net.parameters()) + list(net2.parameters()) + [table]):
+        ok_flat = ok_flat and torch.allclose(p.grad, torch.full_like(p, (world + 1) / 2.0 * (i + 1)))
+    fb.zero()
+    ok_flat = ok_flat and float(table.grad.abs().sum()) == 0.0 and float(net.sigma.weight.grad.abs().sum()) == 0.0
+    q.put((rank, ok_grad and ok_flat, (a, b), ok_gather))
     dist.destroy_process_group()
 
 

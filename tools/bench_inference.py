@@ -76,8 +76,8 @@ def main():
     def frame_fn(H, W):
         cam = synthetic.make_camera(W, H)
         cam_d = [torch.from_numpy(cam[k])[None].to(dev) for k in ("c2w", "focal", "c")]
-        rows = dist_utils.shard_range(H, rank, world)
-        host = {k: torch.empty(1, rows[1] - rows[0], W, c, pin_memory=True)
+        n_rows = len(dist_utils.shard_rows(H, rank, world))
+        host = {k: torch.empty(1, n_rows, W, c, pin_memory=True)
                 for k, c in (("rgbs_fine", 3), ("alphas_fine", 1), ("depths_fine", 1))}
 
         def fn(i=0):
