@@ -57,7 +57,20 @@ def build_oracle():
     return out
 
 
+def build_testlib():
+    """Compile tests/csrc/*.cu (on-device fp32 reference kernels used by the GPU tests only) into
+    tests/libanimnerf_b200_ref.so -- test infrastructure, kept out of the product library."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    srcs = sorted(glob.glob(os.path.join(ROOT, "tests", "csrc", "*.cu")))
+    out = os.path.join(ROOT, "tests", "libanimnerf_b200_ref.so")
+    hdrs = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(ROOT, "include", "animnerf_b200.h")]
+    if srcs and _newer(out, srcs + hdrs):
+        subprocess.check_call([nvcc] + NVCC_FLAGS + ["-shared", "-o", out] + srcs + ["-lcudart"])
+    return out
+
+
 if __name__ == "__main__":
     build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv)
     build_oracle()
+    build_testlib()
     print(LIB)

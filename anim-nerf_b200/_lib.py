@@ -27,12 +27,11 @@ SIGNATURES = {
     "an_knn_unpose_fwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _i32,
                                  _vp, _vp, _vp, _i32,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "an_debug_knn_variant": (_i32, [_i32]),
     "an_knn_unpose_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "an_mlp_packed_bytes": (_i64, []),
     "an_mlp_pack": (_i32, [_vp, _vp, _vp, _vp]),
     "an_mlp_stash_bytes": (_i64, [_i64]),
-    "an_mlp_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
+    "an_mlp_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "an_mlp_grad_floats": (_i64, []),
     "an_mlp_bwd_scratch_bytes": (_i64, [_i64]),
     "an_mlp_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

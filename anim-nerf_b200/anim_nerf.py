@@ -62,7 +62,6 @@ class AnimNeRF(nn.Module):
         self.dis_threshold, self.query_inside = dis_threshold, query_inside
         self.weight_std = 0.1
         self.knn_mode = 1          # 1 = grid-pruned exact search (default), 0 = exhaustive
-        self.mlp_impl = 0          # 0 = tcgen05 kernel; 1 = fp32 SIMT reference (tests only)
         self.fused_tables = True   # per-frame tables on the kernels (forward and backward); False: differentiable torch builder
         if body_model_data is None:
             import os
@@ -191,7 +190,7 @@ class AnimNeRF(nn.Module):
             self._grid = (ops.vertex_grid(verts, self.dis_threshold) if self.knn_mode == 1 else None, self.dis_threshold)
         net = self.nerf_fine if use_fine else self.nerf
         return dict(verts=verts, lbs=self.body_model.lbs_weights, grid=self._grid[0], thr=float(self.dis_threshold),
-                    net=net, knn_mode=self.knn_mode, mlp_impl=self.mlp_impl, unpose=self.use_unpose,
+                    net=net, knn_mode=self.knn_mode, unpose=self.use_unpose,
                     grad=torch.is_grad_enabled())
 
     def render_pass(self, rays, z, use_fine=False, sigma_noise=None, white_bkgd=True, want_seed=False, seed=None):

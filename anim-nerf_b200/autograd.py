@@ -27,7 +27,7 @@ def _param_grads(net, g_flat, sink):
 class RenderPass(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rays, z, ober2cano, sigma_noise, cfg, *params):
-        """rays (B,R,8) body space, z (B,R,K); cfg = dict(verts, lbs, grid, thr, net, white, knn_mode, mlp_impl)."""
+        """rays (B,R,8) body space, z (B,R,K); cfg = dict(verts, lbs, grid, thr, net, white, knn_mode)."""
         net = cfg["net"]
         B, R, K = z.shape
         dev = z.device
@@ -49,7 +49,7 @@ class RenderPass(torch.autograd.Function):
         packed = net.packed()
         stash = ops.mlp_stash(B * R * K, dev) if need_grad else None
         ops.mlp_fwd(packed, out["xyz_cano"], sigma, rgb, cidx=out["cidx"], count=out["count"], n_max=B * R * K,
-                    stash=stash, impl=cfg.get("mlp_impl", 0))
+                    stash=stash)
         w, rgb_o, depth, acc = ops.composite(sigma, rgb, z_c, rays_c, cfg["white"], sigma_noise)
         if need_grad:
             ctx.cfg = cfg
@@ -139,10 +139,10 @@ class PointQuery(torch.autograd.Function):
                                  mode=cfg.get("knn_mode", 1), want_idx=need_grad, want_qw=need_grad,
                                  sigma=sigma, rgb=rgb, compact=True)
             ops.mlp_fwd(packed, out["xyz_cano"], sigma, rgb, cidx=out["cidx"], count=out["count"], n_max=B * N,
-                        stash=stash, impl=cfg.get("mlp_impl", 0))
+                        stash=stash)
         else:
             o2c_c, out = None, dict(xyz_cano=xyz_c, cidx=None, count=None)
-            ops.mlp_fwd(packed, xyz_c, sigma, rgb, n_max=B * N, stash=stash, impl=cfg.get("mlp_impl", 0))
+            ops.mlp_fwd(packed, xyz_c, sigma, rgb, n_max=B * N, stash=stash)
         if need_grad:
             ctx.cfg, ctx.packed, ctx.stash, ctx.aux = cfg, packed, stash, out
             ctx.save_for_backward(xyz_c, o2c_c if o2c_c is not None else torch.empty(0), rgb)

@@ -505,22 +505,28 @@ __device__ __forceinline__ bool row_range(const RowCtx& c, int r, const int* __r
     return x0 <= x1;
 }
 
-// VAR 1: nested loops, no shared memory (each lane walks its rows and candidates on its own).
-// VAR 3: rows listed in lockstep into a CAP-entry shared-memory list per thread, then one flat loop in
-//        which every lane that still has a candidate evaluates it; the list is refilled (with the
-//        tightened bound) until the rows run out.
+// Rows are listed in lockstep into a CAP-entry shared-memory list per thread, then one flat loop in which every
+// lane that still has a candidate evaluates it; the list is refilled (with the tightened bound) until the rows
+// run out.  (A variant with nested per-lane loops and no shared memory was measured and dropped: 1.6x slower.)
 // 8 CTAs of 128 threads per SM (64 registers): the search is bound by L2 gather latency (69 % long-scoreboard
 // stalls at 24 resident warps), 32 resident warps hide more of it: 0.71 -> 0.60 ms coarse, 0.82 -> 0.69 ms fine pass
 #ifndef AN_KNN_MINB
 #define AN_KNN_MINB 8
 #endif
-template <int VAR, int CAP>
+#define SEARCH_CAP 16          // row-list entries per thread and round (8 and 50 measured: within 3 %)
+#define SEARCH_DRAIN 8         // lanes left at which the warp drains the remaining lists cooperatively
+#ifdef AN_KNN_STATS            // candidate statistics for tools/bench_knn.py (variant build only)
+#define KNN_STAT(x) x
+#else
+#define KNN_STAT(x)
+#endif
 __global__ void __launch_bounds__(SEARCH_THREADS, AN_KNN_MINB)
 knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, const char* __restrict__ ws,
                   int64_t frame_bytes, QueryWs* __restrict__ qws, const float* __restrict__ ober2cano,
-                  const float* __restrict__ lbsw, int J, float thr, SeedIn sd, UnposeOut o, int want_stats, int drain_t)
+                  const float* __restrict__ lbsw, int J, float thr, SeedIn sd, UnposeOut o)
 {
-    // VAR 3: per-thread list of candidate ranges, layout [entry][thread] (bank = thread: conflict-free for any
+    constexpr int CAP = SEARCH_CAP;
+    // per-thread list of candidate ranges, layout [entry][thread] (bank = thread: conflict-free for any
     // per-lane entry index): .x = start | end << 16 (positions in the cell-sorted table), .y = row slab gap^2
     extern __shared__ uint2 s_ent[];
     const float4* __restrict__ work = (const float4*)(qws + 1);
@@ -529,7 +535,7 @@ knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, cons
     const unsigned n_chunks = (n_work + 31) / 32;
     const float thr2 = thr * thr * (1.0f + 1e-5f);   // prune only what is invalid beyond rounding doubt
     uint2* __restrict__ my_ent = s_ent + threadIdx.x;
-    unsigned n_cand = 0, n_iter = 0, n_redo = 0;   // statistics (tools/bench_knn.py)
+    KNN_STAT(unsigned n_cand = 0; unsigned n_iter = 0; unsigned n_redo = 0;)
     for (;;) {
         unsigned chunk = 0;
         if (lane == 0) chunk = atomicAdd(&qws->next_chunk, 1u);
@@ -570,7 +576,7 @@ knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, cons
         {   // cold lanes -- own cell: usually yields four candidates and a tight bound
             int p = 0, pe = 0;
             if (did_own) { const int c = (cz * h.ny + cy) * h.nx + cx; p = __ldg(cell_start + c); pe = __ldg(cell_start + c + 1); }
-            n_cand += (unsigned)(pe - p);
+            KNN_STAT(n_cand += (unsigned)(pe - p);)
             for (; p < pe; ++p) {
                 const float4 v = __ldg(sorted + p);
                 const float d2 = dist2_rn(qx, qy, qz, v.x, v.y, v.z);
@@ -602,36 +608,7 @@ knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, cons
         rc.qx = qx; rc.fy = qy - (h.oy + cy * h.cell); rc.fz = qz - (h.oz + cz * h.cell);
         rc.ox = h.ox; rc.cell = h.cell; rc.inv_cell = inv_cell; rc.cx = cx; rc.cy = cy; rc.cz = cz;
         rc.nx = h.nx; rc.ny = h.ny; rc.nz = h.nz;
-        if (VAR == 1) {
-            if (active) {
-                for (int r = 0; r < N_ROWS; ++r) {
-                    const int ring = c_row_ring[r];
-                    if (ring >= 2) {                  // nearest row of ring k is at least (k-1) cells away
-                        const float rg = (float)(ring - 1) * h.cell;
-                        if (rg * rg > Bm) break;
-                    }
-                    float g2; int row, x0, x1;
-                    rc.Bm = Bm;
-                    if (!row_range(rc, r, cell_start, g2, row, x0, x1)) continue;
-                    // candidate ranges of the row; an own cell scanned above (row 0) is skipped
-                    int s0 = __ldg(cell_start + row + x0), e0r, s1, e1 = __ldg(cell_start + row + x1 + 1);
-                    if (r == 0 && did_own && cx >= x0 && cx <= x1) { e0r = __ldg(cell_start + row + cx); s1 = __ldg(cell_start + row + cx + 1); }
-                    else { e0r = e1; s1 = e1; }
-                    for (int part = 0; part < 2; ++part) {
-                        const int ps = part ? s1 : s0, pe = part ? e1 : e0r;
-                        n_cand += (unsigned)max(pe - ps, 0);
-                        for (int p = ps; p < pe; ++p) {
-                            const float4 v = __ldg(sorted + p);
-                            const float d2 = dist2_rn(qx, qy, qz, v.x, v.y, v.z);
-                            if (best_accepts(mine, d2, __float_as_int(v.w))) {
-                                best_insert_sorted(mine, d2, __float_as_int(v.w));
-                                Bm = fminf(Bm, mine.d[3] * 1.001f);
-                            }
-                        }
-                    }
-                }
-            }
-        } else {
+        {
             int r = 0;                                // warp-uniform row cursor
             bool done = !active;                      // this lane's ball ends before the current ring
             for (;;) {
@@ -669,13 +646,13 @@ knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, cons
                         }
                     }
                     const unsigned live_mask = __ballot_sync(0xffffffffu, live);
-                    if (__popc(live_mask) <= drain_t) break;      // few lanes left: drain them cooperatively below
-                    ++n_iter;
+                    if (__popc(live_mask) <= SEARCH_DRAIN) break;      // few lanes left: drain them cooperatively below
+                    KNN_STAT(++n_iter;)
                     if (live) {               // two candidates per trip: both loads in flight before the first use
                         const bool two = p + 1 < pe;
                         const float4 v0 = __ldg(sorted + p), v1 = __ldg(sorted + (two ? p + 1 : p));
                         p += 2;
-                        n_cand += two ? 2u : 1u;
+                        KNN_STAT(n_cand += two ? 2u : 1u;)
                         const float d0 = dist2_rn(qx, qy, qz, v0.x, v0.y, v0.z);
                         const float d1 = two ? dist2_rn(qx, qy, qz, v1.x, v1.y, v1.z) : CUDART_INF_F;
                         if (fminf(d0, d1) <= mine.d[3]) {          // cheap reject first: almost every candidate fails it
@@ -712,7 +689,7 @@ knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, cons
                         const int pos = up + lane;
                         const bool in = pos < upe;
                         up += 32;
-                        ++n_iter; n_cand += in ? 1u : 0u;
+                        KNN_STAT(++n_iter; n_cand += in ? 1u : 0u;)
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (in) v = __ldg(usorted + pos);
                         unsigned key = in ? __float_as_uint(dist2_rn(ux, uy, uz, v.x, v.y, v.z)) : 0x7f800000u;   // d2 >= 0: uint order == float order
@@ -739,7 +716,7 @@ knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, cons
         bool have4 = exact4;
         const bool redo = near_ && !exact4;            // rare: 4th neighbour not provably inside the scanned ball
         unsigned redo_mask = __ballot_sync(0xffffffffu, redo);
-        n_redo += redo ? 1 : 0;
+        KNN_STAT(n_redo += redo ? 1 : 0;)
         while (redo_mask) {                            // exhaustive rescan, warp-cooperative
             const int qi = __ffs(redo_mask) - 1;
             redo_mask &= redo_mask - 1;
@@ -757,10 +734,8 @@ knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, cons
         }
         unpose_epilogue(mine, have4, have4 && near_, qx, qy, qz, gid, b, V, J, ober2cano, lbsw, thr, o, active);
     }
-    if (want_stats) {
-        atomicAdd(&qws->stats[0], (unsigned long long)n_cand); atomicAdd(&qws->stats[1], (unsigned long long)n_iter);
-        atomicAdd(&qws->stats[2], (unsigned long long)n_redo);
-    }
+    KNN_STAT(atomicAdd(&qws->stats[0], (unsigned long long)n_cand); atomicAdd(&qws->stats[1], (unsigned long long)n_iter);
+             atomicAdd(&qws->stats[2], (unsigned long long)n_redo);)
 }
 
 // ------------------------------------------------------------------ backward
@@ -822,25 +797,16 @@ extern "C" int64_t an_knn_query_ws_bytes(int B, int64_t N)
     return (B > 0 && N > 0) ? (int64_t)sizeof(QueryWs) + (int64_t)B * N * (int64_t)sizeof(float4) : 0;
 }
 
-// Search-kernel variant (tools/bench_knn.py A/B switch; the default is the shipped one).
-static int g_knn_variant = 3 | (8 << 12);     // bits 0-7 kernel, 8 statistics, 12-17 drain threshold (lanes)
-extern "C" int an_debug_knn_variant(int v) { const int old = g_knn_variant; if (v > 0) g_knn_variant = v; return old; }
-
-template <int VAR, int CAP>
 static int launch_search(int sms, int64_t total, cudaStream_t st, int K, int64_t N, const float* verts, int V,
                          const char* grid_ws, int64_t frame_bytes, QueryWs* qws, const float* ober2cano,
-                         const float* lbsw, int J, float thr, SeedIn sd, UnposeOut o, int want_stats, int drain_t)
+                         const float* lbsw, int J, float thr, SeedIn sd, UnposeOut o)
 {
-    const int smem = VAR == 3 ? CAP * SEARCH_THREADS * 8 : 0;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(knn_search_kernel<VAR, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-    }
+    const int smem = SEARCH_CAP * SEARCH_THREADS * 8;
     // persistent search CTAs pull 32-query chunks from the work list (its length is device-side)
     int64_t sb = (total + SEARCH_THREADS - 1) / SEARCH_THREADS;
     if (sb > (int64_t)sms * 8) sb = (int64_t)sms * 8;
-    knn_search_kernel<VAR, CAP><<<(unsigned)sb, SEARCH_THREADS, smem, st>>>(
-        K, N, verts, V, grid_ws, frame_bytes, qws, ober2cano, lbsw, J, thr, sd, o, want_stats, drain_t);
+    knn_search_kernel<<<(unsigned)sb, SEARCH_THREADS, smem, st>>>(
+        K, N, verts, V, grid_ws, frame_bytes, qws, ober2cano, lbsw, J, thr, sd, o);
     AN_CHECK_LAUNCH();
     return AN_OK;
 }
@@ -891,15 +857,8 @@ extern "C" int an_knn_unpose_fwd(const float* xyz, const float* rays, const floa
             xyz, rays, z, K, N, total, verts, V, (const char*)grid_ws, grid_frame_bytes(V), qws, ober2cano, lbs_weights, J,
             dis_threshold, sd, o);
         AN_CHECK_LAUNCH();
-        const int var = g_knn_variant & 0xff, stats = (g_knn_variant >> 8) & 1, drain = (g_knn_variant >> 12) & 0x3f;
-        const char* gw = (const char*)grid_ws;
-        const int64_t fb = grid_frame_bytes(V);
-        int rc;
-        if (var == 1) rc = launch_search<1, 1>(sms, total, st, K, N, verts, V, gw, fb, qws, ober2cano, lbs_weights, J, dis_threshold, sd, o, stats, drain);
-        else if (var == 2) rc = launch_search<3, 50>(sms, total, st, K, N, verts, V, gw, fb, qws, ober2cano, lbs_weights, J, dis_threshold, sd, o, stats, drain);
-        else if (var == 4) rc = launch_search<3, 8>(sms, total, st, K, N, verts, V, gw, fb, qws, ober2cano, lbs_weights, J, dis_threshold, sd, o, stats, drain);
-        else rc = launch_search<3, 16>(sms, total, st, K, N, verts, V, gw, fb, qws, ober2cano, lbs_weights, J, dis_threshold, sd, o, stats, drain);
-        return rc;
+        return launch_search(sms, total, st, K, N, verts, V, (const char*)grid_ws, grid_frame_bytes(V), qws, ober2cano,
+                             lbs_weights, J, dis_threshold, sd, o);
     } else return AN_ERR_ARG;
     AN_CHECK_LAUNCH();
     return AN_OK;

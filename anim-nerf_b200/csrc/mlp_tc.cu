@@ -373,9 +373,6 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
     if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
 }
 
-int mlp_fwd_ref_launch(const void* packed, const float* xyz_cano, const int32_t* cidx, const int32_t* count,
-                       int64_t n_max, float* sigma, float* rgb, cudaStream_t stream);
-
 #ifdef AN_MLP_TRACE
 extern "C" int an_debug_trace_fwd(void* buf) {
     return (int)cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf));
@@ -397,14 +394,12 @@ static inline int pair_grid(int64_t n_max)
 }
 
 extern "C" int an_mlp_fwd(const void* packed, const float* xyz_cano, const int32_t* cidx, const int32_t* count,
-                          int64_t n_max, float* sigma, float* rgb, void* stash, int impl, void* stream)
+                          int64_t n_max, float* sigma, float* rgb, void* stash, void* stream)
 {
     if (!packed || !xyz_cano || !sigma || !rgb || n_max <= 0) return AN_ERR_ARG;
     if (cidx && !count) return AN_ERR_ARG;
     if (((uintptr_t)packed) & 1023) return AN_ERR_ALIGN;
     if (stash && (((uintptr_t)stash) & 127)) return AN_ERR_ALIGN;
-    if (impl == 1) return mlp_fwd_ref_launch(packed, xyz_cano, cidx, count, n_max, sigma, rgb, (cudaStream_t)stream);
-    if (impl != 0) return AN_ERR_ARG;
     cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);

@@ -218,12 +218,12 @@ def mlp_pack(weights, biases, packed=None):
     return view
 
 
-def mlp_fwd(packed, xyz_cano, sigma, rgb, cidx=None, count=None, n_max=None, stash=None, impl=0):
+def mlp_fwd(packed, xyz_cano, sigma, rgb, cidx=None, count=None, n_max=None, stash=None):
     """A9-A11 over compacted ids (or all n_max points when cidx is None); writes sigma/rgb in place."""
     if n_max is None:
         n_max = xyz_cano.numel() // 3
     call("an_mlp_fwd", ptr(packed), ptr(xyz_cano), ptr(cidx), ptr(count), int(n_max), ptr(sigma), ptr(rgb),
-         ptr(stash), int(impl), stream())
+         ptr(stash), stream())
 
 
 def mlp_stash(n_max, device):

@@ -226,18 +226,27 @@ def nerf_layer_shapes(W=256, in_xyz=63):
     return shapes
 
 
-def make_nerf_weights(seed, sigma_bias=5.0):
+def make_nerf_weights(seed, sigma_bias=5.0, trained_scale=False):
     """Deterministic nn.Linear-style init (U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight
     and bias) from numpy so fixtures do not depend on torch's RNG stream.  `sigma_bias`
     is added to the density head's bias: random-init sigma is ~0.016 and would render
-    pure white."""
+    pure white.
+    trained_scale=True: a stand-in for a trained network's dynamic range -- the trunk / final / colour-branch
+    weights are scaled by 2.7 (just above the critical ReLU gain, so the output varies strongly with the input),
+    the density head by 40 with bias 25: over canonical points in [-1,1]^3 sigma then spans about -13 .. 76
+    (1st..99th percentile; max > 100) and rgb 0.15 .. 0.95, instead of 5.016 +- 0.003 and 0.5 +- 0.02."""
     rs = np.random.RandomState(seed)
     out = {}
     for name, (o, i) in nerf_layer_shapes().items():
         bound = 1.0 / math.sqrt(i)
         w = rs.uniform(-bound, bound, size=(o, i)).astype(np.float32)
         b = rs.uniform(-bound, bound, size=(o,)).astype(np.float32)
-        if name == "sigma":
+        if trained_scale:
+            if name == "sigma":
+                w, b = w * np.float32(40.0), b * 0 + np.float32(25.0)
+            elif name != "rgb.0":
+                w = w * np.float32(2.7)
+        elif name == "sigma":
             b = b + np.float32(sigma_bias)
         out[name + ".weight"] = w
         out[name + ".bias"] = b

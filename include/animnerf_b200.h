@@ -118,10 +118,6 @@ int an_knn_unpose_fwd(const float* xyz, const float* rays, const float* z, int B
                       float* xyz_cano, uint8_t* valid, int32_t* idx, float* dist, float* qw,
                       float* sigma, float* rgb, int32_t* cidx, int32_t* count, void* stream);
 
-/* tools/bench_knn.py only: selects the search-kernel variant (bit 8: collect candidate statistics in the
- * query workspace); returns the previous value, v <= 0 only queries.                                   */
-int an_debug_knn_variant(int v);
-
 /* backward of the blend + affine apply (autograd of models/anim_nerf.py:173-174,188; no
  * gradient through dist/idx/valid, as under the reference's no_grad KNN).
  * g_xyz_cano (B*N,3) is read at the `*count` compacted ids in cidx.  Accumulates (atomically)
@@ -144,12 +140,11 @@ int an_mlp_pack(const float* const* w_host, const float* const* b_host, void* pa
 
 /* forward over the compacted points: for p < *count: point id = cidx[p] (cidx NULL: id = p and
  * the count is n_max), reads xyz_cano[id], writes sigma[id], rgb[id*3..].
- * impl 0 = tcgen05 kernel (product), 1 = fp32 SIMT reference kernel (tests / bring-up only).
  * stash: NULL for inference; else an_mlp_stash_bytes(n_max) bytes receiving the bf16
  * activations the backward needs.                                                            */
 int64_t an_mlp_stash_bytes(int64_t n_max);
 int an_mlp_fwd(const void* packed, const float* xyz_cano, const int32_t* cidx, const int32_t* count,
-               int64_t n_max, float* sigma, float* rgb, void* stash, int impl, void* stream);
+               int64_t n_max, float* sigma, float* rgb, void* stash, void* stream);
 
 /* backward: g_sigma (ids), g_rgb (ids,3), rgb = the forward's output (ids,3) -> g_params (fp32 vector
  * of an_mlp_grad_floats() floats: the first 592 388 are the gradient, per nn.Linear weight then

@@ -1,10 +1,11 @@
-// fp32 SIMT restatement of the NeRF MLP forward (impl=1 of an_mlp_fwd): one thread per point,
-// activations in (thread-interleaved) local memory, weights read through the warp-broadcast
-// read-only path from the flat fp32 copy inside the packed buffer.  Bring-up / test kernel:
-// it is the on-device fp32 reference the tcgen05 kernel is bisected against; the product path
-// (impl=0) never calls it.  Follows models/embedding.py:22-39 and models/nerf.py:129-175.
-#include "common.cuh"
-#include "mlp_layout.cuh"
+// TEST INFRASTRUCTURE (built into tests/libanimnerf_b200_ref.so, never into the product library):
+// fp32 SIMT restatement of the NeRF MLP forward: one thread per point, activations in
+// (thread-interleaved) local memory, weights read through the warp-broadcast read-only path from
+// the flat fp32 copy inside the packed buffer.  It is the on-device fp32 reference the tcgen05
+// kernel is bisected against in the GPU tests (tests/util.py: ref_mlp()).  Follows
+// models/embedding.py:22-39 and models/nerf.py:129-175.
+#include "../../anim-nerf_b200/csrc/common.cuh"
+#include "../../anim-nerf_b200/csrc/mlp_layout.cuh"
 
 __global__ void __launch_bounds__(128)
 mlp_fwd_ref_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ xyz_cano,
@@ -74,12 +75,13 @@ mlp_fwd_ref_kernel(const uint8_t* __restrict__ packed, const float* __restrict__
     }
 }
 
-int mlp_fwd_ref_launch(const void* packed, const float* xyz_cano, const int32_t* cidx, const int32_t* count,
-                       int64_t n_max, float* sigma, float* rgb, cudaStream_t stream)
+extern "C" int an_test_mlp_fwd_ref(const void* packed, const float* xyz_cano, const int32_t* cidx, const int32_t* count,
+                                  int64_t n_max, float* sigma, float* rgb, void* stream)
 {
+    if (!packed || !xyz_cano || !sigma || !rgb || n_max <= 0) return AN_ERR_ARG;
     const int64_t want = (n_max + 127) / 128;
     const int64_t cap = (int64_t)an_num_sms() * 8;
-    mlp_fwd_ref_kernel<<<(int)(want < cap ? want : cap), 128, 0, stream>>>(
+    mlp_fwd_ref_kernel<<<(int)(want < cap ? want : cap), 128, 0, (cudaStream_t)stream>>>(
         (const uint8_t*)packed, xyz_cano, cidx, count, n_max, sigma, rgb);
     AN_CHECK_LAUNCH();
     return AN_OK;

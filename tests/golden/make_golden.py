@@ -49,7 +49,7 @@ def to_t(d):
     return {k: torch.from_numpy(np.asarray(v)).float() for k, v in d.items()}
 
 
-def build_reference(tmp):
+def build_reference(tmp, trained_scale=False):
     install_shim()
     from models.anim_nerf import AnimNeRF
     from models.volume_rendering import VolumeRenderer
@@ -58,12 +58,14 @@ def build_reference(tmp):
                    use_view=False, use_unpose=True, k_neigh=4, use_knn=True, use_fine=True,
                    share_fine=False, dis_threshold=0.2)
     for name, seed in (("nerf", 10), ("nerf_fine", 11)):
-        sd = {k: torch.from_numpy(v) for k, v in synthetic.make_nerf_weights(seed).items()}
+        sd = {k: torch.from_numpy(v) for k, v in synthetic.make_nerf_weights(seed, trained_scale=trained_scale).items()}
         getattr(net, name).load_state_dict(sd, strict=True)
     return net, VolumeRenderer
 
 
-def run_case(net, VolumeRenderer, B, R, Kc, Kf, perturb, tag, with_grad=True):
+def run_case(net, VolumeRenderer, B, R, Kc, Kf, perturb, tag, with_grad=True, compact=False):
+    """compact=True (the cfg1-sized cases, R = 1024): only what the tests assert is kept, in narrow dtypes
+    (indices int16, validity uint8, per-point MLP outputs dropped), so that a fixture stays at a few MB."""
     posed_np, tmpl_np = synthetic.make_body_params(B, seed=1)
     posed = to_t(posed_np)
     tmpl = to_t(tmpl_np)
@@ -142,9 +144,10 @@ def run_case(net, VolumeRenderer, B, R, Kc, Kf, perturb, tag, with_grad=True):
     fx["ober2cano_row3_maxdev"] = np.float32(
         (net.ober2cano_transform.detach()[:, :, 3, :] - torch.tensor([0, 0, 0, 1.0])).abs().max())
     sub = slice(0, None, 53)
-    for k in ("vertices", "vertices_transform", "shape_offsets", "pose_offsets", "vertices_template"):
-        fx["body_" + k] = body_out[k].numpy()[:, sub]
-    fx["body_joints_transform"] = body_out["joints_transform"].numpy()
+    if not compact:
+        for k in ("vertices", "vertices_transform", "shape_offsets", "pose_offsets", "vertices_template"):
+            fx["body_" + k] = body_out[k].numpy()[:, sub]
+        fx["body_joints_transform"] = body_out["joints_transform"].numpy()
     for k, v in out.items():
         fx["out_" + k] = v.detach().numpy()
     # coarse pass intermediates
@@ -152,14 +155,18 @@ def run_case(net, VolumeRenderer, B, R, Kc, Kf, perturb, tag, with_grad=True):
     fx["weights_coarse"] = comp_calls[0][1].numpy()
     fx["z_combine"] = comp_calls[1][0].numpy()
     fx["weights_fine"] = comp_calls[1][1].numpy()
-    fx["knn_dist_coarse"] = knn_calls[0][0].numpy()
     fx["knn_idx_coarse"] = knn_calls[0][1].numpy().astype(np.int16)
     fx["knn_idx_fine"] = knn_calls[1][1].numpy().astype(np.int16)
-    fx["xyz_cano_coarse"] = unpose_calls[0][0].numpy()
     fx["valid_coarse"] = unpose_calls[0][1].numpy().astype(np.uint8)
     fx["valid_fine"] = unpose_calls[1][1].numpy().astype(np.uint8)
-    fx["rgb_pts_coarse"] = query_calls[0][0].numpy().astype(np.float16)   # raw MLP output, pre-mask
-    fx["sigma_pts_coarse"] = query_calls[0][1].numpy()
+    if not compact:
+        fx["knn_dist_coarse"] = knn_calls[0][0].numpy()
+        fx["xyz_cano_coarse"] = unpose_calls[0][0].numpy()
+        fx["rgb_pts_coarse"] = query_calls[0][0].numpy().astype(np.float16)   # raw MLP output, pre-mask
+        fx["sigma_pts_coarse"] = query_calls[0][1].numpy()
+    else:       # range of the raw density over the valid coarse points (documents the fixture's dynamic range)
+        sg = query_calls[0][1].numpy()[fx["valid_coarse"] > 0]
+        fx["sigma_valid_percentiles"] = np.percentile(sg, [0, 1, 25, 50, 75, 99, 100]).astype(np.float32)
     fx["cdf"], fx["u"], fx["inds"] = ss_calls[0][0].numpy(), ss_calls[0][1].numpy(), ss_calls[0][2].numpy().astype(np.int16)
     if perturb > 0:
         fx["noise_coarse_u"] = (rand_calls[0] ).numpy()      # perturb * rand -> the oracle multiplies again
@@ -366,15 +373,26 @@ if __name__ == "__main__":
     if "--pixel-sampling-only" in sys.argv:
         pixel_sampling_case()
         sys.exit(0)
-    regularizers_case()
-    pixel_sampling_case()
-    api_signatures_case()
-    with tempfile.TemporaryDirectory() as tmp:
-        state_dict_case(tmp)
+    if "--cfg1-only" not in sys.argv:
+        regularizers_case()
+        pixel_sampling_case()
+        api_signatures_case()
+        with tempfile.TemporaryDirectory() as tmp:
+            state_dict_case(tmp)
     with tempfile.TemporaryDirectory() as tmp:
         net, VR = build_reference(tmp)
-        run_case(net, VR, B=2, R=96, Kc=64, Kf=64, perturb=0.0, tag="det")
-        run_case(net, VR, B=1, R=64, Kc=64, Kf=32, perturb=1.0, tag="perturb")
+        if "--cfg1-only" not in sys.argv:
+            run_case(net, VR, B=2, R=96, Kc=64, Kf=64, perturb=0.0, tag="det")
+            run_case(net, VR, B=1, R=64, Kc=64, Kf=32, perturb=1.0, tag="perturb")
+        # BASELINE configs[0] at full size: 1024 rays, 64 + 64 samples, deterministic and perturbed
+        run_case(net, VR, B=1, R=1024, Kc=64, Kf=64, perturb=0.0, tag="cfg1_det", with_grad=False, compact=True)
+        run_case(net, VR, B=1, R=1024, Kc=64, Kf=64, perturb=1.0, tag="cfg1_perturb", with_grad=False, compact=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        # trained-scale weights (synthetic.make_nerf_weights(trained_scale=True)): sigma spans ~0..100, saturated colours
+        net, VR = build_reference(tmp, trained_scale=True)
+        run_case(net, VR, B=1, R=256, Kc=64, Kf=64, perturb=0.0, tag="trained_det", with_grad=False, compact=True)
+    if "--cfg1-only" in sys.argv:
+        sys.exit(0)
     try:
         gen_rays_case()
     except Exception as e:  # cv2/torchvision import problems should not lose the main fixtures

@@ -45,7 +45,7 @@ def stats_of(qws):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--variants", default="1,2,3,4")
+    ap.add_argument("--variants-unused", default="1,2,3,4")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--check", type=int, default=1)
     args = ap.parse_args()
@@ -76,39 +76,32 @@ def main():
         print("valid fraction fine %.3f" % ref["f"]["valid"].float().mean().item())
         t0 = timed(lambda: ops.knn_unpose(verts, o2c, lbs, thr, rays=rays, z=zc, mode=0, want_idx=True, compact=True), 3)
         print("mode 0 (exhaustive) coarse: %.3f ms" % t0)
-    # variant spec "k" or "k:d" = kernel k with cooperative-drain threshold d lanes (default 8)
-    def spec(v):
-        k, _, d = v.partition(":")
-        return int(k) | ((int(d) if d else 8) << 12)
-    for var in [spec(v) for v in args.variants.split(",")]:
-        lib.an_debug_knn_variant(var | 0x100)
-        qc = torch.empty(lib.an_knn_query_ws_bytes(B, R * 64), device=dev, dtype=torch.uint8)
-        qf = torch.empty(lib.an_knn_query_ws_bytes(B, R * 128), device=dev, dtype=torch.uint8)
-        out_c = ops.knn_unpose(verts, o2c, lbs, thr, rays=rays, z=zc, mode=1, qws=qc, want_dist=True, **kw)
-        sc = stats_of(qc)
-        seed = dict(src=src, nn=nn, idx=out_c["idx"])
-        out_f = ops.knn_unpose(verts, o2c, lbs, thr, rays=rays, z=z_all, mode=1, qws=qf, want_dist=True, **kw)
-        sf = stats_of(qf)
-        out_s = ops.knn_unpose(verts, o2c, lbs, thr, rays=rays, z=z_all, mode=1, qws=qf, want_dist=True, seed=seed, **kw)
-        ss = stats_of(qf)
-        ok = "unchecked"
-        if args.check:
-            ok = True
-            for out, r in ((out_c, ref["c"]), (out_f, ref["f"]), (out_s, ref["f"])):
-                f = out["idx"][..., 0] >= 0
-                ok = ok and torch.equal(out["valid"], r["valid"]) and torch.equal(out["idx"][f], r["idx"][f]) \
-                    and torch.equal(out["dist"][f], r["dist"][f]) and bool((f | ~r["valid"].bool()).all())
-                v = r["valid"].bool()
-                ok = ok and torch.equal(out["xyz_cano"][v], r["xyz_cano"][v])
-        lib.an_debug_knn_variant(var)
-        tc = timed(lambda: ops.knn_unpose(verts, o2c, lbs, thr, rays=rays, z=zc, mode=1, qws=qc, **kw), args.reps)
-        tf = timed(lambda: ops.knn_unpose(verts, o2c, lbs, thr, rays=rays, z=z_all, mode=1, qws=qf, **kw), args.reps)
-        ts = timed(lambda: ops.knn_unpose(verts, o2c, lbs, thr, rays=rays, z=z_all, mode=1, qws=qf, seed=seed, **kw), args.reps)
-        for name, t, s, nq in (("coarse", tc, sc, B * R * 64), ("fine", tf, sf, B * R * 128), ("fine+seed", ts, ss, B * R * 128)):
-            n_work, n_cand, n_iter, n_redo = s
-            print("variant %x %-9s %.3f ms  queries %d searched %d (%.3f)  cand/searched %.1f  lane-eff %.2f  redo %d  exact=%s"
-                  % (var, name, t, nq, n_work, n_work / nq, n_cand / max(n_work, 1), n_cand / max(n_iter, 1), n_redo, ok))
-    lib.an_debug_knn_variant(spec("3"))
+    # candidate statistics need a variant build: AN_LIB_PATH=... AN_NVCC_EXTRA=-DAN_KNN_STATS python -m anim_nerf_b200._build
+    qc = torch.empty(lib.an_knn_query_ws_bytes(B, R * 64), device=dev, dtype=torch.uint8)
+    qf = torch.empty(lib.an_knn_query_ws_bytes(B, R * 128), device=dev, dtype=torch.uint8)
+    out_c = ops.knn_unpose(verts, o2c, lbs, thr, rays=rays, z=zc, mode=1, qws=qc, want_dist=True, **kw)
+    sc = stats_of(qc)
+    seed = dict(src=src, nn=nn, idx=out_c["idx"])
+    out_f = ops.knn_unpose(verts, o2c, lbs, thr, rays=rays, z=z_all, mode=1, qws=qf, want_dist=True, **kw)
+    sf = stats_of(qf)
+    out_s = ops.knn_unpose(verts, o2c, lbs, thr, rays=rays, z=z_all, mode=1, qws=qf, want_dist=True, seed=seed, **kw)
+    ss = stats_of(qf)
+    ok = "unchecked"
+    if args.check:
+        ok = True
+        for out, r in ((out_c, ref["c"]), (out_f, ref["f"]), (out_s, ref["f"])):
+            f = out["idx"][..., 0] >= 0
+            ok = ok and torch.equal(out["valid"], r["valid"]) and torch.equal(out["idx"][f], r["idx"][f]) \
+                and torch.equal(out["dist"][f], r["dist"][f]) and bool((f | ~r["valid"].bool()).all())
+            v = r["valid"].bool()
+            ok = ok and torch.equal(out["xyz_cano"][v], r["xyz_cano"][v])
+    tc = timed(lambda: ops.knn_unpose(verts, o2c, lbs, thr, rays=rays, z=zc, mode=1, qws=qc, **kw), args.reps)
+    tf = timed(lambda: ops.knn_unpose(verts, o2c, lbs, thr, rays=rays, z=z_all, mode=1, qws=qf, **kw), args.reps)
+    ts = timed(lambda: ops.knn_unpose(verts, o2c, lbs, thr, rays=rays, z=z_all, mode=1, qws=qf, seed=seed, **kw), args.reps)
+    for name, t, s, nq in (("coarse", tc, sc, B * R * 64), ("fine", tf, sf, B * R * 128), ("fine+seed", ts, ss, B * R * 128)):
+        n_work, n_cand, n_iter, n_redo = s
+        print("%-9s %.3f ms  queries %d searched %d (%.3f)  cand/searched %.1f  lane-eff %.2f  redo %d  exact=%s"
+              % (name, t, nq, n_work, n_work / nq, n_cand / max(n_work, 1), n_cand / max(n_iter, 1), n_redo, ok))
 
 
 if __name__ == "__main__":
