@@ -34,11 +34,12 @@ SIGNATURES = {
     "an_mlp_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "an_mlp_grad_floats": (_i64, []),
     "an_mlp_bwd_scratch_bytes": (_i64, [_i64]),
-    "an_mlp_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "an_mlp_wgrad_ws_bytes": (_i64, []),
+    "an_mlp_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "an_mlp_bwd_dgrad": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
-    "an_mlp_bwd_wgrad": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "an_mlp_bwd_wgrad": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "an_mlp_fwd_tangent": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
-    "an_mlp_bwd_wgrad_scaled": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "an_mlp_bwd_wgrad_scaled": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "an_adam_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp]),
     "an_composite_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "an_composite_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -93,7 +94,7 @@ def check(code, what):
 
 
 # kernels launched per entry point (for bench.py's gpu_launches claim)
-KERNELS_PER_CALL = {"an_mlp_bwd": 3, "an_mlp_bwd_wgrad": 2, "an_mlp_bwd_wgrad_scaled": 2, "an_mlp_pack": 2, "an_knn_unpose_fwd": 2,
+KERNELS_PER_CALL = {"an_mlp_bwd": 4, "an_mlp_bwd_wgrad": 3, "an_mlp_bwd_wgrad_scaled": 3, "an_mlp_pack": 2, "an_knn_unpose_fwd": 2,
                     "an_body_tables_bwd_ws_bytes": (_i64, [_i32]),
     "an_body_tables_bwd": (_i32, [_vp] * 5 + [_i32] + [_vp] * 6 + [_i32, _i32, _i32] + [_vp] * 7),
     "an_body_tables_fwd": 2, "an_body_tables_bwd": 2}

@@ -14,7 +14,9 @@
 //     operands are the row-major point images already in HBM, consumed as MN-major UMMA operands
 //     (no transposes).  One CTA owns one (layer, point-split) and keeps the full dW_g tile
 //     (2 x 128 x N fp32) in TMEM across its whole K loop; bias gradients are column sums of the
-//     dY image taken from shared memory by the otherwise idle warps.  HBM-bound by construction
+//     dY image taken from shared memory by the otherwise idle warps.  Every CTA stores its partial
+//     dW / db into its own slice of a workspace; mlp_wgrad_reduce_kernel then adds the slices to the
+//     gradient in a fixed order -- no floating-point atomics, so the gradient is reproducible bit for bit.  HBM-bound by construction
 //     (128 FLOP/B < ridge 214 FLOP/B): ~9.4 KB read per point.  The head-layer and rgb jobs run
 //     transposed (A = X, B = dY) because their dY is narrower than one UMMA M.
 //  3. mlp_unfuse_grad_kernel (mlp_pack.cu) -- chain rule from the fused head layer's dW', db' to
@@ -345,11 +347,12 @@ constexpr uint32_t WG_BAR = WG_STAGES * WG_STAGE_BYTES;
 constexpr uint32_t WG_ALLOC = WG_BAR + 128 + 1024;
 }  // namespace
 
-// grid = (splits, NJOBS).  CTA (sp, j) accumulates dW_j over tiles sp, sp+splits, ...
+// grid = (splits, NJOBS).  CTA (sp, j) accumulates dW_j over tiles sp, sp+splits, ... and stores the result into
+// slice sp of `partial` ([splits][GRAD_FLOATS], indexed like the gradient vector).
 __global__ void __launch_bounds__(WG_THREADS, 1)
 mlp_bwd_wgrad_kernel(const uint8_t* __restrict__ stash, const uint8_t* __restrict__ dy,
                      const int32_t* __restrict__ count, int has_count, int64_t n_max,
-                     float* __restrict__ g_params, const float* __restrict__ bias_scale)
+                     float* __restrict__ partial, const float* __restrict__ bias_scale)
 {
     using namespace mlp;
     using namespace tc;
@@ -364,6 +367,7 @@ mlp_bwd_wgrad_kernel(const uint8_t* __restrict__ stash, const uint8_t* __restric
     int64_t n = n_max;
     if (has_count) { const int64_t c = *count; n = c < n_max ? c : n_max; }
     const int64_t n_tiles = n_tiles_for(n);              // tiles written by the forward / dgrad pairs (zero dY rows beyond n)
+    float* __restrict__ g_params = partial + (int64_t)blockIdx.x * GRAD_FLOATS;     // this split's slice
     const WJob job = wjob(blockIdx.y);
     const int M_halves = (job.a_chunks + 1) / 2;          // 128 accumulator lanes per half
     const int N = job.N;                                  // accumulator columns per half
@@ -463,7 +467,7 @@ mlp_bwd_wgrad_kernel(const uint8_t* __restrict__ stash, const uint8_t* __restric
             if (job.kind == 0) dst = g_params + flat_b_off(job.lin) + e;
             else if (job.kind == 1) dst = e < 128 ? g_params + GRAD_FUSED_B + e : g_params + flat_b_off(10);   // db', d b_sigma
             else dst = g_params + flat_b_off(11) + e;
-            atomicAdd(dst, bsum);
+            *dst = bsum;
         }
         // drain the accumulators
         if (n_tiles > (int64_t)blockIdx.x) {
@@ -489,7 +493,7 @@ mlp_bwd_wgrad_kernel(const uint8_t* __restrict__ stash, const uint8_t* __restric
                         else if (job.kind == 1)                                                              // lane = in (h8), col = out
                             dst = col < 128 ? g_params + GRAD_FUSED_W + col * 256 + lane_row : g_params + flat_w_off(10) + lane_row;
                         else dst = g_params + flat_w_off(11) + col * 128 + lane_row;                         // lane = in (c), col = rgb channel
-                        atomicAdd(dst, __uint_as_float(v[c]));
+                        *dst = __uint_as_float(v[c]);
                     }
                 }
             }
@@ -501,7 +505,32 @@ mlp_bwd_wgrad_kernel(const uint8_t* __restrict__ stash, const uint8_t* __restric
     if (warp == 1) { __syncwarp(); tmem_dealloc(tmem_base, 512); }
 }
 
+// g[i] += sum over the active splits (in order) of partial[s][i], for every entry the job table writes: the weights
+// and biases of the eight trunk linears, the density head, the rgb head and the fused head layer's scratch tail;
+// xyz_encoding_final / dir_encoding (flat ids 8, 9) come from the chain rule kernel that follows.
+__global__ void __launch_bounds__(256)
+mlp_wgrad_reduce_kernel(const float* __restrict__ partial, int splits, const int32_t* __restrict__ count, int has_count,
+                        int64_t n_max, float* __restrict__ g)
+{
+    using namespace mlp;
+    int64_t n = n_max;
+    if (has_count) { const int64_t c = *count; n = c < n_max ? c : n_max; }
+    const int64_t n_tiles = n_tiles_for(n);
+    const int active = (int)(n_tiles < splits ? n_tiles : splits);     // splits beyond the tile count wrote nothing
+    const int64_t skip0 = flat_w_off(8), skip1 = flat_w_off(10);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < GRAD_FLOATS; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i >= skip0 && i < skip1) continue;
+        float acc = 0.f;
+        for (int s = 0; s < active; ++s) acc += partial[(int64_t)s * GRAD_FLOATS + i];
+        g[i] += acc;
+    }
+}
+
 int mlp_unfuse_grad_launch(const void* packed, float* g_params, cudaStream_t stream);
+
+static inline int wgrad_splits() { const int s = an_num_sms() / NJOBS; return s < 1 ? 1 : s; }    // 13 on a 148-SM part -> 143 CTAs, one wave
+
+extern "C" int64_t an_mlp_wgrad_ws_bytes(void) { return (int64_t)wgrad_splits() * mlp::GRAD_FLOATS * 4; }
 
 extern "C" int64_t an_mlp_bwd_scratch_bytes(int64_t n_max)
 {
@@ -539,48 +568,50 @@ extern "C" int an_mlp_bwd_dgrad(const void* packed, const void* stash, const flo
 }
 
 static int wgrad_launch(const void* packed, const void* stash, const void* scratch, const int32_t* cidx,
-                        const int32_t* count, int64_t n_max, float* g_params, const float* bias_scale, void* stream)
+                        const int32_t* count, int64_t n_max, float* g_params, void* wgrad_ws, const float* bias_scale, void* stream)
 {
-    if (!g_params || !packed) return AN_ERR_ARG;
+    if (!g_params || !packed || !wgrad_ws) return AN_ERR_ARG;
+    if (((uintptr_t)wgrad_ws) & 15) return AN_ERR_ALIGN;
     int rc = bwd_check(packed, stash, scratch, n_max, cidx, count);
     if (rc) return rc;
     cudaError_t e = cudaFuncSetAttribute(mlp_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_ALLOC);
     if (e != cudaSuccess) return (int)e;
-    const int sms = an_num_sms();
     const int64_t tiles = mlp::n_tiles_for(n_max);
-    int64_t splits = sms / NJOBS;                      // 13 on a 148-SM part -> 143 CTAs, one wave
+    int64_t splits = wgrad_splits();
     if (splits > tiles) splits = tiles;
-    if (splits < 1) splits = 1;
     dim3 wgrid((unsigned)splits, NJOBS);
     mlp_bwd_wgrad_kernel<<<wgrid, WG_THREADS, WG_ALLOC, (cudaStream_t)stream>>>(
-        (const uint8_t*)stash, (const uint8_t*)scratch, count, cidx ? 1 : 0, n_max, g_params, bias_scale);
+        (const uint8_t*)stash, (const uint8_t*)scratch, count, cidx ? 1 : 0, n_max, (float*)wgrad_ws, bias_scale);
+    AN_CHECK_LAUNCH();
+    mlp_wgrad_reduce_kernel<<<an_num_sms() * 2, 256, 0, (cudaStream_t)stream>>>(
+        (const float*)wgrad_ws, (int)splits, count, cidx ? 1 : 0, n_max, g_params);
     AN_CHECK_LAUNCH();
     // chain rule through the fused head layer: dW', db' -> xyz_encoding_final / dir_encoding gradients
     return mlp_unfuse_grad_launch(packed, g_params, (cudaStream_t)stream);
 }
 
 extern "C" int an_mlp_bwd_wgrad(const void* packed, const void* stash, const void* scratch, const int32_t* cidx,
-                                const int32_t* count, int64_t n_max, float* g_params, void* stream)
+                                const int32_t* count, int64_t n_max, float* g_params, void* wgrad_ws, void* stream)
 {
-    return wgrad_launch(packed, stash, scratch, cidx, count, n_max, g_params, nullptr, stream);
+    return wgrad_launch(packed, stash, scratch, cidx, count, n_max, g_params, wgrad_ws, nullptr, stream);
 }
 
 // same, with the bias gradients weighted per point: db = sum_p bias_scale[p] dY_p (p in compact order, n_max entries);
 // the weight gradients are unchanged (dY^T X).  Pairs with an_mlp_fwd_tangent(tscale) -- see there.
 extern "C" int an_mlp_bwd_wgrad_scaled(const void* packed, const void* stash, const void* scratch, const int32_t* cidx,
                                        const int32_t* count, int64_t n_max, const float* bias_scale, float* g_params,
-                                       void* stream)
+                                       void* wgrad_ws, void* stream)
 {
     if (!bias_scale) return AN_ERR_ARG;
-    return wgrad_launch(packed, stash, scratch, cidx, count, n_max, g_params, bias_scale, stream);
+    return wgrad_launch(packed, stash, scratch, cidx, count, n_max, g_params, wgrad_ws, bias_scale, stream);
 }
 
 extern "C" int an_mlp_bwd(const void* packed, const void* stash, const float* xyz_cano, const float* rgb,
                           const int32_t* cidx, const int32_t* count, int64_t n_max,
                           const float* g_sigma, const float* g_rgb, float* g_params, float* g_xyz_cano,
-                          void* scratch, void* stream)
+                          void* scratch, void* wgrad_ws, void* stream)
 {
     int rc = an_mlp_bwd_dgrad(packed, stash, xyz_cano, rgb, cidx, count, n_max, g_sigma, g_rgb, g_xyz_cano, scratch, stream);
     if (rc) return rc;
-    return an_mlp_bwd_wgrad(packed, stash, scratch, cidx, count, n_max, g_params, stream);
+    return an_mlp_bwd_wgrad(packed, stash, scratch, cidx, count, n_max, g_params, wgrad_ws, stream);
 }

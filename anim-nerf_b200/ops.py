@@ -245,6 +245,18 @@ def _grad_target(g_params, dev):
 
 
 FLAT_FLOATS = 592388          # mlp_layout.cuh: parameters of one NeRF (the gradient vector's head)
+_wgrad_ws = {}
+
+
+def _wgrad_workspace(dev):
+    """Per-device workspace of the weight-gradient kernel's per-CTA partial sums (33 MB; reused by every call on the
+    device: calls are stream-ordered and each reduces its partials before it returns the stream to the next)."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    ws = _wgrad_ws.get(key)
+    if ws is None:
+        ws = torch.empty(_lib.load().an_mlp_wgrad_ws_bytes(), device=dev, dtype=torch.uint8)
+        _wgrad_ws[key] = ws
+    return ws
 
 
 def mlp_bwd(packed, stash, xyz_cano, rgb, g_sigma, g_rgb, cidx=None, count=None, n_max=None, want_g_xyz=True, g_params=None):
@@ -261,7 +273,8 @@ def mlp_bwd(packed, stash, xyz_cano, rgb, g_sigma, g_rgb, cidx=None, count=None,
     scr = ptr(_last_bwd_scratch)
     call("an_mlp_bwd_dgrad", ptr(packed), ptr(stash), ptr(xyz_cano), ptr(rgb), ptr(cidx), ptr(count), int(n_max),
          ptr(g_sigma), ptr(g_rgb), ptr(g_xyz), scr, stream())
-    call("an_mlp_bwd_wgrad", ptr(packed), ptr(stash), scr, ptr(cidx), ptr(count), int(n_max), ptr(g_params), stream())
+    call("an_mlp_bwd_wgrad", ptr(packed), ptr(stash), scr, ptr(cidx), ptr(count), int(n_max), ptr(g_params),
+         ptr(_wgrad_workspace(dev)), stream())
     return g_params, g_xyz
 
 
@@ -291,10 +304,11 @@ def mlp_bwd_wgrad(packed, stash, scratch, cidx=None, count=None, n_max=None, g_p
     bias_scale (n_max, compact order): db = sum_p bias_scale[p] dY_p instead of the plain column sums."""
     g_params = _grad_target(g_params, stash.device)
     if bias_scale is None:
-        call("an_mlp_bwd_wgrad", ptr(packed), ptr(stash), ptr(scratch), ptr(cidx), ptr(count), int(n_max), ptr(g_params), stream())
+        call("an_mlp_bwd_wgrad", ptr(packed), ptr(stash), ptr(scratch), ptr(cidx), ptr(count), int(n_max), ptr(g_params),
+             ptr(_wgrad_workspace(stash.device)), stream())
     else:
         call("an_mlp_bwd_wgrad_scaled", ptr(packed), ptr(stash), ptr(scratch), ptr(cidx), ptr(count), int(n_max),
-             ptr(_f32c(bias_scale)), ptr(g_params), stream())
+             ptr(_f32c(bias_scale)), ptr(g_params), ptr(_wgrad_workspace(stash.device)), stream())
     return g_params
 
 

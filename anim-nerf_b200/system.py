@@ -234,6 +234,8 @@ class AnimNeRFSystem(nn.Module):
     def training_step(self, batch, batch_idx=0, with_regularizers=True):
         (_, _, frame_idx, rays, rgbs, alphas, params, params_t, fg, bg) = self.decode_batch(batch)
         if self.hparams.optim_body_params:                       # train.py:330-331: the table's rows, not the batch's copies
+            if frame_idx is None:
+                raise KeyError("training_step with optim_body_params=True needs batch['frame_idx'] (rows of the SMPL table)")
             params = self.body_model_params(frame_idx)
         results = self(rays, params, params_t)
         loss, details = self.compute_loss(rgbs, alphas, results, frame_idx=frame_idx, fg_points=fg, bg_points=bg,

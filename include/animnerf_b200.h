@@ -150,13 +150,16 @@ int an_mlp_fwd(const void* packed, const float* xyz_cano, const int32_t* cidx, c
  * of an_mlp_grad_floats() floats: the first 592 388 are the gradient, per nn.Linear weight then
  * bias, in an_mlp_pack's order; the tail is scratch for the fused head layer; accumulated, caller
  * zeroes the whole vector) and g_xyz_cano (ids,3) when non-NULL (caller zeroes).
- * scratch: an_mlp_bwd_scratch_bytes(n_max).                                                  */
+ * scratch: an_mlp_bwd_scratch_bytes(n_max).  wgrad_ws: an_mlp_wgrad_ws_bytes() bytes, 16-byte aligned: per-CTA
+ * partial weight gradients, summed into g_params in a fixed order (no floating-point atomics: for given inputs the
+ * gradient is reproducible bit for bit).                                                       */
 int64_t an_mlp_grad_floats(void);
 int64_t an_mlp_bwd_scratch_bytes(int64_t n_max);
+int64_t an_mlp_wgrad_ws_bytes(void);
 int an_mlp_bwd(const void* packed, const void* stash, const float* xyz_cano, const float* rgb,
                const int32_t* cidx, const int32_t* count, int64_t n_max,
                const float* g_sigma, const float* g_rgb,
-               float* g_params, float* g_xyz_cano, void* scratch, void* stream);
+               float* g_params, float* g_xyz_cano, void* scratch, void* wgrad_ws, void* stream);
 /* the two stages of an_mlp_bwd, callable separately:
  *   dgrad  activation-gradient chain (writes the dY images to scratch, g_xyz_cano)
  *   wgrad  dW/db of every layer (both heads included) from stash (X) and scratch (dY) on the tensor
@@ -166,7 +169,7 @@ int an_mlp_bwd_dgrad(const void* packed, const void* stash, const float* xyz_can
                      const float* g_sigma, const float* g_rgb, float* g_xyz_cano,
                      void* scratch, void* stream);
 int an_mlp_bwd_wgrad(const void* packed, const void* stash, const void* scratch, const int32_t* cidx,
-                     const int32_t* count, int64_t n_max, float* g_params, void* stream);
+                     const int32_t* count, int64_t n_max, float* g_params, void* wgrad_ws, void* stream);
 
 /* ---- A18 (normal-smoothness regulariser): second-order path of NeRF.get_normal --------------
  * replaces the torch double backward of models/nerf.py:177-190 (get_normal: autograd.grad of
@@ -190,7 +193,7 @@ int an_mlp_fwd_tangent(const void* packed, const float* xyz_cano, const float* t
                        float* tsigma, void* tstash, void* stream);
 int an_mlp_bwd_wgrad_scaled(const void* packed, const void* stash, const void* scratch, const int32_t* cidx,
                             const int32_t* count, int64_t n_max, const float* bias_scale, float* g_params,
-                            void* stream);
+                            void* wgrad_ws, void* stream);
 
 /* ---- A18 (optimiser): Adam over a list of tensors in one launch -----------------------------------
  * replaces torch.optim.Adam as train.py:217-226 / utils/__init__.py:33-45 configure it (eps 1e-8, betas

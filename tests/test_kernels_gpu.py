@@ -457,6 +457,32 @@ def test_mlp_backward(n, with_gx, emu):
     assert not bad, bad
 
 
+def test_mlp_backward_is_bit_reproducible():
+    """The weight gradient is reduced in a fixed order (per-CTA partial slices + mlp_wgrad_reduce_kernel, no
+    floating-point atomics): two runs over the same inputs give bit-identical gradients, also when accumulating
+    into a caller-owned buffer."""
+    from anim_nerf_b200 import ops as o
+    packed = _packed(10)
+    n = 40000
+    rs = np.random.RandomState(8)
+    xc = torch.from_numpy(rs.uniform(-1, 1, size=(n, 3)).astype(np.float32)).to(DEV)
+    gs = torch.from_numpy(rs.normal(size=(n,)).astype(np.float32)).to(DEV)
+    grgb = torch.from_numpy(rs.normal(size=(n, 3)).astype(np.float32)).to(DEV)
+    sigma, rgb = torch.zeros(n, device=DEV), torch.zeros(n, 3, device=DEV)
+    stash = o.mlp_stash(n, DEV)
+    o.mlp_fwd(packed, xc, sigma, rgb, stash=stash)
+    runs = []
+    for _ in range(3):
+        g, gx = o.mlp_bwd(packed, stash, xc, rgb, gs, grgb)
+        runs.append((g.clone(), gx.clone()))
+    for g, gx in runs[1:]:
+        assert torch.equal(g, runs[0][0]) and torch.equal(gx, runs[0][1])
+    acc = torch.zeros_like(runs[0][0])
+    o.mlp_bwd(packed, stash, xc, rgb, gs, grgb, g_params=acc)
+    o.mlp_bwd(packed, stash, xc, rgb, gs, grgb, g_params=acc)
+    assert torch.equal(acc[:o.FLAT_FLOATS], 2 * runs[0][0][:o.FLAT_FLOATS])
+
+
 # ------------------------------------------------------------------ per-frame tables (A16, 8(f)#1)
 @pytest.mark.parametrize("shared_template", [False, True])
 def test_body_tables_match_torch_builder(shared_template):

@@ -204,17 +204,18 @@ def test_compute_loss_with_regularisers_runs_on_kernels():
     from anim_nerf_b200.body_model import BodyModel
     data = synthetic.make_smpl_dict(0)
     B = 2
-    sysm = AnimNeRFSystem(body_model_data=data, n_samples=64, n_importance=64).to(DEV)
+    sysm = AnimNeRFSystem(body_model_data=data, n_samples=64, n_importance=64, num_frames=B).to(DEV)    # optim_body_params=True (default)
     for name, seed in (("nerf", 10), ("nerf_fine", 11)):
         getattr(sysm.anim_nerf, name).load_state_dict(
             {k: torch.from_numpy(v) for k, v in synthetic.make_nerf_weights(seed).items()}, strict=True)
     posed_np, tmpl_np = synthetic.make_body_params(B, seed=1)
+    sysm.init_body_model_params({k: torch.from_numpy(v) for k, v in posed_np.items()})
     with torch.no_grad():
         verts = BodyModel(data)(**{k: torch.from_numpy(v) for k, v in posed_np.items()})["vertices"].numpy()
     batch_np = synthetic.make_training_batch(verts, n_side=8, seed=3)
     rs = np.random.RandomState(5)
     batch = dict(rays=torch.from_numpy(batch_np["rays"]).to(DEV), rgbs=torch.from_numpy(batch_np["rgbs"]).to(DEV),
-                 alphas=torch.from_numpy(batch_np["alphas"]).to(DEV),
+                 alphas=torch.from_numpy(batch_np["alphas"]).to(DEV), frame_idx=torch.arange(B, device=DEV),
                  body_model_params={k: torch.from_numpy(v).to(DEV) for k, v in posed_np.items()},
                  body_model_params_template={k: torch.from_numpy(v).to(DEV) for k, v in tmpl_np.items()},
                  fg_points=torch.from_numpy(rs.normal(0, 0.1, size=(B, 128, 3)).astype(np.float32)).to(DEV),
@@ -230,3 +231,6 @@ def test_compute_loss_with_regularisers_runs_on_kernels():
         for pname, prm in getattr(sysm.anim_nerf, name).named_parameters():
             assert prm.grad is not None and torch.isfinite(prm.grad).all(), (name, pname)
         assert float(getattr(sysm.anim_nerf, name).sigma.weight.grad.abs().max()) > 0
+    # the shipped configuration optimises the SMPL table: its rows received gradients through the kernels
+    for pname, prm in sysm.body_model_params.named_parameters():
+        assert prm.grad is not None and torch.isfinite(prm.grad).all() and float(prm.grad.abs().max()) > 0, pname
