@@ -20,6 +20,9 @@ SIGNATURES = {
     "an_error_string": (_c.c_char_p, [_i32]),
     "an_raygen_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp]),
     "an_sample_training_rays_fwd": (_i32, [_vp] * 11 + [_i32] * 5 + [_f32, _f32, _i32, _i32, _vp, _u64] + [_vp] * 5),
+    "an_rays_sample_fwd": (_i32, [_vp] * 6 + [_i32] * 5 + [_f32, _f32, _f32, _vp, _u64, _vp, _vp, _vp]),
+    "an_rays_sample_bwd": (_i32, [_vp] * 9 + [_i32] * 5 + [_f32, _f32, _vp, _vp]),
+    "an_ray_point_grad": (_i32, [_vp] * 6 + [_i64, _i32, _vp, _vp, _vp]),
     "an_sample_coarse_fwd": (_i32, [_vp, _i64, _i32, _f32, _vp, _u64, _vp, _vp]),
     "an_vertex_grid_bytes": (_i64, [_i32, _i32]),
     "an_vertex_grid_build": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp]),
@@ -97,7 +100,7 @@ def check(code, what):
 KERNELS_PER_CALL = {"an_mlp_bwd": 4, "an_mlp_bwd_wgrad": 3, "an_mlp_bwd_wgrad_scaled": 3, "an_mlp_pack": 2, "an_knn_unpose_fwd": 2,
                     "an_body_tables_bwd_ws_bytes": (_i64, [_i32]),
     "an_body_tables_bwd": (_i32, [_vp] * 5 + [_i32] + [_vp] * 6 + [_i32, _i32, _i32] + [_vp] * 7),
-    "an_body_tables_fwd": 2, "an_body_tables_bwd": 2}
+    "an_body_tables_fwd": 2, "an_body_tables_bwd": 2}      # (memsets are not counted)
 launch_count = 0
 _timing = None          # bench.py: dict name -> list of (start_event, stop_event) on the launching stream
 

@@ -72,15 +72,10 @@ class RenderPass(torch.autograd.Function):
                                    count=aux["count"], n_max=B * R * K, want_g_xyz=need_geo, g_params=sink)
         g_rays = g_zz = g_o2c = None
         if need_geo:
-            g_o2c, g_xyz = ops.knn_unpose_bwd(g_xc, aux["cidx"], aux["count"], aux["idx"], aux["qw"], o2c, rays=rays, z=z)
-            g_xyz = g_xyz.view(B, R, K, 3)
-            if ctx.needs_input_grad[0]:
-                g_rays = torch.zeros_like(rays)
-                g_rays[..., 0:3] = g_xyz.sum(2)
-                g_rays[..., 3:6] = (g_xyz * z[..., None]).sum(2)
-                g_rays[..., 7] = g_far
-            if ctx.needs_input_grad[1]:
-                g_zz = g_z + (g_xyz * rays[:, :, None, 3:6]).sum(-1)
+            g_o2c, g_xyz = ops.knn_unpose_bwd(g_xc, aux["cidx"], aux["count"], aux["idx"], aux["qw"], o2c, rays=rays, z=z,
+                                              zero_g_xyz=False)
+            if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:      # x = o + z d: one warp-per-ray kernel
+                g_rays, g_zz = ops.ray_point_grad(rays, z, aux["valid"], g_xyz, g_z, g_far)
             if not ctx.needs_input_grad[2]:
                 g_o2c = None
         g_params = _param_grads(net, g_flat, sink)
@@ -226,6 +221,29 @@ def mlp_query(net, xyz):
     """Canonical-space NeRF query (no unposing): xyz (B,N,3) -> rgb (B,N,3), sigma (B,N,1)."""
     cfg = dict(net=net, unpose=False, grad=torch.is_grad_enabled())
     return PointQuery.apply(xyz, None, cfg, *net.param_list())
+
+
+class RaysSample(torch.autograd.Function):
+    """A1 + A2 + A3 fused (`an_rays_sample_fwd`): rays from a camera or given world-space rays -> body-space rays
+    (models/anim_nerf.py:128-137) and stratified depths (models/volume_rendering.py:29-56) in one launch.
+    Differentiable with respect to ginv (the inverse SMPL root transform): `an_rays_sample_bwd`."""
+
+    @staticmethod
+    def forward(ctx, ginv, src, n_coarse, perturb, noise_u, seed):
+        rays_body, z = ops.rays_sample(n_coarse, perturb, noise_u, seed, rays_world=src.get("rays_world"),
+                                       camera=src.get("camera"), ginv=ginv)
+        ctx.src = src
+        ctx.save_for_backward(rays_body, z)
+        return rays_body, z
+
+    @staticmethod
+    def backward(ctx, g_rays, g_z):
+        rays_body, z = ctx.saved_tensors
+        if g_rays is None:
+            g_rays = torch.zeros_like(rays_body)
+        g_ginv = ops.rays_sample_bwd(rays_body, z, g_rays.contiguous(), None if g_z is None else g_z.contiguous(),
+                                     rays_world=ctx.src.get("rays_world"), camera=ctx.src.get("camera"))
+        return g_ginv, None, None, None, None, None
 
 
 class SampleCoarse(torch.autograd.Function):

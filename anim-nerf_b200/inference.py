@@ -38,11 +38,13 @@ def batched_inference(volume_renderer, anim_nerf, rays, body_model_params, body_
                       latent_code=None, P=None, chunk=None):
     """reference novel_view.py:75-116.  rays (B,R,8) world space -> dict of (B,R,.) outputs.
     `P` (B,1|R,4,4): extra rigid transform of the rays in body space (the novel-view turntable)."""
-    bs, n_rays = rays.shape[:2]
-    rays, _ = anim_nerf.setup_frame(body_model_params, body_model_params_template, rays)
+    _, ginv = anim_nerf.setup_frame(body_model_params, body_model_params_template, None)
     if latent_code is not None:
         anim_nerf.set_latent_code(latent_code)
-    return _render_body_space(volume_renderer, anim_nerf, rays, P, chunk)
+    if P is None and chunk is None:      # body-space transform + stratified sampling fused into the renderer's front end
+        return volume_renderer(anim_nerf, rays, perturb=0.0, ginv=ginv)
+    rays_body, _ = ops.rays_sample(volume_renderer.n_coarse, 0.0, rays_world=rays, ginv=ginv)     # same kernel, same bits
+    return _render_body_space(volume_renderer, anim_nerf, rays_body, P, chunk)
 
 
 def _render_body_space(volume_renderer, anim_nerf, rays, P=None, chunk=None):
@@ -80,8 +82,13 @@ def render_frame(volume_renderer, anim_nerf, c2w, focal, center, H, W, body_mode
         n_rows = rr.numel()
         cc = torch.arange(W, device=c2w.device, dtype=torch.int32)
         pix = torch.stack(torch.meshgrid(rr, cc, indexing="ij"), -1).view(1, -1, 2).expand(B, -1, -1).contiguous()
-    rays = ops.raygen(c2w, focal, center, H, W, near, far, pix=pix, ginv=ginv)
-    out = _render_body_space(volume_renderer, anim_nerf, rays, P, chunk)
+    if P is None and chunk is None:
+        # ray generation + body-space transform + stratified sampling in ONE launch (an_rays_sample_fwd)
+        cam = dict(c2w=c2w, focal=focal, center=center, H=H, W=W, near=near, far=far, pix=pix)
+        out = volume_renderer(anim_nerf, None, perturb=0.0, ginv=ginv, camera=cam)
+    else:
+        rays = ops.raygen(c2w, focal, center, H, W, near, far, pix=pix, ginv=ginv)
+        out = _render_body_space(volume_renderer, anim_nerf, rays, P, chunk)
     return {k: v.view(B, n_rows, W, -1) for k, v in out.items()}
 
 

@@ -68,6 +68,67 @@ def sample_coarse(rays, n_coarse, perturb=0.0, noise_u=None, seed=0):
     return z
 
 
+def rays_sample(n_coarse, perturb=0.0, noise_u=None, seed=0, rays_world=None, camera=None, ginv=None):
+    """A1 + A2 + A3 in one launch (an_rays_sample_fwd).  Rays come from `rays_world` (B,R,8) or from
+    camera = dict(c2w (B,3,4), focal (B,2), center (B,2), H, W, near, far[, pix (B,R,2) int32 (row,col)]);
+    ginv (B,4,4) takes them to the body's root frame (near/far clamp included).  -> rays_body (B,R,8), z (B,R,Kc)."""
+    c2w = focal = center = pix = None
+    H = W = 0
+    near, far = 0.1, 10.0
+    if rays_world is not None:
+        rays_world = _f32c(rays_world)
+        B, R = rays_world.shape[:2]
+        dev = rays_world.device
+    else:
+        c2w, focal, center = _f32c(camera["c2w"]), _f32c(camera["focal"]), _f32c(camera["center"])
+        H, W, near, far = int(camera["H"]), int(camera["W"]), float(camera.get("near", 0.1)), float(camera.get("far", 10.0))
+        pix = camera.get("pix")
+        if pix is not None:
+            pix = pix.contiguous().to(torch.int32)
+        B, R = c2w.shape[0], (pix.shape[1] if pix is not None else H * W)
+        dev = c2w.device
+    if ginv is not None:
+        ginv = _f32c(ginv)
+    if noise_u is not None:
+        noise_u = _f32c(noise_u)
+    rays_body = torch.empty(B, R, 8, device=dev)
+    z = torch.empty(B, R, n_coarse, device=dev)
+    call("an_rays_sample_fwd", ptr(c2w), ptr(focal), ptr(center), ptr(pix), ptr(rays_world), ptr(ginv), B, R, H, W, int(n_coarse),
+         near, far, float(perturb), ptr(noise_u), int(seed), ptr(rays_body), ptr(z), stream())
+    return rays_body, z
+
+
+def rays_sample_bwd(rays_body, z, g_rays_body, g_z, rays_world=None, camera=None):
+    """Gradient of `rays_sample` with respect to ginv -> (B,4,4)."""
+    c2w = focal = center = pix = None
+    H = W = 0
+    near, far = 0.1, 10.0
+    if rays_world is not None:
+        rays_world = _f32c(rays_world)
+    else:
+        c2w, focal, center = _f32c(camera["c2w"]), _f32c(camera["focal"]), _f32c(camera["center"])
+        H, W, near, far = int(camera["H"]), int(camera["W"]), float(camera.get("near", 0.1)), float(camera.get("far", 10.0))
+        pix = camera.get("pix")
+        if pix is not None:
+            pix = pix.contiguous().to(torch.int32)
+    B, R, Kc = z.shape
+    g_ginv = torch.empty(B, 4, 4, device=z.device)
+    call("an_rays_sample_bwd", ptr(c2w), ptr(focal), ptr(center), ptr(pix), ptr(rays_world), ptr(rays_body), ptr(z),
+         ptr(_f32c(g_rays_body)), ptr(None if g_z is None else _f32c(g_z)), B, R, H, W, Kc, near, far, ptr(g_ginv), stream())
+    return g_ginv
+
+
+def ray_point_grad(rays, z, valid, g_xyz, g_z_comp=None, g_far_comp=None):
+    """Ray-side gradients of one render pass (an_ray_point_grad): -> g_rays (B,R,8) = [sum g_x, sum z g_x, 0, g_far],
+    g_z (B,R,K) = g_z_comp + g_x . d.  g_xyz is read at valid samples only (it may be uninitialised elsewhere)."""
+    B, R, K = z.shape
+    g_rays = torch.empty(B, R, 8, device=z.device)
+    g_z = torch.empty(B, R, K, device=z.device)
+    call("an_ray_point_grad", ptr(rays), ptr(z), ptr(valid), ptr(g_xyz), ptr(g_z_comp), ptr(g_far_comp), B * R, K,
+         ptr(g_rays), ptr(g_z), stream())
+    return g_rays, g_z
+
+
 # ------------------------------------------------------------------------ per-frame tables
 def _body_params(d):
     """dict(betas (B|1,10), global_orient (B,3), body_pose (B,69), transl (B,3)|None) -> B, betas (B,10), pose (B,72), transl."""
@@ -178,7 +239,8 @@ def knn_unpose(verts, ober2cano, lbs_weights, dis_threshold, xyz=None, rays=None
     return out
 
 
-def knn_unpose_bwd(g_xyz_cano, cidx, count, idx, qw, ober2cano, xyz=None, rays=None, z=None, want_g_xyz=True):
+def knn_unpose_bwd(g_xyz_cano, cidx, count, idx, qw, ober2cano, xyz=None, rays=None, z=None, want_g_xyz=True, zero_g_xyz=True):
+    """zero_g_xyz=False: g_xyz is left uninitialised at invalid points (for consumers that read valid points only)."""
     ober2cano = _f32c(ober2cano)
     B, V = ober2cano.shape[:2]
     if xyz is not None:
@@ -187,7 +249,7 @@ def knn_unpose_bwd(g_xyz_cano, cidx, count, idx, qw, ober2cano, xyz=None, rays=N
         R, K = z.shape[1], z.shape[2]
         N = R * K
     g_o2c = torch.zeros_like(ober2cano)
-    g_xyz = torch.zeros(B, N, 3, device=ober2cano.device) if want_g_xyz else None
+    g_xyz = (torch.zeros if zero_g_xyz else torch.empty)(B, N, 3, device=ober2cano.device) if want_g_xyz else None
     call("an_knn_unpose_bwd", ptr(g_xyz_cano), ptr(cidx), ptr(count), ptr(xyz), ptr(rays), ptr(z), B, R, K, N, V,
          ptr(idx), ptr(qw), ptr(ober2cano), ptr(g_o2c), ptr(g_xyz), stream())
     return g_o2c, g_xyz

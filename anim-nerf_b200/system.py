@@ -5,8 +5,9 @@ compatible with a LightningModule (`forward`, `training_step`, `configure_optimi
 `forward(rays (B,h,w,8), body_model_params, body_model_params_template, latent_code, perturb)`
 follows train.py:189-215: per-frame tables -> rays to body space -> render -> dict of (B,h,w,.).
 The reference's `chunk` loop (train.py:205-210) exists to bound the memory of its materialised
-gathers; the fused kernels need no chunking, so `chunk` only caps the rays per launch
-(default: all rays of the call at once).
+gathers; the fused kernels need no chunking: all rays of the call go through in one pass
+(`hparams.render_chunk`, when set, caps the rays per launch; the reference's own `chunk` = 2048 is
+accepted in the config and ignored, as it changes no value).
 
 Losses (train.py:228-322): rgb MSE + 0.1 * alpha L1 on coarse and fine run on the render outputs;
 the foreground/background density and the normal-smoothness regularisers query the MLP through
@@ -116,11 +117,14 @@ class AnimNeRFSystem(nn.Module):
         bs, h, w = rays.shape[:3]
         n_rays = h * w
         rays = rays.view(bs, n_rays, rays.shape[-1])
-        rays, _ = self.anim_nerf.setup_frame(body_model_params, body_model_params_template, rays)
-        chunk = getattr(self.hparams, "chunk", None) or n_rays
+        # per-frame tables; the rays stay in world space: their transform to the body's root frame is fused with the
+        # stratified sampling in the renderer's front-end kernel (ginv carries the gradient to the SMPL root)
+        _, ginv = self.anim_nerf.setup_frame(body_model_params, body_model_params_template, None)
+        chunk = getattr(self.hparams, "render_chunk", None) or n_rays      # the reference's `chunk` (2048) bounds ITS gathers' memory
         results = defaultdict(list)
         for i in range(0, max(n_rays, 1), max(chunk, 1)):
-            out = self.volume_renderer(self.anim_nerf, rays[:, i:i + chunk, :], perturb=perturb, noise=noise)
+            out = self.volume_renderer(self.anim_nerf, rays[:, i:i + chunk, :], perturb=perturb, ginv=ginv,
+                                       noise=None if noise is None else {k: (v[:, i:i + chunk] if v is not None else None) for k, v in noise.items()})
             for k, v in out.items():
                 results[k].append(v)
         return {k: torch.cat(v, 1).view(bs, h, w, v[0].shape[-1]) for k, v in results.items()}

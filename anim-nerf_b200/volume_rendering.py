@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .autograd import SampleCoarse, SampleFineMerge
+from .autograd import RaysSample, SampleCoarse, SampleFineMerge
 
 
 class VolumeRenderer(nn.Module):
@@ -45,6 +45,22 @@ class VolumeRenderer(nn.Module):
         return SampleCoarse.apply(rays, self.n_coarse, float(perturb), noise_u,
                                   self._seed() if (perturb > 0 and noise_u is None) else 0)
 
+    def rays_and_coarse_samples(self, ginv, rays_world=None, camera=None, perturb=0., noise_u=None):
+        """Fused front end (one launch): rays from `camera` (dict, see `ops.rays_sample`) or the given world-space
+        rays, taken to the body's root frame by ginv (None: left as they are) and sampled -> (rays_body, z_coarse)."""
+        src = {"rays_world": rays_world[..., :8].contiguous()} if rays_world is not None else {"camera": camera}
+        if self.device_rng and perturb > 0 and noise_u is None:
+            ref = rays_world if rays_world is not None else camera["c2w"]
+            B = ref.shape[0]
+            R = rays_world.shape[1] if rays_world is not None else (camera["pix"].shape[1] if camera.get("pix") is not None
+                                                                    else camera["H"] * camera["W"])
+            noise_u = torch.rand(B, R, self.n_coarse, device=ref.device)
+        seed = self._seed() if (perturb > 0 and noise_u is None) else 0
+        if ginv is not None and ginv.requires_grad and torch.is_grad_enabled():
+            return RaysSample.apply(ginv, src, self.n_coarse, float(perturb), noise_u, seed)
+        return ops.rays_sample(self.n_coarse, float(perturb), noise_u, seed, rays_world=src.get("rays_world"),
+                               camera=src.get("camera"), ginv=None if ginv is None else ginv.detach())
+
     def sample_fine_merge(self, z_coarse, weights, det=False, u=None):
         """Fused `sample_fine` + cat + sort (reference :199-207): takes the coarse depths and the full
         coarse weights (the kernel forms the mid-point bins and the w[1:-1] slice itself); returns
@@ -73,17 +89,26 @@ class VolumeRenderer(nn.Module):
                                            z_samp.contiguous(), rays[..., :8].contiguous(), self.white_bkgd, sigma_noise)
         return w, rgb, depth, acc
 
-    def forward(self, model, rays, perturb=0., noise=None, **kwargs):
+    def forward(self, model, rays, perturb=0., noise=None, ginv=None, camera=None, **kwargs):
+        """reference `VolumeRenderer.forward(model, rays, perturb, **kwargs)`.  Extensions: `noise` (explicit draws),
+        and the fused front end -- `ginv` (B,4,4): `rays` are WORLD-space rays (or None with `camera`: rays are
+        generated from the camera) and the body-space transform + stratified sampling run in one launch."""
         noise = noise or {}
-        rays = rays[..., :8].contiguous()
-        if rays.shape[0] * rays.shape[1] == 0:
+        fused_front = ginv is not None or camera is not None
+        if rays is not None:
+            rays = rays[..., :8].contiguous()
+        if rays is not None and rays.shape[0] * rays.shape[1] == 0:
             # no rays: the reference's torch chain returns empty tensors of the right shapes; the kernels are not launched
             bs, n = rays.shape[:2]
             keys = ["rgbs", "alphas", "depths"]
             if self.n_fine > 0 and not self.share_fine:
                 keys += ["rgbs_fine", "alphas_fine", "depths_fine"]
             return {k: rays.new_zeros(bs, n, 3 if k.startswith("rgbs") else 1) for k in keys}
-        z_coarse = self.sample_coarse(rays, perturb=perturb, noise_u=noise.get("coarse_u"))
+        if fused_front:
+            rays, z_coarse = self.rays_and_coarse_samples(ginv, rays_world=rays, camera=camera, perturb=perturb,
+                                                          noise_u=noise.get("coarse_u"))
+        else:
+            z_coarse = self.sample_coarse(rays, perturb=perturb, noise_u=noise.get("coarse_u"))
         no_grad_coarse = self.n_fine > 0 and self.share_fine
         # the fine pass re-queries the coarse samples of the same rays plus n_fine new depths: a fused model
         # hands its coarse-pass neighbour table over as seeds for the fine pass's search (bit-identical results)

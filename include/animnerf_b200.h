@@ -74,6 +74,29 @@ int an_sample_training_rays_fwd(const uint8_t* images, const uint8_t* masks,
 int an_sample_coarse_fwd(const float* rays, int64_t n_rays, int Kc, float perturb,
                          const float* noise_u, uint64_t seed, float* z, void* stream);
 
+/* ---- A1 + A2 + A3 in one launch ------------------------------------------------------------------
+ * an_rays_sample_fwd: ray generation (camera + pixel list / full grid, as an_raygen_fwd) OR given world-space rays
+ * rays_world (B,R,8) (the reference's training batches carry rays, train.py:172; then c2w/focal/center/pix may be
+ * NULL and near/far come from the rays), the body-space transform with the near/far clamp (ginv (B,4,4) or NULL)
+ * and the stratified depths of an_sample_coarse_fwd, fused: rays_body (B,R,8), z (B,R,Kc).
+ * an_rays_sample_bwd: gradient with respect to ginv (models/anim_nerf.py:131: the inverse SMPL root transform, the
+ * route from the rays to the body parameters under optim_body_params): g_rays_body (B,R,8) = gradients of
+ * [o', d', near', far'], g_z (B,R,Kc) or NULL -> g_ginv (B,4,4) (written; rows 0-2).  No gradient to the world rays.
+ * an_ray_point_grad: the ray-side gradients of one render pass from its per-point gradients (x = o + z d): g_xyz
+ * (n_rays*K,3) is read at valid samples only; g_z_comp (n_rays,K) / g_far_comp (n_rays) from an_composite_bwd or NULL;
+ * writes g_rays (n_rays,8) = [sum g_x, sum z g_x, 0, g_far_comp] and g_z (n_rays,K) = g_z_comp + g_x . d.        */
+int an_rays_sample_fwd(const float* c2w, const float* focal, const float* center, const int32_t* pix,
+                       const float* rays_world, const float* ginv, int B, int R, int H, int W, int Kc,
+                       float near_, float far_, float perturb, const float* noise_u, uint64_t seed,
+                       float* rays_body, float* z, void* stream);
+int an_rays_sample_bwd(const float* c2w, const float* focal, const float* center, const int32_t* pix,
+                       const float* rays_world, const float* rays_body, const float* z,
+                       const float* g_rays_body, const float* g_z, int B, int R, int H, int W, int Kc,
+                       float near_, float far_, float* g_ginv, void* stream);
+int an_ray_point_grad(const float* rays, const float* z, const uint8_t* valid, const float* g_xyz,
+                      const float* g_z_comp, const float* g_far_comp, int64_t n_rays, int K,
+                      float* g_rays, float* g_z, void* stream);
+
 /* ---- A5-A8 (+A4): K-nearest-vertex search fused with inverse skinning --------------------
  * replaces knn_cuda.KNN(k=4, transpose_mode=True).forward (call site
  * models/anim_nerf.py:82-83,158-159) + get_neighbs (:153-178) + unpose (:180-192) +

@@ -564,3 +564,60 @@ def test_body_tables_backward_matches_torch_builder(shared_template):
             print(shared_betas, k, "rel err %.3g" % err, "norm %.3g" % float(g_ref[k].norm()))
             assert g_ker[k].shape == g_ref[k].shape and err < 2e-4, (k, err)
     net.fused_tables = True
+
+
+# ------------------------------------------------------------------ fused ray front end (A1 + A2 + A3) and its backward
+def test_rays_sample_fused_matches_separate_kernels_and_autograd():
+    """an_rays_sample_fwd == an_raygen_fwd + an_sample_coarse_fwd bit for bit (camera and world-ray input, with explicit
+    noise); an_rays_sample_bwd == torch autograd of the reference arithmetic (models/anim_nerf.py:128-137 +
+    models/volume_rendering.py:29-56) with respect to ginv; an_ray_point_grad == the torch reductions it replaces."""
+    from anim_nerf_b200 import ops as o
+    rs = np.random.RandomState(12)
+    B, H, W, Kc = 3, 9, 7, 64
+    R = H * W
+    c2w = torch.from_numpy(np.stack([np.concatenate([np.linalg.qr(rs.normal(size=(3, 3)))[0], rs.normal(size=(3, 1))], 1) for _ in range(B)]).astype(np.float32)).to(DEV)
+    focal = torch.from_numpy(rs.uniform(8, 12, size=(B, 2)).astype(np.float32)).to(DEV)
+    center = torch.from_numpy(rs.uniform(3, 5, size=(B, 2)).astype(np.float32)).to(DEV)
+    A = rs.normal(size=(B, 3, 3)).astype(np.float32) * 0.3 + np.eye(3, dtype=np.float32)
+    g = np.zeros((B, 4, 4), np.float32); g[:, :3, :3] = A; g[:, :3, 3] = rs.normal(size=(B, 3)) * 0.5 + np.array([0, 0, 2.5]); g[:, 3, 3] = 1
+    ginv = torch.from_numpy(g).to(DEV)
+    noise = torch.rand(B, R, Kc, device=DEV, generator=torch.Generator(DEV).manual_seed(1))
+    cam = dict(c2w=c2w, focal=focal, center=center, H=H, W=W, near=0.1, far=10.0)
+    for perturb in (0.0, 1.0):
+        rays_ref = o.raygen(c2w, focal, center, H, W, 0.1, 10.0, ginv=ginv)
+        z_ref = o.sample_coarse(rays_ref, Kc, perturb, noise_u=noise if perturb > 0 else None)
+        rb, z = o.rays_sample(Kc, perturb, noise if perturb > 0 else None, camera=cam, ginv=ginv)
+        assert torch.equal(rb, rays_ref) and torch.equal(z, z_ref)
+        rays_w = o.raygen(c2w, focal, center, H, W, 0.1, 10.0)
+        rb2, z2 = o.rays_sample(Kc, perturb, noise if perturb > 0 else None, rays_world=rays_w, ginv=ginv)
+        assert (rb2 - rays_ref).abs().max() < 1e-5 and (z2 - z_ref).abs().max() < 1e-5
+    # backward w.r.t. ginv against torch autograd of the same arithmetic
+    from anim_nerf_b200.anim_nerf import AnimNeRF
+    c_r = torch.from_numpy(rs.normal(size=(B, R, 8)).astype(np.float32)).to(DEV)
+    c_z = torch.from_numpy(rs.normal(size=(B, R, Kc)).astype(np.float32)).to(DEV)
+    gi = ginv.clone().requires_grad_(True)
+    rb_t = AnimNeRF.rays_to_body_space(rays_w, gi)
+    near, far = rb_t[..., 6:7], rb_t[..., 7:8]
+    t = torch.linspace(0, 1 - 1.0 / Kc, Kc, device=DEV)
+    zt = near * (1 - t) + far * t
+    mid = 0.5 * (zt[..., 1:] + zt[..., :-1])
+    zt = torch.cat([zt[..., :1], mid], -1) + (torch.cat([mid, zt[..., -1:]], -1) - torch.cat([zt[..., :1], mid], -1)) * noise
+    ((rb_t * c_r).sum() + (zt * c_z).sum()).backward()
+    rb, z = o.rays_sample(Kc, 1.0, noise, rays_world=rays_w, ginv=ginv)
+    g_k = o.rays_sample_bwd(rb, z, c_r, c_z, rays_world=rays_w)
+    err = float((g_k[:, :3] - gi.grad[:, :3]).norm() / gi.grad[:, :3].norm())
+    assert err < 1e-4, err
+    g_c = o.rays_sample_bwd(rb, z, c_r, c_z, camera=cam)          # world rays regenerated from the camera
+    assert float((g_c[:, :3] - gi.grad[:, :3]).norm() / gi.grad[:, :3].norm()) < 1e-4
+    # ray-side gradients of a pass
+    K = 96
+    zz = torch.sort(torch.rand(B, R, K, device=DEV) * 3 + 1, -1)[0]
+    valid = (torch.rand(B, R, K, device=DEV) < 0.4).to(torch.uint8)
+    gx = torch.randn(B, R, K, 3, device=DEV)
+    gx_dirty = torch.where(valid[..., None].bool(), gx, torch.full_like(gx, float("nan")))      # invalid entries must not be read
+    gzc, gfar = torch.randn(B, R, K, device=DEV), torch.randn(B, R, device=DEV)
+    g_rays, g_z = o.ray_point_grad(rb, zz, valid, gx_dirty.view(B, R * K, 3), gzc, gfar)
+    gxm = gx * valid[..., None]
+    assert (g_rays[..., 0:3] - gxm.sum(2)).abs().max() < 1e-4 and (g_rays[..., 3:6] - (gxm * zz[..., None]).sum(2)).abs().max() < 2e-4
+    assert torch.equal(g_rays[..., 7], gfar) and float(g_rays[..., 6].abs().max()) == 0
+    assert (g_z - (gzc + (gxm * rb[:, :, None, 3:6]).sum(-1))).abs().max() < 1e-5
