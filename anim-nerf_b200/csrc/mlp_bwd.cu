@@ -89,13 +89,14 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                     const int s = step_of(i);
                     if (!want_gx && (s == 6 || s == 10)) continue;
                     const uint32_t bytes = bs_chunk_bytes(s) >> 1;       // this CTA's half of the rows
-                    for (int t = 0; t < 2; ++t)
-                        for (int kc = 0; kc < bs_chunks(s); ++kc, ++it) {
-                            const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1u;
-                            mbar_wait(bar_empty + 8 * st, ph ^ 1u);
-                            mbar_expect_tx(bar_full + 8 * st, bytes);
-                            bulk_g2s(sbase + SM_WST + st * STAGE_BYTES, packed + bwd_chunk_off(s, kc) + rank * bytes, bytes, bar_full + 8 * st);
-                        }
+                    // one load per chunk: both tiles of the CTA run their MMAs against the same staged copy (a step has
+                    // at most 4 chunks, the ring 6 stages: the next step's first chunks prefetch meanwhile)
+                    for (int kc = 0; kc < bs_chunks(s); ++kc, ++it) {
+                        const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1u;
+                        mbar_wait(bar_empty + 8 * st, ph ^ 1u);
+                        mbar_expect_tx(bar_full + 8 * st, bytes);
+                        bulk_g2s(sbase + SM_WST + st * STAGE_BYTES, packed + bwd_chunk_off(s, kc) + rank * bytes, bytes, bar_full + 8 * st);
+                    }
                 }
         }
     } else if (warp == 1 && rank != 0) {
@@ -105,7 +106,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                 for (int i = 0; i < 11; ++i) {
                     const int s = step_of(i);
                     if (!want_gx && (s == 6 || s == 10)) continue;
-                    for (int j = 0; j < 2 * bs_chunks(s); ++j, ++it) {
+                    for (int j = 0; j < bs_chunks(s); ++j, ++it) {
                         const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1u;
                         mbar_wait(bar_full + 8 * st, ph);
                         mbar_arrive_remote(bar_full + 8 * st, 0);
@@ -120,23 +121,24 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                     const int s = step_of(i);
                     if (!want_gx && (s == 6 || s == 10)) continue;
                     const uint32_t idesc = make_idesc_bf16(256, bs_rows(s), 0, 0);
+                    const int nc = bs_chunks(s);
                     for (int t = 0; t < 2; ++t) {
                         mbar_wait(bar_act + 8 * t, act_phase);
                         tc_fence_after();
-                        for (int kc = 0; kc < bs_chunks(s); ++kc, ++it) {
-                            const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1u;
-                            mbar_wait(bar_full + 8 * st, ph);
-                            tc_fence_after();
+                        for (int kc = 0; kc < nc; ++kc) {
+                            const uint32_t i2 = it + kc, st = i2 % NSTAGE, ph = (i2 / NSTAGE) & 1u;
+                            if (t == 0) { mbar_wait(bar_full + 8 * st, ph); tc_fence_after(); }       // tile 1 reuses the staged chunk
                             const uint32_t wb = sbase + SM_WST + st * STAGE_BYTES;
                             const uint32_t ab = sbase + SM_ACT + t * 65536u + kc * 16384u;
                             const int nk = bs_ksteps(s, kc);
                             for (int k = 0; k < nk; ++k)
                                 umma_pair(tmem_base + t * 256u, make_desc(ab + k * 32u, 16, 1024),
                                           make_desc(wb + k * 32u, 16, 1024), idesc, (kc > 0 || k > 0) ? 1u : 0u);
-                            umma_commit_pair(bar_empty + 8 * st);
+                            if (t == 1) umma_commit_pair(bar_empty + 8 * st);      // both tiles done with the stage
                         }
                         umma_commit_pair(bar_acc + 8 * t);
                     }
+                    it += nc;
                     act_phase ^= 1u;
                 }
         }
