@@ -32,6 +32,9 @@ def _rank_world(rank, world):
     return rank, world
 
 
+_PIX_CACHE = {}
+
+
 # ------------------------------------------------------------------ full-frame rendering
 @torch.no_grad()
 def batched_inference(volume_renderer, anim_nerf, rays, body_model_params, body_model_params_template,
@@ -74,14 +77,20 @@ def render_frame(volume_renderer, anim_nerf, c2w, focal, center, H, W, body_mode
     B = c2w.shape[0]
     if rows is None or (isinstance(rows, tuple) and tuple(rows) == (0, H)):
         pix, n_rows = None, H
-    else:       # explicit pixel list (row, col)
-        if isinstance(rows, tuple):
-            rr = torch.arange(rows[0], rows[1], device=c2w.device, dtype=torch.int32)
-        else:
-            rr = torch.as_tensor(rows, device=c2w.device, dtype=torch.int32)
-        n_rows = rr.numel()
-        cc = torch.arange(W, device=c2w.device, dtype=torch.int32)
-        pix = torch.stack(torch.meshgrid(rr, cc, indexing="ij"), -1).view(1, -1, 2).expand(B, -1, -1).contiguous()
+    else:       # explicit pixel list (row, col); cached per (rows, W, B, device): a sequence renders the same rows every frame
+        key = (rows if isinstance(rows, tuple) else tuple(int(r) for r in rows), W, B, str(c2w.device))
+        pix = _PIX_CACHE.get(key)
+        if pix is None:
+            if isinstance(rows, tuple):
+                rr = torch.arange(rows[0], rows[1], device=c2w.device, dtype=torch.int32)
+            else:
+                rr = torch.as_tensor(rows, device=c2w.device, dtype=torch.int32)
+            cc = torch.arange(W, device=c2w.device, dtype=torch.int32)
+            pix = torch.stack(torch.meshgrid(rr, cc, indexing="ij"), -1).view(1, -1, 2).expand(B, -1, -1).contiguous()
+            if len(_PIX_CACHE) > 16:
+                _PIX_CACHE.clear()
+            _PIX_CACHE[key] = pix
+        n_rows = pix.shape[1] // W
     if P is None and chunk is None:
         # ray generation + body-space transform + stratified sampling in ONE launch (an_rays_sample_fwd)
         cam = dict(c2w=c2w, focal=focal, center=center, H=H, W=W, near=near, far=far, pix=pix)
@@ -117,15 +126,15 @@ def create_grid(N, x_range, y_range, z_range):
     return np.stack(np.meshgrid(x, y, z), -1)
 
 
-def grid_slab_points(N, x_range, y_range, z_range, center, i0, i1, device):
-    """Points of lattice slab grid[i0:i1] as (1, (i1-i0)*N*N, 3) fp32 on `device`, equal bit for bit
-    to `torch.from_numpy(create_grid(...)[i0:i1].reshape(-1,3)).float() + center` (extract_mesh.py:152-156)
+def grid_slab_points(N, x_range, y_range, z_range, center, i0, i1, device, step=1):
+    """Points of lattice rows grid[i0:i1:step] as (1, n*N*N, 3) fp32 on `device`, equal bit for bit
+    to `torch.from_numpy(create_grid(...)[i0:i1:step].reshape(-1,3)).float() + center` (extract_mesh.py:152-156)
     without materialising the 3.2 GB float64 lattice on the host: the three 1-D axes come from numpy
     (same linspace rounding), the outer product is formed on the device."""
     x = torch.from_numpy(np.linspace(x_range[0], x_range[1], N)).float().to(device)
-    y = torch.from_numpy(np.linspace(y_range[0], y_range[1], N)[i0:i1]).float().to(device)
+    y = torch.from_numpy(np.linspace(y_range[0], y_range[1], N)[i0:i1:step]).float().to(device)
     z = torch.from_numpy(np.linspace(z_range[0], z_range[1], N)).float().to(device)
-    n = i1 - i0
+    n = y.numel()
     pts = torch.empty(n, N, N, 3, device=device)
     pts[..., 0] = x.view(1, N, 1)
     pts[..., 1] = y.view(n, 1, 1)
@@ -153,30 +162,32 @@ def query_density_grid(anim_nerf, N, x_range=(-1.2, 1.2), y_range=(-1.2, 1.2), z
                        center=None, slab=None, slab_rows=None, out=None):
     """relu(sigma) on the N^3 lattice around the posed body (extract_mesh.py:152-160) -> (n_slab,N,N) fp32.
     Uses the per-frame state already set on `anim_nerf` (batch of one frame).  `center` defaults to the
-    posed bounding-box centre (:155).  slab=(i0,i1): only lattice rows i0..i1 of the first axis;
+    posed bounding-box centre (:155).  slab=(i0,i1[,step]): only lattice rows i0, i0+step, ... < i1 of the first axis;
     slab_rows bounds the rows per launch (default: 16 Mi points)."""
     verts = anim_nerf.verts
     dev = verts.device
     if center is None:
         center = (verts.max(dim=1)[0] + verts.min(dim=1)[0]) / 2.0
-    i0, i1 = slab if slab is not None else (0, N)
+    i0, i1, step = (tuple(slab) + (1,))[:3] if slab is not None else (0, N, 1)
+    n_out = len(range(i0, i1, step))
     slab_rows = slab_rows or max(1, (1 << 24) // (N * N))
     if out is None:
-        out = torch.empty(i1 - i0, N, N, device=dev)
-    for a in range(i0, i1, slab_rows):
-        b = min(i1, a + slab_rows)
-        pts = grid_slab_points(N, x_range, y_range, z_range, center[0], a, b, dev)
-        out[a - i0:b - i0] = batched_point_inference(anim_nerf, pts).view(b - a, N, N)
+        out = torch.empty(n_out, N, N, device=dev)
+    for k in range(0, n_out, slab_rows):
+        m = min(slab_rows, n_out - k)
+        a = i0 + k * step
+        pts = grid_slab_points(N, x_range, y_range, z_range, center[0], a, a + (m - 1) * step + 1, dev, step)
+        out[k:k + m] = batched_point_inference(anim_nerf, pts).view(m, N, N)
     return out
 
 
 @torch.no_grad()
 def query_density_grid_sharded(anim_nerf, N, rank=None, world=None, gather=True, **kw):
-    """Slab-sharded grid query: rank r owns lattice rows shard_range(N, r, world); no data-path
-    collective, optional all_gather of the finished slabs."""
+    """Sharded grid query: rank r owns lattice rows r, r + world, ... of the first axis (interleaved: the body fills the
+    middle of the lattice, contiguous slabs would leave the outer ranks idle); no data-path collective, optional
+    all_gather of the finished rows back in lattice order."""
     rank, world = _rank_world(rank, world)
-    slab = shard_range(N, rank, world)
-    out = query_density_grid(anim_nerf, N, slab=slab, **kw)
+    out = query_density_grid(anim_nerf, N, slab=(rank, N, world), **kw)
     if gather and world > 1:
-        out = gather_slabs(out, N, dim=0)
+        out = gather_rows(out, N, dim=0)
     return out

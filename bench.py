@@ -341,8 +341,8 @@ def run_ours(args):
     ms_1080, cov_1080, bytes_1080 = frame_bench(1080, 1080, n_seq_timed, lambda i: seq[(i * 17) % n_seq])
     an.setup_frame(seq[0], t1, None)
     NG = 512
-    slab = dist_utils.shard_range(NG, rank, world)
-    gbuf = torch.empty(slab[1] - slab[0], NG, NG, device=dev)
+    slab = (rank, NG, world)                         # lattice rows rank, rank + world, ... (interleaved)
+    gbuf = torch.empty(len(range(*slab)), NG, NG, device=dev)
 
     def grid():
         inference.query_density_grid(an, NG, slab=slab, out=gbuf)
@@ -435,7 +435,7 @@ def run_ours(args):
                                "d2h_bytes_per_frame": bytes_1080, "foreground_pixel_fraction": cov_1080},
             "grid_512": {"ms": ms_grid, "points_per_s": NG ** 3 / (ms_grid * 1e-3),
                          "workload": "cfg4: extract_mesh density query, 512^3 lattice around the posed body, AnimNeRF.forward on "
-                                     "every point (KNN + unpose, MLP on the valid ones, relu(sigma)), lattice slabs sharded over %d GPU(s)" % world},
+                                     "every point (KNN + unpose, MLP on the valid ones, relu(sigma)), lattice rows interleaved over %d GPU(s)" % world},
             "full_training_step": full,
             "frozen_body_params_step": frozen,
             "weights_in_sync": in_sync,

@@ -133,7 +133,8 @@ def test_density_grid_matches_oracle_and_slabs_are_bit_identical():
     bad = ((sig.cpu() - s_ref).abs() > 5e-2).float().mean()
     assert float(bad) < 2e-3, float(bad)
     for world in (2, 3):
-        slabs = [inference.query_density_grid_sharded(an, N, rank=r, world=world, gather=False) for r in range(world)]
-        assert torch.equal(torch.cat(slabs, 0), sig), world
+        parts = [inference.query_density_grid_sharded(an, N, rank=r, world=world, gather=False) for r in range(world)]
+        for r in range(world):                       # rank r owns lattice rows r, r + world, ...
+            assert torch.equal(parts[r], sig[r::world]), (world, r)
     small = inference.query_density_grid(an, N, slab_rows=3)
     assert torch.equal(small, sig)
