@@ -114,7 +114,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                 }
         }
     } else if (warp == 1) {
-        if (lane == 0) {          // leader: MMA issuer for both CTAs
+        {          // leader: MMA issuer for both CTAs (whole warp runs the loop, one elected lane issues: tc::elect_one)
             uint32_t it = 0, act_phase = 0;
             for (int64_t iter = pair; iter < num_iters; iter += npairs)
                 for (int i = 0; i < 11; ++i) {
@@ -131,12 +131,16 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                             const uint32_t wb = sbase + SM_WST + st * STAGE_BYTES;
                             const uint32_t ab = sbase + SM_ACT + t * 65536u + kc * 16384u;
                             const int nk = bs_ksteps(s, kc);
-                            for (int k = 0; k < nk; ++k)
-                                umma_pair(tmem_base + t * 256u, make_desc(ab + k * 32u, 16, 1024),
-                                          make_desc(wb + k * 32u, 16, 1024), idesc, (kc > 0 || k > 0) ? 1u : 0u);
-                            if (t == 1) umma_commit_pair(bar_empty + 8 * st);      // both tiles done with the stage
+                            if (elect_one()) {
+                                for (int k = 0; k < nk; ++k)
+                                    umma_pair(tmem_base + t * 256u, make_desc(ab + k * 32u, 16, 1024),
+                                              make_desc(wb + k * 32u, 16, 1024), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                                if (t == 1) umma_commit_pair(bar_empty + 8 * st);      // both tiles done with the stage
+                            }
+                            __syncwarp();
                         }
-                        umma_commit_pair(bar_acc + 8 * t);
+                        if (elect_one()) umma_commit_pair(bar_acc + 8 * t);
+                        __syncwarp();
                     }
                     it += nc;
                     act_phase ^= 1u;
@@ -411,7 +415,7 @@ mlp_bwd_wgrad_kernel(const uint8_t* __restrict__ stash, const uint8_t* __restric
                 }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // MMA issuer: whole warp runs the loop, one elected lane issues (tc::elect_one)
             uint32_t it = 0;
             const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);           // both operands MN-major
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
@@ -420,15 +424,19 @@ mlp_bwd_wgrad_kernel(const uint8_t* __restrict__ stash, const uint8_t* __restric
                     mbar_wait(bar_full + 8 * st, ph);
                     tc_fence_after();
                     const uint32_t ab = sbase + st * WG_STAGE_BYTES, bb = ab + 32768u;
-                    for (int h = 0; h < M_halves; ++h)
+                    if (elect_one()) {
+                        for (int h = 0; h < M_halves; ++h)
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)      // 16 points per UMMA K-step = 2 x (8 rows x 128 B)
-                            umma(tmem_base + h * 256u,
-                                 make_desc(ab + h * 16384u + k * 2048u, 8192, 1024),
-                                 make_desc(bb + k * 2048u, 8192, 1024), idesc, (it > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(bar_empty + 8 * st);
+                            for (int k = 0; k < 4; ++k)      // 16 points per UMMA K-step = 2 x (8 rows x 128 B)
+                                umma(tmem_base + h * 256u,
+                                     make_desc(ab + h * 16384u + k * 2048u, 8192, 1024),
+                                     make_desc(bb + k * 2048u, 8192, 1024), idesc, (it > 0 || k > 0) ? 1u : 0u);
+                        umma_commit(bar_empty + 8 * st);
+                    }
+                    __syncwarp();
                 }
-            umma_commit(bar_done);
+            if (elect_one()) umma_commit(bar_done);
+            __syncwarp();
         }
     } else {
         // warps 2..9: bias gradient = column sums of the dY image (thread = dY column), then the

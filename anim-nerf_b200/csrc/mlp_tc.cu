@@ -34,6 +34,7 @@
 // fused head layer executes 1 118 208 of them, the bias steps add 9 x 8192); per 512-point iteration
 // the pair issues (36 chunks x 4 + 9) x 2 tiles MMAs of M = 256.  Algorithmic HBM bytes per point:
 // 16 B in (id + xyz), 16 B out.
+#include <stdlib.h>
 #include "common.cuh"
 #include "mlp_layout.cuh"
 #include "tc_common.cuh"
@@ -156,23 +157,25 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ leader: MMA issuer for both CTAs
-        if (lane == 0) {
+        // (whole warp runs the loop so the operands stay warp-uniform; one elected lane issues, see elect_one())
+        {
             TRACE_DECL;
+            const bool tr = lane == 0; (void)tr;
             uint32_t it = 0, act_phase = 0;
             for (int64_t iter = pair; iter < num_iters; iter += npairs)
                 for (int g = 0; g < NGT; ++g) {
                     const uint32_t idesc = make_idesc_bf16(256, g_N(g), 0, 0);
                     const int nc = g_chunks(g), ns = ring_steps(g);
                     for (int t = 0; t < 2; ++t) {
-                        TRACE(1, 0, g, t);
+                        if (tr) TRACE(1, 0, g, t);
                         mbar_wait(bar_act + 8 * t, act_phase);
-                        TRACE(1, 1, g, t);
+                        if (tr) TRACE(1, 1, g, t);
                         tc_fence_after();
                         for (int kc = 0; kc < ns; ++kc, ++it) {
                             const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
-                            TRACE(1, 3, g, t * 8 + kc);
+                            if (tr) TRACE(1, 3, g, t * 8 + kc);
                             mbar_wait(bar_full + 8 * s, ph);
-                            TRACE(1, 2, g, t * 8 + kc);
+                            if (tr) TRACE(1, 2, g, t * 8 + kc);
                             tc_fence_after();
                             const uint32_t wb = sbase + SM_WST + s * STAGE_BYTES;
                             if (kc < nc) {
@@ -180,18 +183,23 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                                 const int ac = (g == 4) ? kc - 1 : kc;
                                 const uint32_t ab = from_enc ? (sbase + SM_ENC + t * 16384u)
                                                              : (sbase + SM_ACT + t * 65536u + ac * 16384u);
+                                if (elect_one()) {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    umma_pair(tmem_base + t * 256u, make_desc(ab + k * 32u, 16, 1024),
-                                              make_desc(wb + k * 32u, 16, 1024), idesc, (kc > 0 || k > 0) ? 1u : 0u);
-                            } else {
+                                    for (int k = 0; k < 4; ++k)
+                                        umma_pair(tmem_base + t * 256u, make_desc(ab + k * 32u, 16, 1024),
+                                                  make_desc(wb + k * 32u, 16, 1024), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                                    umma_commit_pair(bar_empty + 8 * s);   // stage free (in both CTAs) once these MMAs retire
+                                }
+                            } else if (elect_one()) {
                                 // bias step: A = K-step 3 of the encoding image (column 63 = 1), B = the slab (k = 15 = bias)
                                 umma_pair(tmem_base + t * 256u, make_desc(sbase + SM_ENC + t * 16384u + 96u, 16, 1024),
                                           make_desc_noswz(wb, 128, 256), idesc, 1u);
+                                umma_commit_pair(bar_empty + 8 * s);
                             }
-                            umma_commit_pair(bar_empty + 8 * s);   // stage free (in both CTAs) once these MMAs retire
+                            __syncwarp();
                         }
-                        umma_commit_pair(bar_acc + 8 * t);          // accumulators of (layer g, tile t) complete in both CTAs
+                        if (elect_one()) umma_commit_pair(bar_acc + 8 * t);   // accumulators of (layer g, tile t) complete in both CTAs
+                        __syncwarp();
                     }
                     act_phase ^= 1u;
                 }
@@ -393,6 +401,9 @@ static inline int pair_grid(int64_t n_max)
     return 2 * (int)(iters < pairs ? iters : pairs);
 }
 
+int mlp_fwd_ts_launch(const void* packed, const float* xyz_cano, const int32_t* cidx, const int32_t* count,
+                      int64_t n_max, float* sigma, float* rgb, cudaStream_t stream);      // mlp_ts.cu
+
 extern "C" int an_mlp_fwd(const void* packed, const float* xyz_cano, const int32_t* cidx, const int32_t* count,
                           int64_t n_max, float* sigma, float* rgb, void* stash, void* stream)
 {
@@ -400,6 +411,8 @@ extern "C" int an_mlp_fwd(const void* packed, const float* xyz_cano, const int32
     if (cidx && !count) return AN_ERR_ARG;
     if (((uintptr_t)packed) & 1023) return AN_ERR_ALIGN;
     if (stash && (((uintptr_t)stash) & 127)) return AN_ERR_ALIGN;
+    static const bool ss_only = getenv("AN_MLP_SS") != nullptr;       // A/B switch while the TMEM-operand kernel is evaluated
+    if (!stash && !ss_only) return mlp_fwd_ts_launch(packed, xyz_cano, cidx, count, n_max, sigma, rgb, (cudaStream_t)stream);
     cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);

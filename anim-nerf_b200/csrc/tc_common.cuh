@@ -164,6 +164,16 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 }
 
 // ---- thread-block cluster
+// One lane of a converged warp.  The MMA issuers run their loops with the WHOLE warp and issue under elect_one():
+// behind a data-dependent `lane == 0` the compiler cannot prove that a single lane is active and wraps every
+// tcgen05.mma / commit in a vote + R2UR.BROADCAST loop (~100 issue cycles per MMA, measured with tools/micro/mma_rate.cu:
+// N = 128 back-to-back MMAs 143 clk each behind lane == 0, 79 behind elect.sync).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
