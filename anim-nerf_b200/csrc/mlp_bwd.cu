@@ -82,7 +82,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
     // roles as in the forward (mlp_tc.cu): producer in both CTAs, MMA issuer in the leader / stage relay in the
     // peer, epilogue warps; the tiles of a CTA ping-pong: MMAs of one tile overlap the other tile's epilogue
     if (warp == 0) {
-        if (lane == 0) {
+        {   // whole warp runs the loop, one elected lane issues (tc::elect_one)
             uint32_t it = 0;
             for (int64_t iter = pair; iter < num_iters; iter += npairs)
                 for (int i = 0; i < 11; ++i) {
@@ -94,8 +94,11 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                     for (int kc = 0; kc < bs_chunks(s); ++kc, ++it) {
                         const uint32_t st = it % NSTAGE, ph = (it / NSTAGE) & 1u;
                         mbar_wait(bar_empty + 8 * st, ph ^ 1u);
-                        mbar_expect_tx(bar_full + 8 * st, bytes);
-                        bulk_g2s(sbase + SM_WST + st * STAGE_BYTES, packed + bwd_chunk_off(s, kc) + rank * bytes, bytes, bar_full + 8 * st);
+                        if (elect_one()) {
+                            mbar_expect_tx(bar_full + 8 * st, bytes);
+                            bulk_g2s(sbase + SM_WST + st * STAGE_BYTES, packed + bwd_chunk_off(s, kc) + rank * bytes, bytes, bar_full + 8 * st);
+                        }
+                        __syncwarp();
                     }
                 }
         }
@@ -174,7 +177,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                 dp0 = g_rgb[id * 3] * a0 * (1.f - a0); dp1 = g_rgb[id * 3 + 1] * a1 * (1.f - a1); dp2 = g_rgb[id * 3 + 2] * a2 * (1.f - a2);
             }
             // this warp's bulk stores of the previous iteration must have finished reading its rows of the image
-            if (lane == 0) bulk_wait_read0();
+            if (elect_one()) bulk_wait_read0();
             __syncwarp();
             {   // d rgb_pre -> A image of step 0 (K = 16: units 0,1 of chunk 0; columns 0..2 carry data)
                 *(uint4*)(act_row + ((0u ^ sw) << 4)) = make_uint4(pack_bf16(dp0, dp1), pack_bf16(dp2, 0.f), 0u, 0u);
@@ -182,7 +185,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
             }
             fence_proxy_async();
             __syncwarp();         // every warp streams its own 32 rows (4 KB, contiguous in the image) to the scratch
-            if (lane == 0) { bulk_s2g(dy_tile + DY_RGB + q * 4096, act_s + q * 4096u, 4096); bulk_commit(); }
+            if (elect_one()) { bulk_s2g(dy_tile + DY_RGB + q * 4096, act_s + q * 4096u, 4096); bulk_commit(); }
             mbar_arrive_remote(my_act, 0);
 
             // encoding derivative factors (same double-angle recurrence as the forward)
@@ -216,7 +219,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                     // this warp's bulk stores of the previous image must have drained before this step overwrites its
                     // rows; waited for here (the overwrite itself happens after the accumulator wait, i.e. after the
                     // MMAs that read the image as their A operand), off the critical path
-                    if (lane == 0) bulk_wait_read0();
+                    if (elect_one()) bulk_wait_read0();
                     __syncwarp();
                 }
                 mbar_wait(my_acc, acc_phase); acc_phase ^= 1u;
@@ -283,7 +286,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                         // the scratch now -- small stores spread over the epilogue, no 128-thread barrier
                         fence_proxy_async();
                         __syncwarp();
-                        if (lane == 0) {
+                        if (elect_one()) {
                             const uint32_t off = (uint32_t)(cb >> 1) * 16384u + (uint32_t)q * 4096u;
                             bulk_s2g(dy_tile + dy_off + off, act_s + off, 4096);
                             bulk_commit();
@@ -298,7 +301,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                 fence_proxy_async();
                 if (s == 0) {   // the d sigma chunk of the head layer's dY
                     __syncwarp();
-                    if (lane == 0) {
+                    if (elect_one()) {
                         const uint32_t off = 2u * 16384u + (uint32_t)q * 4096u;
                         bulk_s2g(dy_tile + dy_off + off, act_s + off, 4096);
                         bulk_commit();
@@ -307,7 +310,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                 if (!(s == 9 && !want_gx)) mbar_arrive_remote(my_act, 0);      // last step has no consumer MMA
             }
         }
-        if (lane == 0) bulk_wait0();
+        if (elect_one()) bulk_wait0();
     }
     tc_fence_before();
     cluster_sync_all();          // the peer's shared memory / TMEM stay alive until the leader's last MMA has retired
@@ -399,19 +402,22 @@ mlp_bwd_wgrad_kernel(const uint8_t* __restrict__ stash, const uint8_t* __restric
 
     // stage layout: A chunks (a_chunks x 8 KB: 64 points x 128 B each) then B chunks at +32 KB
     if (warp == 0) {
-        if (lane == 0) {
+        {   // whole warp runs the loop, one elected lane issues (tc::elect_one)
             uint32_t it = 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
                 for (int half = 0; half < 2; ++half, ++it) {
                     const uint32_t st = it % WG_STAGES, ph = (it / WG_STAGES) & 1u;
                     mbar_wait(bar_empty + 8 * st, ph ^ 1u);
                     mbar_wait(bar_cs + 8 * st, ph ^ 1u);          // column-sum readers are done with the stage too
-                    mbar_expect_tx(bar_full + 8 * st, a_half_bytes + b_half_bytes);
                     const uint32_t dst = sbase + st * WG_STAGE_BYTES;
                     const uint8_t* asrc = a_base + tile * a_tile + job.a_off + half * 8192;
                     const uint8_t* bsrc = b_base + tile * b_tile + job.b_off + half * 8192;
-                    for (int c = 0; c < job.a_chunks; ++c) bulk_g2s(dst + c * 8192u, asrc + c * 16384, 8192, bar_full + 8 * st);
-                    for (int c = 0; c < job.b_chunks; ++c) bulk_g2s(dst + 32768u + c * 8192u, bsrc + c * 16384, 8192, bar_full + 8 * st);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_full + 8 * st, a_half_bytes + b_half_bytes);
+                        for (int c = 0; c < job.a_chunks; ++c) bulk_g2s(dst + c * 8192u, asrc + c * 16384, 8192, bar_full + 8 * st);
+                        for (int c = 0; c < job.b_chunks; ++c) bulk_g2s(dst + 32768u + c * 8192u, bsrc + c * 16384, 8192, bar_full + 8 * st);
+                    }
+                    __syncwarp();
                 }
         }
     } else if (warp == 1) {

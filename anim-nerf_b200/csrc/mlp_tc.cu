@@ -34,7 +34,6 @@
 // fused head layer executes 1 118 208 of them, the bias steps add 9 x 8192); per 512-point iteration
 // the pair issues (36 chunks x 4 + 9) x 2 tiles MMAs of M = 256.  Algorithmic HBM bytes per point:
 // 16 B in (id + xyz), 16 B out.
-#include <stdlib.h>
 #include "common.cuh"
 #include "mlp_layout.cuh"
 #include "tc_common.cuh"
@@ -124,7 +123,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
 
     if (warp == 0) {
         // ------------------------------------------------------------ weight producer (this CTA's half of every B operand)
-        if (lane == 0) {
+        {   // whole warp runs the loop, one elected lane issues (uniform operands, see tc::elect_one)
             TRACE_DECL;
             uint32_t it = 0;
             for (int64_t iter = pair; iter < num_iters; iter += npairs)
@@ -135,9 +134,12 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                             const uint32_t bytes = (kc < nc ? g_chunk_bytes(g) : g_bias_bytes(g)) >> 1;
                             const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1u;
                             mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                            TRACE(0, 0, g, t * 8 + kc);
-                            mbar_expect_tx(bar_full + 8 * s, bytes);
-                            bulk_g2s(sbase + SM_WST + s * STAGE_BYTES, packed + fwd_chunk_off(g, kc) + rank * bytes, bytes, bar_full + 8 * s);
+                            if (lane == 0) TRACE(0, 0, g, t * 8 + kc);
+                            if (elect_one()) {
+                                mbar_expect_tx(bar_full + 8 * s, bytes);
+                                bulk_g2s(sbase + SM_WST + s * STAGE_BYTES, packed + fwd_chunk_off(g, kc) + rank * bytes, bytes, bar_full + 8 * s);
+                            }
+                            __syncwarp();
                         }
                 }
         }
@@ -262,7 +264,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 }
                 ev[63] = TAN ? tsc : 1.f;
                 if (TRAIN) {      // this warp's TMA stores of the previous iteration must have drained its rows
-                    if (lane == 0) bulk_wait_read0();
+                    if (elect_one()) bulk_wait_read0();
                     __syncwarp();
                 }
 #pragma unroll
@@ -276,7 +278,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             fence_proxy_async();
             if (TRAIN) {          // every warp streams its own 32 rows (4 KB, contiguous in the image) to the stash
                 __syncwarp();
-                if (lane == 0) { bulk_s2g(st_tile + ST_ENC + q * 4096, enc_s + q * 4096u, 4096); bulk_commit(); }
+                if (elect_one()) { bulk_s2g(st_tile + ST_ENC + q * 4096, enc_s + q * 4096u, 4096); bulk_commit(); }
             }
             mbar_arrive_remote(my_act, 0);
 
@@ -292,7 +294,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 // this warp's rows of the layer g-1 image are being stored: those bulk stores must have drained before
                 // the rows are overwritten below (after the accumulator wait); waited for here, off the critical path
                 if (TRAIN && g > 0) {
-                    if (lane == 0) bulk_wait_read0();
+                    if (elect_one()) bulk_wait_read0();
                     __syncwarp();
                 }
                 mbar_wait(my_acc, acc_phase); acc_phase ^= 1u;
@@ -357,7 +359,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                             // instead of one 64 KB burst behind a 128-thread barrier at its end
                             fence_proxy_async();
                             __syncwarp();
-                            if (lane == 0) {
+                            if (elect_one()) {
                                 const uint32_t off = (uint32_t)(blk >> 1) * 16384u + (uint32_t)q * 4096u;
                                 bulk_s2g(st_tile + (g == 8 ? ST_C : ST_H + (int64_t)g * 65536) + off, act_s + off, 4096);
                                 bulk_commit();
@@ -374,7 +376,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                 if (leader) TRACE(2 + t, 3, g, 0);
             }
         }
-        if (TRAIN && lane == 0) bulk_wait0();
+        if (TRAIN && elect_one()) bulk_wait0();
     }
     tc_fence_before();
     cluster_sync_all();          // the peer's shared memory / TMEM stay alive until the leader's last MMA has retired
@@ -401,9 +403,6 @@ static inline int pair_grid(int64_t n_max)
     return 2 * (int)(iters < pairs ? iters : pairs);
 }
 
-int mlp_fwd_ts_launch(const void* packed, const float* xyz_cano, const int32_t* cidx, const int32_t* count,
-                      int64_t n_max, float* sigma, float* rgb, cudaStream_t stream);      // mlp_ts.cu
-
 extern "C" int an_mlp_fwd(const void* packed, const float* xyz_cano, const int32_t* cidx, const int32_t* count,
                           int64_t n_max, float* sigma, float* rgb, void* stash, void* stream)
 {
@@ -411,8 +410,6 @@ extern "C" int an_mlp_fwd(const void* packed, const float* xyz_cano, const int32
     if (cidx && !count) return AN_ERR_ARG;
     if (((uintptr_t)packed) & 1023) return AN_ERR_ALIGN;
     if (stash && (((uintptr_t)stash) & 127)) return AN_ERR_ALIGN;
-    static const bool ss_only = getenv("AN_MLP_SS") != nullptr;       // A/B switch while the TMEM-operand kernel is evaluated
-    if (!stash && !ss_only) return mlp_fwd_ts_launch(packed, xyz_cano, cidx, count, n_max, sigma, rgb, (cudaStream_t)stream);
     cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_ALLOC);

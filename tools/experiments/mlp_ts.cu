@@ -1,3 +1,9 @@
+// EXPERIMENT (not built into the library; kept as the record of a measured negative result).
+// To try it: copy into anim-nerf_b200/csrc/, declare mlp_fwd_ts_launch in mlp_tc.cu and call it from an_mlp_fwd when
+// stash == NULL.  Parity-green on the inference tests; 1.79 ms per 2^20 points against 0.81 ms for mlp_tc.cu: with one
+// 128-row tile per CTA every CTA re-streams the whole weight set per 128 rows (twice mlp_tc.cu's L2 -> SM traffic, four
+// times mlp_bwd.cu's), and a half-layer's MMAs (N = 128) overlap only a quarter of the other half's epilogue.
+//
 // A9-A11, second organisation of the MLP forward: activations never touch shared memory.
 // Reference: models/embedding.py:22-39 + models/nerf.py:129-175.
 //
