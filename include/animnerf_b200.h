@@ -230,6 +230,24 @@ int an_adam_step(float* const* params, const float* const* grads, float* const* 
                  float beta1, float beta2, float one_minus_beta1, float one_minus_beta2, float eps,
                  float weight_decay, unsigned int* done_counter, void* stream);
 
+/* ---- 8(f)#4: marching cubes of the density lattice -----------------------------------------------------------
+ * replaces `mcubes.marching_cubes(-sigmas, 0.)` (extract_mesh.py:165; PyMCubes, CPU).  volume (nx,ny,nz) fp32, last
+ * axis fastest; a lattice point is inside when its value < iso.  tri_table: (256,16) int8, cube-edge ids of each
+ * configuration's triangles, -1 terminated (bit i of the configuration = corner i inside; corners / edges numbered as
+ * in anim-nerf_b200/mesh.py).  Three launches:
+ *   an_mc_count  voff (nx*ny*nz) uint16 = each lattice point's vertex offset inside its 1024-point block,
+ *                block_counts (ceil(n/1024), 2) int32 = (vertices, triangles) per block;
+ *   an_mc_scan   block_counts -> exclusive prefix sums in place, totals[2] int64 = (n_vertices, n_faces): the caller
+ *                reads them back and allocates the outputs;
+ *   an_mc_emit   vertices (n_vertices,3) fp32 in lattice-index coordinates (linear interpolation along the lattice
+ *                edge), faces (n_faces,3) int32, normals from inside to outside.  Vertex and face order depend on the
+ *                lattice only (no atomics).                                                                          */
+int an_mc_count(const float* volume, int nx, int ny, int nz, float iso, const int8_t* tri_table,
+                uint16_t* voff, int32_t* block_counts, void* stream);
+int an_mc_scan(int32_t* block_counts, int64_t n_blocks, int64_t* totals, void* stream);
+int an_mc_emit(const float* volume, int nx, int ny, int nz, float iso, const int8_t* tri_table,
+               const uint16_t* voff, const int32_t* block_offsets, float* vertices, int32_t* faces, void* stream);
+
 /* ---- A12: alpha compositing ------------------------------------------------------------
  * replaces models/volume_rendering.py:128-160 (composite tail), far=True, white_bkgd flag.
  * sigma (n_rays,K), rgb (n_rays,K,3), z (n_rays,K), rays (n_rays,8) (far = rays[:,7]);
