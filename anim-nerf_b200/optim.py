@@ -2,10 +2,14 @@
 utils/__init__.py:33-45: eps 1e-8, betas (0.9, 0.999), L2 weight decay, no amsgrad) with the update of a whole
 parameter group done by one `an_adam_step` launch (<= 64 tensors per launch) instead of torch's multi-tensor chain.
 
-Same constructor arguments, `param_groups` (so LR schedulers work unchanged), `zero_grad`, `state_dict` layout of the
-moments (`state[p]["exp_avg"]`, `["exp_avg_sq"]`).  Graph-capturable: the step count lives in device memory and is
-advanced by the kernel; the learning rate is read from a device scalar that `sync_lr()` refreshes from
-`group["lr"]` (called by `step()` outside capture, and by `GraphedTrainStep` before every replay)."""
+Same constructor arguments, `param_groups` (so LR schedulers work unchanged), `zero_grad`, and torch.optim.Adam's
+`state_dict` layout (`state[p]["step"]`, `["exp_avg"]`, `["exp_avg_sq"]`): a checkpoint written by either optimiser
+resumes in the other.  Graph-capturable: the step count lives in device memory (one scalar per launch, which
+`state[p]["step"]` aliases) and is advanced by the kernel; the learning rate is read from a device scalar that
+`sync_lr()` refreshes from `group["lr"]` (called by `step()` outside capture, and by `GraphedTrainStep` before every
+replay).  The parameters of a group that take part in the update are fixed by its first step (torch.optim.Adam skips a
+parameter whose grad is None and keeps a per-parameter step; here a launch shares one step, so a later change of the
+set raises instead of drifting)."""
 import ctypes
 
 import torch
@@ -60,7 +64,7 @@ class FusedAdam(torch.optim.Optimizer):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
             raise ValueError("invalid Adam hyper-parameter")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
-        self._g = {}        # group index -> dict(lr_t, lr_host, chunks: list of dict(step, done))
+        self._g = {}        # group index -> dict(lr_t, lr_host, members, chunks: list of dict(step, done))
         self.flat = None    # FlatGradBuffer when the gradients live in one buffer (zero_grad is then one memset)
         self.on_step = []   # callbacks after every update (the NeRFs' packed-weight invalidation)
 
@@ -70,15 +74,40 @@ class FusedAdam(torch.optim.Optimizer):
             return
         super().zero_grad(set_to_none=set_to_none)
 
-    def _gstate(self, gi, device, n_chunks):
+    def _gstate(self, gi, device, ps):
+        """Device scalars of group gi, created at its first step over the parameters `ps` (or after load_state_dict: the
+        step count then continues from the loaded state[p]["step"])."""
         st = self._g.get(gi)
-        if st is None or st["lr_t"].device != device or len(st["chunks"]) < n_chunks:
-            old = st["chunks"] if st is not None and st["lr_t"].device == device else []
-            st = dict(lr_t=torch.zeros(1, device=device), lr_host=None,
-                      chunks=old + [dict(step=torch.zeros(1, device=device), done=torch.zeros(1, device=device, dtype=torch.int32))
-                                    for _ in range(n_chunks - len(old))])
-            self._g[gi] = st
+        if st is not None and st["lr_t"].device == device:
+            if st["members"] != [id(p) for p in ps]:
+                raise RuntimeError("FusedAdam: the set of parameters with gradients in group %d changed after its first step "
+                                   "(one device step count is shared per launch)" % gi)
+            return st
+        chunks = []
+        for ci in range((len(ps) + _MAX - 1) // _MAX):
+            loaded = [float(self.state[p]["step"]) for p in ps[ci * _MAX:(ci + 1) * _MAX] if "step" in self.state[p]]
+            if loaded and min(loaded) != max(loaded):
+                raise RuntimeError("FusedAdam: loaded state has different step counts inside one launch group")
+            step = torch.full((1,), loaded[0] if loaded else 0.0, device=device)
+            for p in ps[ci * _MAX:(ci + 1) * _MAX]:
+                self.state[p]["step"] = step[0]          # a view: state_dict() sees the kernel's count
+            chunks.append(dict(step=step, done=torch.zeros(1, device=device, dtype=torch.int32)))
+        st = dict(lr_t=torch.zeros(1, device=device), lr_host=None, members=[id(p) for p in ps], chunks=chunks)
+        self._g[gi] = st
         return st
+
+    def state_dict(self):
+        """torch.optim.Adam's layout; the step counts as host scalars (what a non-capturable torch.optim.Adam expects)."""
+        sd = super().state_dict()
+        sd["state"] = {k: {n: (v.detach().to("cpu", copy=True) if n == "step" and torch.is_tensor(v) else v) for n, v in s.items()}
+                       for k, s in sd["state"].items()}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        """torch.optim.Adam / Lightning checkpoints load as they are; the device step scalars are rebuilt from the
+        loaded per-parameter steps at the next step()."""
+        super().load_state_dict(state_dict)
+        self._g = {}
 
     def sync_lr(self):
         """Copy every group's `lr` to its device scalar when it changed (a host-side write: not inside graph capture)."""
@@ -105,7 +134,9 @@ class FusedAdam(torch.optim.Optimizer):
             if capturing is None:
                 capturing = torch.cuda.is_current_stream_capturing()
             n_chunks = (len(ps) + _MAX - 1) // _MAX
-            st = self._gstate(gi, dev, n_chunks)
+            if gi not in self._g and capturing:
+                raise RuntimeError("FusedAdam: take one eager step before capturing a CUDA graph")
+            st = self._gstate(gi, dev, ps)
             if not capturing:
                 self.sync_lr()
             elif st["lr_host"] is None:

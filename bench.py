@@ -350,6 +350,15 @@ def run_ours(args):
         grid()
     ms_grid, _, _ = _timed_replays(grid, 3, barrier, dev, world)
     ms_grid /= 3
+    mesh_512 = None
+    if world == 1:      # the lattice is whole on this GPU: marching cubes of it (extract_mesh.py:165), device-side
+        from anim_nerf_b200 import mesh as mesh_mod
+        field = 2.0 - gbuf            # random-init sigma is ~5 inside the body: threshold 2 puts the surface at the body's boundary
+        mv, mf = mesh_mod.marching_cubes(field, 0.0)
+        ms_mc, _, _ = _timed_replays(lambda: mesh_mod.marching_cubes(field, 0.0), 3, barrier, dev, world)
+        mesh_512 = {"ms": ms_mc / 3, "vertices": int(mv.shape[0]), "faces": int(mf.shape[0]),
+                    "workload": "marching cubes of the 512^3 lattice (count + scan + emit kernels, one D2H of the two totals)"}
+        del field, mv, mf
 
     total_rays = n_rays * world * args.steps
     value = total_rays / (ms * 1e-3)
@@ -436,6 +445,7 @@ def run_ours(args):
             "grid_512": {"ms": ms_grid, "points_per_s": NG ** 3 / (ms_grid * 1e-3),
                          "workload": "cfg4: extract_mesh density query, 512^3 lattice around the posed body, AnimNeRF.forward on "
                                      "every point (KNN + unpose, MLP on the valid ones, relu(sigma)), lattice rows interleaved over %d GPU(s)" % world},
+            "mesh_512": mesh_512,
             "full_training_step": full,
             "frozen_body_params_step": frozen,
             "weights_in_sync": in_sync,

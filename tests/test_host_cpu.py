@@ -252,3 +252,19 @@ def test_host_mirrors_keep_the_reference_signatures():
                 if default is not None and d != default:          # (a default where the reference has none is a superset)
                     problems.append(("default", cname, m, n, default, d))
     assert not problems, problems
+
+
+def test_graph_step_tree_helpers_mirror_nested_batches():
+    """GraphedTrainStep's static buffers follow the nesting of the example batch (dicts / lists of tensors, other leaves
+    kept as they are); a copy reaches every tensor leaf and nothing else."""
+    from anim_nerf_b200.graph_step import _tree_map, _tree_copy
+    batch = {"rays": torch.arange(6.0).view(2, 3), "smpl": {"posed": {"transl": torch.zeros(2, 3)}, "list": [torch.ones(2), 5]}, "tag": "x"}
+    static = _tree_map(lambda t: t.clone(), batch)
+    assert static["tag"] == "x" and static["smpl"]["list"][1] == 5
+    assert static["rays"].data_ptr() != batch["rays"].data_ptr()
+    new = {"rays": batch["rays"] + 1, "smpl": {"posed": {"transl": torch.full((2, 3), 7.0)}, "list": [torch.full((2,), 3.0), 5]}, "tag": "y"}
+    ptrs = (static["rays"].data_ptr(), static["smpl"]["posed"]["transl"].data_ptr())
+    _tree_copy(static, new)
+    assert torch.equal(static["rays"], new["rays"]) and float(static["smpl"]["posed"]["transl"].min()) == 7.0
+    assert torch.equal(static["smpl"]["list"][0], new["smpl"]["list"][0])
+    assert ptrs == (static["rays"].data_ptr(), static["smpl"]["posed"]["transl"].data_ptr())      # in place: the graph's addresses

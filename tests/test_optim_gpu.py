@@ -85,3 +85,59 @@ def test_more_tensors_than_one_launch_and_graph_replay():
     torch.cuda.synchronize()
     for p, q in zip(a, b):
         assert float((q.detach() - p.detach()).abs().max()) < 1e-3 * 1e-3
+
+
+def test_state_dict_resume_parity_with_torch_adam():
+    """Checkpoint / resume (ADVICE r1): the step count travels in state_dict() as torch.optim.Adam's state[p]['step'];
+    a FusedAdam checkpoint resumes in FusedAdam, a torch.optim.Adam checkpoint (what a Lightning .ckpt of the reference
+    holds) resumes in FusedAdam, and a FusedAdam checkpoint resumes in torch.optim.Adam -- each continuing exactly like an
+    uninterrupted torch.optim.Adam run (bias correction included: a restart at t = 1 would be off by ~30x at step 4)."""
+    import copy
+    from anim_nerf_b200.optim import FusedAdam
+    shapes = [(64, 63), (64,), (3, 64), (3,)]
+    mk = lambda cls, ps: cls(ps, lr=5e-4, eps=1e-8)        # noqa: E731
+
+    def run(opt, ps, its):
+        for it in its:
+            for p, g in zip(ps, _grads(shapes, 300 + it)):
+                p.grad = g
+            opt.step()
+
+    a = _params(shapes, 2)                                 # uninterrupted torch run: 3 + 3 steps
+    ref = mk(torch.optim.Adam, a)
+    run(ref, a, range(3))
+    ref_mid = copy.deepcopy(ref.state_dict()); a_mid = [p.detach().clone() for p in a]
+    run(ref, a, range(3, 6))
+
+    b = _params(shapes, 2)                                 # FusedAdam: 3 steps, checkpoint
+    ours = mk(FusedAdam, b)
+    run(ours, b, range(3))
+    sd = copy.deepcopy(ours.state_dict())
+    assert all(float(s["step"]) == 3.0 for s in sd["state"].values()), [float(s["step"]) for s in sd["state"].values()]
+
+    def resumed(cls, state, start):
+        ps = [p.clone().requires_grad_(True) for p in start]
+        opt = mk(cls, ps)
+        opt.load_state_dict(copy.deepcopy(state))
+        run(opt, ps, range(3, 6))
+        return ps, opt
+
+    for label, (ps, opt) in {"fused->fused": resumed(FusedAdam, sd, [p.detach() for p in b]),
+                             "torch->fused": resumed(FusedAdam, ref_mid, a_mid),
+                             "fused->torch": resumed(torch.optim.Adam, sd, [p.detach() for p in b])}.items():
+        for p, q in zip(a, ps):
+            assert float((q.detach() - p.detach()).abs().max()) < 5e-4 * 1e-3, label
+        assert all(float(s["step"]) == 6.0 for s in opt.state_dict()["state"].values()), label
+
+
+def test_changing_the_set_of_parameters_with_gradients_raises():
+    from anim_nerf_b200.optim import FusedAdam
+    shapes = [(8, 4), (8,)]
+    ps = _params(shapes, 3)
+    opt = FusedAdam(ps, lr=1e-3)
+    for p, g in zip(ps, _grads(shapes, 1)):
+        p.grad = g
+    opt.step()
+    ps[1].grad = None
+    with pytest.raises(RuntimeError, match="changed after its first step"):
+        opt.step()

@@ -311,6 +311,34 @@ def test_training_steps_see_updated_weights_eager_and_graphed():
     np.testing.assert_allclose(graphed, eager[n_warm:], rtol=2e-2)
 
 
+def test_graphed_step_takes_nested_batches_and_refuses_host_rng():
+    """the batch of INTEGRATION.md section 4 is nested (rays + a dict of SMPL tensors) -- the static buffers
+    mirror the nesting and a replay copies every leaf; a renderer that draws its noise seed on the host is refused
+    (the seed would be frozen into the graph and every replay would reuse the same noise)."""
+    from anim_nerf_b200.graph_step import GraphedTrainStep
+    sysm, opt, params, batch, _ = _train_setup()
+    posed_np, tmpl_np = synthetic.make_body_params(2, seed=1)
+    posed = {k: torch.from_numpy(v).to(DEV) for k, v in posed_np.items()}
+    tmpl = {k: torch.from_numpy(v).to(DEV) for k, v in tmpl_np.items()}
+    mse = torch.nn.functional.mse_loss
+
+    def loss_fn(b):
+        out = sysm(b["rays"], b["smpl"]["posed"], b["smpl"]["template"], perturb=0.0)
+        return mse(out["rgbs"], b["rgbs"]) + mse(out["rgbs_fine"], b["rgbs"])
+    nested = {"rays": batch["rays"], "rgbs": batch["rgbs"], "smpl": {"posed": posed, "template": tmpl}, "tag": "frame-3"}
+    g = GraphedTrainStep(loss_fn, opt, params, nested, world=1, warmup=2, model=sysm.anim_nerf)
+    first = float(g(nested))
+    moved = {**nested, "smpl": {"posed": {k: (v + 0.05 if k == "transl" else v) for k, v in posed.items()}, "template": tmpl}}
+    second = float(g(moved))                       # a different leaf deep in the nesting reaches the replay
+    again = float(g(nested))
+    assert abs(second - first) > 1e-6 * abs(first) and np.isfinite([first, second, again]).all(), (first, second, again)
+    assert float((g.static["smpl"]["posed"]["transl"] - posed["transl"]).abs().max()) == 0.0
+    vr = sysm.volume_renderer if hasattr(sysm, "volume_renderer") else sysm.renderer
+    vr.device_rng = False
+    with pytest.raises(ValueError, match="device_rng"):
+        GraphedTrainStep(loss_fn, opt, params, nested, world=1, warmup=1, renderer=vr)
+
+
 def test_edge_shapes_empty_single_ray_and_all_background():
     """Edge cases of the public call (B3): no rays -> empty outputs of the right shapes;
     one single ray and a ragged batch (3 frames x 37 rays) match the oracle; rays that miss the body entirely
