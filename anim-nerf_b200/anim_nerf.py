@@ -207,6 +207,22 @@ class AnimNeRF(nn.Module):
         self.last_knn_idx = cfg.get("knn_idx") if (want_seed and self.knn_mode == 1) else None
         return w, rgb, depth, acc
 
+    @torch.no_grad()
+    def lattice_sigma(self, x_axis, y_rows, z_axis, center, use_fine=False):
+        """sigma of `forward` on the lattice points (x[j], y[i], z[k]) + center of the frame set on this model, in the
+        order of extract_mesh.py's grid ((i*nj + j)*nk + k), without materialising the points: they are generated in
+        the KNN kernel (cfg4).  -> (ni*nj*nk,) fp32, -1e5 at invalid points.  Inference only."""
+        if not (self.use_unpose and self.knn_mode == 1):
+            raise NotImplementedError("lattice queries run on the grid-pruned KNN kernel with use_unpose=True")
+        cfg = self._cfg(use_fine)
+        n = y_rows.numel() * x_axis.numel() * z_axis.numel()
+        dev = cfg["verts"].device
+        sigma, rgb = torch.empty(n, device=dev), torch.empty(n, 3, device=dev)
+        out = ops.knn_unpose_lattice(cfg["verts"], self.ober2cano_transform.contiguous(), cfg["lbs"], cfg["thr"], x_axis, y_rows,
+                                     z_axis, center, grid=cfg["grid"], sigma=sigma, rgb=rgb)
+        ops.mlp_fwd(cfg["net"].packed(), out["xyz_cano"], sigma, rgb, cidx=out["cidx"], count=out["count"], n_max=n)
+        return sigma
+
     # ------------------------------------------------------------------ point queries (B2)
     def unpose(self, xyz, viewdir=None):
         cfg = self._cfg(False)

@@ -85,17 +85,30 @@ __device__ __forceinline__ float dist2_rn(float qx, float qy, float qz, float vx
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// Query point gid from one of three sources: explicit points `xyz`; rays (B*R, 8) + depths z (B*R, K); or -- both xyz and
+// z NULL -- a LATTICE (extract_mesh.py:27-35,152-156): `rays` then points to [cx, cy, cz, (float)nj, x[nj], z[K], y[ni]],
+// the point is lattice[i][j][k] = (x[j], y[i], z[k]) + centre, gid = (i * nj + j) * K + k.
 __device__ __forceinline__ void load_query(const float* __restrict__ xyz, const float* __restrict__ rays,
                                            const float* __restrict__ z, int64_t gid, int K,
                                            float& qx, float& qy, float& qz)
 {
     if (xyz) { qx = xyz[gid * 3]; qy = xyz[gid * 3 + 1]; qz = xyz[gid * 3 + 2]; }
-    else {
+    else if (z) {
         const int64_t ray = gid / K;                 // rays are (B*R, 8), z is (B*R, K)
         const float4 r0 = __ldg((const float4*)rays + ray * 2), r1 = __ldg((const float4*)rays + ray * 2 + 1);
         const float zz = z[gid];
         // o + z*d with the product rounded first (torch evaluates mul and add separately; no FMA)
         qx = __fadd_rn(r0.x, __fmul_rn(zz, r0.w)); qy = __fadd_rn(r0.y, __fmul_rn(zz, r1.x)); qz = __fadd_rn(r0.z, __fmul_rn(zz, r1.y));
+    } else {
+        const int nj = (int)__ldg(rays + 3);
+        const int64_t t = gid / K;
+        const int k = (int)(gid - t * K);
+        const int64_t i = t / nj;
+        const int j = (int)(t - i * nj);
+        // the reference adds the centre to the fp32 lattice point (extract_mesh.py:156): one fp32 add per coordinate
+        qx = __fadd_rn(__ldg(rays + 4 + j), __ldg(rays));
+        qy = __fadd_rn(__ldg(rays + 4 + nj + K + i), __ldg(rays + 1));
+        qz = __fadd_rn(__ldg(rays + 4 + nj + k), __ldg(rays + 2));
     }
 }
 
@@ -820,7 +833,9 @@ extern "C" int an_knn_unpose_fwd(const float* xyz, const float* rays, const floa
                                  float* sigma, float* rgb, int32_t* cidx, int32_t* count, void* stream)
 {
     if (!verts || !ober2cano || !lbs_weights || !xyz_cano || !valid || B <= 0 || N <= 0 || V < 4 || J <= 0) return AN_ERR_ARG;
-    if (!xyz && (!rays || !z || K <= 0 || (int64_t)R * K != N)) return AN_ERR_ARG;
+    if (!xyz && (!rays || K <= 0)) return AN_ERR_ARG;
+    if (!xyz && z && (int64_t)R * K != N) return AN_ERR_ARG;
+    if (!xyz && !z && (R != 0 || B != 1 || N % K)) return AN_ERR_ARG;         // lattice mode (an_knn_unpose_lattice_fwd)
     if (cidx && !count) return AN_ERR_ARG;
     if ((int64_t)B * N > 0x7fffffffLL) return AN_ERR_UNSUPPORTED;        // compact ids are int32
     if ((((uintptr_t)ober2cano) | ((uintptr_t)rays) | ((uintptr_t)idx) | ((uintptr_t)dist) | ((uintptr_t)qw)) & 15) return AN_ERR_ALIGN;
@@ -862,6 +877,21 @@ extern "C" int an_knn_unpose_fwd(const float* xyz, const float* rays, const floa
     } else return AN_ERR_ARG;
     AN_CHECK_LAUNCH();
     return AN_OK;
+}
+
+// A5-A8 over the density lattice of extract_mesh.py (cfg4): the query points are generated in the kernel from the three
+// axes and the centre instead of being materialised (12 B/point written and read back, plus the torch outer product).
+extern "C" int an_knn_unpose_lattice_fwd(const float* lattice, int ni, int nj, int nk, const float* verts, int V,
+                                         const void* grid_ws, void* query_ws, const float* ober2cano,
+                                         const float* lbs_weights, int J, float dis_threshold,
+                                         float* xyz_cano, uint8_t* valid, float* sigma, float* rgb,
+                                         int32_t* cidx, int32_t* count, void* stream)
+{
+    if (!lattice || ni <= 0 || nj <= 0 || nk <= 0 || nj >= (1 << 24)) return AN_ERR_ARG;
+    const int64_t N = (int64_t)ni * nj * nk;
+    return an_knn_unpose_fwd(nullptr, lattice, nullptr, 1, 0, nk, N, verts, V, grid_ws, query_ws, ober2cano, lbs_weights, J,
+                             dis_threshold, 1, nullptr, nullptr, nullptr, 0, xyz_cano, valid, nullptr, nullptr, nullptr,
+                             sigma, rgb, cidx, count, stream);
 }
 
 extern "C" int an_knn_unpose_bwd(const float* g_xyz_cano, const int32_t* cidx, const int32_t* count,

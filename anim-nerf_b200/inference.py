@@ -173,11 +173,18 @@ def query_density_grid(anim_nerf, N, x_range=(-1.2, 1.2), y_range=(-1.2, 1.2), z
     slab_rows = slab_rows or max(1, (1 << 24) // (N * N))
     if out is None:
         out = torch.empty(n_out, N, N, device=dev)
+    fused = anim_nerf.use_unpose and getattr(anim_nerf, "knn_mode", 1) == 1
+    if fused:       # lattice points generated inside the KNN kernel: same fp32 values as grid_slab_points, nothing materialised
+        ax = [torch.from_numpy(np.linspace(r[0], r[1], N)).float().to(dev) for r in (x_range, y_range, z_range)]
     for k in range(0, n_out, slab_rows):
         m = min(slab_rows, n_out - k)
         a = i0 + k * step
-        pts = grid_slab_points(N, x_range, y_range, z_range, center[0], a, a + (m - 1) * step + 1, dev, step)
-        out[k:k + m] = batched_point_inference(anim_nerf, pts).view(m, N, N)
+        if fused:
+            sig = anim_nerf.lattice_sigma(ax[0], ax[1][a:a + (m - 1) * step + 1:step], ax[2], center[0], use_fine=anim_nerf.use_fine)
+            torch.clamp(sig.view(m, N, N), min=0.0, out=out[k:k + m])
+        else:
+            pts = grid_slab_points(N, x_range, y_range, z_range, center[0], a, a + (m - 1) * step + 1, dev, step)
+            out[k:k + m] = batched_point_inference(anim_nerf, pts).view(m, N, N)
     return out
 
 

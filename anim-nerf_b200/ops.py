@@ -239,6 +239,28 @@ def knn_unpose(verts, ober2cano, lbs_weights, dis_threshold, xyz=None, rays=None
     return out
 
 
+def knn_unpose_lattice(verts, ober2cano, lbs_weights, dis_threshold, x_axis, y_rows, z_axis, center, grid=None,
+                       sigma=None, rgb=None):
+    """A5-A8 on the lattice points (x[j], y[i], z[k]) + center (extract_mesh.py:27-35,152-156; flat index (i*nj + j)*nk + k)
+    of ONE frame, generated inside the kernel.  x_axis/y_rows/z_axis: 1-D fp32 tensors, center (3,).  Returns xyz_cano
+    (1,N,3), valid (1,N), cidx, count like `knn_unpose(compact=True)`."""
+    verts, ober2cano, lbs_weights = _f32c(verts), _f32c(ober2cano), _f32c(lbs_weights)
+    assert verts.shape[0] == 1, "lattice queries address one frame"
+    V, dev = verts.shape[1], verts.device
+    ni, nj, nk = y_rows.numel(), x_axis.numel(), z_axis.numel()
+    N = ni * nj * nk
+    lat = torch.cat([center.reshape(3).float(), torch.tensor([float(nj)], device=dev), x_axis.float(), z_axis.float(), y_rows.float()])
+    out = dict(xyz_cano=torch.empty(1, N, 3, device=dev), valid=torch.empty(1, N, device=dev, dtype=torch.uint8),
+               cidx=torch.empty(N, device=dev, dtype=torch.int32), count=torch.zeros(1, device=dev, dtype=torch.int32))
+    if grid is None:
+        grid = vertex_grid(verts, dis_threshold)
+    qws = torch.empty(_lib.load().an_knn_query_ws_bytes(1, N), device=dev, dtype=torch.uint8)
+    call("an_knn_unpose_lattice_fwd", ptr(lat), ni, nj, nk, ptr(verts), V, ptr(grid), ptr(qws), ptr(ober2cano), ptr(lbs_weights),
+         lbs_weights.shape[1], float(dis_threshold), ptr(out["xyz_cano"]), ptr(out["valid"]), ptr(sigma), ptr(rgb),
+         ptr(out["cidx"]), ptr(out["count"]), stream())
+    return out
+
+
 def knn_unpose_bwd(g_xyz_cano, cidx, count, idx, qw, ober2cano, xyz=None, rays=None, z=None, want_g_xyz=True, zero_g_xyz=True):
     """zero_g_xyz=False: g_xyz is left uninitialised at invalid points (for consumers that read valid points only)."""
     ober2cano = _f32c(ober2cano)

@@ -141,6 +141,17 @@ int an_knn_unpose_fwd(const float* xyz, const float* rays, const float* z, int B
                       float* xyz_cano, uint8_t* valid, int32_t* idx, float* dist, float* qw,
                       float* sigma, float* rgb, int32_t* cidx, int32_t* count, void* stream);
 
+/* ---- A5-A8 over the density lattice (cfg4: extract_mesh.py:27-35,152-160) ---------------------------------------
+ * Same search / blend / mask as an_knn_unpose_fwd (mode 1) for one frame, the query points generated in the kernel:
+ * point (i,j,k) = (x[j], y[i], z[k]) + centre, flat index (i*nj + j)*nk + k -- numpy's 'xy' meshgrid order, the centre
+ * added in fp32 as the reference does.  lattice: device floats [cx, cy, cz, (float)nj, x[nj], z[nk], y[ni]], 16-byte
+ * aligned.  Outputs as an_knn_unpose_fwd (xyz_cano (N,3), valid (N), sigma/rgb sentinels at invalid points, compact ids). */
+int an_knn_unpose_lattice_fwd(const float* lattice, int ni, int nj, int nk, const float* verts, int V,
+                              const void* grid_ws, void* query_ws, const float* ober2cano,
+                              const float* lbs_weights, int J, float dis_threshold,
+                              float* xyz_cano, uint8_t* valid, float* sigma, float* rgb,
+                              int32_t* cidx, int32_t* count, void* stream);
+
 /* backward of the blend + affine apply (autograd of models/anim_nerf.py:173-174,188; no
  * gradient through dist/idx/valid, as under the reference's no_grad KNN).
  * g_xyz_cano (B*N,3) is read at the `*count` compacted ids in cidx.  Accumulates (atomically)

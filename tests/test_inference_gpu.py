@@ -138,3 +138,18 @@ def test_density_grid_matches_oracle_and_slabs_are_bit_identical():
             assert torch.equal(parts[r], sig[r::world]), (world, r)
     small = inference.query_density_grid(an, N, slab_rows=3)
     assert torch.equal(small, sig)
+    # the lattice mode of the KNN kernel (points generated in the kernel) equals the explicit-points path bit for bit,
+    # canonical points and validity included, on a ragged lattice slab too
+    explicit = inference.batched_point_inference(an, pts_ref).view(N, N, N)
+    assert torch.equal(explicit, sig)
+    ax = [torch.from_numpy(np.linspace(-1.2, 1.2, N)).float().to(DEV) for _ in range(3)]
+    rows = ax[1][3:17:4]
+    from anim_nerf_b200 import ops
+    cfg = an._cfg(True)
+    lat = ops.knn_unpose_lattice(cfg["verts"], an.ober2cano_transform.contiguous(), cfg["lbs"], cfg["thr"], ax[0][:13], rows, ax[2],
+                                 center[0], grid=cfg["grid"])
+    p4 = pts_ref.view(N, N, N, 3)[3:17:4, :13].reshape(1, -1, 3).contiguous()
+    ref = ops.knn_unpose(cfg["verts"], an.ober2cano_transform.contiguous(), cfg["lbs"], cfg["thr"], xyz=p4, grid=cfg["grid"], compact=True)
+    assert torch.equal(lat["valid"], ref["valid"]) and torch.equal(lat["xyz_cano"], ref["xyz_cano"])
+    assert int(lat["count"]) == int(ref["count"]) > 0
+    assert torch.equal(torch.sort(lat["cidx"][:int(lat["count"])])[0], torch.sort(ref["cidx"][:int(ref["count"])])[0])
