@@ -283,3 +283,24 @@ class SampleFineMerge(torch.autograd.Function):
         (src,) = ctx.saved_tensors
         g_cat = torch.zeros_like(g_all).scatter_(-1, src.long(), g_all)
         return None, g_cat[..., :ctx.kc].contiguous(), None, None, None, None
+
+
+class RenderLoss(torch.autograd.Function):
+    """train.py:228-262: mse(rgbs) + mse(rgbs_fine) + lambda_alphas (l1(alphas) + l1(alphas_fine)) and its gradients in
+    one launch (ops.render_loss).  -> (total, terms (4,) detached: mse_c, mse_f, l1_c, l1_f)."""
+
+    @staticmethod
+    def forward(ctx, rgb_c, rgb_f, acc_c, acc_f, tgt_rgb, tgt_acc, lam):
+        terms, g = ops.render_loss(rgb_c, rgb_f, acc_c, acc_f, tgt_rgb, tgt_acc, lam)
+        ctx.shapes = [t.shape if t is not None else None for t in (rgb_c, rgb_f, acc_c, acc_f)]
+        ctx.save_for_backward(*[t for t in g if t is not None])
+        ctx.mark_non_differentiable(terms)
+        return terms[4], terms[:4]
+
+    @staticmethod
+    def backward(ctx, g_total, _g_terms):
+        saved = list(ctx.saved_tensors)
+        out = []
+        for shp in ctx.shapes:
+            out.append(None if shp is None else (saved.pop(0) * g_total).view(shp))
+        return tuple(out) + (None, None, None)

@@ -464,3 +464,22 @@ def sample_fine_merge(weights, z_coarse, n_fine, det, u=None, seed=0, want_src=T
     call("an_sample_fine_merge_fwd", ptr(_f32c(weights)), ptr(_f32c(z_coarse)), ptr(u), n, Kc, n_fine, int(det), int(seed),
          ptr(z_fine), ptr(z_all), ptr(src), ptr(nn), stream())
     return z_fine, z_all, src, nn
+
+
+# ------------------------------------------------------------------------------ losses
+def render_loss(rgb_c, rgb_f, acc_c, acc_f, tgt_rgb, tgt_acc, lambda_alphas):
+    """A18: -> (terms (5,) = mse_c, mse_f, l1_c, l1_f, total; gradients of the total w.r.t. the four inputs).
+    rgb_* (...,3), acc_* (...,1) or (...); the fine pair may be None."""
+    rgb_c, acc_c, tgt_rgb, tgt_acc = _f32c(rgb_c), _f32c(acc_c), _f32c(tgt_rgb), _f32c(tgt_acc)
+    n = acc_c.numel()
+    assert rgb_c.numel() == 3 * n and tgt_rgb.numel() == 3 * n and tgt_acc.numel() == n
+    fine = rgb_f is not None
+    if fine:
+        rgb_f, acc_f = _f32c(rgb_f), _f32c(acc_f)
+        assert rgb_f.numel() == 3 * n and acc_f.numel() == n
+    terms = torch.zeros(5, device=rgb_c.device)
+    g = [torch.empty_like(rgb_c), torch.empty_like(rgb_f) if fine else None, torch.empty_like(acc_c),
+         torch.empty_like(acc_f) if fine else None]
+    call("an_render_loss", ptr(rgb_c), ptr(rgb_f), ptr(acc_c), ptr(acc_f), ptr(tgt_rgb), ptr(tgt_acc), n, float(lambda_alphas),
+         ptr(terms), ptr(g[0]), ptr(g[1]), ptr(g[2]), ptr(g[3]), stream())
+    return terms, g

@@ -188,12 +188,21 @@ class AnimNeRFSystem(nn.Module):
             nonlocal loss
             loss = loss + weight * value
             det[name] = value
-        add("loss_rgb", F.mse_loss(results["rgbs"], rgbs))
-        if fine:
-            add("loss_rgb_fine", F.mse_loss(results["rgbs_fine"], rgbs))
-        add("loss_alphas", F.l1_loss(results["alphas"], alphas), hp.train.lambda_alphas)
-        if fine:
-            add("loss_alphas_fine", F.l1_loss(results["alphas_fine"], alphas), hp.train.lambda_alphas)
+        if results["rgbs"].is_cuda:      # the four render terms and their gradients in one launch (an_render_loss)
+            from .autograd import RenderLoss
+            total, terms = RenderLoss.apply(results["rgbs"], results["rgbs_fine"] if fine else None, results["alphas"],
+                                            results["alphas_fine"] if fine else None, rgbs, alphas, float(hp.train.lambda_alphas))
+            loss = total
+            det.update(loss_rgb=terms[0], loss_alphas=terms[2])
+            if fine:
+                det.update(loss_rgb_fine=terms[1], loss_alphas_fine=terms[3])
+        else:                            # host tensors (CPU unit tests of the loss arithmetic)
+            add("loss_rgb", F.mse_loss(results["rgbs"], rgbs))
+            if fine:
+                add("loss_rgb_fine", F.mse_loss(results["rgbs_fine"], rgbs))
+            add("loss_alphas", F.l1_loss(results["alphas"], alphas), hp.train.lambda_alphas)
+            if fine:
+                add("loss_alphas_fine", F.l1_loss(results["alphas_fine"], alphas), hp.train.lambda_alphas)
         if not with_regularizers:
             return loss, det
         k = -2.0 / hp.n_samples

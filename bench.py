@@ -185,8 +185,7 @@ def run_ours(args):
             if regularizers:
                 return sysm.compute_loss(batch_dev["rgbs"], batch_dev["alphas"], out, fg_points=batch_dev["fg_points"],
                                          bg_points=batch_dev["bg_points"], with_regularizers=True)[0]
-            return (mse(out["rgbs"], batch_dev["rgbs"]) + mse(out["rgbs_fine"], batch_dev["rgbs"])
-                    + lam * (l1(out["alphas"], batch_dev["alphas"]) + l1(out["alphas_fine"], batch_dev["alphas"])))
+            return sysm.compute_loss(batch_dev["rgbs"], batch_dev["alphas"], out, with_regularizers=False)[0]     # train.py:228-262
         return sysm, opt, loss_fn
 
     sysm, opt, loss_fn = make_system(True)

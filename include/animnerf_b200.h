@@ -259,6 +259,15 @@ int an_mc_scan(int32_t* block_counts, int64_t n_blocks, int64_t* totals, void* s
 int an_mc_emit(const float* volume, int nx, int ny, int nz, float iso, const int8_t* tri_table,
                const uint16_t* voff, const int32_t* block_offsets, float* vertices, int32_t* faces, void* stream);
 
+/* ---- A18 (losses): the four render-loss terms and their gradients in one launch ------------------------------------
+ * replaces train.py:228-262 (F.mse_loss on rgbs / rgbs_fine, lambda_alphas * F.l1_loss on alphas / alphas_fine) and their
+ * autograd.  rgb_* (n_rays,3), acc_* (n_rays), targets likewise; the fine inputs may both be NULL (n_importance = 0 or
+ * share_fine).  terms[5] (device) = mse_c, mse_f, l1_c, l1_f, total = mse_c + mse_f + lambda (l1_c + l1_f); g_* receive
+ * d total / d input (sign(0) = 0 as torch).  Sums are combined in a fixed order (one CTA): reproducible.                */
+int an_render_loss(const float* rgb_coarse, const float* rgb_fine, const float* acc_coarse, const float* acc_fine,
+                   const float* tgt_rgb, const float* tgt_acc, int64_t n_rays, float lambda_alphas, float* terms,
+                   float* g_rgb_coarse, float* g_rgb_fine, float* g_acc_coarse, float* g_acc_fine, void* stream);
+
 /* ---- A12: alpha compositing ------------------------------------------------------------
  * replaces models/volume_rendering.py:128-160 (composite tail), far=True, white_bkgd flag.
  * sigma (n_rays,K), rgb (n_rays,K,3), z (n_rays,K), rays (n_rays,8) (far = rays[:,7]);

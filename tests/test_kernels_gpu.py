@@ -621,3 +621,33 @@ def test_rays_sample_fused_matches_separate_kernels_and_autograd():
     assert (g_rays[..., 0:3] - gxm.sum(2)).abs().max() < 1e-4 and (g_rays[..., 3:6] - (gxm * zz[..., None]).sum(2)).abs().max() < 2e-4
     assert torch.equal(g_rays[..., 7], gfar) and float(g_rays[..., 6].abs().max()) == 0
     assert (g_z - (gzc + (gxm * rb[:, :, None, 3:6]).sum(-1))).abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("fine", [True, False])
+def test_render_loss_matches_torch_losses_and_autograd(fine):
+    """A18: an_render_loss against F.mse_loss / F.l1_loss (train.py:228-262) -- the four terms, the total and the
+    gradients through autograd (scaled by an upstream factor), sign(0) = 0 at exact hits, ragged ray counts."""
+    from anim_nerf_b200.autograd import RenderLoss
+    F = torch.nn.functional
+    for n, seed in ((16384, 0), (1, 1), (1237, 2)):
+        g = torch.Generator().manual_seed(seed)
+        mk = lambda *s: torch.rand(*s, generator=g).to(DEV)                   # noqa: E731
+        rc, rf, ac, af = mk(n, 3), mk(n, 3), mk(n, 1), mk(n, 1)
+        tr, ta = mk(n, 3), (mk(n, 1) > 0.5).float()
+        ac[: n // 3] = ta[: n // 3]                                            # exact hits: l1 gradient 0 there
+        lam = 0.1
+        a = [t.clone().requires_grad_(True) for t in (rc, rf, ac, af)]
+        b = [t.clone().requires_grad_(True) for t in (rc, rf, ac, af)]
+        total, terms = RenderLoss.apply(a[0], a[1] if fine else None, a[2], a[3] if fine else None, tr, ta, lam)
+        want_terms = [F.mse_loss(b[0], tr), F.mse_loss(b[1], tr), F.l1_loss(b[2], ta), F.l1_loss(b[3], ta)]
+        want = want_terms[0] + lam * want_terms[2] + ((want_terms[1] + lam * want_terms[3]) if fine else 0.0)
+        (3.0 * total).backward()
+        (3.0 * want).backward()
+        assert abs(float(total) - float(want)) <= 2e-6 * abs(float(want)) + 1e-9, (float(total), float(want))
+        for k in range(4):
+            if fine or k in (0, 2):
+                assert abs(float(terms[k]) - float(want_terms[k])) <= 2e-6 * abs(float(want_terms[k])) + 1e-9
+                np.testing.assert_allclose(a[k].grad.cpu().numpy(), b[k].grad.cpu().numpy(), rtol=1e-6, atol=1e-12)
+            else:
+                assert a[k].grad is None
+        assert float(a[2].grad[: n // 3].abs().max()) == 0.0 if n >= 3 else True
