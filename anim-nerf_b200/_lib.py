@@ -53,7 +53,8 @@ SIGNATURES = {
     "an_body_tables_fwd": (_i32, [_vp] * 6 + [_i32, _i32] + [_vp] * 7 + [_i32, _i32, _i32] + [_vp] * 6),
     "an_sample_fine_merge_fwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _u64, _vp, _vp, _vp, _vp, _vp]),
     "an_knn_unpose_lattice_fwd": (_i32, [_vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "an_render_loss": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "an_render_loss_ws_bytes": (_i64, []),
+    "an_render_loss": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "an_mc_count": (_i32, [_vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "an_mc_scan": (_i32, [_vp, _i64, _vp, _vp]),
     "an_mc_emit": (_i32, [_vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -467,6 +467,9 @@ def sample_fine_merge(weights, z_coarse, n_fine, det, u=None, seed=0, want_src=T
 
 
 # ------------------------------------------------------------------------------ losses
+_LOSS_WS = {}
+
+
 def render_loss(rgb_c, rgb_f, acc_c, acc_f, tgt_rgb, tgt_acc, lambda_alphas):
     """A18: -> (terms (5,) = mse_c, mse_f, l1_c, l1_f, total; gradients of the total w.r.t. the four inputs).
     rgb_* (...,3), acc_* (...,1) or (...); the fine pair may be None."""
@@ -477,9 +480,14 @@ def render_loss(rgb_c, rgb_f, acc_c, acc_f, tgt_rgb, tgt_acc, lambda_alphas):
     if fine:
         rgb_f, acc_f = _f32c(rgb_f), _f32c(acc_f)
         assert rgb_f.numel() == 3 * n and acc_f.numel() == n
-    terms = torch.zeros(5, device=rgb_c.device)
+    dev = rgb_c.device
+    terms = torch.empty(5, device=dev)
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _LOSS_WS.get(key)
+    if ws is None:          # per (device, stream) scratch: the kernel leaves it zeroed for its next launch
+        ws = _LOSS_WS[key] = torch.zeros(_lib.load().an_render_loss_ws_bytes(), device=dev, dtype=torch.uint8)
     g = [torch.empty_like(rgb_c), torch.empty_like(rgb_f) if fine else None, torch.empty_like(acc_c),
          torch.empty_like(acc_f) if fine else None]
     call("an_render_loss", ptr(rgb_c), ptr(rgb_f), ptr(acc_c), ptr(acc_f), ptr(tgt_rgb), ptr(tgt_acc), n, float(lambda_alphas),
-         ptr(terms), ptr(g[0]), ptr(g[1]), ptr(g[2]), ptr(g[3]), stream())
+         ptr(terms), ptr(ws), ptr(g[0]), ptr(g[1]), ptr(g[2]), ptr(g[3]), stream())
     return terms, g

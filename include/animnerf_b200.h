@@ -263,9 +263,11 @@ int an_mc_emit(const float* volume, int nx, int ny, int nz, float iso, const int
  * replaces train.py:228-262 (F.mse_loss on rgbs / rgbs_fine, lambda_alphas * F.l1_loss on alphas / alphas_fine) and their
  * autograd.  rgb_* (n_rays,3), acc_* (n_rays), targets likewise; the fine inputs may both be NULL (n_importance = 0 or
  * share_fine).  terms[5] (device) = mse_c, mse_f, l1_c, l1_f, total = mse_c + mse_f + lambda (l1_c + l1_f); g_* receive
- * d total / d input (sign(0) = 0 as torch).  Sums are combined in a fixed order (one CTA): reproducible.                */
+ * d total / d input (sign(0) = 0 as torch).  ws: an_render_loss_ws_bytes() of device scratch, zero before its first
+ * use (the kernel leaves it zeroed; one scratch per stream).  Partial sums are combined in CTA order: reproducible.   */
+int64_t an_render_loss_ws_bytes(void);
 int an_render_loss(const float* rgb_coarse, const float* rgb_fine, const float* acc_coarse, const float* acc_fine,
-                   const float* tgt_rgb, const float* tgt_acc, int64_t n_rays, float lambda_alphas, float* terms,
+                   const float* tgt_rgb, const float* tgt_acc, int64_t n_rays, float lambda_alphas, float* terms, void* ws,
                    float* g_rgb_coarse, float* g_rgb_fine, float* g_acc_coarse, float* g_acc_fine, void* stream);
 
 /* ---- A12: alpha compositing ------------------------------------------------------------

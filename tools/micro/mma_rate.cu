@@ -11,16 +11,10 @@ __device__ __forceinline__ void umma_pair_ts(uint32_t d, uint32_t a, uint64_t bd
                  ::"r"(d), "r"(a), "l"(bd), "r"(id), "r"(acc) : "memory");
 }
 
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
-    return pred != 0;
-}
-
 // mode bit0: TS form; nb = distinct 8 KB-spaced B buffers cycled per group; na = accumulators cycled per group;
 // kper = MMAs per group (commit after each group); wait_every = groups between barrier waits
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
-rate_kernel(int N, int ts, int nb, int na, int kper, int groups, int uni, long long* out)
+rate_kernel(int N, int ts, int nb, int na, int kper, int groups, int uni, int flags, long long* out)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t raw = smem_u32(smem);
@@ -40,12 +34,14 @@ rate_kernel(int N, int ts, int nb, int na, int kper, int groups, int uni, long l
         uint32_t phase = 0;
         long long t0 = clock64();
         for (int g = 0; g < groups; ++g) {
-            const uint32_t acc = N > 128 ? tm + (ts ? 256u : (uint32_t)(g % na) * 256u) : tm + 256 + (uint32_t)(g % na) * 128u;
-            const uint32_t wb = sb + 32768 + (uint32_t)(g % nb) * 16384u;
+            const uint32_t ga = (flags & 1) ? 0u : (uint32_t)(g & (na - 1)), gb = (flags & 1) ? 0u : (uint32_t)(g & (nb - 1));
+            const uint32_t acc = N > 128 ? tm + (ts ? 256u : ga * 256u) : tm + 256 + ga * 128u;
+            const uint32_t wb = sb + 32768 + gb * 16384u;
+            const uint32_t always = (flags & 2) ? 1u : 0u;
             if (elect_one()) {
                 for (int k = 0; k < kper; ++k) {
-                    if (ts) umma_pair_ts(acc, tm + (uint32_t)(k & 3) * 8u, make_desc(wb + (k & 3) * 32u, 16, 1024), idesc, k > 0);
-                    else umma_pair(acc, make_desc(sb + (k & 3) * 32u, 16, 1024), make_desc(wb + (k & 3) * 32u, 16, 1024), idesc, k > 0);
+                    if (ts) umma_pair_ts(acc, tm + (uint32_t)(k & 3) * 8u, make_desc(wb + (k & 3) * 32u, 16, 1024), idesc, (k > 0) | always);
+                    else umma_pair(acc, make_desc(sb + (k & 3) * 32u, 16, 1024), make_desc(wb + (k & 3) * 32u, 16, 1024), idesc, (k > 0) | always);
                 }
             }
             __syncwarp();
@@ -91,18 +87,18 @@ int main()
     const int smem = 202 * 1024 + 1024;
     cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     struct { int N, ts, nb, na, kper; } cfg[] = {
-        {256, 0, 1, 1, 4}, {256, 0, 4, 2, 4}, {256, 1, 4, 2, 4}, {128, 0, 4, 2, 4}, {128, 1, 4, 2, 4}, {128, 1, 1, 1, 4},
-        {128, 1, 4, 2, 16}, {256, 1, 4, 2, 16}, {64, 1, 4, 2, 4}, {16, 0, 4, 2, 4}, {256, 0, 4, 2, 1}, {128, 1, 4, 2, 1}};
-    for (int uni = 0; uni < 2; ++uni)
+        {256, 0, 4, 2, 4}, {256, 0, 4, 2, 16}, {128, 0, 4, 2, 4}, {128, 1, 4, 2, 4}, {128, 1, 4, 2, 16}, {128, 1, 4, 2, 1}};
+    for (int flags = 0; flags < 4; ++flags)
+    for (int uni = 1; uni < 2; ++uni)
     for (auto c : cfg) {
         const int groups = 512;
         for (int rep = 0; rep < 2; ++rep) {
-            rate_kernel<<<148, 128, smem>>>(c.N, c.ts, c.nb, c.na, c.kper, groups, uni, out);
+            rate_kernel<<<148, 128, smem>>>(c.N, c.ts, c.nb, c.na, c.kper, groups, uni, flags, out);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
         }
         long long h; cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost);
-        printf("uni=%d N=%3d %s nb=%d na=%d kper=%2d : %7.1f clk / MMA (ideal %d)\n", uni, c.N, c.ts ? "TS" : "SS", c.nb, c.na, c.kper,
+        printf("flags=%d uni=%d N=%3d %s nb=%d na=%d kper=%2d : %7.1f clk / MMA (ideal %d)\n", flags, uni, c.N, c.ts ? "TS" : "SS", c.nb, c.na, c.kper,
                (double)h / (groups * c.kper), c.N / 2);
     }
     return 0;
