@@ -28,7 +28,7 @@ SIGNATURES = {
     "an_vertex_grid_build": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp]),
     "an_knn_query_ws_bytes": (_i64, [_i32, _i64]),
     "an_knn_unpose_fwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _i32,
-                                 _vp, _vp, _vp, _i32,
+                                 _vp, _vp, _vp, _i32, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "an_knn_unpose_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "an_mlp_packed_bytes": (_i64, []),

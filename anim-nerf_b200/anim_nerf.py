@@ -204,7 +204,9 @@ class AnimNeRF(nn.Module):
         if self.knn_mode == 1:
             cfg["want_seed"], cfg["seed"] = bool(want_seed), seed
         rgb, depth, acc, w = RenderPass.apply(rays, z, self.ober2cano_transform, sigma_noise, cfg, *cfg["net"].param_list())
-        self.last_knn_idx = cfg.get("knn_idx") if (want_seed and self.knn_mode == 1) else None
+        keep = want_seed and self.knn_mode == 1
+        self.last_knn_idx = cfg.get("knn_idx") if keep else None
+        self.last_knn_out = cfg.get("knn_out") if keep else None
         return w, rgb, depth, acc
 
     @torch.no_grad()

@@ -44,6 +44,7 @@ class RenderPass(torch.autograd.Function):
                              mode=cfg.get("knn_mode", 1), want_idx=want_idx, want_qw=need_grad,
                              sigma=sigma, rgb=rgb, compact=True, seed=cfg.get("seed"))
         cfg["knn_idx"] = out["idx"]
+        cfg["knn_out"] = out          # the fine pass takes over this pass's results at the samples they share
         if COUNT_LOG is not None:
             COUNT_LOG.append((K, out["count"]))
         packed = net.packed()

@@ -117,13 +117,14 @@ struct UnposeOut {
     float* sigma; float* rgb; int32_t* cidx; int32_t* count;
 };
 
-// Epilogue shared by the search kernels.  `have4`: best holds the exact 4-NN (idx/dist are emitted);
+// Result of the blend for one query: validity, canonical point, neighbour distances and blend weights.
+struct Unposed { bool valid; float xc0, xc1, xc2; float dd[4]; float q[4]; };
+
+// Blend shared by the search kernels.  `have4`: best holds the exact 4-NN (distances are emitted);
 // `found`: ... and the nearest one is within the threshold, so the point may be valid (blend evaluated).
-__device__ __forceinline__ void unpose_epilogue(const Best4& best, bool have4, bool found, float qx, float qy, float qz,
-                                                int64_t gid, int b, int V, int J,
-                                                const float* __restrict__ ober2cano,
-                                                const float* __restrict__ lbsw, float thr,
-                                                const UnposeOut& o, bool active)
+__device__ __forceinline__ void unpose_compute(const Best4& best, bool have4, bool found, float qx, float qy, float qz,
+                                               int b, int V, int J, const float* __restrict__ ober2cano,
+                                               const float* __restrict__ lbsw, float thr, bool active, Unposed& u)
 {
     bool valid = false;
     float xc0 = 0.f, xc1 = 0.f, xc2 = 0.f;
@@ -178,15 +179,25 @@ __device__ __forceinline__ void unpose_epilogue(const Best4& best, bool have4, b
         xc1 = m[4] * qx + m[5] * qy + m[6] * qz + m[7];
         xc2 = m[8] * qx + m[9] * qy + m[10] * qz + m[11];
     }
+    u.valid = valid; u.xc0 = xc0; u.xc1 = xc1; u.xc2 = xc2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { u.dd[j] = dd[j]; u.q[j] = q[j]; }
+}
+
+// Outputs of one query + the warp-aggregated compaction of the valid ids (every lane of the warp must call it).
+__device__ __forceinline__ void unpose_write(const Unposed& u, const Best4& best, bool have4, int64_t gid,
+                                             const UnposeOut& o, bool active)
+{
+    const bool valid = u.valid;
     if (active) {
-        o.xyz_cano[gid * 3] = xc0; o.xyz_cano[gid * 3 + 1] = xc1; o.xyz_cano[gid * 3 + 2] = xc2;
+        o.xyz_cano[gid * 3] = u.xc0; o.xyz_cano[gid * 3 + 1] = u.xc1; o.xyz_cano[gid * 3 + 2] = u.xc2;
         o.valid[gid] = valid ? 1 : 0;
         if (o.idx) {
             int4 v = have4 ? make_int4(best.i[0], best.i[1], best.i[2], best.i[3]) : make_int4(-1, -1, -1, -1);
             ((int4*)o.idx)[gid] = v;
         }
-        if (o.dist) ((float4*)o.dist)[gid] = make_float4(dd[0], dd[1], dd[2], dd[3]);
-        if (o.qw) ((float4*)o.qw)[gid] = make_float4(q[0], q[1], q[2], q[3]);
+        if (o.dist) ((float4*)o.dist)[gid] = make_float4(u.dd[0], u.dd[1], u.dd[2], u.dd[3]);
+        if (o.qw) ((float4*)o.qw)[gid] = make_float4(u.q[0], u.q[1], u.q[2], u.q[3]);
         if (!valid) {
             if (o.sigma) o.sigma[gid] = -1e5f;
             if (o.rgb) { o.rgb[gid * 3] = 0.f; o.rgb[gid * 3 + 1] = 0.f; o.rgb[gid * 3 + 2] = 0.f; }
@@ -203,6 +214,17 @@ __device__ __forceinline__ void unpose_epilogue(const Best4& best, bool have4, b
             if (valid) o.cidx[base + __popc(mask & ((1u << lane) - 1))] = (int32_t)gid;
         }
     }
+}
+
+__device__ __forceinline__ void unpose_epilogue(const Best4& best, bool have4, bool found, float qx, float qy, float qz,
+                                                int64_t gid, int b, int V, int J,
+                                                const float* __restrict__ ober2cano,
+                                                const float* __restrict__ lbsw, float thr,
+                                                const UnposeOut& o, bool active)
+{
+    Unposed u;
+    unpose_compute(best, have4, found, qx, qy, qz, b, V, J, ober2cano, lbsw, thr, active, u);
+    unpose_write(u, best, have4, gid, o, active);
 }
 
 // ------------------------------------------------------------------ mode 0: exhaustive
@@ -372,8 +394,10 @@ struct QueryWs { unsigned int n_work; unsigned int next_chunk; unsigned int pad[
 
 // Seeds from an earlier pass over the same rays (all NULL/0 when absent): src[g] < Kc says query g is
 // coarse sample src[g] of its ray, nn[g] is the coarse sample nearest in depth, idx is the earlier
-// pass's (B*R*Kc, 4) neighbour table.
-struct SeedIn { const uint8_t* src; const uint8_t* nn; const int32_t* idx; int Kc; };
+// pass's (B*R*Kc, 4) neighbour table.  With xc / valid (and qw when this pass emits qw) the results of a shared sample
+// are copied from the earlier pass instead of being re-blended (same inputs, same arithmetic: same bits).
+struct SeedIn { const uint8_t* src; const uint8_t* nn; const int32_t* idx; int Kc;
+                const float* xc; const uint8_t* valid; const float* qw; };      // earlier pass's xyz_cano / valid / qw (optional)
 
 __device__ __forceinline__ void warp_merge4(Best4& lb, Best4& g)
 {
@@ -423,6 +447,8 @@ knn_classify_kernel(const float* __restrict__ xyz, const float* __restrict__ ray
     float4* __restrict__ work = (float4*)(qws + 1);
     const int lane = threadIdx.x & 31;
     const float thr2 = thr * thr * (1.0f + 1e-5f);
+    // shared samples take the seeding pass's result as it is when that pass handed over everything this pass emits
+    const bool copy = sd.idx && sd.xc && sd.valid && !o.dist && (!o.qw || sd.qw);
     for (int64_t g0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) & ~31ll; g0 < total; g0 += (int64_t)gridDim.x * blockDim.x) {
         const int64_t gid = g0 + lane;
         const bool active = gid < total;
@@ -430,18 +456,22 @@ knn_classify_kernel(const float* __restrict__ xyz, const float* __restrict__ ray
         float qx = 0.f, qy = 0.f, qz = 0.f;
         Best4 sb; best_init(sb);
         const int b = active ? (int)(gid / N) : 0;
+        int64_t cg = 0;                                   // shared sample: its index in the seeding pass
         if (active) {
             load_query(xyz, rays, z, gid, K, qx, qy, qz);
             if (sd.idx) {
                 const int s = sd.src[gid];
                 if (s < sd.Kc) {          // this sample IS coarse sample s of its ray: reuse that pass's neighbours
                     same = true;
-                    const int4 si = __ldg((const int4*)sd.idx + (gid / K) * sd.Kc + s);
+                    cg = (gid / K) * sd.Kc + s;
+                    const int4 si = __ldg((const int4*)sd.idx + cg);
                     if (si.x >= 0) {
                         have4 = true;
-                        seed_distances(verts + (int64_t)b * V * 3, si, qx, qy, qz, sb.d);
                         sb.i[0] = si.x; sb.i[1] = si.y; sb.i[2] = si.z; sb.i[3] = si.w;
-                        found = sb.d[0] < thr2;
+                        if (!copy) {
+                            seed_distances(verts + (int64_t)b * V * 3, si, qx, qy, qz, sb.d);
+                            found = sb.d[0] < thr2;
+                        }
                     }
                 }
             }
@@ -465,8 +495,21 @@ knn_classify_kernel(const float* __restrict__ xyz, const float* __restrict__ ray
                 }
             }
         }
-        if (sd.idx)      // (warp-uniform) samples shared with the seeding pass finish here
-            unpose_epilogue(sb, have4, found, qx, qy, qz, gid, b, V, J, ober2cano, lbsw, thr, o, active && same);
+        if (sd.idx) {    // (warp-uniform) samples shared with the seeding pass finish here
+            Unposed u;
+            if (copy) {  // ... with that pass's own result for the same point
+                u.valid = false; u.xc0 = u.xc1 = u.xc2 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { u.dd[j] = 0.f; u.q[j] = 0.f; }
+                if (active && same) {
+                    u.valid = sd.valid[cg] != 0;
+                    u.xc0 = sd.xc[cg * 3]; u.xc1 = sd.xc[cg * 3 + 1]; u.xc2 = sd.xc[cg * 3 + 2];
+                    if (o.qw) { const float4 q4 = __ldg((const float4*)sd.qw + cg); u.q[0] = q4.x; u.q[1] = q4.y; u.q[2] = q4.z; u.q[3] = q4.w; }
+                }
+            } else
+                unpose_compute(sb, have4, found, qx, qy, qz, b, V, J, ober2cano, lbsw, thr, active && same, u);
+            unpose_write(u, sb, have4, gid, o, active && same);
+        }
         const unsigned mask = __ballot_sync(0xffffffffu, maybe);
         if (mask) {
             const int leader = __ffs(mask) - 1;
@@ -829,6 +872,7 @@ extern "C" int an_knn_unpose_fwd(const float* xyz, const float* rays, const floa
                                  const float* ober2cano, const float* lbs_weights, int J,
                                  float dis_threshold, int mode,
                                  const uint8_t* seed_src, const uint8_t* seed_nn, const int32_t* seed_idx, int seed_Kc,
+                                 const float* seed_xyz_cano, const uint8_t* seed_valid, const float* seed_qw,
                                  float* xyz_cano, uint8_t* valid, int32_t* idx, float* dist, float* qw,
                                  float* sigma, float* rgb, int32_t* cidx, int32_t* count, void* stream)
 {
@@ -864,7 +908,9 @@ extern "C" int an_knn_unpose_fwd(const float* xyz, const float* rays, const floa
         cudaStream_t st = (cudaStream_t)stream;
         cudaError_t e = cudaMemsetAsync(qws, 0, sizeof(QueryWs), st);
         if (e != cudaSuccess) return (int)e;
-        const SeedIn sd{seed_idx ? seed_src : nullptr, seed_idx ? seed_nn : nullptr, seed_idx, seed_Kc};
+        if (seed_qw && (((uintptr_t)seed_qw) & 15)) return AN_ERR_ALIGN;
+        const SeedIn sd{seed_idx ? seed_src : nullptr, seed_idx ? seed_nn : nullptr, seed_idx, seed_Kc,
+                        seed_idx ? seed_xyz_cano : nullptr, seed_idx ? seed_valid : nullptr, seed_idx ? seed_qw : nullptr};
         const int64_t total = (int64_t)B * N;
         int64_t cb = (total + KNN_THREADS - 1) / KNN_THREADS;
         if (cb > (int64_t)sms * 32) cb = (int64_t)sms * 32;
@@ -890,8 +936,8 @@ extern "C" int an_knn_unpose_lattice_fwd(const float* lattice, int ni, int nj, i
     if (!lattice || ni <= 0 || nj <= 0 || nk <= 0 || nj >= (1 << 24)) return AN_ERR_ARG;
     const int64_t N = (int64_t)ni * nj * nk;
     return an_knn_unpose_fwd(nullptr, lattice, nullptr, 1, 0, nk, N, verts, V, grid_ws, query_ws, ober2cano, lbs_weights, J,
-                             dis_threshold, 1, nullptr, nullptr, nullptr, 0, xyz_cano, valid, nullptr, nullptr, nullptr,
-                             sigma, rgb, cidx, count, stream);
+                             dis_threshold, 1, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, xyz_cano, valid, nullptr,
+                             nullptr, nullptr, sigma, rgb, cidx, count, stream);
 }
 
 extern "C" int an_knn_unpose_bwd(const float* g_xyz_cano, const int32_t* cidx, const int32_t* count,

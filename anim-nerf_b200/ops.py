@@ -203,7 +203,8 @@ def knn_unpose(verts, ober2cano, lbs_weights, dis_threshold, xyz=None, rays=None
     """A5-A8.  Query points: xyz (B,N,3) or rays (B,R,8) + z (B,R,K).  Returns a dict with
     xyz_cano (B,N,3), valid (B,N) uint8 and the optional idx/dist/qw/cidx/count.
     seed (mode 1, rays+z): dict(src, nn (B,R,K) uint8 from `sample_fine_merge`, idx (B,R*Kc,4) int32 = the
-    `idx` output of the coarse pass over the same rays): same results, far less search."""
+    `idx` output of the coarse pass over the same rays; optionally that pass's xyz_cano / valid / qw, which the shared
+    samples then take over unchanged): same results, far less search."""
     verts, ober2cano, lbs_weights = _f32c(verts), _f32c(ober2cano), _f32c(lbs_weights)
     B, V = verts.shape[:2]
     dev = verts.device
@@ -224,16 +225,22 @@ def knn_unpose(verts, ober2cano, lbs_weights, dis_threshold, xyz=None, rays=None
         grid = vertex_grid(verts, dis_threshold)
     if mode == 1 and qws is None:   # work list of the queries that survive the occupancy test (scratch, freed on return)
         qws = torch.empty(_lib.load().an_knn_query_ws_bytes(B, N), device=dev, dtype=torch.uint8)
-    s_src = s_nn = s_idx = None
+    s_src = s_nn = s_idx = s_xc = s_valid = s_qw = None
     s_kc = 0
     if seed is not None and mode == 1 and xyz is None:
         s_src, s_nn, s_idx = seed["src"], seed["nn"], seed["idx"]
         s_kc = s_idx.numel() // (4 * B * R)
         assert s_src.dtype == torch.uint8 and s_nn.dtype == torch.uint8 and s_idx.dtype == torch.int32
         assert s_src.numel() == B * N and s_nn.numel() == B * N and s_idx.numel() == B * R * s_kc * 4
+        # the seeding pass's own results for the shared samples (copied instead of re-blended)
+        s_xc, s_valid, s_qw = seed.get("xyz_cano"), seed.get("valid"), seed.get("qw")
+        if s_xc is not None:
+            assert s_valid is not None and s_xc.numel() == B * R * s_kc * 3 and s_valid.numel() == B * R * s_kc
+            assert s_xc.dtype == torch.float32 and s_valid.dtype == torch.uint8 and s_xc.is_contiguous()
+            assert s_qw is None or (s_qw.numel() == B * R * s_kc * 4 and s_qw.dtype == torch.float32)
     call("an_knn_unpose_fwd", ptr(xyz), ptr(rays), ptr(z), B, R, K, N, ptr(verts), V, ptr(grid), ptr(qws),
          ptr(ober2cano), ptr(lbs_weights), lbs_weights.shape[1], float(dis_threshold), int(mode),
-         ptr(s_src), ptr(s_nn), ptr(s_idx), int(s_kc),
+         ptr(s_src), ptr(s_nn), ptr(s_idx), int(s_kc), ptr(s_xc), ptr(s_valid), ptr(s_qw),
          ptr(out["xyz_cano"]), ptr(out["valid"]), ptr(out["idx"]), ptr(out["dist"]), ptr(out["qw"]),
          ptr(sigma), ptr(rgb), ptr(out["cidx"]), ptr(out["count"]), stream())
     return out

@@ -122,12 +122,13 @@ class VolumeRenderer(nn.Module):
         if self.n_fine > 0:
             z_combine, _, src, nn = self.sample_fine_merge(z_coarse, weights, det=(perturb == 0), u=noise.get("fine_u"))
             if fused:
-                idx_c = getattr(model, "last_knn_idx", None)
-                kwargs = dict(kwargs, want_seed=False, seed=dict(src=src, nn=nn, idx=idx_c) if idx_c is not None else None)
+                idx_c, out_c = getattr(model, "last_knn_idx", None), getattr(model, "last_knn_out", None) or {}
+                seed = dict(src=src, nn=nn, idx=idx_c, xyz_cano=out_c.get("xyz_cano"), valid=out_c.get("valid"), qw=out_c.get("qw"))
+                kwargs = dict(kwargs, want_seed=False, seed=seed if idx_c is not None else None)
             _, rgbs_f, depths_f, alphas_f = self.composite(model, rays, z_combine, coarse=False, far=True, perturb=perturb,
                                                            sigma_noise=noise.get("sigma_f"), **kwargs)
             if fused:
-                model.last_knn_idx = None
+                model.last_knn_idx = model.last_knn_out = None
             if self.share_fine:
                 output = {"rgbs": rgbs_f, "alphas": alphas_f, "depths": depths_f}
             else:

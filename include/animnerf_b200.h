@@ -131,6 +131,9 @@ int an_vertex_grid_build(const float* verts, int B, int V, float cell, void* ws,
  * K = seed_Kc; seed_src/seed_nn (B*N) u8 come from an_sample_fine_merge_fwd: seed_src[g] < seed_Kc
  * means query g IS that coarse sample (its neighbours are reused, distances re-evaluated: same bits),
  * seed_nn[g] = the coarse sample nearest in depth, whose four neighbours bound the search ball.
+ * seed_xyz_cano (B*R*seed_Kc,3), seed_valid (B*R*seed_Kc) u8 and seed_qw (B*R*seed_Kc,4) (optional; qw is needed
+ * only when this call emits qw): that previous call's outputs -- a shared sample then takes them as they are
+ * instead of re-evaluating the blend (same point, same arithmetic: same bits; not used when dist is requested).
  * Results are bit-identical with and without seeds.                                          */
 int64_t an_knn_query_ws_bytes(int B, int64_t N);
 int an_knn_unpose_fwd(const float* xyz, const float* rays, const float* z, int B, int R, int K,
@@ -138,6 +141,7 @@ int an_knn_unpose_fwd(const float* xyz, const float* rays, const float* z, int B
                       const float* ober2cano, const float* lbs_weights, int J,
                       float dis_threshold, int mode,
                       const uint8_t* seed_src, const uint8_t* seed_nn, const int32_t* seed_idx, int seed_Kc,
+                      const float* seed_xyz_cano, const uint8_t* seed_valid, const float* seed_qw,
                       float* xyz_cano, uint8_t* valid, int32_t* idx, float* dist, float* qw,
                       float* sigma, float* rgb, int32_t* cidx, int32_t* count, void* stream);
 

@@ -162,6 +162,17 @@ def test_knn_seeded_fine_pass_bit_identical(det):
             na, nb = int(a["count"]), int(b["count"])
             assert na == nb == int(v.sum())
             assert torch.equal(torch.sort(a["cidx"][:na])[0], torch.sort(b["cidx"][:nb])[0])
+            # ... and when the coarse pass also hands over its xyz_cano / valid / qw, the shared samples copy them
+            # (no dist output in that mode): still the same bits everywhere, invalid points included
+            kw2 = dict(want_idx=True, want_qw=True, compact=True)
+            seed2 = dict(seed, xyz_cano=coarse["xyz_cano"], valid=coarse["valid"], qw=coarse["qw"])
+            for kwv, sd in ((kw2, seed2), (dict(compact=True), dict(seed2, qw=None))):        # training / inference outputs
+                d = ops().knn_unpose(verts, o2c, lbs, 0.2, rays=rays, z=z_all, mode=1, seed=sd, **kwv)
+                assert torch.equal(d["valid"], b["valid"]) and torch.equal(d["xyz_cano"], b["xyz_cano"])
+                assert int(d["count"]) == nb and torch.equal(torch.sort(d["cidx"][:nb])[0], torch.sort(b["cidx"][:nb])[0])
+                if kwv.get("want_qw"):
+                    assert torch.equal(d["qw"], b["qw"])
+                    assert torch.equal(d["idx"][v], b["idx"][v])
 
 
 # ------------------------------------------------------------------------------ MLP
