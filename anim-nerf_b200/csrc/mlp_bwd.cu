@@ -84,6 +84,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
     if (warp == 0) {
         {   // whole warp runs the loop, one elected lane issues (tc::elect_one)
             uint32_t it = 0;
+            const uint64_t keep = l2_policy_keep();
             for (int64_t iter = pair; iter < num_iters; iter += npairs)
                 for (int i = 0; i < 11; ++i) {
                     const int s = step_of(i);
@@ -96,7 +97,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                         mbar_wait(bar_empty + 8 * st, ph ^ 1u);
                         if (elect_one()) {
                             mbar_expect_tx(bar_full + 8 * st, bytes);
-                            bulk_g2s(sbase + SM_WST + st * STAGE_BYTES, packed + bwd_chunk_off(s, kc) + rank * bytes, bytes, bar_full + 8 * st);
+                            bulk_g2s_hint(sbase + SM_WST + st * STAGE_BYTES, packed + bwd_chunk_off(s, kc) + rank * bytes, bytes, bar_full + 8 * st, keep);
                         }
                         __syncwarp();
                     }
@@ -161,6 +162,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
         const float* small = (const float*)(packed + SMALL_OFF);
         const bool leader = (e & 127) == 0;
         const uint32_t my_act = bar_act + 8 * t, my_acc = bar_acc + 8 * t;
+        const uint64_t stream_pol = l2_policy_stream();
         uint32_t acc_phase = 0;
 
         for (int64_t iter = pair; iter < num_iters; iter += npairs) {
@@ -185,7 +187,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
             }
             fence_proxy_async();
             __syncwarp();         // every warp streams its own 32 rows (4 KB, contiguous in the image) to the scratch
-            if (elect_one()) { bulk_s2g(dy_tile + DY_RGB + q * 4096, act_s + q * 4096u, 4096); bulk_commit(); }
+            if (elect_one()) { bulk_s2g_hint(dy_tile + DY_RGB + q * 4096, act_s + q * 4096u, 4096, stream_pol); bulk_commit(); }
             mbar_arrive_remote(my_act, 0);
 
             // encoding derivative factors (same double-angle recurrence as the forward)
@@ -288,7 +290,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                         __syncwarp();
                         if (elect_one()) {
                             const uint32_t off = (uint32_t)(cb >> 1) * 16384u + (uint32_t)q * 4096u;
-                            bulk_s2g(dy_tile + dy_off + off, act_s + off, 4096);
+                            bulk_s2g_hint(dy_tile + dy_off + off, act_s + off, 4096, stream_pol);
                             bulk_commit();
                         }
                     }
@@ -303,7 +305,7 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
                     __syncwarp();
                     if (elect_one()) {
                         const uint32_t off = 2u * 16384u + (uint32_t)q * 4096u;
-                        bulk_s2g(dy_tile + dy_off + off, act_s + off, 4096);
+                        bulk_s2g_hint(dy_tile + dy_off + off, act_s + off, 4096, stream_pol);
                         bulk_commit();
                     }
                 }

@@ -126,6 +126,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
         {   // whole warp runs the loop, one elected lane issues (uniform operands, see tc::elect_one)
             TRACE_DECL;
             uint32_t it = 0;
+            const uint64_t keep = l2_policy_keep();
             for (int64_t iter = pair; iter < num_iters; iter += npairs)
                 for (int g = 0; g < NGT; ++g) {
                     const int nc = g_chunks(g), ns = ring_steps(g);
@@ -137,7 +138,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                             if (lane == 0) TRACE(0, 0, g, t * 8 + kc);
                             if (elect_one()) {
                                 mbar_expect_tx(bar_full + 8 * s, bytes);
-                                bulk_g2s(sbase + SM_WST + s * STAGE_BYTES, packed + fwd_chunk_off(g, kc) + rank * bytes, bytes, bar_full + 8 * s);
+                                bulk_g2s_hint(sbase + SM_WST + s * STAGE_BYTES, packed + fwd_chunk_off(g, kc) + rank * bytes, bytes, bar_full + 8 * s, keep);
                             }
                             __syncwarp();
                         }
@@ -220,6 +221,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
         const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
         const uint32_t my_act = bar_act + 8 * t, my_acc = bar_acc + 8 * t;
         const float* small = (const float*)(packed + SMALL_OFF);
+        const uint64_t stream_pol = l2_policy_stream(); (void)stream_pol;
         const float b_sigma = __ldg(small + SM_BIAS + 8 * 256 + 128);
         const float b_rgb0 = __ldg(small + SM_BIAS + 9 * 256), b_rgb1 = __ldg(small + SM_BIAS + 9 * 256 + 1),
                     b_rgb2 = __ldg(small + SM_BIAS + 9 * 256 + 2);
@@ -232,7 +234,11 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             const int64_t p = tile * 128 + row;
             const bool in = p < n;
             const int64_t id = in ? (cidx ? (int64_t)cidx[p] : p) : 0;
+#ifdef AN_EXP_L2STASH     // experiment: all stash stores land in 32 tiles (L2-resident): same shared-memory reads, no HBM writes
+            uint8_t* st_tile = TRAIN ? stash + (tile & 31) * ST_TILE : nullptr;
+#else
             uint8_t* st_tile = TRAIN ? stash + tile * ST_TILE : nullptr;
+#endif
             const uint8_t* pst_tile = TAN ? pstash + tile * ST_TILE : nullptr;
             float x[3] = {0.f, 0.f, 0.f};
             float tv[3] = {0.f, 0.f, 0.f};
@@ -278,7 +284,9 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             fence_proxy_async();
             if (TRAIN) {          // every warp streams its own 32 rows (4 KB, contiguous in the image) to the stash
                 __syncwarp();
-                if (elect_one()) { bulk_s2g(st_tile + ST_ENC + q * 4096, enc_s + q * 4096u, 4096); bulk_commit(); }
+#ifndef AN_EXP_NOSTASH
+                if (elect_one()) { bulk_s2g_hint(st_tile + ST_ENC + q * 4096, enc_s + q * 4096u, 4096, stream_pol); bulk_commit(); }
+#endif
             }
             mbar_arrive_remote(my_act, 0);
 
@@ -361,7 +369,9 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                             __syncwarp();
                             if (elect_one()) {
                                 const uint32_t off = (uint32_t)(blk >> 1) * 16384u + (uint32_t)q * 4096u;
-                                bulk_s2g(st_tile + (g == 8 ? ST_C : ST_H + (int64_t)g * 65536) + off, act_s + off, 4096);
+#ifndef AN_EXP_NOSTASH
+                                bulk_s2g_hint(st_tile + (g == 8 ? ST_C : ST_H + (int64_t)g * 65536) + off, act_s + off, 4096, stream_pol);
+#endif
                                 bulk_commit();
                             }
                         }
