@@ -53,6 +53,8 @@ SIGNATURES = {
     "an_body_tables_fwd": (_i32, [_vp] * 6 + [_i32, _i32] + [_vp] * 7 + [_i32, _i32, _i32] + [_vp] * 6),
     "an_sample_fine_merge_fwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _u64, _vp, _vp, _vp, _vp, _vp]),
     "an_knn_unpose_lattice_fwd": (_i32, [_vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "an_compact_ws_bytes": (_i64, []),
+    "an_compact_valid": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "an_render_loss_ws_bytes": (_i64, []),
     "an_render_loss": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "an_mc_count": (_i32, [_vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
@@ -103,7 +105,7 @@ def check(code, what):
 
 
 # kernels launched per entry point (for bench.py's gpu_launches claim)
-KERNELS_PER_CALL = {"an_mlp_bwd": 4, "an_mlp_bwd_wgrad": 3, "an_mlp_bwd_wgrad_scaled": 3, "an_mlp_pack": 2, "an_knn_unpose_fwd": 2, "an_knn_unpose_lattice_fwd": 2,
+KERNELS_PER_CALL = {"an_mlp_bwd": 4, "an_mlp_bwd_wgrad": 3, "an_mlp_bwd_wgrad_scaled": 3, "an_mlp_pack": 2, "an_knn_unpose_fwd": 2, "an_knn_unpose_lattice_fwd": 2, "an_compact_valid": 2,
                     "an_body_tables_fwd": 2, "an_body_tables_bwd": 2}      # (memsets are not counted)
 launch_count = 0
 _timing = None          # bench.py: dict name -> list of (start_event, stop_event) on the launching stream

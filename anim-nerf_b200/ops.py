@@ -219,8 +219,9 @@ def knn_unpose(verts, ober2cano, lbs_weights, dis_threshold, xyz=None, rays=None
     out["idx"] = torch.empty(B, N, 4, device=dev, dtype=torch.int32) if want_idx else None
     out["dist"] = torch.empty(B, N, 4, device=dev) if want_dist else None
     out["qw"] = torch.empty(B, N, 4, device=dev) if want_qw else None
+    ordered = compact and ORDERED_COMPACTION
     out["cidx"] = torch.empty(B * N, device=dev, dtype=torch.int32) if compact else None
-    out["count"] = torch.zeros(1, device=dev, dtype=torch.int32) if compact else None
+    out["count"] = (torch.empty if ordered else torch.zeros)(1, device=dev, dtype=torch.int32) if compact else None
     if mode == 1 and grid is None:
         grid = vertex_grid(verts, dis_threshold)
     if mode == 1 and qws is None:   # work list of the queries that survive the occupancy test (scratch, freed on return)
@@ -242,8 +243,19 @@ def knn_unpose(verts, ober2cano, lbs_weights, dis_threshold, xyz=None, rays=None
          ptr(ober2cano), ptr(lbs_weights), lbs_weights.shape[1], float(dis_threshold), int(mode),
          ptr(s_src), ptr(s_nn), ptr(s_idx), int(s_kc), ptr(s_xc), ptr(s_valid), ptr(s_qw),
          ptr(out["xyz_cano"]), ptr(out["valid"]), ptr(out["idx"]), ptr(out["dist"]), ptr(out["qw"]),
-         ptr(sigma), ptr(rgb), ptr(out["cidx"]), ptr(out["count"]), stream())
+         ptr(sigma), ptr(rgb), None if ordered else ptr(out["cidx"]), None if ordered else ptr(out["count"]), stream())
+    if ordered:
+        compact_valid(out["valid"], out["cidx"], out["count"])
     return out
+
+
+ORDERED_COMPACTION = True      # valid ids in ascending order (reproducible); False: appended by the KNN kernels in scheduling order
+
+
+def compact_valid(valid, cidx, count):
+    """A11: cidx[:count] = ids of the non-zero flags in ascending order (an_compact_valid)."""
+    ws = torch.empty(_lib.load().an_compact_ws_bytes(), device=valid.device, dtype=torch.uint8)
+    call("an_compact_valid", ptr(valid), valid.numel(), ptr(cidx), ptr(count), ptr(ws), stream())
 
 
 def knn_unpose_lattice(verts, ober2cano, lbs_weights, dis_threshold, x_axis, y_rows, z_axis, center, grid=None,
@@ -264,7 +276,9 @@ def knn_unpose_lattice(verts, ober2cano, lbs_weights, dis_threshold, x_axis, y_r
     qws = torch.empty(_lib.load().an_knn_query_ws_bytes(1, N), device=dev, dtype=torch.uint8)
     call("an_knn_unpose_lattice_fwd", ptr(lat), ni, nj, nk, ptr(verts), V, ptr(grid), ptr(qws), ptr(ober2cano), ptr(lbs_weights),
          lbs_weights.shape[1], float(dis_threshold), ptr(out["xyz_cano"]), ptr(out["valid"]), ptr(sigma), ptr(rgb),
-         ptr(out["cidx"]), ptr(out["count"]), stream())
+         None if ORDERED_COMPACTION else ptr(out["cidx"]), None if ORDERED_COMPACTION else ptr(out["count"]), stream())
+    if ORDERED_COMPACTION:
+        compact_valid(out["valid"], out["cidx"], out["count"])
     return out
 
 

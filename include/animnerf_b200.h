@@ -145,6 +145,14 @@ int an_knn_unpose_fwd(const float* xyz, const float* rays, const float* z, int B
                       float* xyz_cano, uint8_t* valid, int32_t* idx, float* dist, float* qw,
                       float* sigma, float* rgb, int32_t* cidx, int32_t* count, void* stream);
 
+/* ---- A11: ordered list of the valid points ------------------------------------------------------------------------
+ * cidx[0..count) = the ids g with valid[g] != 0 in ascending order (valid: n bytes, 16-byte aligned; n < 2^31).
+ * an_knn_unpose_fwd can append valid ids itself (cidx/count arguments) but then in scheduling order; this list is a
+ * function of the flags only, which makes everything downstream (MLP tiles, the weight gradient's summation order)
+ * reproducible bit for bit.  ws: an_compact_ws_bytes() bytes of scratch.  Two launches.                               */
+int64_t an_compact_ws_bytes(void);
+int an_compact_valid(const uint8_t* valid, int64_t n, int32_t* cidx, int32_t* count, void* ws, void* stream);
+
 /* ---- A5-A8 over the density lattice (cfg4: extract_mesh.py:27-35,152-160) ---------------------------------------
  * Same search / blend / mask as an_knn_unpose_fwd (mode 1) for one frame, the query points generated in the kernel:
  * point (i,j,k) = (x[j], y[i], z[k]) + centre, flat index (i*nj + j)*nk + k -- numpy's 'xy' meshgrid order, the centre

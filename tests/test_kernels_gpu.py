@@ -662,3 +662,62 @@ def test_render_loss_matches_torch_losses_and_autograd(fine):
             else:
                 assert a[k].grad is None
         assert float(a[2].grad[: n // 3].abs().max()) == 0.0 if n >= 3 else True
+
+
+def test_compact_valid_is_the_ordered_nonzero_list():
+    """A11: an_compact_valid against torch.nonzero on ragged sizes (one flag, partial 16-byte groups, more ranges than
+    one block handles, ranges that double to stay within 1024 blocks), dense, sparse and empty flag arrays."""
+    g = torch.Generator().manual_seed(5)
+    for n, p in ((1, 1.0), (1, 0.0), (15, 0.5), (16, 1.0), (4096, 0.3), (4097, 0.3), (70001, 0.02), (1 << 20, 0.6),
+                 ((1 << 23) + 5, 0.25)):
+        valid = (torch.rand(n, generator=g) < p).to(torch.uint8).to(DEV)
+        cidx = torch.full((n,), -7, dtype=torch.int32, device=DEV)
+        count = torch.full((1,), -1, dtype=torch.int32, device=DEV)
+        ops().compact_valid(valid, cidx, count)
+        want = torch.nonzero(valid).flatten().to(torch.int32)
+        assert int(count) == want.numel(), (n, p, int(count), want.numel())
+        assert torch.equal(cidx[:want.numel()], want), (n, p)
+        assert bool((cidx[want.numel():] == -7).all())          # nothing written past the list
+
+
+def test_training_steps_are_bit_reproducible_with_frozen_body_params():
+    """Two runs of three optimiser steps from the same weights on the same rays give identical bits (losses, gradients,
+    weights): ordered compaction + fixed-order weight-gradient reduction + no floating-point atomics on the MLP path."""
+    from anim_nerf_b200.anim_nerf import AnimNeRF
+    from anim_nerf_b200.volume_rendering import VolumeRenderer
+    from anim_nerf_b200.optim import FlatGradBuffer, FusedAdam
+    from util import body_model, oracle
+    posed_np, tmpl_np = synthetic.make_body_params(1, seed=5)
+    posed = {k: torch.from_numpy(v) for k, v in posed_np.items()}
+    with torch.no_grad():
+        po = body_model()(**posed)
+        rays_w = torch.from_numpy(synthetic.rays_at_bbox(po["vertices"].numpy(), 96, seed=4, margin=0.02))
+        rays = oracle.rays_to_body_space(rays_w, po["joints_transform"][:, 0]).to(DEV)
+    posed_d = {k: v.to(DEV) for k, v in posed.items()}
+    tmpl_d = {k: torch.from_numpy(v).to(DEV) for k, v in tmpl_np.items()}
+    tgt = torch.rand(1, 96, 3, generator=torch.Generator().manual_seed(1)).to(DEV)
+
+    def run():
+        net = AnimNeRF(use_unpose=True, use_knn=True, use_fine=True, freqs_dir=0, body_model_data=synthetic.make_smpl_dict(0)).to(DEV)
+        for name, seed in (("nerf", 10), ("nerf_fine", 11)):
+            getattr(net, name).load_state_dict({k: torch.from_numpy(v) for k, v in synthetic.make_nerf_weights(seed).items()}, strict=True)
+        vr = VolumeRenderer(n_coarse=64, n_fine=64, white_bkgd=True)
+        params = [p for n in ("nerf", "nerf_fine") for p in getattr(net, n).parameters()]
+        opt = FusedAdam(params, lr=5e-4, eps=1e-8)
+        flat = FlatGradBuffer([net.nerf, net.nerf_fine])
+        opt.flat = flat
+        opt.on_step.append(lambda: (net.nerf.mark_dirty(), net.nerf_fine.mark_dirty()))
+        rec = []
+        for _ in range(3):
+            net.setup_frame(posed_d, tmpl_d, None)
+            out = vr(net, rays, perturb=0.0)
+            loss = ((out["rgbs"] - tgt) ** 2).mean() + ((out["rgbs_fine"] - tgt) ** 2).mean()
+            opt.zero_grad()
+            loss.backward()
+            rec.append((loss.detach().clone(), flat.buf.clone()))
+            opt.step()
+        return rec, torch.cat([p.detach().flatten() for p in params])
+    (ra, wa), (rb, wb) = run(), run()
+    for (la, ga), (lb, gb) in zip(ra, rb):
+        assert torch.equal(la, lb) and torch.equal(ga, gb)
+    assert torch.equal(wa, wb)

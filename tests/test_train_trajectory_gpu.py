@@ -39,13 +39,15 @@ def test_200_step_trajectory_matches_fp32_oracle():
       steps 180..199  mean loss not above 3 x the worst of the fp32 runs (the oracle and three twins); PSNR of the fine
                       render against the teacher above 48 dB and not more than 6 dB below the worst fp32 run
       and every run's loss fell by more than 100 x.
-    The kernels' own runs differ from visit to visit: in-body points get their compact slots by atomic allocation
-    (knn_classify_kernel), the slot order permutes the fp32 summation order of the weight gradient (last-bit differences
-    in ~half of its entries, tools/probe_determinism.py), and Adam's normalisation turns those into +-lr steps on the
-    weights whose gradient is at noise level -- two runs differ by 5e-4 in some weights after five steps.  Measured over
-    12 runs: end loss 2.1e-4 .. 6.5e-4 (oracle 3.6e-4, first twin 3.8e-4), PSNR 53.1 .. 61.4 dB (oracle 58.3, first twin
-    59.8) -- at this level (rgb rms error ~1e-3) the fit is at the bf16 MLP's own error floor (mean |d rgb| 7e-4 on the
-    trained-scale fixture), three orders of magnitude below what a fit to real images reaches (~30 dB)."""
+    The kernels' run is reproducible bit for bit (ordered compaction of the valid points, fixed-order weight-gradient
+    reduction: tests/test_kernels_gpu.py::test_training_steps_are_bit_reproducible_with_frozen_body_params); measured:
+    end loss 3.2e-4 (oracle 3.6e-4, twins 3.8e-4 / 2.1e-4 / 2.5e-4), PSNR 56.8 dB (oracle 58.3, twins 59.8 / 59.0 / ...).
+    Before the compaction was ordered the valid points got their slots by atomic allocation, the slot order permuted the
+    fp32 summation order of the weight gradient, and Adam's normalisation turned those last-bit differences into +-lr
+    steps on the weights whose gradient is at noise level: over 12 such runs the end loss spanned 2.1e-4 .. 6.5e-4 and the
+    PSNR 53.1 .. 61.4 dB -- the spread the bands below were sized for, and the same sensitivity the fp32 twins show.  At
+    this level (rgb rms error ~1e-3) the fit is at the bf16 MLP's own error floor (mean |d rgb| 7e-4 on the trained-scale
+    fixture), three orders of magnitude below what a fit to real images reaches (~30 dB)."""
     from anim_nerf_b200.anim_nerf import AnimNeRF
     from anim_nerf_b200.volume_rendering import VolumeRenderer
     from anim_nerf_b200.optim import FlatGradBuffer, FusedAdam
