@@ -59,7 +59,7 @@ SIGNATURES = {
     "an_render_loss": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "an_mc_count": (_i32, [_vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "an_mc_scan": (_i32, [_vp, _i64, _vp, _vp]),
-    "an_mc_emit": (_i32, [_vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "an_mc_emit": (_i32, [_vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

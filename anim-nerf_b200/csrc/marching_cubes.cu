@@ -17,7 +17,9 @@
 
 namespace {
 
-constexpr int MC_BLOCK = 1024;
+constexpr int MC_BLOCK = 1024;        // lattice points per block (the unit of voff / block_counts)
+constexpr int MC_THREADS = 256;       // each thread owns MC_PER consecutive points
+constexpr int MC_PER = MC_BLOCK / MC_THREADS;
 
 struct Site { int nv, nt, cfg; bool hx, hy, hz; float v0, vx, vy, vz; };
 
@@ -84,16 +86,44 @@ __device__ __forceinline__ void block_scan2(int a, int b, int& ea, int& eb, int&
     ta = wa[31]; tb = wb[31];
     __syncthreads();
 }
+// (warp totals of warps that do not exist read as zero: wa/wb are filled for blockDim.x / 32 warps, the second-level scan
+//  runs over all 32 slots, so blocks of fewer than 1024 threads must clear the tail first)
+__device__ __forceinline__ void block_scan2_small(int a, int b, int& ea, int& eb, int& ta, int& tb)
+{
+    __shared__ int wa[32], wb[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int ia = a, ib = b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int ya = __shfl_up_sync(0xffffffffu, ia, d), yb = __shfl_up_sync(0xffffffffu, ib, d);
+        if (lane >= d) { ia += ya; ib += yb; }
+    }
+    if (lane == 31) { wa[warp] = ia; wb[warp] = ib; }
+    __syncthreads();
+    int pa = 0, pb = 0, sa = 0, sb = 0;
+    for (int k = 0; k < nw; ++k) { const int xa = wa[k], xb = wb[k]; if (k < warp) { pa += xa; pb += xb; } sa += xa; sb += xb; }
+    ea = pa + ia - a; eb = pb + ib - b; ta = sa; tb = sb;
+    __syncthreads();
+}
 
-__global__ void __launch_bounds__(MC_BLOCK)
+__global__ void __launch_bounds__(MC_THREADS)
 mc_count_kernel(const float* __restrict__ vol, int nx, int ny, int nz, float iso, const int8_t* __restrict__ tri,
                 uint16_t* __restrict__ voff, int32_t* __restrict__ counts)
 {
-    const int64_t s = (int64_t)blockIdx.x * MC_BLOCK + threadIdx.x;
-    const Site r = classify(vol, nx, ny, nz, iso, s, tri);
+    const int64_t s0 = (int64_t)blockIdx.x * MC_BLOCK + (int64_t)threadIdx.x * MC_PER;
+    const int64_t n = (int64_t)nx * ny * nz;
+    int nv[MC_PER], sv = 0, st = 0;
+#pragma unroll
+    for (int q = 0; q < MC_PER; ++q) {
+        const Site r = classify(vol, nx, ny, nz, iso, s0 + q, tri);
+        nv[q] = r.nv; sv += r.nv; st += r.nt;
+    }
     int ev, et, tv, tt;
-    block_scan2(r.nv, r.nt, ev, et, tv, tt);
-    if (s < (int64_t)nx * ny * nz) voff[s] = (uint16_t)ev;
+    block_scan2_small(sv, st, ev, et, tv, tt);
+    if (tv) {            // blocks without a vertex leave their voff untouched: no triangle refers to them
+#pragma unroll
+        for (int q = 0; q < MC_PER; ++q) { if (s0 + q < n) voff[s0 + q] = (uint16_t)ev; ev += nv[q]; }
+    }
     if (threadIdx.x == 0) { counts[2 * blockIdx.x] = tv; counts[2 * blockIdx.x + 1] = tt; }
 }
 
@@ -124,39 +154,55 @@ __constant__ int8_t c_edge_owner[12][4] = {
     {0, 0, 0, 0}, {1, 0, 0, 1}, {0, 1, 0, 0}, {0, 0, 0, 1}, {0, 0, 1, 0}, {1, 0, 1, 1},
     {0, 1, 1, 0}, {0, 0, 1, 1}, {0, 0, 0, 2}, {1, 0, 0, 2}, {1, 1, 0, 2}, {0, 1, 0, 2}};
 
-__global__ void __launch_bounds__(MC_BLOCK)
+__global__ void __launch_bounds__(MC_THREADS)
 mc_emit_kernel(const float* __restrict__ vol, int nx, int ny, int nz, float iso, const int8_t* __restrict__ tri,
-               const uint16_t* __restrict__ voff, const int32_t* __restrict__ block_off,
+               const uint16_t* __restrict__ voff, const int32_t* __restrict__ block_off, const int64_t* __restrict__ totals,
                float* __restrict__ verts, int32_t* __restrict__ faces)
 {
     const int64_t n = (int64_t)nx * ny * nz;
-    const int64_t s = (int64_t)blockIdx.x * MC_BLOCK + threadIdx.x;
-    const Site r = classify(vol, nx, ny, nz, iso, s, tri);
+    const int64_t n_blocks = (n + MC_BLOCK - 1) / MC_BLOCK;
+    // this block's totals from the offsets: nothing to emit -> nothing to classify (most blocks of a lattice)
+    const int v0 = block_off[2 * blockIdx.x], t0 = block_off[2 * blockIdx.x + 1];
+    const int64_t v1 = blockIdx.x + 1 < n_blocks ? block_off[2 * blockIdx.x + 2] : totals[0];
+    const int64_t t1 = blockIdx.x + 1 < n_blocks ? block_off[2 * blockIdx.x + 3] : totals[1];
+    if (v1 == v0 && t1 == t0) return;
+    const int64_t s0 = (int64_t)blockIdx.x * MC_BLOCK + (int64_t)threadIdx.x * MC_PER;
+    Site r[MC_PER];
+    int sv = 0, st = 0;
+#pragma unroll
+    for (int q = 0; q < MC_PER; ++q) { r[q] = classify(vol, nx, ny, nz, iso, s0 + q, tri); sv += r[q].nv; st += r[q].nt; }
     int ev, et, tv, tt;
-    block_scan2(r.nv, r.nt, ev, et, tv, tt);
-    if (s >= n) return;
-    const int k = (int)(s % nz), j = (int)((s / nz) % ny), i = (int)(s / ((int64_t)nz * ny));
-    if (r.nv) {
-        float* v = verts + ((int64_t)block_off[2 * blockIdx.x] + ev) * 3;
-        if (r.hx) { v[0] = (float)i + (iso - r.v0) / (r.vx - r.v0); v[1] = (float)j; v[2] = (float)k; v += 3; }
-        if (r.hy) { v[0] = (float)i; v[1] = (float)j + (iso - r.v0) / (r.vy - r.v0); v[2] = (float)k; v += 3; }
-        if (r.hz) { v[0] = (float)i; v[1] = (float)j; v[2] = (float)k + (iso - r.v0) / (r.vz - r.v0); }
-    }
-    if (r.nt) {
-        const int64_t sx = (int64_t)ny * nz, sy = nz;
-        int32_t* f = faces + ((int64_t)block_off[2 * blockIdx.x + 1] + et) * 3;
-        const int8_t* t = tri + r.cfg * 16;
-        for (int m = 0; m < 3 * r.nt; ++m) {
-            const int e = t[m];
-            const int di = c_edge_owner[e][0], dj = c_edge_owner[e][1], dk = c_edge_owner[e][2], axis = c_edge_owner[e][3];
-            const int64_t o = s + di * sx + dj * sy + dk;
-            int rank = 0;
-            if (axis > 0) {       // the owner's earlier edges (x, then y) exist when they are inside the lattice and straddle the isovalue
-                const bool oin = vol[o] < iso;
-                if (i + di + 1 < nx) rank += ((vol[o + sx] < iso) != oin) ? 1 : 0;
-                if (axis > 1 && j + dj + 1 < ny) rank += ((vol[o + sy] < iso) != oin) ? 1 : 0;
+    block_scan2_small(sv, st, ev, et, tv, tt);
+    const int64_t sx = (int64_t)ny * nz, sy = nz;
+#pragma unroll
+    for (int q = 0; q < MC_PER; ++q) {
+        const int64_t s = s0 + q;
+        if (s >= n) break;
+        const int k = (int)(s % nz), j = (int)((s / nz) % ny), i = (int)(s / ((int64_t)nz * ny));
+        const Site& c = r[q];
+        if (c.nv) {
+            float* v = verts + ((int64_t)v0 + ev) * 3;
+            if (c.hx) { v[0] = (float)i + (iso - c.v0) / (c.vx - c.v0); v[1] = (float)j; v[2] = (float)k; v += 3; }
+            if (c.hy) { v[0] = (float)i; v[1] = (float)j + (iso - c.v0) / (c.vy - c.v0); v[2] = (float)k; v += 3; }
+            if (c.hz) { v[0] = (float)i; v[1] = (float)j; v[2] = (float)k + (iso - c.v0) / (c.vz - c.v0); }
+            ev += c.nv;
+        }
+        if (c.nt) {
+            int32_t* f = faces + ((int64_t)t0 + et) * 3;
+            const int8_t* t = tri + c.cfg * 16;
+            for (int m = 0; m < 3 * c.nt; ++m) {
+                const int e = t[m];
+                const int di = c_edge_owner[e][0], dj = c_edge_owner[e][1], dk = c_edge_owner[e][2], axis = c_edge_owner[e][3];
+                const int64_t o = s + di * sx + dj * sy + dk;
+                int rank = 0;
+                if (axis > 0) {       // the owner's earlier edges (x, then y) exist when they are inside the lattice and straddle the isovalue
+                    const bool oin = vol[o] < iso;
+                    if (i + di + 1 < nx) rank += ((vol[o + sx] < iso) != oin) ? 1 : 0;
+                    if (axis > 1 && j + dj + 1 < ny) rank += ((vol[o + sy] < iso) != oin) ? 1 : 0;
+                }
+                f[m] = block_off[2 * (o / MC_BLOCK)] + (int32_t)voff[o] + rank;
             }
-            f[m] = block_off[2 * (o / MC_BLOCK)] + (int32_t)voff[o] + rank;
+            et += c.nt;
         }
     }
 }
@@ -168,7 +214,7 @@ extern "C" int an_mc_count(const float* volume, int nx, int ny, int nz, float is
 {
     if (!volume || !tri_table || !voff || !block_counts || nx < 2 || ny < 2 || nz < 2) return AN_ERR_ARG;
     const int64_t n = (int64_t)nx * ny * nz;
-    mc_count_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, (cudaStream_t)stream>>>(
+    mc_count_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_THREADS, 0, (cudaStream_t)stream>>>(
         volume, nx, ny, nz, iso, tri_table, voff, block_counts);
     AN_CHECK_LAUNCH();
     return AN_OK;
@@ -183,12 +229,13 @@ extern "C" int an_mc_scan(int32_t* block_counts, int64_t n_blocks, int64_t* tota
 }
 
 extern "C" int an_mc_emit(const float* volume, int nx, int ny, int nz, float iso, const int8_t* tri_table,
-                          const uint16_t* voff, const int32_t* block_offsets, float* vertices, int32_t* faces, void* stream)
+                          const uint16_t* voff, const int32_t* block_offsets, const int64_t* totals, float* vertices,
+                          int32_t* faces, void* stream)
 {
-    if (!volume || !tri_table || !voff || !block_offsets || !vertices || !faces || nx < 2 || ny < 2 || nz < 2) return AN_ERR_ARG;
+    if (!volume || !tri_table || !voff || !block_offsets || !totals || !vertices || !faces || nx < 2 || ny < 2 || nz < 2) return AN_ERR_ARG;
     const int64_t n = (int64_t)nx * ny * nz;
-    mc_emit_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_BLOCK, 0, (cudaStream_t)stream>>>(
-        volume, nx, ny, nz, iso, tri_table, voff, block_offsets, vertices, faces);
+    mc_emit_kernel<<<(unsigned)((n + MC_BLOCK - 1) / MC_BLOCK), MC_THREADS, 0, (cudaStream_t)stream>>>(
+        volume, nx, ny, nz, iso, tri_table, voff, block_offsets, totals, vertices, faces);
     AN_CHECK_LAUNCH();
     return AN_OK;
 }

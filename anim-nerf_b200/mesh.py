@@ -107,7 +107,7 @@ def marching_cubes(volume, isovalue=0.0):
     faces = torch.empty(n_f, 3, dtype=torch.int32, device=dev)
     if n_v:
         _lib.call("an_mc_emit", vol.data_ptr(), nx, ny, nz, float(isovalue), table.data_ptr(), voff.data_ptr(), counts.data_ptr(),
-                  verts.data_ptr(), faces.data_ptr(), stream)
+                  totals.data_ptr(), verts.data_ptr(), faces.data_ptr(), stream)
     return verts, faces
 
 

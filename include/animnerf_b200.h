@@ -262,14 +262,15 @@ int an_adam_step(float* const* params, const float* const* grads, float* const* 
  *                block_counts (ceil(n/1024), 2) int32 = (vertices, triangles) per block;
  *   an_mc_scan   block_counts -> exclusive prefix sums in place, totals[2] int64 = (n_vertices, n_faces): the caller
  *                reads them back and allocates the outputs;
- *   an_mc_emit   vertices (n_vertices,3) fp32 in lattice-index coordinates (linear interpolation along the lattice
+ *   an_mc_emit   (block_counts as left by an_mc_scan, totals as written by it) vertices (n_vertices,3) fp32 in lattice-index coordinates (linear interpolation along the lattice
  *                edge), faces (n_faces,3) int32, normals from inside to outside.  Vertex and face order depend on the
  *                lattice only (no atomics).                                                                          */
 int an_mc_count(const float* volume, int nx, int ny, int nz, float iso, const int8_t* tri_table,
                 uint16_t* voff, int32_t* block_counts, void* stream);
 int an_mc_scan(int32_t* block_counts, int64_t n_blocks, int64_t* totals, void* stream);
 int an_mc_emit(const float* volume, int nx, int ny, int nz, float iso, const int8_t* tri_table,
-               const uint16_t* voff, const int32_t* block_offsets, float* vertices, int32_t* faces, void* stream);
+               const uint16_t* voff, const int32_t* block_offsets, const int64_t* totals, float* vertices, int32_t* faces,
+               void* stream);
 
 /* ---- A18 (losses): the four render-loss terms and their gradients in one launch ------------------------------------
  * replaces train.py:228-262 (F.mse_loss on rgbs / rgbs_fine, lambda_alphas * F.l1_loss on alphas / alphas_fine) and their
