@@ -234,11 +234,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             const int64_t p = tile * 128 + row;
             const bool in = p < n;
             const int64_t id = in ? (cidx ? (int64_t)cidx[p] : p) : 0;
-#ifdef AN_EXP_L2STASH     // experiment: all stash stores land in 32 tiles (L2-resident): same shared-memory reads, no HBM writes
-            uint8_t* st_tile = TRAIN ? stash + (tile & 31) * ST_TILE : nullptr;
-#else
             uint8_t* st_tile = TRAIN ? stash + tile * ST_TILE : nullptr;
-#endif
             const uint8_t* pst_tile = TAN ? pstash + tile * ST_TILE : nullptr;
             float x[3] = {0.f, 0.f, 0.f};
             float tv[3] = {0.f, 0.f, 0.f};
@@ -284,9 +280,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
             fence_proxy_async();
             if (TRAIN) {          // every warp streams its own 32 rows (4 KB, contiguous in the image) to the stash
                 __syncwarp();
-#ifndef AN_EXP_NOSTASH
                 if (elect_one()) { bulk_s2g_hint(st_tile + ST_ENC + q * 4096, enc_s + q * 4096u, 4096, stream_pol); bulk_commit(); }
-#endif
             }
             mbar_arrive_remote(my_act, 0);
 
@@ -369,9 +363,7 @@ mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, const float* __restrict__ 
                             __syncwarp();
                             if (elect_one()) {
                                 const uint32_t off = (uint32_t)(blk >> 1) * 16384u + (uint32_t)q * 4096u;
-#ifndef AN_EXP_NOSTASH
                                 bulk_s2g_hint(st_tile + (g == 8 ? ST_C : ST_H + (int64_t)g * 65536) + off, act_s + off, 4096, stream_pol);
-#endif
                                 bulk_commit();
                             }
                         }

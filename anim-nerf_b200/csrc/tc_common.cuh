@@ -62,16 +62,10 @@ __device__ __forceinline__ uint64_t l2_policy_stream() {
     uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
 }
 __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
-#ifdef AN_NO_L2_HINTS      // A/B switch (tools/gpu_ab.sh)
-    (void)pol; bulk_g2s(dst_smem, src, bytes, bar); return;
-#endif
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void bulk_s2g_hint(void* dst, uint32_t src_smem, uint32_t bytes, uint64_t pol) {
-#ifdef AN_NO_L2_HINTS
-    (void)pol; bulk_s2g(dst, src_smem, bytes); return;
-#endif
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
                  ::"l"(dst), "r"(src_smem), "r"(bytes), "l"(pol) : "memory");
 }

@@ -82,6 +82,11 @@ def tri_table():
     return table
 
 
+@functools.lru_cache(maxsize=None)
+def _device_table(device):
+    return torch.from_numpy(tri_table()).to(device)
+
+
 def marching_cubes(volume, isovalue=0.0):
     """`mcubes.marching_cubes(volume, isovalue)` on the device: volume (nx,ny,nz) fp32 CUDA tensor ->
     (vertices (V,3) fp32 in lattice-index coordinates, faces (F,3) int32).  A lattice point is inside when its value is
@@ -93,7 +98,7 @@ def marching_cubes(volume, isovalue=0.0):
     vol = volume.contiguous().float()
     nx, ny, nz = vol.shape
     dev = vol.device
-    table = torch.from_numpy(tri_table()).to(dev)
+    table = _device_table(dev)
     n_sites = nx * ny * nz
     n_blocks = (n_sites + 1023) // 1024
     voff = torch.empty(n_sites, dtype=torch.int16, device=dev)
