@@ -52,6 +52,7 @@ class GraphedTrainStep:
         self.loss_fn, self.opt, self.params, self.world, self.flat = loss_fn, optimizer, list(params or ()), world, flat
         self.static = _tree_map(lambda t: t.clone(), example_batch)
         self.bucket = None
+        self._staging = None
         if model is not None:
             model.clear_frame_state()
         if flat is not None and hasattr(optimizer, "flat"):
@@ -135,3 +136,43 @@ class GraphedTrainStep:
         for fn in getattr(self.opt, "on_step", ()):     # a replay runs no Python: invalidate the packed weights here
             fn()
         return self.loss
+
+    # ---- pipelined input feed: the next batch's host->device copy runs on a copy stream while the current step computes,
+    # and a step's loss is read back without stalling the launch of the next one
+    def stage(self, batch):
+        """Start copying `batch` (pinned host tensors, same nesting as the example) into the staging buffers on the copy
+        stream; returns at once.  `run_staged()` consumes it."""
+        if self._staging is None:
+            self._staging = _tree_map(lambda t: torch.empty_like(t), self.static)
+            self._copy_stream = torch.cuda.Stream()
+            self._staged, self._consumed = torch.cuda.Event(), torch.cuda.Event()
+            self._consumed.record()
+        self._copy_stream.wait_event(self._consumed)        # the previous staging content has been moved on
+        with torch.cuda.stream(self._copy_stream):
+            _tree_copy(self._staging, batch)
+            self._staged.record()
+
+    def run_staged(self):
+        """Replay the step on the batch handed to `stage()`; returns a `StepResult` whose `.value()` is the step's loss
+        (a host float; blocks only until THIS step has finished, so it can be called one step late without idling the GPU)."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged)
+        _tree_copy(self.static, self._staging)              # device -> device, a few microseconds
+        self._consumed.record(cur)
+        self(None)
+        res = StepResult(self.loss)
+        return res
+
+
+class StepResult:
+    """Loss of one replayed step on its way to the host: a pinned scalar filled by an async copy + the event after it."""
+
+    def __init__(self, loss_dev):
+        self.host = torch.empty((), dtype=loss_dev.dtype, pin_memory=True)
+        self.host.copy_(loss_dev, non_blocking=True)
+        self.done = torch.cuda.Event()
+        self.done.record()
+
+    def value(self):
+        self.done.synchronize()
+        return float(self.host)

@@ -239,12 +239,28 @@ def run_ours(args):
     step_ms = ms / args.steps
 
     # ---- end-to-end arm (pinned host buffers; H2D of the batch + D2H of the loss inside the timed region)
-    def step_e2e():
-        return float(gstep(pin).item())
+    # The loop a training script runs on this API: every step's batch is copied from pinned host memory (on a copy stream,
+    # while the previous step computes) and every step's loss is read back on the host (one step late, so the launch of
+    # the next step is not held up); both inside the timed region.
+    e2e_state = {"pending": None, "losses": []}
 
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
-    ms_e2e, _, _ = _timed_replays(step_e2e, args.steps, barrier, dev, world)
+    def step_e2e():
+        res = gstep.run_staged()                 # this step: staged batch -> static buffers, replay, loss D2H started
+        gstep.stage(pin)                         # H2D of the next step's batch
+        if e2e_state["pending"] is not None:
+            e2e_state["losses"].append(e2e_state["pending"].value())
+        e2e_state["pending"] = res
+
+    def e2e_loop(n):
+        gstep.stage(pin)
+        for _ in range(n):
+            step_e2e()
+        e2e_state["losses"].append(e2e_state["pending"].value())       # the last step's loss: the loop ends with the GPU idle
+        e2e_state["pending"] = None
+
+    e2e_loop(max(1, args.warmup // 2))
+    ms_e2e, _, _ = _timed_replays(lambda: e2e_loop(args.steps), 1, barrier, dev, world)
+    assert len(e2e_state["losses"]) == max(1, args.warmup // 2) + args.steps and all(np.isfinite(e2e_state["losses"]))
     clk = clocks.stop(t_region0, t_region1)
 
     # every rank must hold the same weights after the same number of averaged updates
@@ -431,7 +447,9 @@ def run_ours(args):
                        "l2": "per-step working set (bf16 activation stash + dY scratch, > 5 GB) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in pin.values())),
-                    "d2h_bytes_per_step": 4},
+                    "d2h_bytes_per_step": 4,
+                    "loop": "GraphedTrainStep.stage / run_staged: the next batch's H2D runs on a copy stream during the step, "
+                            "each step's loss is read on the host one step late (all of them inside the timed region)"},
             "frame_512": {"ms": ms_frame, "rays_per_s": 512 * 512 / (ms_frame * 1e-3), "frames_timed": n_frames_timed,
                           "workload": "cfg3: 512x512 novel-view frame, inference, 64+64 samples, perturb=0, rows interleaved over "
                                       "%d GPU(s); per-frame tables + ray generation + render + D2H of rgb/alpha/depth" % world,

@@ -339,6 +339,37 @@ def test_graphed_step_takes_nested_batches_and_refuses_host_rng():
         GraphedTrainStep(loss_fn, opt, params, nested, world=1, warmup=1, renderer=vr)
 
 
+def test_graphed_step_pipelined_feed_equals_direct_feed():
+    """GraphedTrainStep.stage / run_staged (next batch's H2D on a copy stream during the step, loss read one step late)
+    trains exactly like feeding every batch through __call__: same loss sequence, bit for bit."""
+    from anim_nerf_b200.graph_step import GraphedTrainStep
+    def batches(batch):
+        out = []
+        for i in range(5):
+            b = {k: v.cpu().clone() for k, v in batch.items()}
+            b["rgbs"] = (b["rgbs"] * (1.0 - 0.1 * i)).contiguous()          # a different target every step
+            out.append({k: v.pin_memory() for k, v in b.items()})
+        return out
+    sysm, opt, params, batch, loss_fn = _train_setup()
+    g = GraphedTrainStep(loss_fn, opt, params, batch, world=1, warmup=2)
+    direct = [float(g(b)) for b in batches(batch)]
+    sysm, opt, params, batch, loss_fn = _train_setup()
+    g = GraphedTrainStep(loss_fn, opt, params, batch, world=1, warmup=2)
+    bs = batches(batch)
+    piped, pending = [], None
+    g.stage(bs[0])
+    for i in range(len(bs)):
+        res = g.run_staged()
+        if i + 1 < len(bs):
+            g.stage(bs[i + 1])
+        if pending is not None:
+            piped.append(pending.value())
+        pending = res
+    piped.append(pending.value())
+    assert piped == direct, (piped, direct)
+    assert len(set(round(v, 7) for v in direct)) == len(direct)
+
+
 def test_edge_shapes_empty_single_ray_and_all_background():
     """Edge cases of the public call (B3): no rays -> empty outputs of the right shapes;
     one single ray and a ragged batch (3 frames x 37 rays) match the oracle; rays that miss the body entirely
