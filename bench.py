@@ -89,7 +89,7 @@ class ClockSampler:
         rows = [r for ts, r in self.rows if t0 is not None and t0 <= ts <= t1]
         window = "timed region"
         if len(rows) < 2:
-            rows, window = [r for _, r in self.rows], "warm-up + timed region + e2e loop (same load)"
+            rows, window = [r for _, r in self.rows], "warm-up + timed region + e2e loop + untimed replays of the same step (same load)"
         sm, mx, reasons = [], [], set()
         for r in rows:
             try:
@@ -261,6 +261,17 @@ def run_ours(args):
     e2e_loop(max(1, args.warmup // 2))
     ms_e2e, _, _ = _timed_replays(lambda: e2e_loop(args.steps), 1, barrier, dev, world)
     assert len(e2e_state["losses"]) == max(1, args.warmup // 2) + args.steps and all(np.isfinite(e2e_state["losses"]))
+    # nvidia-smi needs up to a second to deliver its first sample (longer with eight of them starting at once): keep the
+    # same load running (untimed replays) until a few samples exist, so that the line always carries clocks under load
+    for _ in range(100):                       # <= 100 x 5 replays (~4 s); every rank runs the same count (NCCL inside the step)
+        need = torch.tensor([1.0 if (clocks.proc is not None and len(clocks.rows) < 3) else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(need, op=dist.ReduceOp.MAX)
+        if float(need[0]) == 0.0:
+            break
+        for _ in range(5):
+            gstep()
+        torch.cuda.synchronize()
     clk = clocks.stop(t_region0, t_region1)
 
     # every rank must hold the same weights after the same number of averaged updates
