@@ -275,12 +275,17 @@ def knn_cdist(verts, xyz, k=4, chunk=16384):
     return torch.cat(ds, 0), torch.cat(is_, 0)
 
 
+# bench.py's gpu_eager_baseline can plug another k-NN in here for CUDA tensors (callable(verts (V,3), xyz (N,3), k) ->
+# (dist (N,k), idx (N,k) int64)): the reference uses the external KNN_CUDA wheel at this point, not cdist + topk
+KNN_OVERRIDE = None
+
+
 def unpose(xyz, verts, ober2cano, lbs_weights, dis_threshold=0.2, k=4, weight_std=0.1):
     """xyz (B,N,3) body space -> (xyz_cano (B,N,3), valid (B,N,1) float, dist (B,N,k), idx (B,N,k)).
     Distances/indices are constants (the reference runs KNN under no_grad)."""
     B, N = xyz.shape[:2]
     if xyz.is_cuda:
-        res = [knn_cdist(verts[b].detach(), xyz[b].detach(), k) for b in range(B)]
+        res = [(KNN_OVERRIDE or knn_cdist)(verts[b].detach(), xyz[b].detach(), k) for b in range(B)]
         dist_t = torch.stack([r[0] for r in res], 0)
         idx_t = torch.stack([r[1] for r in res], 0)
     else:
