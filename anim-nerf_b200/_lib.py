@@ -25,7 +25,7 @@ SIGNATURES = {
     "an_ray_point_grad": (_i32, [_vp] * 6 + [_i64, _i32, _vp, _vp, _vp]),
     "an_sample_coarse_fwd": (_i32, [_vp, _i64, _i32, _f32, _vp, _u64, _vp, _vp]),
     "an_vertex_grid_bytes": (_i64, [_i32, _i32]),
-    "an_vertex_grid_build": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp]),
+    "an_vertex_grid_build": (_i32, [_vp, _i32, _i32, _f32, _f32, _vp, _vp]),
     "an_knn_query_ws_bytes": (_i64, [_i32, _i64]),
     "an_knn_unpose_fwd": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _f32, _i32,
                                  _vp, _vp, _vp, _i32, _vp, _vp, _vp,
@@ -105,7 +105,7 @@ def check(code, what):
 
 
 # kernels launched per entry point (for bench.py's gpu_launches claim)
-KERNELS_PER_CALL = {"an_mlp_bwd": 4, "an_mlp_bwd_wgrad": 3, "an_mlp_bwd_wgrad_scaled": 3, "an_mlp_pack": 2, "an_knn_unpose_fwd": 2, "an_knn_unpose_lattice_fwd": 2, "an_compact_valid": 2,
+KERNELS_PER_CALL = {"an_mlp_bwd": 4, "an_mlp_bwd_wgrad": 3, "an_mlp_bwd_wgrad_scaled": 3, "an_mlp_pack": 2, "an_knn_unpose_fwd": 2, "an_knn_unpose_lattice_fwd": 2, "an_compact_valid": 2, "an_vertex_grid_build": 2,
                     "an_body_tables_fwd": 2, "an_body_tables_bwd": 2}      # (memsets are not counted)
 launch_count = 0
 _timing = None          # bench.py: dict name -> list of (start_event, stop_event) on the launching stream

@@ -30,7 +30,7 @@
 #define KNN_B0_SCALE 1.25f   // must match the cell the host passes: 3*cell >= KNN_B0_SCALE * dis_threshold
 #define GRID_MAXC (AN_GRID_MAX_DIM * AN_GRID_MAX_DIM * AN_GRID_MAX_DIM)
 
-struct GridHeader { float ox, oy, oz, cell; int nx, ny, nz, pad; };
+struct GridHeader { float ox, oy, oz, cell; int nx, ny, nz; float flag_r; };    // flag_r > 0: flags = "some vertex within flag_r of the cell's box"
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 #define GRID_R 3                                    // search box radius in cells: GRID_R * cell >= dis_threshold
@@ -262,7 +262,7 @@ knn_unpose_brute_kernel(const float* __restrict__ xyz, const float* __restrict__
 
 // ------------------------------------------------------------------ grid build
 __global__ void __launch_bounds__(1024)
-vertex_grid_build_kernel(const float* __restrict__ verts, int V, float cell_in, char* __restrict__ ws,
+vertex_grid_build_kernel(const float* __restrict__ verts, int V, float cell_in, float flag_r, char* __restrict__ ws,
                          int64_t frame_bytes)
 {
     __shared__ float s_red[6][32];
@@ -303,7 +303,7 @@ vertex_grid_build_kernel(const float* __restrict__ verts, int V, float cell_in, 
         s_h.nx = min(AN_GRID_MAX_DIM, (int)floorf((h[0] - l[0]) / cell) + 1);
         s_h.ny = min(AN_GRID_MAX_DIM, (int)floorf((h[1] - l[1]) / cell) + 1);
         s_h.nz = min(AN_GRID_MAX_DIM, (int)floorf((h[2] - l[2]) / cell) + 1);
-        s_h.pad = 0;
+        s_h.flag_r = flag_r;
         *hdr = s_h;
     }
     __syncthreads();
@@ -334,24 +334,6 @@ vertex_grid_build_kernel(const float* __restrict__ verts, int V, float cell_in, 
     for (int c = tid * per; c < min(ncell, (tid + 1) * per); ++c) { cell_start[c] = run; run += counts[c]; }
     if (tid == 0) cell_start[ncell] = V;
     __syncthreads();
-    {   // occupancy of the GRID_R-dilated neighbourhood for every cell of the extended grid
-        uint8_t* flags = (uint8_t*)(base + GRID_OFF_FLAGS);
-        const int ex_n = h.nx + 2 * GRID_R, ey_n = h.ny + 2 * GRID_R, ez_n = h.nz + 2 * GRID_R;
-        for (int e = tid; e < ex_n * ey_n * ez_n; e += blockDim.x) {
-            const int ex = e % ex_n, ey = (e / ex_n) % ey_n, ez = e / (ex_n * ey_n);
-            // extended index = grid index + GRID_R; neighbourhood of grid cell g is [g-R, g+R] = [e-2R, e]
-            const int x0 = max(ex - 2 * GRID_R, 0), x1 = min(ex, h.nx - 1);
-            int any = 0;
-            if (x0 <= x1)
-                for (int gz = max(ez - 2 * GRID_R, 0); gz <= min(ez, h.nz - 1) && !any; ++gz)
-                    for (int gy = max(ey - 2 * GRID_R, 0); gy <= min(ey, h.ny - 1); ++gy) {
-                        const int row = (gz * h.ny + gy) * h.nx;
-                        if (cell_start[row + x1 + 1] > cell_start[row + x0]) { any = 1; break; }
-                    }
-            flags[e] = (uint8_t)any;
-        }
-    }
-    __syncthreads();
     for (int v = tid; v < V; v += blockDim.x) {
         const float x = vb[v * 3], y = vb[v * 3 + 1], zc = vb[v * 3 + 2];
         const int cx = min(h.nx - 1, max(0, (int)floorf((x - h.ox) / h.cell)));
@@ -360,6 +342,71 @@ vertex_grid_build_kernel(const float* __restrict__ verts, int V, float cell_in, 
         const int c = (cz * h.ny + cy) * h.nx + cx;
         const int pos = cell_start[c] + atomicSub(&counts[c], 1) - 1;
         sorted[pos] = make_float4(x, y, zc, __int_as_float(v));
+    }
+}
+
+// Validity pre-filter for every cell of the extended grid (grid dilated by GRID_R cells): can a query inside this cell have
+// a vertex within the threshold?  flag_r > 0: exact test on the cell's BOX -- some vertex of the neighbourhood lies within
+// flag_r of the box (a query q in the box with |q - v| < flag_r implies that, so a zero flag proves d_min >= flag_r for
+// every query of the cell).  flag_r <= 0: the coarser test "any vertex in the 7^3-cell neighbourhood" (valid for
+// thresholds up to GRID_R cells).  One warp per extended cell, all frames in one launch (grid.y = frame).
+__global__ void __launch_bounds__(256)
+vertex_grid_flags_kernel(char* __restrict__ ws, int64_t frame_bytes)
+{
+    char* base = ws + (int64_t)blockIdx.y * frame_bytes;
+    const GridHeader h = *(const GridHeader*)base;
+    const int* __restrict__ cell_start = (const int*)(base + GRID_OFF_START);
+    const float4* __restrict__ sorted = (const float4*)(base + GRID_OFF_SORTED);
+    uint8_t* flags = (uint8_t*)(base + GRID_OFF_FLAGS);
+    const int ex_n = h.nx + 2 * GRID_R, ey_n = h.ny + 2 * GRID_R, ez_n = h.nz + 2 * GRID_R;
+    const int lane = threadIdx.x & 31;
+    const float flag_r = h.flag_r;
+    const float rr = flag_r * 1.0001f + 1e-6f, r2 = rr * rr;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    // one warp per extended cell (lanes share its candidates), warps stride over the cells of the frame
+    for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < ex_n * ey_n * ez_n; e += n_warps) {
+    const int ex = e % ex_n, ey = (e / ex_n) % ey_n, ez = e / (ex_n * ey_n);
+    // extended index = grid index + GRID_R; neighbourhood of grid cell g is [g-R, g+R] = [e-2R, e]
+    const int x0 = max(ex - 2 * GRID_R, 0), x1 = min(ex, h.nx - 1);
+    const float bx0 = h.ox + (float)(ex - GRID_R) * h.cell, by0 = h.oy + (float)(ey - GRID_R) * h.cell,
+                bz0 = h.oz + (float)(ez - GRID_R) * h.cell;
+    bool any = false;                                                     // warp-uniform
+    if (x0 <= x1)
+        for (int rbase = 0; rbase < (2 * GRID_R + 1) * (2 * GRID_R + 1) && !any; rbase += 32) {
+            // every lane looks up one (gz, gy) row of the neighbourhood (its two loads run in parallel across the warp) ...
+            const int r = rbase + lane;
+            const int gz = ez - 2 * GRID_R + r / (2 * GRID_R + 1), gy = ey - 2 * GRID_R + r % (2 * GRID_R + 1);
+            int s0 = 0, e1 = 0;
+            if (r < (2 * GRID_R + 1) * (2 * GRID_R + 1) && gz >= 0 && gz < h.nz && gy >= 0 && gy < h.ny) {
+                // gap between this row's (y,z) cell and the box: whole cells in between
+                const float gy_ = fmaxf(0.f, (float)(abs(gy - (ey - GRID_R)) - 1)) * h.cell;
+                const float gz_ = fmaxf(0.f, (float)(abs(gz - (ez - GRID_R)) - 1)) * h.cell;
+                if (!(flag_r > 0.f) || gy_ * gy_ + gz_ * gz_ < r2) {
+                    const int row = (gz * h.ny + gy) * h.nx;
+                    s0 = __ldg(cell_start + row + x0); e1 = __ldg(cell_start + row + x1 + 1);
+                }
+            }
+            unsigned rows = __ballot_sync(0xffffffffu, e1 > s0);
+            if (!(flag_r > 0.f)) { any = rows != 0u; continue; }
+            // ... then the warp scans the vertices of the non-empty rows, 32 at a time, until one lies within the radius
+            while (rows && !any) {
+                const int src = __ffs(rows) - 1;
+                rows &= rows - 1;
+                const int rs0 = __shfl_sync(0xffffffffu, s0, src), re1 = __shfl_sync(0xffffffffu, e1, src);
+                for (int p0 = rs0; p0 < re1 && !any; p0 += 32) {
+                    bool hit = false;
+                    if (p0 + lane < re1) {
+                        const float4 v = __ldg(sorted + p0 + lane);
+                        const float dx = fmaxf(fmaxf(bx0 - v.x, v.x - (bx0 + h.cell)), 0.f);
+                        const float dy = fmaxf(fmaxf(by0 - v.y, v.y - (by0 + h.cell)), 0.f);
+                        const float dz = fmaxf(fmaxf(bz0 - v.z, v.z - (bz0 + h.cell)), 0.f);
+                        hit = dx * dx + dy * dy + dz * dz < r2;
+                    }
+                    any = __any_sync(0xffffffffu, hit);
+                }
+            }
+        }
+    if (lane == 0) flags[e] = (uint8_t)any;
     }
 }
 
@@ -483,7 +530,8 @@ knn_classify_kernel(const float* __restrict__ xyz, const float* __restrict__ ray
                           ez = (int)floorf((qz - h.oz) * inv_cell) + GRID_R;
                 const int ex_n = h.nx + 2 * GRID_R, ey_n = h.ny + 2 * GRID_R, ez_n = h.nz + 2 * GRID_R;
                 maybe = ex >= 0 && ex < ex_n && ey >= 0 && ey < ey_n && ez >= 0 && ez < ez_n;
-                if (maybe) maybe = __ldg(flags + ((int64_t)ez * ey_n + ey) * ex_n + ex) != 0;
+                // (flags built for a smaller radius than this call's threshold cannot reject anything)
+                if (maybe && !(h.flag_r > 0.f && thr > h.flag_r)) maybe = __ldg(flags + ((int64_t)ez * ey_n + ey) * ex_n + ex) != 0;
                 if (!maybe) {            // no vertex within the box radius (>= threshold): final outputs of an invalid point
                     o.xyz_cano[gid * 3] = 0.f; o.xyz_cano[gid * 3 + 1] = 0.f; o.xyz_cano[gid * 3 + 2] = 0.f;
                     o.valid[gid] = 0;
@@ -839,11 +887,15 @@ knn_unpose_bwd_kernel(const float* __restrict__ g_xc, const int32_t* __restrict_
 // ------------------------------------------------------------------ C ABI
 extern "C" int64_t an_vertex_grid_bytes(int B, int V) { return B > 0 && V > 0 ? (int64_t)B * grid_frame_bytes(V) : 0; }
 
-extern "C" int an_vertex_grid_build(const float* verts, int B, int V, float cell, void* ws, void* stream)
+extern "C" int an_vertex_grid_build(const float* verts, int B, int V, float cell, float flag_radius, void* ws, void* stream)
 {
     if (!verts || !ws || B <= 0 || V <= 0 || !(cell > 0.f)) return AN_ERR_ARG;
+    if (flag_radius > (float)GRID_R * cell) return AN_ERR_ARG;          // the flags look GRID_R cells around a cell
     if (((uintptr_t)ws) & 15) return AN_ERR_ALIGN;
-    vertex_grid_build_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(verts, V, cell, (char*)ws, grid_frame_bytes(V));
+    vertex_grid_build_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(verts, V, cell, flag_radius, (char*)ws, grid_frame_bytes(V));
+    AN_CHECK_LAUNCH();
+    vertex_grid_flags_kernel<<<dim3(B >= 8 ? 128 : 512, B), 256, 0, (cudaStream_t)stream>>>(
+        (char*)ws, grid_frame_bytes(V));
     AN_CHECK_LAUNCH();
     return AN_OK;
 }

@@ -185,15 +185,18 @@ def body_tables_bwd(ctx, g_o2c, g_ginv=None):
 
 
 # ------------------------------------------------------------------------ KNN + unpose
-def vertex_grid(verts, dis_threshold):
+def vertex_grid(verts, dis_threshold, exact_flags=True):
     """Per-frame vertex grid for the pruned search.  cell = 1.25*threshold/3 (+0.1 %): the kernel's
     7^3-cell search box then covers radius >= 1.25*threshold, so 'nothing found' proves
-    d_min > threshold and a 4th neighbour up to 25 % beyond the threshold needs no exhaustive rescan."""
+    d_min > threshold and a 4th neighbour up to 25 % beyond the threshold needs no exhaustive rescan.
+    exact_flags: cells are marked "a query in here can be valid" by the exact box-to-vertex distance (< threshold)
+    instead of "a vertex in the 7^3-cell neighbourhood": ~40 % fewer coarse-pass queries reach the search."""
     verts = _f32c(verts)
     B, V = verts.shape[:2]
     nbytes = _lib.load().an_vertex_grid_bytes(B, V)
     ws = torch.empty(nbytes, device=verts.device, dtype=torch.uint8)
-    call("an_vertex_grid_build", ptr(verts), B, V, float(dis_threshold) * 1.25 / 3.0 * 1.001, ptr(ws), stream())
+    call("an_vertex_grid_build", ptr(verts), B, V, float(dis_threshold) * 1.25 / 3.0 * 1.001, float(dis_threshold) if exact_flags else 0.0,
+         ptr(ws), stream())
     return ws
 
 

@@ -106,9 +106,14 @@ int an_ray_point_grad(const float* rays, const float* z, const uint8_t* valid, c
  * an_vertex_grid_build: per-frame uniform grid over the posed vertices used by the exact pruned
  * search.  REQUIRED: 3*cell >= dis_threshold of the later queries (the kernel scans a 7^3-cell box);
  * pass cell = 1.25 * dis_threshold/3 * 1.001 (a smaller cell only triggers more exhaustive rescans).  The cell grows automatically if the body would need more
- * than AN_GRID_MAX_DIM cells per axis.  ws: an_vertex_grid_bytes(B,V) bytes, 16-byte aligned.    */
+ * than AN_GRID_MAX_DIM cells per axis.  ws: an_vertex_grid_bytes(B,V) bytes, 16-byte aligned.
+ * flag_radius: the build also marks, for every cell of the grid dilated by 3 cells, whether a query inside the cell can
+ * be valid.  flag_radius > 0 (<= 3*cell; pass dis_threshold): exact test "some vertex lies within flag_radius of the
+ * cell's box" -- queries in unmarked cells are farther than flag_radius from every vertex and are finished without a
+ * search (a later call with a larger dis_threshold ignores the marks).  flag_radius <= 0: the coarser mark "a vertex in
+ * the 7^3-cell neighbourhood".                                                                                       */
 int64_t an_vertex_grid_bytes(int B, int V);
-int an_vertex_grid_build(const float* verts, int B, int V, float cell, void* ws, void* stream);
+int an_vertex_grid_build(const float* verts, int B, int V, float cell, float flag_radius, void* ws, void* stream);
 
 /* Query points are either xyz (B,N,3) (rays,z NULL) or generated as o + z*d from rays
  * (B,R,8), z (B,R,K) with N = R*K (xyz NULL).
