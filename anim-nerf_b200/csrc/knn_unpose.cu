@@ -569,22 +569,38 @@ knn_classify_kernel(const float* __restrict__ xyz, const float* __restrict__ ray
     }
 }
 
-// Insert a candidate known to beat the current 4th entry: overwrite it, then three predicated
-// compare-exchanges restore the (d2, index) order -- no data-dependent branches inside.
-__device__ __forceinline__ void best_insert_sorted(Best4& b, float d2, int idx) {
-    b.d[3] = d2; b.i[3] = idx;
+// The grid search keeps its four best as packed 64-bit keys, (bits of d2) << 32 | vertex index: d2 >= +0 and never NaN
+// for finite inputs, so unsigned order of the bits == float order and ONE 64-bit compare is the (d2, index) order of the
+// contract above (a NaN d2 packs above the +inf sentinel and is never taken, as with the float compare).
+struct Key4 { unsigned long long k[4]; };
+__device__ __forceinline__ unsigned long long key_pack(float d2, int idx) {
+    return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)idx;
+}
+__device__ __forceinline__ float key_d2(unsigned long long k) { return __uint_as_float((unsigned)(k >> 32)); }
+__device__ __forceinline__ void key_init(Key4& b) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b.k[j] = key_pack(CUDART_INF_F, 0x7fffffff);
+}
+// Insert a key known to beat the current 4th entry: overwrite it, then three compare-exchanges restore the order --
+// no data-dependent branches inside.
+__device__ __forceinline__ void key_insert_sorted(Key4& b, unsigned long long key) {
+    b.k[3] = key;
 #pragma unroll
     for (int k = 3; k > 0; --k) {
-        const bool sw = key_less(b.d[k], b.i[k], b.d[k - 1], b.i[k - 1]);
-        const float td = sw ? b.d[k - 1] : b.d[k]; const int ti = sw ? b.i[k - 1] : b.i[k];
-        b.d[k - 1] = sw ? b.d[k] : b.d[k - 1]; b.i[k - 1] = sw ? b.i[k] : b.i[k - 1];
-        b.d[k] = td; b.i[k] = ti;
+        const bool sw = b.k[k] < b.k[k - 1];
+        const unsigned long long lo = sw ? b.k[k] : b.k[k - 1], hi = sw ? b.k[k - 1] : b.k[k];
+        b.k[k - 1] = lo; b.k[k] = hi;
     }
 }
 // A vertex may be met twice (a seed, then again in its cell): equal keys never pass the strict
-// comparison against slot 3, slots 0-2 are checked by index.
-__device__ __forceinline__ bool best_accepts(const Best4& b, float d2, int idx) {
-    return key_less(d2, idx, b.d[3], b.i[3]) && idx != b.i[0] && idx != b.i[1] && idx != b.i[2];
+// comparison against slot 3, slots 0-2 are checked by index (the key's low word).
+__device__ __forceinline__ bool key_accepts(const Key4& b, unsigned long long key) {
+    const unsigned i = (unsigned)key;
+    return key < b.k[3] && i != (unsigned)b.k[0] && i != (unsigned)b.k[1] && i != (unsigned)b.k[2];
+}
+__device__ __forceinline__ void key_unpack(const Key4& b, Best4& o) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { o.d[j] = key_d2(b.k[j]); o.i[j] = (int)(unsigned)b.k[j]; }
 }
 
 #define SEARCH_THREADS 128
@@ -664,7 +680,7 @@ knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, cons
         const int cx = (int)floorf((qx - h.ox) * inv_cell), cy = (int)floorf((qy - h.oy) * inv_cell),
                   cz = (int)floorf((qz - h.oz) * inv_cell);
         const bool own = active && cx >= 0 && cx < h.nx && cy >= 0 && cy < h.ny && cz >= 0 && cz < h.nz;
-        Best4 mine; best_init(mine);
+        Key4 mine; key_init(mine);
         bool warm = false;
         if (active && sd.idx) {       // seeds: the 4-NN of the nearest coarse sample of this ray
             const int4 si = __ldg((const int4*)sd.idx + (gid / K) * sd.Kc + sd.nn[gid]);
@@ -672,8 +688,8 @@ knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, cons
                 warm = true;
                 float d[4];
                 seed_distances(verts + (int64_t)b * V * 3, si, qx, qy, qz, d);
-                best_insert_sorted(mine, d[0], si.x); best_insert_sorted(mine, d[1], si.y);
-                best_insert_sorted(mine, d[2], si.z); best_insert_sorted(mine, d[3], si.w);
+                key_insert_sorted(mine, key_pack(d[0], si.x)); key_insert_sorted(mine, key_pack(d[1], si.y));
+                key_insert_sorted(mine, key_pack(d[2], si.z)); key_insert_sorted(mine, key_pack(d[3], si.w));
             }
         }
         const bool did_own = own && !warm;
@@ -683,13 +699,13 @@ knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, cons
             KNN_STAT(n_cand += (unsigned)(pe - p);)
             for (; p < pe; ++p) {
                 const float4 v = __ldg(sorted + p);
-                const float d2 = dist2_rn(qx, qy, qz, v.x, v.y, v.z);
-                if (key_less(d2, __float_as_int(v.w), mine.d[3], mine.i[3])) best_insert_sorted(mine, d2, __float_as_int(v.w));
+                const unsigned long long key = key_pack(dist2_rn(qx, qy, qz, v.x, v.y, v.z), __float_as_int(v.w));
+                if (key < mine.k[3]) key_insert_sorted(mine, key);
             }
         }
         {   // bounds travel along the warp (neighbouring lanes are neighbouring samples of a ray):
             // d4(q) <= d4(q') + |q - q'|, doubling strides in both directions
-            float u = active ? sqrtf(fminf(mine.d[3], B)) : CUDART_INF_F;
+            float u = active ? sqrtf(fminf(key_d2(mine.k[3]), B)) : CUDART_INF_F;
 #pragma unroll
             for (int s = 1; s < 32; s <<= 1) {
 #pragma unroll
@@ -707,7 +723,7 @@ knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, cons
             }
             B = fminf(B, u * u * (1.0f + 1e-4f));
         }
-        float Bm = fminf(fminf(B, mine.d[3]) * 1.001f, box_r2 * 1.01f);
+        float Bm = fminf(fminf(B, key_d2(mine.k[3])) * 1.001f, box_r2 * 1.01f);
         RowCtx rc;
         rc.qx = qx; rc.fy = qy - (h.oy + cy * h.cell); rc.fz = qz - (h.oz + cz * h.cell);
         rc.ox = h.ox; rc.cell = h.cell; rc.inv_cell = inv_cell; rc.cx = cx; rc.cy = cy; rc.cz = cz;
@@ -752,17 +768,34 @@ knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, cons
                     const unsigned live_mask = __ballot_sync(0xffffffffu, live);
                     if (__popc(live_mask) <= SEARCH_DRAIN) break;      // few lanes left: drain them cooperatively below
                     KNN_STAT(++n_iter;)
-                    if (live) {               // two candidates per trip: both loads in flight before the first use
-                        const bool two = p + 1 < pe;
-                        const float4 v0 = __ldg(sorted + p), v1 = __ldg(sorted + (two ? p + 1 : p));
-                        p += 2;
-                        KNN_STAT(n_cand += two ? 2u : 1u;)
-                        const float d0 = dist2_rn(qx, qy, qz, v0.x, v0.y, v0.z);
-                        const float d1 = two ? dist2_rn(qx, qy, qz, v1.x, v1.y, v1.z) : CUDART_INF_F;
-                        if (fminf(d0, d1) <= mine.d[3]) {          // cheap reject first: almost every candidate fails it
-                            if (best_accepts(mine, d0, __float_as_int(v0.w))) best_insert_sorted(mine, d0, __float_as_int(v0.w));
-                            if (two && best_accepts(mine, d1, __float_as_int(v1.w))) best_insert_sorted(mine, d1, __float_as_int(v1.w));
-                            Bm = fminf(Bm, mine.d[3] * 1.001f);
+                    if (live) {
+                        // four candidates per trip (all loads in flight before the first use), then a per-lane loop that
+                        // takes the trip's closest remaining candidate while it can still enter the list: the insert
+                        // code runs once per ACCEPTED candidate of the busiest lane (about two per trip) instead of
+                        // once per candidate slot, and every lane inside the loop is inserting
+                        const int last = pe - 1;
+                        const float4 v0 = __ldg(sorted + p), v1 = __ldg(sorted + min(p + 1, last)),
+                                     v2 = __ldg(sorted + min(p + 2, last)), v3 = __ldg(sorted + min(p + 3, last));
+                        KNN_STAT(n_cand += (unsigned)min(4, pe - p);)
+                        float d0 = dist2_rn(qx, qy, qz, v0.x, v0.y, v0.z);
+                        float d1 = p + 1 < pe ? dist2_rn(qx, qy, qz, v1.x, v1.y, v1.z) : CUDART_INF_F;
+                        float d2 = p + 2 < pe ? dist2_rn(qx, qy, qz, v2.x, v2.y, v2.z) : CUDART_INF_F;
+                        float d3 = p + 3 < pe ? dist2_rn(qx, qy, qz, v3.x, v3.y, v3.z) : CUDART_INF_F;
+                        p += 4;
+                        float lim = key_d2(mine.k[3]);
+                        float m = fminf(fminf(d0, d1), fminf(d2, d3));
+                        if (m <= lim) {                            // cheap reject first: almost every trip fails it late in the walk
+                            do {
+                                const bool s0 = d0 == m, s1 = !s0 && d1 == m, s2 = !s0 && !s1 && d2 == m;
+                                const float vw = s0 ? v0.w : (s1 ? v1.w : (s2 ? v2.w : v3.w));
+                                d0 = s0 ? CUDART_INF_F : d0; d1 = s1 ? CUDART_INF_F : d1; d2 = s2 ? CUDART_INF_F : d2;
+                                d3 = (s0 || s1 || s2) ? d3 : CUDART_INF_F;
+                                const unsigned long long key = key_pack(m, __float_as_int(vw));
+                                if (key_accepts(mine, key)) key_insert_sorted(mine, key);
+                                lim = key_d2(mine.k[3]);
+                                m = fminf(fminf(d0, d1), fminf(d2, d3));
+                            } while (m <= lim && m < CUDART_INF_F);
+                            Bm = fminf(Bm, lim * 1.001f);
                         }
                     }
                 }
@@ -777,7 +810,7 @@ knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, cons
                     const float ux = __shfl_sync(0xffffffffu, qx, L), uy = __shfl_sync(0xffffffffu, qy, L), uz = __shfl_sync(0xffffffffu, qz, L);
                     int up = __shfl_sync(0xffffffffu, p, L), upe = __shfl_sync(0xffffffffu, pe, L), uk = __shfl_sync(0xffffffffu, k, L);
                     const int un = __shfl_sync(0xffffffffu, n_ent, L);
-                    float uBm = __shfl_sync(0xffffffffu, Bm, L), bd3 = __shfl_sync(0xffffffffu, mine.d[3], L);
+                    float uBm = __shfl_sync(0xffffffffu, Bm, L), bd3 = __shfl_sync(0xffffffffu, key_d2(mine.k[3]), L);
                     const int ub = __shfl_sync(0xffffffffu, b, L);
                     const float4* __restrict__ usorted = (const float4*)(ws + (int64_t)ub * frame_bytes + GRID_OFF_SORTED);
                     const uint2* __restrict__ uent = s_ent + (threadIdx.x & ~31) + L;
@@ -802,21 +835,24 @@ knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, cons
                             if (mn >= 0x7f800000u || __uint_as_float(mn) > bd3) break;    // ties with the 4th best go to the exact test
                             const int w = __ffs(__ballot_sync(0xffffffffu, key == mn)) - 1;
                             const int vi = __shfl_sync(0xffffffffu, __float_as_int(v.w), w);
-                            if (lane == L && best_accepts(mine, __uint_as_float(mn), vi)) best_insert_sorted(mine, __uint_as_float(mn), vi);
+                            const unsigned long long k64 = ((unsigned long long)mn << 32) | (unsigned)vi;
+                            if (lane == L && key_accepts(mine, k64)) key_insert_sorted(mine, k64);
                             if (lane == w) key = 0x7f800000u;
-                            bd3 = __shfl_sync(0xffffffffu, mine.d[3], L);
+                            bd3 = __shfl_sync(0xffffffffu, key_d2(mine.k[3]), L);
                         }
                         uBm = fminf(uBm, bd3 * 1.001f);
                     }
-                    if (lane == L) Bm = fminf(Bm, mine.d[3] * 1.001f);
+                    if (lane == L) Bm = fminf(Bm, key_d2(mine.k[3]) * 1.001f);
                 }
                 if (r >= N_ROWS) break;
                 __syncwarp();     // ... and the next round's list writes after those reads
             }
         }
         // the walk saw every vertex within sqrt(min(B, box_r2)): four of them => the 4-NN are exact
-        const bool exact4 = active && mine.d[3] <= B && mine.d[3] <= box_r2;
-        const bool near_ = active && mine.d[0] < thr2;          // may be valid: needs the exact 4-NN
+        Best4 best;
+        key_unpack(mine, best);
+        const bool exact4 = active && best.d[3] <= B && best.d[3] <= box_r2;
+        const bool near_ = active && best.d[0] < thr2;          // may be valid: needs the exact 4-NN
         bool have4 = exact4;
         const bool redo = near_ && !exact4;            // rare: 4th neighbour not provably inside the scanned ball
         unsigned redo_mask = __ballot_sync(0xffffffffu, redo);
@@ -834,9 +870,9 @@ knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, cons
             }
             Best4 g;
             warp_merge4(lb, g);
-            if (lane == qi) { mine = g; have4 = true; }
+            if (lane == qi) { best = g; have4 = true; }
         }
-        unpose_epilogue(mine, have4, have4 && near_, qx, qy, qz, gid, b, V, J, ober2cano, lbsw, thr, o, active);
+        unpose_epilogue(best, have4, have4 && near_, qx, qy, qz, gid, b, V, J, ober2cano, lbsw, thr, o, active);
     }
     KNN_STAT(atomicAdd(&qws->stats[0], (unsigned long long)n_cand); atomicAdd(&qws->stats[1], (unsigned long long)n_iter);
              atomicAdd(&qws->stats[2], (unsigned long long)n_redo);)
