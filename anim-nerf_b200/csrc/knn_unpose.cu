@@ -603,6 +603,38 @@ __device__ __forceinline__ void key_unpack(const Key4& b, Best4& o) {
     for (int j = 0; j < 4; ++j) { o.d[j] = key_d2(b.k[j]); o.i[j] = (int)(unsigned)b.k[j]; }
 }
 
+// One trip of a lane's candidate walk: up to four table entries [p, min(p + 4, pe)) (all loads in flight before the
+// first use), then a per-lane loop that takes the trip's closest remaining candidate while it can still enter the
+// list: the insert code runs once per ACCEPTED candidate of the busiest lane instead of once per candidate slot, and
+// every lane inside the loop is inserting.  `dedup`: the list may already hold some of these vertices (seeds).
+// Returns true when the list changed (the caller tightens its bound).
+template <bool DEDUP>
+__device__ __forceinline__ bool key_trip4(Key4& mine, const float4* __restrict__ sorted, int p, int pe,
+                                          float qx, float qy, float qz)
+{
+    const int last = pe - 1;
+    const float4 v0 = __ldg(sorted + p), v1 = __ldg(sorted + min(p + 1, last)),
+                 v2 = __ldg(sorted + min(p + 2, last)), v3 = __ldg(sorted + min(p + 3, last));
+    float d0 = dist2_rn(qx, qy, qz, v0.x, v0.y, v0.z);
+    float d1 = p + 1 < pe ? dist2_rn(qx, qy, qz, v1.x, v1.y, v1.z) : CUDART_INF_F;
+    float d2 = p + 2 < pe ? dist2_rn(qx, qy, qz, v2.x, v2.y, v2.z) : CUDART_INF_F;
+    float d3 = p + 3 < pe ? dist2_rn(qx, qy, qz, v3.x, v3.y, v3.z) : CUDART_INF_F;
+    float lim = key_d2(mine.k[3]);
+    float m = fminf(fminf(d0, d1), fminf(d2, d3));
+    if (!(m <= lim)) return false;             // cheap reject first: almost every trip fails it late in the walk
+    do {
+        const bool s0 = d0 == m, s1 = !s0 && d1 == m, s2 = !s0 && !s1 && d2 == m;
+        const float vw = s0 ? v0.w : (s1 ? v1.w : (s2 ? v2.w : v3.w));
+        d0 = s0 ? CUDART_INF_F : d0; d1 = s1 ? CUDART_INF_F : d1; d2 = s2 ? CUDART_INF_F : d2;
+        d3 = (s0 || s1 || s2) ? d3 : CUDART_INF_F;
+        const unsigned long long key = key_pack(m, __float_as_int(vw));
+        if (DEDUP ? key_accepts(mine, key) : key < mine.k[3]) key_insert_sorted(mine, key);
+        lim = key_d2(mine.k[3]);
+        m = fminf(fminf(d0, d1), fminf(d2, d3));
+    } while (m <= lim && m < CUDART_INF_F);
+    return true;
+}
+
 #define SEARCH_THREADS 128
 
 // One row of the cell box for one query: slab gap^2 and the candidate range [s0, e1) of the cell-sorted
@@ -613,9 +645,10 @@ __device__ __forceinline__ bool row_range(const RowCtx& c, int r, const int* __r
 {
     const int dy = c_row_dy[r], dz = c_row_dz[r];
     const int gy = c.cy + dy, gz = c.cz + dz;
-    const float gapy = dy == 0 ? 0.f : (dy > 0 ? (float)dy * c.cell - c.fy : c.fy - (float)(dy + 1) * c.cell);
-    const float gapz = dz == 0 ? 0.f : (dz > 0 ? (float)dz * c.cell - c.fz : c.fz - (float)(dz + 1) * c.cell);
-    g2 = (gapy > 0.f ? gapy * gapy : 0.f) + (gapz > 0.f ? gapz * gapz : 0.f);
+    // distance from the query to the row's slab per axis: below it, above it, or inside (0) -- branch-free
+    const float gapy = fmaxf(fmaxf((float)dy * c.cell - c.fy, c.fy - (float)(dy + 1) * c.cell), 0.f);
+    const float gapz = fmaxf(fmaxf((float)dz * c.cell - c.fz, c.fz - (float)(dz + 1) * c.cell), 0.f);
+    g2 = gapy * gapy + gapz * gapz;
     if (!(gz >= 0 && gz < c.nz && gy >= 0 && gy < c.ny && g2 <= c.Bm)) return false;
     const float w = sqrtf(fmaxf(c.Bm - g2, 0.f)) + 1e-3f * c.cell;
     x0 = max(c.cx - GRID_R, (int)floorf((c.qx - w - c.ox) * c.inv_cell));
@@ -697,11 +730,7 @@ knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, cons
             int p = 0, pe = 0;
             if (did_own) { const int c = (cz * h.ny + cy) * h.nx + cx; p = __ldg(cell_start + c); pe = __ldg(cell_start + c + 1); }
             KNN_STAT(n_cand += (unsigned)(pe - p);)
-            for (; p < pe; ++p) {
-                const float4 v = __ldg(sorted + p);
-                const unsigned long long key = key_pack(dist2_rn(qx, qy, qz, v.x, v.y, v.z), __float_as_int(v.w));
-                if (key < mine.k[3]) key_insert_sorted(mine, key);
-            }
+            for (; p < pe; p += 4) key_trip4<false>(mine, sorted, p, pe, qx, qy, qz);
         }
         {   // bounds travel along the warp (neighbouring lanes are neighbouring samples of a ray):
             // d4(q) <= d4(q') + |q - q'|, doubling strides in both directions
@@ -769,34 +798,9 @@ knn_search_kernel(int K, int64_t N, const float* __restrict__ verts, int V, cons
                     if (__popc(live_mask) <= SEARCH_DRAIN) break;      // few lanes left: drain them cooperatively below
                     KNN_STAT(++n_iter;)
                     if (live) {
-                        // four candidates per trip (all loads in flight before the first use), then a per-lane loop that
-                        // takes the trip's closest remaining candidate while it can still enter the list: the insert
-                        // code runs once per ACCEPTED candidate of the busiest lane (about two per trip) instead of
-                        // once per candidate slot, and every lane inside the loop is inserting
-                        const int last = pe - 1;
-                        const float4 v0 = __ldg(sorted + p), v1 = __ldg(sorted + min(p + 1, last)),
-                                     v2 = __ldg(sorted + min(p + 2, last)), v3 = __ldg(sorted + min(p + 3, last));
                         KNN_STAT(n_cand += (unsigned)min(4, pe - p);)
-                        float d0 = dist2_rn(qx, qy, qz, v0.x, v0.y, v0.z);
-                        float d1 = p + 1 < pe ? dist2_rn(qx, qy, qz, v1.x, v1.y, v1.z) : CUDART_INF_F;
-                        float d2 = p + 2 < pe ? dist2_rn(qx, qy, qz, v2.x, v2.y, v2.z) : CUDART_INF_F;
-                        float d3 = p + 3 < pe ? dist2_rn(qx, qy, qz, v3.x, v3.y, v3.z) : CUDART_INF_F;
+                        if (key_trip4<true>(mine, sorted, p, pe, qx, qy, qz)) Bm = fminf(Bm, key_d2(mine.k[3]) * 1.001f);
                         p += 4;
-                        float lim = key_d2(mine.k[3]);
-                        float m = fminf(fminf(d0, d1), fminf(d2, d3));
-                        if (m <= lim) {                            // cheap reject first: almost every trip fails it late in the walk
-                            do {
-                                const bool s0 = d0 == m, s1 = !s0 && d1 == m, s2 = !s0 && !s1 && d2 == m;
-                                const float vw = s0 ? v0.w : (s1 ? v1.w : (s2 ? v2.w : v3.w));
-                                d0 = s0 ? CUDART_INF_F : d0; d1 = s1 ? CUDART_INF_F : d1; d2 = s2 ? CUDART_INF_F : d2;
-                                d3 = (s0 || s1 || s2) ? d3 : CUDART_INF_F;
-                                const unsigned long long key = key_pack(m, __float_as_int(vw));
-                                if (key_accepts(mine, key)) key_insert_sorted(mine, key);
-                                lim = key_d2(mine.k[3]);
-                                m = fminf(fminf(d0, d1), fminf(d2, d3));
-                            } while (m <= lim && m < CUDART_INF_F);
-                            Bm = fminf(Bm, lim * 1.001f);
-                        }
                     }
                 }
                 // The lanes still holding candidates (long lists: far queries with a wide ball) are drained one
