@@ -37,6 +37,9 @@ __device__ __forceinline__ float warp_excl_suffix_sum(float v, int lane, float& 
     return lane == 31 ? 0.0f : ex;
 }
 
+// NR = rounds of 32 samples (K <= 32 * NR): every load of a ray is issued before the first use, the next
+// depth comes from the neighbouring lane / the next round by shuffle (no second z load).
+template <int NR>
 __global__ void __launch_bounds__(COMP_WARPS * 32)
 composite_fwd_kernel(const float* __restrict__ sigma, const float* __restrict__ rgb,
                      const float* __restrict__ z, const float* __restrict__ rays,
@@ -52,19 +55,29 @@ composite_fwd_kernel(const float* __restrict__ sigma, const float* __restrict__ 
         const float* sr = sigma + ray * K;
         const float* nr = noise ? noise + ray * K : nullptr;
         const float* cr = rgb + ray * K * 3;
+        float zi[NR], sg[NR], c0[NR], c1[NR], c2[NR];
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+            const int i = j * 32 + lane;
+            const bool in = i < K;
+            zi[j] = in ? zr[i] : 0.f;
+            sg[j] = in ? sr[i] : 0.f;
+            if (nr && in) sg[j] += nr[i];
+            c0[j] = in ? cr[3 * i] : 0.f; c1[j] = in ? cr[3 * i + 1] : 0.f; c2[j] = in ? cr[3 * i + 2] : 0.f;
+        }
         float carry = 1.0f, s_acc = 0.f, s_r = 0.f, s_g = 0.f, s_b = 0.f, s_d = 0.f;
 #pragma unroll
-        for (int j = 0; j < COMP_MAXS; ++j) {
+        for (int j = 0; j < NR; ++j) {
             if (j * 32 >= K) break;
             const int i = j * 32 + lane;
             const bool in = i < K;
-            float zi = 0.f, alpha = 0.f;
+            float zn = __shfl_down_sync(0xffffffffu, zi[j], 1);
+            const float z0n = __shfl_sync(0xffffffffu, zi[j + 1 < NR ? j + 1 : j], 0);
+            if (lane == 31) zn = z0n;
+            float alpha = 0.f;
             if (in) {
-                zi = zr[i];
-                float sg = sr[i];
-                if (nr) sg += nr[i];
-                const float delta = (i + 1 < K) ? (zr[i + 1] - zi) : 1e10f;
-                alpha = 1.0f - expf(-delta * fmaxf(sg, 0.0f));
+                const float delta = (i + 1 < K) ? (zn - zi[j]) : 1e10f;
+                alpha = 1.0f - expf(-delta * fmaxf(sg[j], 0.0f));
             }
             const float t = in ? (1.0f - alpha + 1e-10f) : 1.0f;
             float tot;
@@ -74,8 +87,8 @@ composite_fwd_kernel(const float* __restrict__ sigma, const float* __restrict__ 
             if (in) {
                 if (weights) weights[ray * K + i] = w;
                 s_acc += w;
-                s_d += w * zi;
-                s_r += w * cr[3 * i]; s_g += w * cr[3 * i + 1]; s_b += w * cr[3 * i + 2];
+                s_d += w * zi[j];
+                s_r += w * c0[j]; s_g += w * c1[j]; s_b += w * c2[j];
             }
         }
         s_acc = warp_sum(s_acc); s_d = warp_sum(s_d);
@@ -178,9 +191,13 @@ composite_bwd_kernel(const float* __restrict__ sigma, const float* __restrict__ 
     }
 }
 
-static inline int comp_blocks(int64_t n_rays) {
+// grid = what is resident at once (occupancy x SMs): the grid-stride loop then gives every CTA the same share of rays
+template <typename Kern>
+static inline int comp_blocks(Kern kern, int64_t n_rays) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, COMP_WARPS * 32, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
     const int64_t want = (n_rays + COMP_WARPS - 1) / COMP_WARPS;
-    const int64_t cap = (int64_t)an_num_sms() * 8;
+    const int64_t cap = (int64_t)an_num_sms() * per_sm;
     return (int)(want < cap ? want : cap);
 }
 
@@ -190,8 +207,10 @@ extern "C" int an_composite_fwd(const float* sigma, const float* rgb, const floa
 {
     if (!sigma || !rgb || !z || !rays || !rgb_out || !depth || !acc || n_rays <= 0 || K <= 0) return AN_ERR_ARG;
     if (K > COMP_MAXS * 32) return AN_ERR_UNSUPPORTED;
-    composite_fwd_kernel<<<comp_blocks(n_rays), COMP_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        sigma, rgb, z, rays, sigma_noise, n_rays, K, white_bkgd, weights, rgb_out, depth, acc);
+#define COMP_FWD(NR) composite_fwd_kernel<NR><<<comp_blocks(composite_fwd_kernel<NR>, n_rays), COMP_WARPS * 32, 0, (cudaStream_t)stream>>>( \
+        sigma, rgb, z, rays, sigma_noise, n_rays, K, white_bkgd, weights, rgb_out, depth, acc)
+    if (K <= 64) COMP_FWD(2); else if (K <= 128) COMP_FWD(4); else COMP_FWD(COMP_MAXS);
+#undef COMP_FWD
     AN_CHECK_LAUNCH();
     return AN_OK;
 }
@@ -203,7 +222,7 @@ extern "C" int an_composite_bwd(const float* sigma, const float* rgb, const floa
 {
     if (!sigma || !rgb || !z || !rays || !g_rgb_out || n_rays <= 0 || K <= 0) return AN_ERR_ARG;
     if (K > COMP_MAXS * 32) return AN_ERR_UNSUPPORTED;
-    composite_bwd_kernel<<<comp_blocks(n_rays), COMP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    composite_bwd_kernel<<<comp_blocks(composite_bwd_kernel, n_rays), COMP_WARPS * 32, 0, (cudaStream_t)stream>>>(
         sigma, rgb, z, rays, sigma_noise, n_rays, K, white_bkgd, g_rgb_out, g_depth, g_acc,
         g_sigma, g_rgb, g_z, g_far);
     AN_CHECK_LAUNCH();

@@ -666,8 +666,12 @@ __device__ __forceinline__ bool row_range(const RowCtx& c, int r, const int* __r
 #ifndef AN_KNN_MINB
 #define AN_KNN_MINB 8
 #endif
+#ifndef SEARCH_CAP
 #define SEARCH_CAP 16          // row-list entries per thread and round (8 and 50 measured: within 3 %)
+#endif
+#ifndef SEARCH_DRAIN
 #define SEARCH_DRAIN 8         // lanes left at which the warp drains the remaining lists cooperatively
+#endif
 #ifdef AN_KNN_STATS            // candidate statistics for tools/bench_knn.py (variant build only)
 #define KNN_STAT(x) x
 #else
