@@ -409,3 +409,34 @@ def test_edge_shapes_empty_single_ray_and_all_background():
         got = sysm(rays_w.view(B, 16, 1, 8).to(DEV), d(posed), d(tmpl), perturb=0.0)
     assert float(got["alphas_fine"].abs().max()) == 0.0 and float(got["alphas"].abs().max()) == 0.0
     assert torch.equal(got["rgbs_fine"], torch.ones_like(got["rgbs_fine"]))
+
+
+@pytest.mark.parametrize("n_coarse,n_fine", [(64, 32), (48, 24), (96, 40)])
+def test_other_sample_counts_vs_oracle(n_coarse, n_fine):
+    """Sample counts other than BASELINE's 64+64: the shipped yaml's 64+32 (configs/people_snapshot/*.yaml:
+    n_importance 32) and counts that are not multiples of a warp -- every kernel of the path takes K from
+    its arguments (sort padding, compositing rounds, ray/sample tiling)."""
+    from anim_nerf_b200.system import AnimNeRFSystem
+    sysm = AnimNeRFSystem(body_model_data=synthetic.make_smpl_dict(0), n_samples=n_coarse, n_importance=n_fine).to(DEV)
+    for name, seed in (("nerf", 10), ("nerf_fine", 11)):
+        getattr(sysm.anim_nerf, name).load_state_dict(
+            {k: torch.from_numpy(v) for k, v in synthetic.make_nerf_weights(seed).items()}, strict=True)
+    B, R = 2, 53
+    posed_np, tmpl_np = synthetic.make_body_params(B, seed=3)
+    posed = {k: torch.from_numpy(v) for k, v in posed_np.items()}
+    tmpl = {k: torch.from_numpy(v) for k, v in tmpl_np.items()}
+    bm = body_model()
+    with torch.no_grad():
+        po, to = bm(**posed), bm(**tmpl)
+    d = lambda t: {k: v.to(DEV) for k, v in t.items()}                                     # noqa: E731
+    verts_b, o2c = oracle.ober2cano_tables(po, to)
+    rays_w = torch.from_numpy(synthetic.rays_at_bbox(po["vertices"].numpy(), R, seed=21))
+    with torch.no_grad():
+        got = sysm(rays_w.view(B, R, 1, 8).to(DEV), d(posed), d(tmpl), perturb=0.0)
+    rays_b = oracle.rays_to_body_space(rays_w, po["joints_transform"][:, 0])
+    ref = oracle.render_rays(nerf_params(10), nerf_params(11), rays_b, (verts_b, o2c, bm.lbs_weights),
+                             n_coarse=n_coarse, n_fine=n_fine)
+    for k in ("rgbs", "alphas", "depths", "rgbs_fine", "alphas_fine", "depths_fine"):
+        err = float((got[k].view(B, R, -1).cpu() - ref[k]).abs().max())
+        assert err < (1e-2 if "depth" not in k else 5e-2), (k, err)
+    assert float(ref["alphas_fine"].max()) > 0.5            # the rays do hit the body: not a vacuous comparison
