@@ -440,3 +440,47 @@ def test_other_sample_counts_vs_oracle(n_coarse, n_fine):
         err = float((got[k].view(B, R, -1).cpu() - ref[k]).abs().max())
         assert err < (1e-2 if "depth" not in k else 5e-2), (k, err)
     assert float(ref["alphas_fine"].max()) > 0.5            # the rays do hit the body: not a vacuous comparison
+
+
+def test_full_size_batch_is_bit_invariant_to_the_order_of_its_rays():
+    """Size-independent property at BASELINE cfg2's full size (16 frames x 1024 rays, 64 + 64 samples, 3.1 M points):
+    every ray is rendered independently of the others, so shuffling the rays of each frame must shuffle the outputs
+    and leave every bit unchanged -- although the shuffle changes which queries share a warp in the neighbour search
+    (bounds travel between lanes, heavy lanes are drained cooperatively), which points share an MMA tile, and the
+    order of the compacted point list.  The unshuffled outputs are checked against the oracle on a sample of rays."""
+    import bench
+    from anim_nerf_b200.system import AnimNeRFSystem
+    data, host, params, tmpl = bench.build_batch(0)
+    sysm = AnimNeRFSystem(body_model_data=data, n_samples=64, n_importance=64, num_frames=bench.N_FRAMES,
+                          optim_body_params=False).to(DEV)
+    for name, seed in (("nerf", 10), ("nerf_fine", 11)):
+        getattr(sysm.anim_nerf, name).load_state_dict(
+            {k: torch.from_numpy(v) for k, v in synthetic.make_nerf_weights(seed).items()}, strict=True)
+    d = lambda t: {k: v.to(DEV) for k, v in t.items()}                                     # noqa: E731
+    B = bench.N_FRAMES
+    rays = host["rays"].reshape(B, -1, 8)
+    R = rays.shape[1]
+    g = torch.Generator().manual_seed(5)
+    perm = torch.stack([torch.randperm(R, generator=g) for _ in range(B)])
+    rays_p = torch.gather(rays, 1, perm[..., None].expand(-1, -1, 8))
+    with torch.no_grad():
+        a = sysm(rays.view(B, R, 1, 8).to(DEV), d(params), d(tmpl), perturb=0.0)
+        b = sysm(rays_p.view(B, R, 1, 8).to(DEV), d(params), d(tmpl), perturb=0.0)
+    pd = perm.to(DEV)
+    for k in ("rgbs", "alphas", "depths", "rgbs_fine", "alphas_fine", "depths_fine"):
+        va = a[k].view(B, R, -1)
+        want = torch.gather(va, 1, pd[..., None].expand(-1, -1, va.shape[-1]))
+        assert torch.equal(b[k].view(B, R, -1), want), k
+    assert float(a["alphas_fine"].mean()) > 0.3             # most rays hit the body (90 % foreground sampling)
+    # a sample of the rays against the oracle
+    bm = body_model()
+    sel = torch.arange(0, R, 64)
+    with torch.no_grad():
+        po, to = bm(**params), bm(**tmpl)
+    verts_b, o2c = oracle.ober2cano_tables(po, to)
+    rays_b = oracle.rays_to_body_space(rays[:, sel], po["joints_transform"][:, 0])
+    ref = oracle.render_rays(nerf_params(10), nerf_params(11), rays_b, (verts_b, o2c, bm.lbs_weights), n_coarse=64, n_fine=64)
+    for k in ("rgbs", "alphas", "rgbs_fine", "alphas_fine"):
+        got = a[k].view(B, R, -1)[:, sel.to(DEV)].cpu()
+        bad = ((got - ref[k]).abs() > 1e-2).float().mean()
+        assert float(bad) < 0.01, (k, float(bad))           # tables rebuilt on the GPU: a handful of samples may flip validity
