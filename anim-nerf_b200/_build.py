@@ -44,7 +44,7 @@ def build_lib(force=False, verbose=False):
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % s)
     if force or procs or _newer(LIB, objs):
-        subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"])
+        subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"])
     return LIB
 
 

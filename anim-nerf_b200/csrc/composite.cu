@@ -105,6 +105,8 @@ composite_fwd_kernel(const float* __restrict__ sigma, const float* __restrict__ 
     }
 }
 
+// NR = rounds of 32 samples, as in the forward: register arrays sized to the actual sample count (K <= 32 NR)
+template <int NR>
 __global__ void __launch_bounds__(COMP_WARPS * 32)
 composite_bwd_kernel(const float* __restrict__ sigma, const float* __restrict__ rgb,
                      const float* __restrict__ z, const float* __restrict__ rays,
@@ -113,7 +115,7 @@ composite_bwd_kernel(const float* __restrict__ sigma, const float* __restrict__ 
                      const float* __restrict__ g_acc, float* __restrict__ g_sigma,
                      float* __restrict__ g_rgb, float* __restrict__ g_z, float* __restrict__ g_far)
 {
-    __shared__ float s_gdelta[COMP_WARPS][COMP_MAXS * 32];
+    __shared__ float s_gdelta[COMP_WARPS][NR * 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -126,10 +128,10 @@ composite_bwd_kernel(const float* __restrict__ sigma, const float* __restrict__ 
         const float gd = g_depth ? g_depth[ray] : 0.f, ga = g_acc ? g_acc[ray] : 0.f;
         const float far_ = rays[ray * 8 + 7];
         const float bkg = white ? (gr + gg + gb + gd * far_) : 0.0f;
-        float a_[COMP_MAXS], t_[COMP_MAXS], T_[COMP_MAXS], gw_[COMP_MAXS], sg_[COMP_MAXS], dl_[COMP_MAXS];
+        float a_[NR], t_[NR], T_[NR], gw_[NR], sg_[NR], dl_[NR];
         float carry = 1.0f, s_acc = 0.f;
 #pragma unroll
-        for (int j = 0; j < COMP_MAXS; ++j) {
+        for (int j = 0; j < NR; ++j) {
             a_[j] = 0.f; t_[j] = 1.f; T_[j] = 0.f; gw_[j] = 0.f; sg_[j] = 0.f; dl_[j] = 0.f;
             if (j * 32 >= K) continue;
             const int i = j * 32 + lane;
@@ -159,7 +161,7 @@ composite_bwd_kernel(const float* __restrict__ sigma, const float* __restrict__ 
         // reverse pass: S_i = sum_{j>i} gw_j w_j
         float rcarry = 0.f;
 #pragma unroll
-        for (int j = COMP_MAXS - 1; j >= 0; --j) {
+        for (int j = NR - 1; j >= 0; --j) {
             if (j * 32 >= K) continue;
             const int i = j * 32 + lane;
             const bool in = i < K;
@@ -178,7 +180,7 @@ composite_bwd_kernel(const float* __restrict__ sigma, const float* __restrict__ 
         __syncwarp();
         if (g_z) {
 #pragma unroll
-            for (int j = 0; j < COMP_MAXS; ++j) {
+            for (int j = 0; j < NR; ++j) {
                 if (j * 32 >= K) continue;
                 const int i = j * 32 + lane;
                 if (i < K) {
@@ -222,9 +224,10 @@ extern "C" int an_composite_bwd(const float* sigma, const float* rgb, const floa
 {
     if (!sigma || !rgb || !z || !rays || !g_rgb_out || n_rays <= 0 || K <= 0) return AN_ERR_ARG;
     if (K > COMP_MAXS * 32) return AN_ERR_UNSUPPORTED;
-    composite_bwd_kernel<<<comp_blocks(composite_bwd_kernel, n_rays), COMP_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        sigma, rgb, z, rays, sigma_noise, n_rays, K, white_bkgd, g_rgb_out, g_depth, g_acc,
-        g_sigma, g_rgb, g_z, g_far);
+#define COMP_BWD(NR) composite_bwd_kernel<NR><<<comp_blocks(composite_bwd_kernel<NR>, n_rays), COMP_WARPS * 32, 0, (cudaStream_t)stream>>>( \
+        sigma, rgb, z, rays, sigma_noise, n_rays, K, white_bkgd, g_rgb_out, g_depth, g_acc, g_sigma, g_rgb, g_z, g_far)
+    if (K <= 64) COMP_BWD(2); else if (K <= 128) COMP_BWD(4); else COMP_BWD(COMP_MAXS);
+#undef COMP_BWD
     AN_CHECK_LAUNCH();
     return AN_OK;
 }

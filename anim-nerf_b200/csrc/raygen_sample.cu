@@ -104,21 +104,23 @@ __global__ void rays_sample_kernel(const float* __restrict__ c2w, const float* _
                                    const float* __restrict__ rays_world, const float* __restrict__ ginv,
                                    int B, int R, int W, int Kc, float near_, float far_, float perturb,
                                    const float* __restrict__ noise_u, uint64_t seed,
-                                   float4* __restrict__ rays_body, float* __restrict__ z)
+                                   float4* __restrict__ rays_body, float* __restrict__ z, int G)
 {
-    // a warp takes 32 rays at a time: lane l builds ray l once (and writes it), then the warp walks the 32 rays with
+    // a warp takes G (32) rays at a time: lane l builds ray l once (and writes it), then the warp walks the 32 rays with
     // the lanes over the samples (near'/far' by shuffle) -- every store coalesced, no per-sample ray rebuild
     const int lane = threadIdx.x & 31;
     const int64_t n_rays = (int64_t)B * R;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t base = warp0 * 32; base < n_rays; base += nwarps * 32) {
+    // G rays per warp and round (a power of two <= 32: 32 for full frames, 4 for a training batch of a few thousand
+    // rays, which would otherwise leave most SMs without a warp)
+    for (int64_t base = warp0 * G; base < n_rays; base += nwarps * G) {
         const int64_t ray = base + lane;
         float4 rb[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-        if (ray < n_rays) {
+        if (lane < G && ray < n_rays) {
             body_ray(c2w, focal, center, pix, rays_world, ginv, ray, R, W, near_, far_, rb);
             rays_body[2 * ray] = rb[0]; rays_body[2 * ray + 1] = rb[1];
         }
-        const int cnt = (int)(n_rays - base < 32 ? n_rays - base : 32);
+        const int cnt = (int)(n_rays - base < G ? n_rays - base : G);
         for (int r = 0; r < cnt; ++r) {
             const float nr = __shfl_sync(0xffffffffu, rb[1].z, r), fr = __shfl_sync(0xffffffffu, rb[1].w, r);
             const int64_t e0 = (base + r) * Kc;
@@ -250,8 +252,9 @@ extern "C" int an_rays_sample_fwd(const float* c2w, const float* focal, const fl
     if (!rays_world && (!c2w || !focal || !center)) return AN_ERR_ARG;
     if (!rays_world && !pix && (H <= 0 || W <= 0 || (int64_t)H * W != R)) return AN_ERR_ARG;
     if ((((uintptr_t)rays_body) | ((uintptr_t)rays_world)) & 15) return AN_ERR_ALIGN;
-    rays_sample_kernel<<<launch_blocks((int64_t)B * R, 128), 128, 0, (cudaStream_t)stream>>>(     // one thread per ray
-        c2w, focal, center, pix, rays_world, ginv, B, R, W, Kc, near_, far_, perturb, noise_u, seed, (float4*)rays_body, z);
+    const int G = (int64_t)B * R >= 131072 ? 32 : 4;
+    rays_sample_kernel<<<launch_blocks((int64_t)B * R * (32 / G), 128), 128, 0, (cudaStream_t)stream>>>(     // one warp per G rays
+        c2w, focal, center, pix, rays_world, ginv, B, R, W, Kc, near_, far_, perturb, noise_u, seed, (float4*)rays_body, z, G);
     AN_CHECK_LAUNCH();
     return AN_OK;
 }
