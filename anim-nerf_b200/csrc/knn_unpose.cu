@@ -511,7 +511,9 @@ knn_classify_kernel(const float* __restrict__ xyz, const float* __restrict__ ray
                 if (s < sd.Kc) {          // this sample IS coarse sample s of its ray: reuse that pass's neighbours
                     same = true;
                     cg = (gid / K) * sd.Kc + s;
-                    const int4 si = __ldg((const int4*)sd.idx + cg);
+                    // (a copied sample needs its neighbour record only when this pass emits indices: every inference
+                    //  frame skips this load -- a third of the kernel's reads and one level of its dependent-load chain)
+                    const int4 si = (copy && !o.idx) ? make_int4(-1, -1, -1, -1) : __ldg((const int4*)sd.idx + cg);
                     if (si.x >= 0) {
                         have4 = true;
                         sb.i[0] = si.x; sb.i[1] = si.y; sb.i[2] = si.z; sb.i[3] = si.w;
