@@ -35,8 +35,16 @@ class BodyModelParams(nn.Module):
         getattr(self, param_name).weight.requires_grad = requires_grad
 
     def forward(self, frame_ids):
+        # The rows an nn.Embedding lookup returns (`emb(ids)`, as the reference writes it), read with one elementwise
+        # gather per table: the embedding kernel for a handful of indices is serial (7-14 us per table and step);
+        # betas is a single shared row: an expand, no launch.  Gradients: scatter-add into the rows / a sum over the batch.
         out = {}
+        flat = frame_ids.reshape(-1)
         for name in self.param_names:
-            ids = torch.zeros_like(frame_ids) if name == "betas" else frame_ids
-            out[name] = getattr(self, name)(ids)
+            w = getattr(self, name).weight
+            if name == "betas":
+                rows = w[0].expand(flat.shape[0], -1)
+            else:
+                rows = torch.gather(w, 0, flat[:, None].expand(-1, w.shape[1]))
+            out[name] = rows.reshape(*frame_ids.shape, w.shape[1])
         return out

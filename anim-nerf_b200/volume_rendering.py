@@ -75,7 +75,9 @@ class VolumeRenderer(nn.Module):
             raise NotImplementedError("far=False is never used by the reference's callers")
         bs, n_rays, K = z_samp.shape
         if self.noise_std > 0.0 and perturb > 0 and sigma_noise is None:
-            sigma_noise = torch.randn(bs, n_rays, K, device=z_samp.device) * self.noise_std
+            sigma_noise = torch.randn(bs, n_rays, K, device=z_samp.device)
+            if self.noise_std != 1.0:       # (x * 1.0 is x: the reference's default needs no second launch)
+                sigma_noise = sigma_noise * self.noise_std
         if hasattr(model, "render_pass"):
             return model.render_pass(rays[..., :8].contiguous(), z_samp, use_fine=not coarse,
                                      sigma_noise=sigma_noise, white_bkgd=self.white_bkgd,

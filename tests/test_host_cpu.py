@@ -268,3 +268,27 @@ def test_graph_step_tree_helpers_mirror_nested_batches():
     assert torch.equal(static["rays"], new["rays"]) and float(static["smpl"]["posed"]["transl"].min()) == 7.0
     assert torch.equal(static["smpl"]["list"][0], new["smpl"]["list"][0])
     assert ptrs == (static["rays"].data_ptr(), static["smpl"]["posed"]["transl"].data_ptr())      # in place: the graph's addresses
+
+
+def test_body_model_params_lookup_equals_the_reference_embedding_lookup():
+    """`BodyModelParams.forward` (reference models/body_model_params.py:60-66: `emb(ids)` per table, betas looked up at
+    id 0) reads the rows with gathers / an expand: same values, same shapes (1-D and 2-D id tensors, repeated ids) and
+    the same gradients as the nn.Embedding lookups."""
+    import torch
+    from anim_nerf_b200.body_model_params import BodyModelParams
+    m = BodyModelParams(20)
+    g = torch.Generator().manual_seed(0)
+    for n, d in m.params_dim.items():
+        m.init_parameters(n, torch.randn(20, d, generator=g), requires_grad=True)
+    for ids in (torch.tensor([3, 7, 7, 0, 19]), torch.tensor([[5], [5], [11]])):
+        out = m(ids)
+        ref = {n: getattr(m, n)(torch.zeros_like(ids) if n == "betas" else ids) for n in m.param_names}
+        grads = []
+        for res in (out, ref):
+            for n in m.param_names:
+                getattr(m, n).weight.grad = None
+            sum((o * torch.arange(o.numel(), dtype=torch.float32).view_as(o)).sum() for o in res.values()).backward()
+            grads.append({n: getattr(m, n).weight.grad.clone() for n in m.param_names})
+        for n in m.param_names:
+            assert out[n].shape == ref[n].shape and torch.equal(out[n], ref[n]), n
+            assert torch.allclose(grads[0][n], grads[1][n], rtol=1e-6, atol=0), n
