@@ -159,8 +159,6 @@ mlp_bwd_dgrad_kernel(const uint8_t* __restrict__ packed, const uint8_t* __restri
         uint8_t* act_row = sgen + SM_ACT + t * 65536 + row * 128;
         const uint32_t act_s = sbase + SM_ACT + t * 65536u;
         const uint32_t tm = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)t * 256u;
-        const float* small = (const float*)(packed + SMALL_OFF);
-        const bool leader = (e & 127) == 0;
         const uint32_t my_act = bar_act + 8 * t, my_acc = bar_acc + 8 * t;
         const uint64_t stream_pol = l2_policy_stream();
         uint32_t acc_phase = 0;
