@@ -292,3 +292,25 @@ def test_body_model_params_lookup_equals_the_reference_embedding_lookup():
         for n in m.param_names:
             assert out[n].shape == ref[n].shape and torch.equal(out[n], ref[n]), n
             assert torch.allclose(grads[0][n], grads[1][n], rtol=1e-6, atol=0), n
+
+
+def test_packed_neighbour_keys_order_like_the_distance_index_contract():
+    """The grid search keeps its best list as 64-bit keys (bits(d2) << 32 | index) and the fine-depth merge sorts
+    (ordered bits(z) << 32 | draw index) (csrc/knn_unpose.cu `key_pack`, csrc/sample_fine.cu `ord_bits`): unsigned order of
+    the packed keys must be the (value, index) order of the contract -- for squared distances (>= +0, incl. +inf and
+    exact ties) and, with the sign-flip map, for depths of either sign."""
+    import numpy as np
+    rs = np.random.RandomState(0)
+    d2 = np.concatenate([rs.uniform(0, 4, 4000).astype(np.float32) ** 2, np.zeros(50, np.float32),
+                         np.full(50, np.inf, np.float32), np.float32([1e-38, 1e-45, 3.4e38])])
+    d2[:2000] = rs.choice(d2[2000:2100], 2000)                       # many exact ties
+    idx = rs.randint(0, 6890, d2.size).astype(np.int64)
+    key = (d2.view(np.uint32).astype(np.uint64) << np.uint64(32)) | idx.astype(np.uint64)
+    assert np.array_equal(np.argsort(key, kind="stable"), np.lexsort((idx, d2)))
+    z = np.concatenate([rs.normal(0, 3, 5000).astype(np.float32), np.float32([0.0, -0.0, 1e-45, -1e-45])])
+    b = z.view(np.uint32)
+    ob = np.where(b & np.uint32(0x80000000), ~b, b | np.uint32(0x80000000)).astype(np.uint32)
+    back = np.where(ob & np.uint32(0x80000000), ob & np.uint32(0x7fffffff), ~ob).astype(np.uint32).view(np.float32)
+    assert np.array_equal(back.view(np.uint32), b)                   # the map round-trips every bit pattern
+    order = np.argsort(ob, kind="stable")
+    assert np.all(np.diff(z[order]) >= 0)                            # ... and is monotone (-0.0 sorts before +0.0)
