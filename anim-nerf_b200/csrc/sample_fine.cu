@@ -135,7 +135,8 @@ sample_fine_merge_kernel(const float* __restrict__ weights, const float* __restr
             for (int j = lane; j + 1 < Kf; j += 32) asc = asc && key[j] < key[j + 1];
             if (!__all_sync(0xffffffffu, asc)) warp_bitonic_sort(key, nsort, lane);
         }
-        // rank merge (coarse first on ties; equal fine depths in draw order)
+        // rank merge (coarse first on ties; equal fine depths in draw order).  The two sides compare differently -- packed
+        // keys here, floats below -- which agree for every pair of depths except (+0.0, -0.0); depths are >= near > 0.
         const int Ka = Kc + Kf;
         for (int i = lane; i < Kc; i += 32) {
             const float a = zc[i];
